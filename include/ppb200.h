@@ -1,0 +1,186 @@
+/*
+ * ppb200.h -- C ABI of the B200-native wideband-TOA engine.
+ *
+ * This is the drop-in boundary for ONE hot path of pennucci/PulsePortraiture:
+ * the extended-FFTFIT fit.  Plain pointers and sizes only; no torch / numpy
+ * types.  Every entry point cites the reference interface it replaces
+ * (file:line into the reference tree).  The Python facade in
+ * pulseportraiture_b200/ binds these symbols with ctypes (see INTEGRATION.md
+ * for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - All array arguments may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes); outputs are written where they point.
+ *   - Row-major, C-contiguous.  data/model are float32 (the device storage
+ *     type); every scalar/vector parameter is float64.
+ *   - A plan is bound to one device and one stream; calls are synchronous
+ *     with respect to the caller (they return after results are complete)
+ *     unless stated otherwise.  One plan per (device, host thread).
+ *   - Return value 0 = success, negative = error (see pp_last_error()).
+ *   - nbin must be a power of two, 64 <= nbin <= 4096.
+ *   - The DC harmonic is ignored (reference F0_fact = 0, pplib.py:66) and
+ *     Dconst = 1/0.000241 (pplib.py:48-51).
+ */
+#ifndef PPB200_H
+#define PPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPB200_ABI_VERSION 1
+
+typedef struct pp_plan pp_plan_t;
+
+/* ---- plan ---------------------------------------------------------------
+ * Replaces the implicit per-call setup of pplib.fit_portrait
+ * (pplib.py:2127-2138) / pptoaslib.fit_portrait_full (pptoaslib.py:972-989):
+ * FFT twiddles, device scratch, the model-side spectra. */
+int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device,
+                   pp_plan_t** plan_out);
+void pp_plan_destroy(pp_plan_t* plan);
+
+/* Use an externally created cudaStream_t (e.g. a torch stream) for all work
+ * of this plan.  NULL restores the plan's own stream. */
+int pp_plan_set_stream(pp_plan_t* plan, void* cuda_stream);
+
+/* Number of subints processed per pipeline chunk (0 = automatic: sized so a
+ * chunk's cross-spectra stay L2-resident). */
+int pp_plan_set_chunk(pp_plan_t* plan, int32_t subints_per_chunk);
+
+/* FFT arithmetic of the data rows: 0 = automatic (double when the noise level
+ * is measured from a small portrait, float otherwise), 32, 64. */
+int pp_plan_set_fft_precision(pp_plan_t* plan, int32_t bits);
+
+/* Channel frequencies [nchan] MHz only (enough for pp_rotate_batch). */
+int pp_set_freqs(pp_plan_t* plan, const double* freqs);
+
+/* Model portrait [nchan, nbin] float32 and channel frequencies [nchan] MHz.
+ * Computes conj(rfft(model)), |rfft(model)|^2 and p_n = sum_k |m_nk|^2 once
+ * (pplib.py:2129-2130, 2138; pptoaslib.py:978-979). */
+int pp_set_model(pp_plan_t* plan, const float* model, const double* freqs);
+
+/* ---- batched wideband fit ------------------------------------------------
+ * Replaces, per subint, the sequence of pptoas.GetTOAs.get_TOAs
+ * (pptoas.py:402-486): [FFTFIT initial guess] -> fit_portrait_full
+ * (pptoaslib.py:928-1096); with fit_flags = {1,1,0,0,0} and
+ * semantics = PP_SEM_FIT_PORTRAIT it is pplib.fit_portrait
+ * (pplib.py:2102-2204). */
+enum {
+  PP_SEM_FIT_PORTRAIT_FULL = 0, /* pptoaslib.py:928: covariance incl. amplitudes */
+  PP_SEM_FIT_PORTRAIT = 1       /* pplib.py:2102: scale_errs = (p_n/sigma^2)^-1/2 */
+};
+
+typedef struct {
+  const float* data;        /* [nsub,nchan,nbin] float32                       */
+  int32_t nsub;
+  int32_t semantics;        /* PP_SEM_*                                        */
+  const double* P;          /* [nsub] spin period [s]                          */
+  const double* errs;       /* [nsub,nchan] time-domain noise sigma, or NULL:
+                               measured as get_noise_PS (pplib.py:2227-2253)   */
+  const uint8_t* chan_mask; /* [nsub,nchan] 1 = use channel; NULL = all        */
+  const double* weights;    /* [nsub,nchan] weights of the frequency average
+                               used for the initial guess (pptoas.py:424);
+                               NULL = 1                                        */
+  const double* init;       /* [nsub,5] phi,DM,GM,tau(or log10),alpha at
+                               nu_fits; NULL = FFTFIT guess (pptoas.py:421-456)*/
+  const double* DM_guess;   /* [nsub] DM used to dedisperse for the guess and
+                               as DM start value (pptoas.py:421); NULL = 0     */
+  const double* snrs;       /* [nsub,nchan] per-channel S/N for guess_fit_freq
+                               (pplib.py:2618) when nu_fits==NULL and
+                               nu_fit_mode==1; NULL = ones                     */
+  const double* nu_fits;    /* [nsub,3] fit reference freqs or NULL            */
+  int32_t nu_fit_mode;      /* with nu_fits==NULL: 0 = mean of used freqs
+                               (pptoaslib.py:986-989); 1 = guess_fit_freq
+                               (pptoas.py:402)                                 */
+  const double* nu_outs;    /* [nsub,3] output reference freqs; NaN (or NULL)
+                               = zero-covariance frequency (pptoaslib.py:1040) */
+  uint8_t fit_flags[5];     /* phi, DM, GM, tau, alpha                         */
+  int32_t log10_tau;        /* pptoaslib.py:931                                */
+  int32_t option;           /* get_nu_zeros option (pptoaslib.py:734)          */
+  int32_t is_toa;           /* pptoaslib.py:1048-1050                          */
+  int32_t Ns;               /* FFTFIT grid size (pplib.py:2054), default 100   */
+  int32_t max_iter;         /* Newton passes per subint (0 = default)          */
+  double tol;               /* convergence: |step| < tol * 1-sigma (0=default) */
+} pp_fit_args_t;
+
+typedef struct {
+  double* params;       /* [nsub,5] at the output reference frequencies        */
+  double* param_errs;   /* [nsub,5] (0 for parameters not fit)                 */
+  double* nu_out;       /* [nsub,3] nu_DM, nu_GM, nu_tau                       */
+  double* cov;          /* [nsub,5,5] parameter covariance (0 rows if not fit) */
+  double* chi2;         /* [nsub]                                              */
+  double* red_chi2;     /* [nsub]                                              */
+  double* snr;          /* [nsub]                                              */
+  int32_t* nfeval;      /* [nsub] objective passes used                        */
+  int32_t* return_code; /* [nsub] 0 converged, 1 max_iter, 3 non-finite        */
+  double* scales;       /* [nsub,nchan]                                        */
+  double* scale_errs;   /* [nsub,nchan]                                        */
+  double* channel_snrs; /* [nsub,nchan]                                        */
+  double* noise;        /* [nsub,nchan] time-domain sigma actually used        */
+  int32_t* lag_index;   /* [nsub] FFTFIT integer grid argmin (-1 if init given)*/
+  double* phi_guess;    /* [nsub] initial phase handed to the solver           */
+  double* chan_sums;    /* [nsub,nchan,9] per-channel C,Cth,Cthth,Ct,Ctt,Ctht,
+                           S,St,Stt at the solution (for host epilogues)       */
+} pp_fit_out_t;          /* any member may be NULL                              */
+
+int pp_fit_batch(pp_plan_t* plan, const pp_fit_args_t* args,
+                 const pp_fit_out_t* out);
+
+/* ---- batched 1-D FFTFIT ---------------------------------------------------
+ * Replaces pplib.fit_phase_shift (pplib.py:2054-2100) for n profiles.
+ * models: [nmodel, nbin] with nmodel == n or 1.  noise: [n] time-domain
+ * sigma or NULL (-> get_noise, pplib.py:2076).  The brute-force grid is
+ * np.mgrid[-0.5:0.5:Ns*1j]; lag_index is its argmin; phase is the exact
+ * minimiser reached from there (the reference's Nelder-Mead polish is only
+ * 1e-4 accurate). */
+typedef struct {
+  double* phase; double* phase_err; double* scale; double* scale_err;
+  double* snr; double* red_chi2; int32_t* lag_index;
+} pp_pshift_out_t;
+
+int pp_fit_phase_shift_batch(pp_plan_t* plan, const float* profiles, int32_t n,
+                             const float* models, int32_t nmodel,
+                             const double* noise, int32_t Ns,
+                             const pp_pshift_out_t* out);
+
+/* ---- batched Fourier-domain rotation -------------------------------------
+ * Replaces pplib.rotate_data / rotate_portrait (pplib.py:2338-2460) for
+ * [nsub,nchan,nbin] float32: harmonic k of channel n is multiplied by
+ * exp(+2 pi i k (phase_s + Dconst*DM_s/P_s*(nu_n^-2 - nu_ref_s^-2))).
+ * in/out may alias. */
+int pp_rotate_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
+                    const double* phase, const double* DM, const double* P,
+                    const double* nu_ref);
+
+/* ---- per-channel noise -----------------------------------------------------
+ * Replaces pplib.get_noise(data, chans=True) (pplib.py:2227-2245). */
+int pp_get_noise_batch(pp_plan_t* plan, const float* data, int32_t nsub,
+                       double* noise_out);
+
+/* ---- diagnostics ------------------------------------------------------------ */
+typedef struct {
+  int64_t launches;        /* kernels launched by the last pp_* call            */
+  int64_t pass_launches;   /* of which objective-pass kernels                   */
+  int64_t pass_rows;       /* channel rows actually streamed by pass kernels    */
+  double ms_spectra;       /* CUDA-event time of the FFT/precompute kernels     */
+  double ms_guess;         /* ... FFTFIT guess kernels                          */
+  double ms_pass;          /* ... objective pass kernels                        */
+  double ms_update;        /* ... Newton update / epilogue kernels              */
+  double ms_total;         /* first launch -> last kernel of the call           */
+  int32_t chunk;           /* subints per chunk used                            */
+  int32_t timing_enabled;
+} pp_stats_t;
+
+int pp_plan_enable_timing(pp_plan_t* plan, int32_t on);
+int pp_get_stats(pp_plan_t* plan, pp_stats_t* stats);
+
+const char* pp_last_error(void);
+int pp_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPB200_H */

@@ -1,0 +1,1091 @@
+// Hand-written sm_100a kernels of the wideband-TOA hot path.
+//
+//   k_model    conj(rfft(model)), |m|^2, p_n               (pplib.py:2129-2138)
+//   k_prep     per-subint reference frequencies, counts    (pptoas.py:400-402)
+//   k_spectra  K1+K2: per-channel rfft of the data, noise (get_noise_PS),
+//              Sd, cross-spectrum X = d conj(m), partial frequency-averaged
+//              profile spectra for the FFTFIT guess        (pplib.py:2127-2138,
+//                                                           2227-2253; pptoas.py:422-424)
+//   k_guess    K4: brute-force grid argmin + exact polish  (pplib.py:2054-2100)
+//   k_pass2    K3: fused rotate-reduce C, C', C'' per channel (pplib.py:1315-1381)
+//   k_update2  K3': per-subint reduction, safeguarded Newton step, epilogue
+//              (nu_zero, covariance, scales, chi2)          (pplib.py:2146-2204,
+//                                                           pptoaslib.py:1040-1096)
+//
+// Storage: X is float2 [subint][channel][N], N = nbin/2, slot j holds harmonic
+// j for 1 <= j < N and slot 0 holds the Nyquist harmonic k = N (harmonic 0 is
+// dropped: F0_fact = 0, pplib.py:66).  Rotation phasors and all accumulators
+// are double precision.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "fft.cuh"
+
+namespace ppb {
+
+constexpr double kDconst = 1.0 / 0.000241;  // pplib.py:48-51
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+constexpr int kNCsum = 9;                   // per-channel sums kept per subint
+
+// ----------------------------------------------------------------------------
+// small device helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic CTA-wide sum of NV doubles per thread (result valid in all threads).
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* >= NV * NT/32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[i * NW + w] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) s += sh[i * NW + j];
+    v[i] = s;
+  }
+}
+
+// e^{2 pi i x} in double precision for any finite x (range-reduced first).
+__device__ __forceinline__ void cis2pi(double x, double& c, double& s) {
+  x -= rint(x);
+  sincospi(2.0 * x, &s, &c);
+}
+
+__device__ __forceinline__ double wrap_phase(double phi) {
+  // pplib.py:2611-2613 / pptoaslib.py:1056-1057: onto [-0.5, 0.5)
+  if (fabs(phi) >= 0.5) phi = phi - floor(phi);
+  if (phi >= 0.5) phi -= 1.0;
+  return phi;
+}
+
+// ----------------------------------------------------------------------------
+// k_model: one CTA of 256 threads, RowGeom<N>::kRows channels at a time.
+// Always runs in double (once per model); stores conj(m) both as double and
+// rounded to float, |m|^2 as float, p_n as double.
+// ----------------------------------------------------------------------------
+struct ModelArgs {
+  const float* model;   // [nchan, 2N]
+  cx<float>* mconj32;   // [nchan, N] conj(m), slot layout
+  cx<double>* mconj64;  // [nchan, N]
+  float* mpow;          // [nchan, N] |m|^2, slot layout
+  double* pn;           // [nchan]
+  const cx<double>* twN;
+  const cx<double>* tw2N;
+  int nchan;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) k_model(ModelArgs a) {
+  using G = RowGeom<N>;
+  using T = double;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  __shared__ double red[8];
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  for (int i = tid; i < N; i += 256) twN[i] = a.twN[i];
+  for (int i = tid; i <= N / 2; i += 256) tw2N[i] = a.tw2N[i];
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+  const int ch = blockIdx.x * G::kRows + r;
+  const bool valid = ch < a.nchan;
+  const float4* src = reinterpret_cast<const float4*>(a.model + (size_t)(valid ? ch : 0) * 2 * N);
+#pragma unroll
+  for (int m = 0; m < G::kLoads; ++m) {
+    const int i4 = t_row + m * G::kTRow;
+    const float4 v = valid ? src[i4] : make_float4(0, 0, 0, 0);
+    bufA[2 * i4] = mk<T>(v.x, v.y);
+    bufA[2 * i4 + 1] = mk<T>(v.z, v.w);
+  }
+  __syncthreads();
+  cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  double psum = 0.0;
+  const size_t ro = (size_t)(valid ? ch : 0) * N;
+  auto put = [&](int slot, cx<T> d) {
+    const double pw = d.x * d.x + d.y * d.y;
+    psum += pw;
+    if (valid) {
+      a.mconj64[ro + slot] = cconj(d);
+      a.mconj32[ro + slot] = mk<float>((float)d.x, (float)(-d.y));
+      a.mpow[ro + slot] = (float)pw;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) {
+    const int p = t_row + 1 + i * G::kTRow;
+    if (p <= N / 2) {
+      cx<T> dp, dq;
+      unpack_pair<T>(Z, tw2N, N, p, dp, dq);
+      put(p, dp);
+      if (p < N / 2) put(N - p, dq);
+    }
+  }
+  if (t_row == 0) put(0, mk<T>(Z[0].x - Z[0].y, 0.0));  // harmonic N (real)
+  // reduce psum over the row-slot
+#pragma unroll
+  for (int o = (G::kTRow < 32 ? G::kTRow : 32) / 2; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+  if (G::kTRow > 32) {
+    if ((tid & 31) == 0) red[tid >> 5] = psum;
+    __syncthreads();
+    if (t_row == 0) {
+      double s = 0.0;
+      for (int w = 0; w < G::kTRow / 32; ++w) s += red[r * (G::kTRow / 32) + w];
+      psum = s;
+    }
+  }
+  if (t_row == 0 && valid) a.pn[ch] = psum;
+}
+
+// mean over (all) channels of conj(m): one thread per slot, fixed order.
+__global__ void k_model_mean(const cx<double>* __restrict__ mconj, float2* __restrict__ mmean, int nchan, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double sx = 0.0, sy = 0.0;
+  for (int n = 0; n < nchan; ++n) {
+    const cx<double> v = mconj[(size_t)n * N + i];
+    sx += v.x; sy += v.y;
+  }
+  mmean[i] = make_float2((float)(sx / nchan), (float)(sy / nchan));
+}
+
+// ----------------------------------------------------------------------------
+// k_prep: one warp per subint.
+// ----------------------------------------------------------------------------
+struct PrepArgs {
+  const double* freqs;      // [nchan]
+  const uint8_t* mask;      // [nsub,nchan] or null
+  const double* weights;    // [nsub,nchan] or null
+  const double* snrs;       // [nsub,nchan] or null
+  const double* nu_fits_in; // [nsub,3] or null
+  double* nu_fit;           // [nsub,3] out
+  double* nu_mean;          // [nsub] out
+  double* wsum;             // [nsub] out
+  int* nok;                 // [nsub] out
+  int nsub, nchan, nu_fit_mode;
+};
+
+__global__ void k_prep(PrepArgs a) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= a.nsub) return;
+  double cnt = 0, ws = 0, fs = 0, fmin = 1e300, fmax = -1e300, num = 0, den = 0;
+  for (int n = lane; n < a.nchan; n += 32) {
+    const bool ok = a.mask ? (a.mask[(size_t)s * a.nchan + n] != 0) : true;
+    if (!ok) continue;
+    const double f = a.freqs[n];
+    cnt += 1.0;
+    ws += a.weights ? a.weights[(size_t)s * a.nchan + n] : 1.0;
+    fs += f;
+    fmin = fmin < f ? fmin : f;
+    fmax = fmax > f ? fmax : f;
+  }
+  cnt = warp_sum(cnt); ws = warp_sum(ws); fs = warp_sum(fs);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fmin = fmin < __shfl_xor_sync(0xffffffffu, fmin, o) ? fmin : __shfl_xor_sync(0xffffffffu, fmin, o);
+    fmax = fmax > __shfl_xor_sync(0xffffffffu, fmax, o) ? fmax : __shfl_xor_sync(0xffffffffu, fmax, o);
+  }
+  const double nu0 = 0.5 * (fmin + fmax);
+  for (int n = lane; n < a.nchan; n += 32) {
+    const bool ok = a.mask ? (a.mask[(size_t)s * a.nchan + n] != 0) : true;
+    if (!ok) continue;
+    const double f = a.freqs[n];
+    const double w = (a.snrs ? a.snrs[(size_t)s * a.nchan + n] : 1.0) / (f * f);
+    num += (f - nu0) * w;
+    den += w;
+  }
+  num = warp_sum(num); den = warp_sum(den);
+  if (lane == 0) {
+    const double mean = cnt > 0 ? fs / cnt : 0.0;
+    a.nok[s] = (int)cnt;
+    a.wsum[s] = ws;
+    a.nu_mean[s] = mean;
+    const double dflt = (a.nu_fit_mode == 1) ? (nu0 + num / den) : mean;  // pplib.py:2618-2632
+    for (int i = 0; i < 3; ++i) {
+      double v = a.nu_fits_in ? a.nu_fits_in[(size_t)s * 3 + i] : CUDART_NAN;
+      if (!(v == v)) v = dflt;
+      a.nu_fit[(size_t)s * 3 + i] = v;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_spectra: K1 + K2.  grid = (ceil(nchan/G), subints in chunk), 256 threads.
+// T = arithmetic type of the FFT (float or double); storage of X is float2.
+// ----------------------------------------------------------------------------
+struct SpectraArgs {
+  const float* data;         // [nsub,nchan,2N], global subint index
+  const cx<float>* mconj32;  // [nchan,N]
+  const cx<double>* mconj64; // [nchan,N]
+  const double* pn;          // [nchan]
+  const double* nu2;         // [nchan] nu^-2
+  const double* errs;        // [nsub,nchan] or null
+  const uint8_t* mask;       // or null
+  const double* weights;     // or null
+  const double* P;           // [nsub]
+  const double* DMg;         // [nsub] or null
+  const double* nu_mean;     // [nsub]
+  float2* X;                 // [chunk,nchan,N]  (null: do not store)
+  float2* partial;           // [chunk,nparts,N] (null: no guess)
+  double* sigma;             // [nsub,nchan] out
+  double* Ssn;               // [nsub,nchan] out: p_n / sigma_F^2 (0 = channel unused)
+  double* Sdn;               // [nsub,nchan] out
+  const void* twN;           // cx<T>[N]
+  const void* tw2N;          // cx<T>[N/2+1]
+  int s0;                    // first global subint of the chunk
+  int nchan, G, nparts;
+};
+
+template <int N, typename T>
+__global__ void __launch_bounds__(256) k_spectra(SpectraArgs a) {
+  using G = RowGeom<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  {
+    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.twN);
+    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.tw2N);
+    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
+    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
+  }
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+
+  const int sl = blockIdx.y, s = a.s0 + sl;
+  const int ch_begin = blockIdx.x * a.G;
+  const int ch_end = min(ch_begin + a.G, a.nchan);
+  const int nsteps = (a.G + G::kRows - 1) / G::kRows;
+  constexpr int kc = (3 * (N + 1)) / 4;           // int(0.75*nharm), pplib.py:2244
+  constexpr int ntop = N + 1 - kc;
+  const bool want_guess = a.partial != nullptr;
+  const double dmg = (want_guess && a.DMg) ? a.DMg[s] : 0.0;
+  const double Dfac = dmg != 0.0 ? kDconst * dmg / a.P[s] : 0.0;  // pplib.py:2381
+  const double numean = a.nu_mean[s];
+  const double numean2 = 1.0 / (numean * numean);
+
+  float2 acc[2 * G::kPairs + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * G::kPairs + 1; ++i) acc[i] = make_float2(0.f, 0.f);
+
+  auto row_used = [&](int ch) -> bool {
+    if (ch >= ch_end) return false;
+    return a.mask ? (a.mask[(size_t)s * a.nchan + ch] != 0) : true;
+  };
+  float4 pre[G::kLoads];
+  {
+    const int ch = ch_begin + r;
+    const bool u = row_used(ch);
+    const float4* src = reinterpret_cast<const float4*>(a.data + ((size_t)s * a.nchan + (u ? ch : 0)) * 2 * N);
+#pragma unroll
+    for (int m = 0; m < G::kLoads; ++m) pre[m] = u ? __ldg(src + t_row + m * G::kTRow) : make_float4(0, 0, 0, 0);
+  }
+  for (int step = 0; step < nsteps; ++step) {
+    const int ch = ch_begin + step * G::kRows + r;
+    const bool inrange = ch < ch_end;
+    bool used = row_used(ch);
+#pragma unroll
+    for (int m = 0; m < G::kLoads; ++m) {
+      const int i4 = t_row + m * G::kTRow;
+      bufA[2 * i4] = mk<T>((T)pre[m].x, (T)pre[m].y);
+      bufA[2 * i4 + 1] = mk<T>((T)pre[m].z, (T)pre[m].w);
+    }
+    if (step + 1 < nsteps) {  // prefetch the next row while this one is transformed
+      const int chn = ch + G::kRows;
+      const bool u = row_used(chn);
+      const float4* src = reinterpret_cast<const float4*>(a.data + ((size_t)s * a.nchan + (u ? chn : 0)) * 2 * N);
+#pragma unroll
+      for (int m = 0; m < G::kLoads; ++m) pre[m] = u ? __ldg(src + t_row + m * G::kTRow) : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+
+    // ---- half spectrum of this thread's harmonics -------------------------
+    cx<T> d[2 * G::kPairs + 1];
+    T s_all = 0, s_top = 0;
+#pragma unroll
+    for (int i = 0; i < G::kPairs; ++i) {
+      const int p = t_row + 1 + i * G::kTRow;
+      d[2 * i] = mk<T>(0, 0);
+      d[2 * i + 1] = mk<T>(0, 0);
+      if (p <= N / 2) {
+        unpack_pair<T>(Z, tw2N, N, p, d[2 * i], d[2 * i + 1]);
+        const T pw = d[2 * i].x * d[2 * i].x + d[2 * i].y * d[2 * i].y;
+        s_all += pw;
+        if (p >= kc) s_top += pw;
+        if (p < N / 2) {
+          const T qw = d[2 * i + 1].x * d[2 * i + 1].x + d[2 * i + 1].y * d[2 * i + 1].y;
+          s_all += qw;
+          if (N - p >= kc) s_top += qw;
+        } else {
+          d[2 * i + 1] = mk<T>(0, 0);
+        }
+      }
+    }
+    d[2 * G::kPairs] = mk<T>(0, 0);
+    if (t_row == 0) {
+      const T ny = Z[0].x - Z[0].y;
+      d[2 * G::kPairs] = mk<T>(ny, 0);
+      s_all += ny * ny;
+      s_top += ny * ny;
+    }
+    // ---- row-slot reduction of the two power sums ---------------------------
+    double v_all = s_all, v_top = s_top;
+#pragma unroll
+    for (int o = (G::kTRow < 32 ? G::kTRow : 32) / 2; o > 0; o >>= 1) {
+      v_all += __shfl_xor_sync(0xffffffffu, v_all, o);
+      v_top += __shfl_xor_sync(0xffffffffu, v_top, o);
+    }
+    if (G::kTRow > 32) {
+      if ((tid & 31) == 0) { red[0][tid >> 5] = v_all; red[1][tid >> 5] = v_top; }
+      __syncthreads();
+      double sa = 0.0, st = 0.0;
+#pragma unroll
+      for (int w = 0; w < G::kTRow / 32; ++w) { sa += red[0][r * (G::kTRow / 32) + w]; st += red[1][r * (G::kTRow / 32) + w]; }
+      v_all = sa; v_top = st;
+    }
+    // ---- noise, Sd, S --------------------------------------------------------
+    double sig;
+    if (a.errs) sig = used ? a.errs[(size_t)s * a.nchan + ch] : 0.0;
+    else sig = sqrt(v_top / ((double)(2 * N) * (double)ntop));       // pplib.py:2243-2245
+    const double sF2 = sig * sig * (double)N;                         // sigma^2 * nbin/2
+    if (!(sF2 > 0.0) || !(sF2 < 1e300)) used = false;
+    if (inrange && t_row == 0) {
+      const size_t o = (size_t)s * a.nchan + ch;
+      a.sigma[o] = used ? sig : 0.0;
+      a.Ssn[o] = used ? a.pn[ch] / sF2 : 0.0;
+      a.Sdn[o] = used ? v_all / sF2 : 0.0;
+    }
+    // ---- cross spectrum + guess accumulation ---------------------------------
+    if (inrange) {
+      float2* xr = a.X ? a.X + ((size_t)sl * a.nchan + ch) * N : nullptr;
+      const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
+      const double shift = Dfac != 0.0 ? Dfac * (a.nu2[ch] - numean2) : 0.0;
+#pragma unroll
+      for (int i = 0; i < 2 * G::kPairs + 1; ++i) {
+        const int ip = i >> 1;
+        const int p = t_row + 1 + ip * G::kTRow;
+        int k;  // harmonic index of d[i]
+        bool live;
+        if (i == 2 * G::kPairs) { k = N; live = (t_row == 0); }
+        else if ((i & 1) == 0) { k = p; live = p <= N / 2; }
+        else { k = N - p; live = p < N / 2; }
+        if (!live) continue;
+        const int slot = (k == N) ? 0 : k;
+        if (xr) {
+          float2 xv = make_float2(0.f, 0.f);
+          if (used) {
+            cx<T> m;
+            if constexpr (sizeof(T) == 8) m = a.mconj64[(size_t)ch * N + slot];
+            else m = a.mconj32[(size_t)ch * N + slot];
+            const cx<T> pr = cmul(d[i], m);
+            xv = make_float2((float)pr.x, (float)pr.y);
+          }
+          xr[slot] = xv;
+        }
+        if (wgt != 0.f) {
+          float2 v = make_float2((float)d[i].x, (float)d[i].y);
+          if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
+            double c, sn;
+            cis2pi((double)k * shift, c, sn);
+            const float cf = (float)c, sf = (float)sn;
+            v = make_float2(v.x * cf - v.y * sf, v.x * sf + v.y * cf);
+          }
+          acc[i].x = fmaf(wgt, v.x, acc[i].x);
+          acc[i].y = fmaf(wgt, v.y, acc[i].y);
+        }
+      }
+    }
+    __syncthreads();  // bufA/bufB are rewritten by the next step
+  }
+  if (want_guess) {
+    const int part = blockIdx.x * G::kRows + r;
+    float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
+#pragma unroll
+    for (int i = 0; i < 2 * G::kPairs + 1; ++i) {
+      const int ip = i >> 1;
+      const int p = t_row + 1 + ip * G::kTRow;
+      int k; bool live;
+      if (i == 2 * G::kPairs) { k = N; live = (t_row == 0); }
+      else if ((i & 1) == 0) { k = p; live = p <= N / 2; }
+      else { k = N - p; live = p < N / 2; }
+      if (live) pr[(k == N) ? 0 : k] = acc[i];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_guess: K4, one CTA (256 threads) per profile / subint.
+// ----------------------------------------------------------------------------
+struct GuessArgs {
+  const float2* partial;   // [n, nparts, N] spectra to be summed (slot layout)
+  const float2* mconj;     // [nmodel, N] conj(model spectrum)
+  int nparts, nmodel, N, Ns;
+  const double* wsum;      // [n] divisor of the partial sum, or null (=1)
+  const double* noise;     // [n] time-domain sigma or null (measure from spectrum)
+  const double2* table;    // [Ns-1] e^{2 pi i m/(Ns-1)}
+  int s0;                  // global index offset for per-subint arrays below
+  // outputs of the 1-D fit (global index), any may be null
+  double* phase; double* phase_err; double* scale; double* scale_err; double* snr; double* red_chi2;
+  int* lag;
+  // solver start state (fit batch only; null for the stand-alone 1-D fit)
+  double* x;               // [nsub,5]
+  const double* DMg;       // [nsub] or null
+  const double* P;         // [nsub]
+  const double* nu_mean;   // [nsub]
+  const double* nu_fit;    // [nsub,3]
+  const double* init;      // [nsub,5] or null: template for GM,tau,alpha start values
+};
+
+__global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* Y = reinterpret_cast<double2*>(smem_raw);  // [N]
+  __shared__ double sh[8 * 4];
+  __shared__ double bestv[8];
+  __shared__ int besti[8];
+  __shared__ double bc[4];
+  const int N = a.N, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int il = blockIdx.x, ig = a.s0 + il;
+  const int kc = (3 * (N + 1)) / 4;
+  const double inv_w = a.wsum ? 1.0 / a.wsum[ig] : 1.0;
+  const float2* mc = a.mconj + (size_t)(a.nmodel > 1 ? il : 0) * N;
+  double v[3] = {0.0, 0.0, 0.0};  // sum |d|^2, sum |m|^2, top-quarter power
+  for (int i = tid; i < N; i += 256) {
+    float sx = 0.f, sy = 0.f;
+    for (int q = 0; q < a.nparts; ++q) {
+      const float2 t = a.partial[((size_t)il * a.nparts + q) * N + i];
+      sx += t.x; sy += t.y;
+    }
+    const double dx = (double)sx * inv_w, dy = (double)sy * inv_w;
+    const float2 m = mc[i];
+    Y[i] = make_double2(dx * m.x - dy * m.y, dx * m.y + dy * m.x);
+    const double pw = dx * dx + dy * dy;
+    v[0] += pw;
+    v[1] += (double)m.x * m.x + (double)m.y * m.y;
+    const int k = (i == 0) ? N : i;
+    if (k >= kc) v[2] += pw;
+  }
+  block_sum<3, 256>(v, sh);
+  double err2;  // Fourier-domain variance (pplib.py:2076-2079)
+  if (a.noise) { const double nz = a.noise[ig]; err2 = nz * nz * (double)N; }
+  else err2 = v[2] / ((double)(2 * N) * (double)(N + 1 - kc)) * (double)N;
+  const double d_tot = v[0] / err2, p_tot = v[1] / err2;
+
+  // ---- brute-force grid (scipy.optimize.brute over np.mgrid[-0.5:0.5:Ns j]) ----
+  const int M = a.Ns - 1;
+  double bv = CUDART_INF;
+  int bi = 0x7fffffff;
+  for (int j = w; j < a.Ns; j += 8) {
+    double acc = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const int k = (i == 0) ? N : i;
+      const double2 t = a.table[(int)(((long long)k * j) % M)];
+      const double re = Y[i].x * t.x - Y[i].y * t.y;
+      acc += (k & 1) ? -re : re;  // e^{-i pi k}
+    }
+    acc = warp_sum(acc);
+    const double cj = -acc / err2;
+    if (cj < bv) { bv = cj; bi = j; }  // j ascending: first index wins ties
+  }
+  if (lane == 0) { bestv[w] = bv; besti[w] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    double b = bestv[0]; int ib = besti[0];
+    for (int q = 1; q < 8; ++q)
+      if (bestv[q] < b || (bestv[q] == b && besti[q] < ib)) { b = bestv[q]; ib = besti[q]; }
+    besti[0] = ib;
+  }
+  __syncthreads();
+  const int lagi = besti[0];
+  const double h = 1.0 / (double)M;
+  double x = -0.5 + (double)lagi * h;
+  double lo = x - h, hi = x + h;
+  double C0 = 0, C1 = 0, C2 = 0;
+  // ---- exact polish: safeguarded Newton on C'(phi) = 0 inside the bracket ------
+  for (int it = 0; it < 60; ++it) {
+    double u[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < N; i += 256) {
+      const int k = (i == 0) ? N : i;
+      double c, sn;
+      cis2pi((double)k * x, c, sn);
+      const double re = Y[i].x * c - Y[i].y * sn;
+      const double im = Y[i].x * sn + Y[i].y * c;
+      const double wk = kTwoPi * (double)k;
+      u[0] -= re;            // C   (pplib.py:1244-1256)
+      u[1] += wk * im;       // C'  (1258-1268)
+      u[2] += wk * wk * re;  // C'' (1270-1280)
+    }
+    block_sum<3, 256>(u, sh);
+    C0 = u[0] / err2; C1 = u[1] / err2; C2 = u[2] / err2;
+    if (tid == 0) {
+      if (C1 < 0.0) lo = x; else hi = x;
+      double xn = (C2 > 0.0) ? x - C1 / C2 : CUDART_NAN;
+      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+      bc[0] = xn; bc[1] = lo; bc[2] = hi;
+      bc[3] = (fabs(xn - x) < 1e-14 || C1 == 0.0) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const bool stop = bc[3] != 0.0;
+    if (!stop) { x = bc[0]; lo = bc[1]; hi = bc[2]; }
+    __syncthreads();
+    if (stop) break;
+  }
+  if (tid == 0) {
+    const double fmin = C0;
+    const double scale = -fmin / p_tot;
+    if (a.phase) a.phase[ig] = x;
+    if (a.lag) a.lag[ig] = lagi;
+    if (a.phase_err) a.phase_err[ig] = 1.0 / sqrt(scale * C2);       // pplib.py:2092-2093
+    if (a.scale) a.scale[ig] = scale;
+    if (a.scale_err) a.scale_err[ig] = 1.0 / sqrt(p_tot);
+    if (a.red_chi2) a.red_chi2[ig] = (d_tot - fmin * fmin / p_tot) / (double)(2 * N - 2);
+    if (a.snr) a.snr[ig] = sqrt(scale * scale * p_tot);
+    if (a.x) {
+      const double dmg = a.DMg ? a.DMg[ig] : 0.0;
+      const double nm = a.nu_mean[ig], nf = a.nu_fit[(size_t)ig * 3];
+      // phase_transform(phi, DM_guess, nu_mean, nu_fit_DM, P, mod=True) (pptoas.py:456)
+      double ph = x + kDconst * dmg / a.P[ig] * (1.0 / (nf * nf) - 1.0 / (nm * nm));
+      ph = wrap_phase(ph);
+      double* xs = a.x + (size_t)ig * 5;
+      xs[0] = ph; xs[1] = dmg;
+      xs[2] = a.init ? a.init[(size_t)ig * 5 + 2] : 0.0;
+      xs[3] = a.init ? a.init[(size_t)ig * 5 + 3] : 0.0;
+      xs[4] = a.init ? a.init[(size_t)ig * 5 + 4] : 0.0;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Solver state (struct of arrays, global subint index)
+// ----------------------------------------------------------------------------
+struct SolverState {
+  double* x;        // [nsub,5] current evaluation point (at nu_fit)
+  double* xprev;    // [nsub,5] last accepted point
+  double* step;     // [nsub,5] last proposed step
+  double* fprev;    // [nsub]
+  double* lam;      // [nsub] backtracking factor
+  int* iter;        // [nsub] passes done
+  int* done;        // [nsub] 0 running, 1 finished
+};
+
+// ----------------------------------------------------------------------------
+// k_pass2: K3 for (phi, DM).  8 lanes per channel row, 4 rows per warp,
+// 8 warps per CTA: grid = (ceil(nchan/32), subints in chunk).
+// ----------------------------------------------------------------------------
+struct PassArgs {
+  const float2* X;         // [chunk,nchan,N]
+  const double* nu2;       // [nchan]
+  const double* P;         // [nsub]
+  const double* nu_fit;    // [nsub,3]
+  const double* Ssn;       // [nsub,nchan] (0 => unused channel)
+  const double* sigma;     // [nsub,nchan]
+  double* csum;            // [nsub,nchan,kNCsum]
+  SolverState st;
+  int s0, nchan, N;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) k_pass2(PassArgs a) {
+  const int sl = blockIdx.y, s = a.s0 + sl;
+  if (a.st.done[s]) return;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int sub = lane >> 3, l8 = lane & 7;
+  const int ch = blockIdx.x * 32 + w * 4 + sub;
+  const bool inrange = ch < a.nchan;
+  const int chc = inrange ? ch : a.nchan - 1;
+  const double Ssn = a.Ssn[(size_t)s * a.nchan + chc];
+  const bool used = inrange && Ssn > 0.0;
+
+  double C = 0.0, C1 = 0.0, C2 = 0.0;
+  if (used) {
+    const double phi = a.st.x[(size_t)s * 5 + 0], DM = a.st.x[(size_t)s * 5 + 1];
+    const double nf = a.nu_fit[(size_t)s * 3 + 0];
+    const double g = kDconst * (a.nu2[ch] - 1.0 / (nf * nf)) / a.P[s];
+    double theta = phi + DM * g;               // pplib.py:1319-1320
+    theta -= rint(theta);
+    const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
+    // element (j, e): complex index 16 j + 2 l8 + e, harmonic k = index (slot 0 = Nyquist)
+    double c0, s0, c1, s1, cw, sw;
+    cis2pi((double)(2 * l8) * theta, c0, s0);
+    cis2pi((double)(2 * l8 + 1) * theta, c1, s1);
+    cis2pi(16.0 * theta, cw, sw);
+    double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
+    constexpr int NJ = N / 16;
+#pragma unroll 4
+    for (int j = 0; j < NJ; ++j) {
+      float4 v = __ldg(row + j * 8 + l8);
+      if (j == 0 && l8 == 0) { v.x = 0.f; v.y = 0.f; }  // slot 0 is handled below
+      const double xr0 = v.x, xi0 = v.y, xr1 = v.z, xi1 = v.w;
+      const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
+      const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
+      C += re0 + re1;
+      C1 = fma(k0, im0, C1); C1 = fma(k1, im1, C1);
+      C2 = fma(k0 * k0, re0, C2); C2 = fma(k1 * k1, re1, C2);
+      // advance both phasors by 16 harmonics
+      const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
+      const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
+      k0 += 16.0; k1 += 16.0;
+    }
+    if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
+      const float2 xn = __ldg(reinterpret_cast<const float2*>(row));
+      double cn, sn;
+      cis2pi((double)N * theta, cn, sn);
+      const double re = (double)xn.x * cn - (double)xn.y * sn;
+      const double im = (double)xn.x * sn + (double)xn.y * cn;
+      C += re; C1 = fma((double)N, im, C1); C2 = fma((double)N * (double)N, re, C2);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    C += __shfl_xor_sync(0xffffffffu, C, o);
+    C1 += __shfl_xor_sync(0xffffffffu, C1, o);
+    C2 += __shfl_xor_sync(0xffffffffu, C2, o);
+  }
+  if (inrange && l8 == 0) {
+    double* o = a.csum + ((size_t)s * a.nchan + ch) * kNCsum;
+    if (used) {
+      const double sg = a.sigma[(size_t)s * a.nchan + ch];
+      const double isF2 = 1.0 / (sg * sg * (double)N);
+      o[0] = C * isF2;                         // C_n      (pplib.py:1322)
+      o[1] = -kTwoPi * C1 * isF2;              // dC/dtheta  (1344)
+      o[2] = -kTwoPi * kTwoPi * C2 * isF2;     // d2C/dtheta2 (1380)
+    } else {
+      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_update2: K3' for (phi, DM): one CTA of 128 threads per subint.
+// ----------------------------------------------------------------------------
+struct UpdateArgs {
+  const double* csum;      // [nsub,nchan,kNCsum]
+  const double* Ssn;       // [nsub,nchan]
+  const double* Sdn;       // [nsub,nchan]
+  const double* nu2;       // [nchan]
+  const double* freqs;     // [nchan]
+  const double* P;         // [nsub]
+  const double* nu_fit;    // [nsub,3]
+  const double* nu_outs;   // [nsub,3] or null
+  const int* nok;          // [nsub]
+  SolverState st;
+  // outputs (device arrays, global subint index)
+  double* params; double* param_errs; double* nu_out; double* cov; double* chi2; double* red_chi2;
+  double* snr; int* nfeval; int* rc; double* scales; double* scale_errs; double* channel_snrs;
+  int s0, nchan, nbin, max_iter, semantics, fit_phi, fit_dm, is_toa;
+  double tol;
+};
+
+__global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
+  const int s = a.s0 + blockIdx.x;
+  if (a.st.done[s]) return;
+  __shared__ double sh[8 * 4];
+  __shared__ double bc[16];
+  const int tid = threadIdx.x;
+  const int nchan = a.nchan;
+  const double* cs = a.csum + (size_t)s * nchan * kNCsum;
+  const double* Sv = a.Ssn + (size_t)s * nchan;
+  const double P = a.P[s];
+  const double nf = a.nu_fit[(size_t)s * 3];
+  const double nf2 = 1.0 / (nf * nf);
+  const double KP = kDconst / P;
+
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // f, g0, g1, h00, h01, h11, gmax(unused), Sd
+  double gmax = 0.0;
+  for (int n = tid; n < nchan; n += 128) {
+    const double S = Sv[n];
+    if (!(S > 0.0)) continue;
+    const double C = cs[n * kNCsum], C1 = cs[n * kNCsum + 1], C2 = cs[n * kNCsum + 2];
+    const double g = KP * (a.nu2[n] - nf2);
+    const double t = -2.0 * C * C1 / S;            // pplib.py:1348-1349
+    const double W = (C1 * C1 + C * C2) / S;       // pplib.py:1385-1386
+    v[0] -= C * C / S;
+    v[1] += t; v[2] += t * g;
+    v[3] -= 2.0 * W; v[4] -= 2.0 * W * g; v[5] -= 2.0 * W * g * g;
+    v[7] += a.Sdn[(size_t)s * nchan + n];
+    gmax = fmax(gmax, fabs(g));
+  }
+  block_sum<8, 128>(v, sh);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  __syncthreads();
+  if ((tid & 31) == 0) sh[tid >> 5] = gmax;
+  __syncthreads();
+  gmax = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3]));
+  __syncthreads();
+
+  double* x = a.st.x + (size_t)s * 5;
+  double* xp = a.st.xprev + (size_t)s * 5;
+  double* stp = a.st.step + (size_t)s * 5;
+  // ---- thread 0: safeguarded Newton ----------------------------------------------
+  if (tid == 0) {
+    const int it = a.st.iter[s] + 1;
+    a.st.iter[s] = it;
+    const double f = v[0];
+    int finish = 0, rc = 0;
+    double d0 = 0.0, d1 = 0.0;   // step to apply on top of the evaluated point
+    if (!(f == f) || fabs(f) > 1e300) { finish = 1; rc = 3; }
+    else if (a.max_iter < 0) { finish = 2; rc = 0; }   // evaluate-only (get_scales)
+    else if (it > 1 && f > a.st.fprev[s] + 1e-12 * fabs(a.st.fprev[s])) {
+      // uphill: shrink the previous step and re-evaluate
+      const double lam = a.st.lam[s] * 0.25;
+      a.st.lam[s] = lam;
+      if (it >= a.max_iter || lam < 1e-6) { finish = 2; rc = 1; }  // give up: report this point
+      else { x[0] = xp[0] + lam * stp[0]; x[1] = xp[1] + lam * stp[1]; }
+    } else {
+      double h00 = v[3], h01 = v[4], h11 = v[5], g0 = v[1], g1 = v[2];
+      if (!a.fit_dm) { h01 = 0.0; h11 = 1.0; g1 = 0.0; }
+      if (!a.fit_phi) { h01 = 0.0; h00 = 1.0; g0 = 0.0; }
+      double det = h00 * h11 - h01 * h01;
+      bool pd = h00 > 0.0 && h11 > 0.0 && det > 1e-14 * h00 * h11;
+      if (pd) {
+        d0 = -(h11 * g0 - h01 * g1) / det;
+        d1 = -(-h01 * g0 + h00 * g1) / det;
+      } else {  // not convex here: scaled steepest descent
+        d0 = -g0 / (fabs(h00) + 1e-300);
+        d1 = -g1 / (fabs(h11) + 1e-300);
+      }
+      // keep every channel's rotation change below 0.1 turn
+      const double big = fmax(fabs(d0), fabs(d1) * gmax);
+      if (big > 0.1) { d0 *= 0.1 / big; d1 *= 0.1 / big; }
+      bool conv = false;
+      if (pd) {
+        // 1-sigma from cov = inv(H/2) (pplib.py:2187-2190)
+        const double s0 = sqrt(2.0 * h11 / det), s1 = sqrt(2.0 * h00 / det);
+        conv = (fabs(d0) <= a.tol * s0 || !a.fit_phi) && (fabs(d1) <= a.tol * s1 || !a.fit_dm);
+      }
+      xp[0] = x[0]; xp[1] = x[1];
+      stp[0] = d0; stp[1] = d1;
+      a.st.fprev[s] = f;
+      a.st.lam[s] = 1.0;
+      if (conv) { finish = 1; rc = 0; }
+      else if (it >= a.max_iter) { finish = 1; rc = 1; }
+      else { x[0] += d0; x[1] += d1; }
+    }
+    bc[0] = (double)finish; bc[1] = d0; bc[2] = d1; bc[3] = (double)rc; bc[4] = (double)it;
+  }
+  __syncthreads();
+  const int finish = (int)bc[0];
+  if (!finish) return;
+  // ---- epilogue: sums are at x (= xprev), the final point is x + (d0, d1) --------
+  // finish == 2: back-tracking gave up, report the evaluated point without a step.
+  const double d0 = (finish == 1 && bc[3] != 3.0) ? bc[1] : 0.0;
+  const double d1 = (finish == 1 && bc[3] != 3.0) ? bc[2] : 0.0;
+  const double phi_fit = x[0] + d0, DM_fit = x[1] + d1;
+  // second-order Taylor of the per-channel sums to the final point
+  double u[4] = {0, 0, 0, 0};  // f, sumW, sumW nu^-2, snr^2
+  for (int n = tid; n < nchan; n += 128) {
+    const double S = Sv[n];
+    if (!(S > 0.0)) continue;
+    const double g = KP * (a.nu2[n] - nf2);
+    const double dth = d0 + d1 * g;
+    const double C2 = cs[n * kNCsum + 2];
+    const double C1 = cs[n * kNCsum + 1] + C2 * dth;
+    const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
+    const double W = (C1 * C1 + C * C2) / S;
+    u[0] -= C * C / S;
+    u[1] += W; u[2] += W * a.nu2[n];
+    u[3] += C * C / S;
+  }
+  block_sum<4, 128>(u, sh);
+  const double fmin = u[0];
+  // zero-covariance frequency (pplib.py:1390; pptoaslib.py:746-752)
+  double nu_zero = nf;
+  if (a.fit_phi && a.fit_dm) nu_zero = sqrt(u[1] / u[2]);
+  double nu_o = a.nu_outs ? a.nu_outs[(size_t)s * 3] : CUDART_NAN;
+  if (!(nu_o == nu_o)) nu_o = nu_zero;
+  const double no2 = 1.0 / (nu_o * nu_o);
+  double hh[3] = {0, 0, 0};
+  for (int n = tid; n < nchan; n += 128) {
+    const double S = Sv[n];
+    if (!(S > 0.0)) continue;
+    const double g = KP * (a.nu2[n] - nf2);
+    const double dth = d0 + d1 * g;
+    const double C2 = cs[n * kNCsum + 2];
+    const double C1 = cs[n * kNCsum + 1] + C2 * dth;
+    const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
+    const double W = (C1 * C1 + C * C2) / S;
+    const double go = KP * (a.nu2[n] - no2);
+    hh[0] -= 2.0 * W; hh[1] -= 2.0 * W * go; hh[2] -= 2.0 * W * go * go;
+  }
+  block_sum<3, 128>(hh, sh);
+  double h00 = hh[0], h01 = hh[1], h11 = hh[2];
+  if (!a.fit_dm) { h01 = 0.0; h11 = 1.0; }
+  if (!a.fit_phi) { h01 = 0.0; h00 = 1.0; }
+  const double det = h00 * h11 - h01 * h01;
+  // covariance = inv(H/2) = 2 inv(H)
+  double c00 = 2.0 * h11 / det, c01 = -2.0 * h01 / det, c11 = 2.0 * h00 / det;
+  if (!a.fit_dm) { c11 = 0.0; c01 = 0.0; }
+  if (!a.fit_phi) { c00 = 0.0; c01 = 0.0; }
+  const int nok = a.nok[s];
+  const int nfit = (a.fit_phi ? 1 : 0) + (a.fit_dm ? 1 : 0);
+  const double chi2 = v[7] + fmin;
+  const double dof = (double)nok * a.nbin - (double)(nfit + nok);
+  // per-channel outputs
+  for (int n = tid; n < nchan; n += 128) {
+    const double S = Sv[n];
+    const size_t o = (size_t)s * nchan + n;
+    double sc = 0.0, se = 0.0, csn = 0.0;
+    if (S > 0.0) {
+      const double g = KP * (a.nu2[n] - nf2);
+      const double dth = d0 + d1 * g;
+      const double C2 = cs[n * kNCsum + 2];
+      const double C1 = cs[n * kNCsum + 1] + C2 * dth;
+      const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
+      sc = C / S;                                         // pptoaslib.py:688
+      csn = sc * sqrt(S);                                 // pptoaslib.py:1081
+      if (a.semantics == 1) se = 1.0 / sqrt(S);           // pplib.py:2197
+      else {
+        // diag(2 LR), LR = Cinv + Cinv V Xinv U Cinv (pptoaslib.py:713-724)
+        const double go = KP * (a.nu2[n] - no2);
+        const double U0 = a.fit_phi ? -2.0 * C1 : 0.0, U1 = a.fit_dm ? -2.0 * C1 * go : 0.0;
+        // Xinv = inv(H_out) = cov/2
+        const double q = 0.5 * (U0 * U0 * c00 + 2.0 * U0 * U1 * c01 + U1 * U1 * c11);
+        se = sqrt(1.0 / S + q / (2.0 * S * S));
+      }
+    }
+    if (a.scales) a.scales[o] = sc;
+    if (a.scale_errs) a.scale_errs[o] = se;
+    if (a.channel_snrs) a.channel_snrs[o] = csn;
+  }
+  if (tid == 0) {
+    // phi at the output frequency (pplib.py:2182; pptoaslib.py:1052-1057)
+    double phi_out = phi_fit + KP * DM_fit * (no2 - nf2);
+    phi_out = wrap_phase(phi_out);
+    double* po = a.params + (size_t)s * 5;
+    po[0] = phi_out; po[1] = DM_fit; po[2] = x[2]; po[3] = x[3]; po[4] = x[4];
+    double* pe = a.param_errs + (size_t)s * 5;
+    pe[0] = sqrt(c00); pe[1] = sqrt(c11); pe[2] = 0; pe[3] = 0; pe[4] = 0;
+    double* cv = a.cov + (size_t)s * 25;
+    for (int i = 0; i < 25; ++i) cv[i] = 0.0;
+    cv[0] = c00; cv[1] = c01; cv[5] = c01; cv[6] = c11;
+    double* no = a.nu_out + (size_t)s * 3;
+    no[0] = nu_o;
+    no[1] = (a.is_toa && a.fit_dm) ? nu_o : a.nu_fit[(size_t)s * 3 + 1];   // pptoaslib.py:1048-1050
+    no[2] = a.nu_fit[(size_t)s * 3 + 2];
+    a.chi2[s] = chi2;
+    a.red_chi2[s] = chi2 / dof;
+    a.snr[s] = sqrt(u[3]);
+    a.nfeval[s] = (int)bc[4];
+    a.rc[s] = (int)bc[3];
+    x[0] = phi_fit; x[1] = DM_fit;
+    a.st.done[s] = 1;
+  }
+}
+
+// state initialisation when the caller supplies init params (no FFTFIT guess)
+__global__ void k_init_state(SolverState st, const double* init, int s0, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = s0 + i;
+  for (int q = 0; q < 5; ++q) {
+    const double v = init ? init[(size_t)s * 5 + q] : 0.0;
+    st.x[(size_t)s * 5 + q] = v; st.xprev[(size_t)s * 5 + q] = v; st.step[(size_t)s * 5 + q] = 0.0;
+  }
+  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+}
+
+__global__ void k_reset_state(SolverState st, int s0, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = s0 + i;
+  for (int q = 0; q < 5; ++q) { st.xprev[(size_t)s * 5 + q] = st.x[(size_t)s * 5 + q]; st.step[(size_t)s * 5 + q] = 0.0; }
+  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+}
+
+// ----------------------------------------------------------------------------
+// k_rfft_rows: half-spectra (slot layout, DC dropped) and/or get_noise_PS of
+// independent rows.  Used by the batched 1-D FFTFIT (pplib.py:2073-2079) and
+// by pp_get_noise_batch (pplib.py:2227-2245).
+// ----------------------------------------------------------------------------
+struct RowsArgs {
+  const float* in;      // [nrows, 2N]
+  float2* spec;         // [nrows, N] or null
+  double* noise;        // [nrows] or null
+  const void* twN;
+  const void* tw2N;
+  int nrows, conj;
+};
+
+template <int N, typename T>
+__global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
+  using G = RowGeom<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  __shared__ double red[8];
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  {
+    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.twN);
+    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.tw2N);
+    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
+    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
+  }
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+  const int row = blockIdx.x * G::kRows + r;
+  const bool valid = row < a.nrows;
+  const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)(valid ? row : 0) * 2 * N);
+#pragma unroll
+  for (int m = 0; m < G::kLoads; ++m) {
+    const int i4 = t_row + m * G::kTRow;
+    const float4 v = valid ? __ldg(src + i4) : make_float4(0, 0, 0, 0);
+    bufA[2 * i4] = mk<T>((T)v.x, (T)v.y);
+    bufA[2 * i4 + 1] = mk<T>((T)v.z, (T)v.w);
+  }
+  __syncthreads();
+  cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  constexpr int kc = (3 * (N + 1)) / 4;
+  constexpr int ntop = N + 1 - kc;
+  double top = 0.0;
+  float2* out = (a.spec && valid) ? a.spec + (size_t)row * N : nullptr;
+  const float sgn = a.conj ? -1.f : 1.f;
+  auto put = [&](int k, cx<T> d) {
+    if (k >= kc) top += (double)(d.x * d.x + d.y * d.y);
+    if (out) out[(k == N) ? 0 : k] = make_float2((float)d.x, sgn * (float)d.y);
+  };
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) {
+    const int p = t_row + 1 + i * G::kTRow;
+    if (p <= N / 2) {
+      cx<T> dp, dq;
+      unpack_pair<T>(Z, tw2N, N, p, dp, dq);
+      put(p, dp);
+      if (p < N / 2) put(N - p, dq);
+    }
+  }
+  if (t_row == 0) put(N, mk<T>(Z[0].x - Z[0].y, 0));
+  if (a.noise) {
+#pragma unroll
+    for (int o = (G::kTRow < 32 ? G::kTRow : 32) / 2; o > 0; o >>= 1) top += __shfl_xor_sync(0xffffffffu, top, o);
+    if (G::kTRow > 32) {
+      if ((tid & 31) == 0) red[tid >> 5] = top;
+      __syncthreads();
+      double st = 0.0;
+#pragma unroll
+      for (int w = 0; w < G::kTRow / 32; ++w) st += red[r * (G::kTRow / 32) + w];
+      top = st;
+    }
+    if (t_row == 0 && valid) a.noise[row] = sqrt(top / ((double)(2 * N) * (double)ntop));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_rotate: rfft -> multiply harmonic k by e^{2 pi i k theta} -> irfft
+// (pplib.py:2338-2460).  One row-slot per channel row; rows = nsub*nchan.
+// ----------------------------------------------------------------------------
+struct RotateArgs {
+  const float* in;      // [nsub,nchan,2N]
+  float* out;           // [nsub,nchan,2N]
+  const double* phase;  // [nsub]
+  const double* DM;     // [nsub]
+  const double* P;      // [nsub]
+  const double* nu_ref; // [nsub]
+  const double* nu2;    // [nchan]
+  const void* twN;
+  const void* tw2N;
+  int nsub, nchan;
+};
+
+template <int N, typename T>
+__global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
+  using G = RowGeom<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  {
+    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.twN);
+    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.tw2N);
+    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
+    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
+  }
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+  const long nrows = (long)a.nsub * a.nchan;
+  const long row = (long)blockIdx.x * G::kRows + r;
+  const bool valid = row < nrows;
+  const long rowc = valid ? row : 0;
+  const int s = (int)(rowc / a.nchan), ch = (int)(rowc % a.nchan);
+  const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)rowc * 2 * N);
+#pragma unroll
+  for (int m = 0; m < G::kLoads; ++m) {
+    const int i4 = t_row + m * G::kTRow;
+    const float4 v = valid ? src[i4] : make_float4(0, 0, 0, 0);
+    bufA[2 * i4] = mk<T>((T)v.x, (T)v.y);
+    bufA[2 * i4 + 1] = mk<T>((T)v.z, (T)v.w);
+  }
+  __syncthreads();
+  cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  cx<T>* other = (Z == bufA) ? bufB : bufA;
+  // theta_n = phase + Dconst*DM/P*(nu_n^-2 - nu_ref^-2)  (pplib.py:2381-2411)
+  double theta = a.phase[s];
+  const double dm = a.DM[s];
+  if (dm != 0.0) {
+    const double nr = a.nu_ref[s];
+    theta += kDconst * dm / a.P[s] * (a.nu2[ch] - 1.0 / (nr * nr));
+  }
+  theta -= rint(theta);
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) {
+    const int p = t_row + 1 + i * G::kTRow;
+    if (p <= N / 2) {
+      cx<T> dp, dq;
+      unpack_pair<T>(Z, tw2N, N, p, dp, dq);
+      double c, sn;
+      cis2pi((double)p * theta, c, sn);
+      dp = cmul(dp, mk<T>((T)c, (T)sn));
+      if (p < N / 2) {
+        cis2pi((double)(N - p) * theta, c, sn);
+        dq = cmul(dq, mk<T>((T)c, (T)sn));
+      } else {
+        dq = dp;
+      }
+      cx<T> zp, zq;
+      pack_pair<T>(dp, dq, tw2N[p], zp, zq);
+      Z[p] = cconj(zp);           // conj for the inverse transform
+      if (p < N / 2) Z[N - p] = cconj(zq);
+    }
+  }
+  if (t_row == 0) {
+    const T d0 = Z[0].x + Z[0].y;
+    double c, sn;
+    cis2pi((double)N * theta, c, sn);
+    const T dN = (Z[0].x - Z[0].y) * (T)c;   // irfft keeps the real part of the Nyquist term
+    Z[0] = mk<T>(T(0.5) * (d0 + dN), -T(0.5) * (d0 - dN));
+  }
+  __syncthreads();
+  cx<T>* Y = fft_forward<N, G::kTRow, T>(Z, other, twN, t_row);
+  if (valid) {
+    float4* dst = reinterpret_cast<float4*>(a.out + (size_t)row * 2 * N);
+    const T sc = T(1) / T(N);
+#pragma unroll
+    for (int m = 0; m < G::kLoads; ++m) {
+      const int i4 = t_row + m * G::kTRow;
+      const cx<T> y0 = Y[2 * i4], y1 = Y[2 * i4 + 1];
+      dst[i4] = make_float4((float)(y0.x * sc), (float)(-y0.y * sc), (float)(y1.x * sc), (float)(-y1.y * sc));
+    }
+  }
+}
+
+}  // namespace ppb

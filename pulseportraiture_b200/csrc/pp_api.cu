@@ -1,0 +1,795 @@
+// C-ABI implementation (see include/ppb200.h).  Host orchestration of the
+// sm_100a kernels in kernels.cuh: plan / workspace management, chunked
+// pipeline, pointer staging, timing.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ppb200.h"
+#include "kernels.cuh"
+
+using namespace ppb;
+
+// ----------------------------------------------------------------------------
+// error handling
+// ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(-2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* pp_last_error(void) { return g_err.c_str(); }
+extern "C" int pp_abi_version(void) { return PPB200_ABI_VERSION; }
+
+// ----------------------------------------------------------------------------
+// device buffer that grows on demand
+// ----------------------------------------------------------------------------
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct pp_plan {
+  int nchan = 0, nbin = 0, N = 0, device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  int chunk_req = 0;
+  int l2_bytes = 0, sm_count = 0;
+  bool model_set = false;
+  // tables + model
+  DBuf twN32, tw2N32, twN64, tw2N64, freqs, nu2, mconj32, mconj64, mpow, pn, mmean, model_stage;
+  int fft_precision = 0;   // 0 auto, 32, 64
+  bool freqs_set = false;
+  // FFTFIT grid tables keyed by Ns
+  std::vector<std::pair<int, DBuf>> grid_tables;
+  // per-batch staging of small inputs and per-subint / per-channel workspace
+  DBuf in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
+  DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
+  DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
+  DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
+  DBuf ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
+      rot_phase, rot_dm, rot_P, rot_nuref;
+  // chunk-sized
+  DBuf X, partial, data_stage[2];
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int kind; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  pp_stats_t stats;
+};
+
+enum { SP_SPECTRA = 0, SP_GUESS = 1, SP_PASS = 2, SP_UPDATE = 3, SP_TOTAL = 4 };
+
+static cudaEvent_t get_event(pp_plan* pl) {
+  if (pl->ev_used == pl->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pl->ev_pool.push_back(e);
+  }
+  return pl->ev_pool[pl->ev_used++];
+}
+
+struct SpanGuard {
+  pp_plan* pl; int kind; cudaEvent_t a = nullptr;
+  SpanGuard(pp_plan* p, int k) : pl(p), kind(k) {
+    if (pl->timing) { a = get_event(pl); cudaEventRecord(a, pl->stream); }
+  }
+  ~SpanGuard() {
+    if (pl->timing) {
+      cudaEvent_t b = get_event(pl);
+      cudaEventRecord(b, pl->stream);
+      pl->spans.push_back({kind, a, b});
+    }
+  }
+};
+
+static void stats_begin(pp_plan* pl) {
+  memset(&pl->stats, 0, sizeof pl->stats);
+  pl->stats.timing_enabled = pl->timing ? 1 : 0;
+  pl->ev_used = 0;
+  pl->spans.clear();
+}
+
+static void stats_end(pp_plan* pl) {
+  if (!pl->timing) return;
+  for (auto& sp : pl->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    switch (sp.kind) {
+      case SP_SPECTRA: pl->stats.ms_spectra += ms; break;
+      case SP_GUESS: pl->stats.ms_guess += ms; break;
+      case SP_PASS: pl->stats.ms_pass += ms; break;
+      case SP_UPDATE: pl->stats.ms_update += ms; break;
+      case SP_TOTAL: pl->stats.ms_total += ms; break;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// pointer staging: returns a device pointer for host-or-device input
+// ----------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static int stage_in(pp_plan* pl, DBuf& buf, const T* src, size_t n, const T** out) {
+  if (!src) { *out = nullptr; return 0; }
+  if (is_device_ptr(src)) { *out = src; return 0; }
+  CK(buf.need(n * sizeof(T)));
+  CK(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, pl->stream));
+  *out = buf.as<T>();
+  return 0;
+}
+
+template <typename T>
+static int copy_out(pp_plan* pl, T* dst, const T* dev, size_t n) {
+  if (!dst) return 0;
+  CK(cudaMemcpyAsync(dst, dev, n * sizeof(T), is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                     pl->stream));
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// dispatch on N = nbin/2
+// ----------------------------------------------------------------------------
+template <int N, typename T> static size_t fft_smem_bytes() {
+  return (size_t)(N + N / 2 + 2 + RowGeom<N>::kRows * 2 * N) * sizeof(cx<T>);
+}
+
+#define DISPATCH_N(Nval, ...)                                   \
+  switch (Nval) {                                               \
+    case 32: { constexpr int NN = 32; __VA_ARGS__; } break;     \
+    case 64: { constexpr int NN = 64; __VA_ARGS__; } break;     \
+    case 128: { constexpr int NN = 128; __VA_ARGS__; } break;   \
+    case 256: { constexpr int NN = 256; __VA_ARGS__; } break;   \
+    case 512: { constexpr int NN = 512; __VA_ARGS__; } break;   \
+    case 1024: { constexpr int NN = 1024; __VA_ARGS__; } break; \
+    case 2048: { constexpr int NN = 2048; __VA_ARGS__; } break; \
+    default: return fail(-1, "unsupported nbin %d", 2 * (Nval)); \
+  }
+
+template <int N> static cudaError_t setup_attrs() {
+  const int b32 = (int)fft_smem_bytes<N, float>(), b64 = (int)fft_smem_bytes<N, double>();
+  cudaError_t e;
+#define SET_(fn, bytes) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (e != cudaSuccess) return e;
+  SET_((k_spectra<N, float>), b32)
+  SET_((k_spectra<N, double>), b64)
+  SET_((k_model<N>), b64)
+  SET_((k_rfft_rows<N, float>), b32)
+  SET_((k_rfft_rows<N, double>), b64)
+  SET_((k_rotate<N, float>), b32)
+  SET_((k_rotate<N, double>), b64)
+#undef SET_
+  return cudaFuncSetAttribute(k_guess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double2) * 2048));
+}
+
+// ----------------------------------------------------------------------------
+// plan
+// ----------------------------------------------------------------------------
+extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_plan_t** out) {
+  if (!out) return fail(-1, "plan_out is NULL");
+  *out = nullptr;
+  if (nchan < 1) return fail(-1, "nchan must be >= 1 (got %d)", nchan);
+  if (nbin < 64 || nbin > 4096 || (nbin & (nbin - 1))) return fail(-1, "nbin must be a power of two in [64,4096] (got %d)", nbin);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(-1, "device %d not available (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  pp_plan* pl = new pp_plan();
+  pl->nchan = nchan; pl->nbin = nbin; pl->N = nbin / 2; pl->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  pl->l2_bytes = prop.l2CacheSize;
+  pl->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+  pl->stream = pl->own_stream;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&pl->ev_copy[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pl->ev_free[i], cudaEventDisableTiming));
+  }
+  // twiddle tables in double, rounded once
+  const int N = pl->N;
+  std::vector<float2> t1(N), t2(N / 2 + 1);
+  std::vector<double2> u1(N), u2(N / 2 + 1);
+  for (int j = 0; j < N; ++j) {
+    // octant-reduced so that the table has the exact symmetries of the roots of unity
+    const double a = -2.0 * M_PI * (double)j / (double)N;
+    u1[j] = make_double2(cos(a), sin(a));
+    if (4 * j == N) u1[j] = make_double2(0.0, -1.0);
+    if (2 * j == N) u1[j] = make_double2(-1.0, 0.0);
+    if (4 * j == 3 * N) u1[j] = make_double2(0.0, 1.0);
+    t1[j] = make_float2((float)u1[j].x, (float)u1[j].y);
+  }
+  for (int k = 0; k <= N / 2; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)(2 * N);
+    u2[k] = make_double2(cos(a), sin(a));
+    if (2 * k == N) u2[k] = make_double2(0.0, -1.0);
+    t2[k] = make_float2((float)u2[k].x, (float)u2[k].y);
+  }
+  CK(pl->twN32.need(t1.size() * sizeof(float2)));
+  CK(pl->tw2N32.need(t2.size() * sizeof(float2)));
+  CK(pl->twN64.need(u1.size() * sizeof(double2)));
+  CK(pl->tw2N64.need(u2.size() * sizeof(double2)));
+  CK(cudaMemcpy(pl->twN32.p, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->tw2N32.p, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->twN64.p, u1.data(), u1.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->tw2N64.p, u2.data(), u2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  {
+    cudaError_t e = cudaSuccess;
+    DISPATCH_N(N, e = setup_attrs<NN>());
+    CK(e);
+  }
+  *out = pl;
+  return 0;
+}
+
+extern "C" void pp_plan_destroy(pp_plan_t* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->device);
+  cudaStreamSynchronize(pl->stream);
+  DBuf* all[] = {&pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
+                 &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
+                 &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
+                 &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
+                 &pl->in_nuouts, &pl->in_noise, &pl->in_models, &pl->nu_fit, &pl->nu_mean, &pl->wsum, &pl->nok, &pl->sigma,
+                 &pl->Ssn, &pl->Sdn, &pl->csum, &pl->st_x, &pl->st_xprev, &pl->st_step, &pl->st_fprev, &pl->st_lam,
+                 &pl->st_iter, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
+                 &pl->o_snr, &pl->o_nfev, &pl->o_rc, &pl->o_scales, &pl->o_serrs, &pl->o_csnr, &pl->o_lag, &pl->o_phig,
+                 &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->X,
+                 &pl->partial, &pl->data_stage[0], &pl->data_stage[1]};
+  for (DBuf* b : all) b->release();
+  for (auto& gt : pl->grid_tables) gt.second.release();
+  for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(pl->ev_copy[i]); cudaEventDestroy(pl->ev_free[i]); }
+  cudaStreamDestroy(pl->own_stream);
+  cudaStreamDestroy(pl->copy_stream);
+  delete pl;
+}
+
+extern "C" int pp_plan_set_stream(pp_plan_t* pl, void* s) {
+  if (!pl) return fail(-1, "plan is NULL");
+  pl->stream = s ? reinterpret_cast<cudaStream_t>(s) : pl->own_stream;
+  return 0;
+}
+
+extern "C" int pp_plan_set_chunk(pp_plan_t* pl, int32_t n) {
+  if (!pl) return fail(-1, "plan is NULL");
+  if (n < 0) return fail(-1, "chunk must be >= 0");
+  pl->chunk_req = n;
+  return 0;
+}
+
+extern "C" int pp_plan_enable_timing(pp_plan_t* pl, int32_t on) {
+  if (!pl) return fail(-1, "plan is NULL");
+  pl->timing = on != 0;
+  return 0;
+}
+
+extern "C" int pp_get_stats(pp_plan_t* pl, pp_stats_t* st) {
+  if (!pl || !st) return fail(-1, "NULL argument");
+  *st = pl->stats;
+  return 0;
+}
+
+static int grid_table(pp_plan* pl, int Ns, const double2** out) {
+  for (auto& gt : pl->grid_tables)
+    if (gt.first == Ns) { *out = gt.second.as<double2>(); return 0; }
+  const int M = Ns - 1;
+  std::vector<double2> t(M);
+  for (int m = 0; m < M; ++m) {
+    // e^{2 pi i m/M} with exact quadrant symmetry handled by cos/sin of a reduced angle
+    const double a = 2.0 * M_PI * (double)m / (double)M;
+    t[m] = make_double2(cos(a), sin(a));
+  }
+  pl->grid_tables.emplace_back(Ns, DBuf());
+  DBuf& b = pl->grid_tables.back().second;
+  CK(b.need(sizeof(double2) * M));
+  CK(cudaMemcpyAsync(b.p, t.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));  // t goes out of scope
+  *out = b.as<double2>();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// model
+// ----------------------------------------------------------------------------
+static int set_freqs_impl(pp_plan* pl, const double* freqs) {
+  const int nchan = pl->nchan;
+  std::vector<double> hf(nchan), hn2(nchan);
+  if (is_device_ptr(freqs)) CK(cudaMemcpy(hf.data(), freqs, sizeof(double) * nchan, cudaMemcpyDeviceToHost));
+  else memcpy(hf.data(), freqs, sizeof(double) * nchan);
+  for (int n = 0; n < nchan; ++n) {
+    if (!(hf[n] > 0.0)) return fail(-1, "freqs[%d] = %g is not positive", n, hf[n]);
+    hn2[n] = 1.0 / (hf[n] * hf[n]);
+  }
+  CK(pl->freqs.need(sizeof(double) * nchan));
+  CK(pl->nu2.need(sizeof(double) * nchan));
+  CK(cudaMemcpyAsync(pl->freqs.p, hf.data(), sizeof(double) * nchan, cudaMemcpyHostToDevice, pl->stream));
+  CK(cudaMemcpyAsync(pl->nu2.p, hn2.data(), sizeof(double) * nchan, cudaMemcpyHostToDevice, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));  // hf/hn2 are stack-owned
+  pl->freqs_set = true;
+  return 0;
+}
+
+extern "C" int pp_set_freqs(pp_plan_t* pl, const double* freqs) {
+  if (!pl || !freqs) return fail(-1, "NULL argument");
+  CK(cudaSetDevice(pl->device));
+  return set_freqs_impl(pl, freqs);
+}
+
+extern "C" int pp_plan_set_fft_precision(pp_plan_t* pl, int32_t bits) {
+  if (!pl) return fail(-1, "plan is NULL");
+  if (bits != 0 && bits != 32 && bits != 64) return fail(-1, "fft precision must be 0 (auto), 32 or 64");
+  pl->fft_precision = bits;
+  return 0;
+}
+
+extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* freqs) {
+  if (!pl || !model || !freqs) return fail(-1, "NULL argument");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan;
+  const float* dmodel = nullptr;
+  if (stage_in(pl, pl->model_stage, model, (size_t)nchan * 2 * N, &dmodel)) return -2;
+  if (set_freqs_impl(pl, freqs)) return -2;
+  CK(pl->mconj32.need(sizeof(float2) * (size_t)nchan * N));
+  CK(pl->mconj64.need(sizeof(double2) * (size_t)nchan * N));
+  CK(pl->mpow.need(sizeof(float) * (size_t)nchan * N));
+  CK(pl->pn.need(sizeof(double) * nchan));
+  CK(pl->mmean.need(sizeof(float2) * N));
+  ModelArgs a;
+  a.model = dmodel; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
+  a.mpow = pl->mpow.as<float>(); a.pn = pl->pn.as<double>();
+  a.twN = pl->twN64.as<cx<double>>(); a.tw2N = pl->tw2N64.as<cx<double>>(); a.nchan = nchan;
+  DISPATCH_N(N, {
+    const int rows = RowGeom<NN>::kRows;
+    k_model<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+  });
+  k_model_mean<<<(N + 127) / 128, 128, 0, pl->stream>>>(pl->mconj64.as<cx<double>>(), pl->mmean.as<float2>(), nchan, N);
+  pl->stats.launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(pl->stream));
+  pl->model_set = true;
+  return 0;
+}
+
+// FFT arithmetic for the data rows.  A float FFT has ~1e-7 relative error per
+// harmonic; when the noise level is *measured* from the top quarter of the
+// power spectrum (nbin/8 harmonics) that error scales the whole chi^2 of the
+// channel.  Estimated relative chi^2 error ~ 6e-7 / sqrt(nchan * nbin / 8):
+// use double below 2^20 samples per portrait, float above (and always float
+// when the caller supplies the noise).
+static int pick_fft_precision(pp_plan* pl, bool noise_measured) {
+  if (pl->fft_precision) return pl->fft_precision;
+  if (!noise_measured) return 32;
+  return ((long)pl->nchan * pl->nbin < (1L << 20)) ? 64 : 32;
+}
+
+// ----------------------------------------------------------------------------
+// fit
+// ----------------------------------------------------------------------------
+static int pick_chunk(pp_plan* pl, int nsub) {
+  if (pl->chunk_req > 0) return std::min(pl->chunk_req, nsub);
+  // keep a chunk's cross-spectra (8 N nchan bytes per subint) within ~40% of L2
+  const double per = 8.0 * pl->N * (double)pl->nchan;
+  int c = (int)floor(0.4 * (double)pl->l2_bytes / per);
+  c = std::max(c, 4);
+  // at least ~2 waves of CTAs for the pass kernel
+  return std::min(c, nsub);
+}
+
+static int rows_per_cta(pp_plan* pl, int chunk) {
+  // rows per k_spectra CTA: aim at >= 4 CTAs per SM per launch, multiple of kRows
+  const int rows_conc = std::max(1, 1024 / pl->N);
+  long total_rows = (long)chunk * pl->nchan;
+  long target_ctas = 4L * pl->sm_count;
+  long g = std::max(1L, total_rows / target_ctas);
+  g = std::min<long>(g, 32);
+  g = ((g + rows_conc - 1) / rows_conc) * rows_conc;
+  g = std::min<long>(g, ((pl->nchan + rows_conc - 1) / rows_conc) * rows_conc);
+  return (int)g;
+}
+
+extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_fit_out_t* out) {
+  if (!pl || !args || !out) return fail(-1, "NULL argument");
+  if (!pl->model_set) return fail(-1, "pp_set_model must be called before pp_fit_batch");
+  if (!args->data || !args->P) return fail(-1, "data and P are required");
+  if (args->nsub < 1) return fail(-1, "nsub must be >= 1");
+  const uint8_t* ff = args->fit_flags;
+  if (ff[2] || ff[3] || ff[4])
+    return fail(-3, "fit_flags [%d,%d,%d,%d,%d]: GM/tau/alpha fits are not built in this library version", ff[0], ff[1],
+                ff[2], ff[3], ff[4]);
+  if (!ff[0] && !ff[1]) return fail(-1, "nothing to fit");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int nsub = args->nsub, nchan = pl->nchan, N = pl->N;
+  const int Ns = args->Ns > 0 ? args->Ns : 100;
+  if (Ns < 2) return fail(-1, "Ns must be >= 2");
+  const int max_iter = args->max_iter > 0 ? args->max_iter : (args->max_iter < 0 ? -1 : 8);
+  const int n_launch_iter = max_iter < 0 ? 1 : max_iter;
+  const int fftp = pick_fft_precision(pl, args->errs == nullptr);
+  const double tol = args->tol > 0 ? args->tol : 1e-3;
+  const size_t nsc = (size_t)nsub * nchan;
+
+  // ---- stage small inputs ------------------------------------------------------
+  const double *dP, *derrs, *dw, *dinit, *ddmg, *dsnrs, *dnufits, *dnuouts;
+  const uint8_t* dmask;
+  if (stage_in(pl, pl->in_P, args->P, (size_t)nsub, &dP)) return -2;
+  if (stage_in(pl, pl->in_errs, args->errs, nsc, &derrs)) return -2;
+  if (stage_in(pl, pl->in_mask, args->chan_mask, nsc, &dmask)) return -2;
+  if (stage_in(pl, pl->in_w, args->weights, nsc, &dw)) return -2;
+  if (stage_in(pl, pl->in_init, args->init, (size_t)nsub * 5, &dinit)) return -2;
+  if (stage_in(pl, pl->in_dmg, args->DM_guess, (size_t)nsub, &ddmg)) return -2;
+  if (stage_in(pl, pl->in_snrs, args->snrs, nsc, &dsnrs)) return -2;
+  if (stage_in(pl, pl->in_nufits, args->nu_fits, (size_t)nsub * 3, &dnufits)) return -2;
+  if (stage_in(pl, pl->in_nuouts, args->nu_outs, (size_t)nsub * 3, &dnuouts)) return -2;
+  const bool want_guess = (args->init == nullptr);
+
+  // ---- workspace -------------------------------------------------------------------
+  CK(pl->nu_fit.need(sizeof(double) * nsub * 3));
+  CK(pl->nu_mean.need(sizeof(double) * nsub));
+  CK(pl->wsum.need(sizeof(double) * nsub));
+  CK(pl->nok.need(sizeof(int) * nsub));
+  CK(pl->sigma.need(sizeof(double) * nsc));
+  CK(pl->Ssn.need(sizeof(double) * nsc));
+  CK(pl->Sdn.need(sizeof(double) * nsc));
+  CK(pl->csum.need(sizeof(double) * nsc * kNCsum));
+  CK(pl->st_x.need(sizeof(double) * nsub * 5));
+  CK(pl->st_xprev.need(sizeof(double) * nsub * 5));
+  CK(pl->st_step.need(sizeof(double) * nsub * 5));
+  CK(pl->st_fprev.need(sizeof(double) * nsub));
+  CK(pl->st_lam.need(sizeof(double) * nsub));
+  CK(pl->st_iter.need(sizeof(int) * nsub));
+  CK(pl->st_done.need(sizeof(int) * nsub));
+  CK(pl->o_params.need(sizeof(double) * nsub * 5));
+  CK(pl->o_perrs.need(sizeof(double) * nsub * 5));
+  CK(pl->o_nuout.need(sizeof(double) * nsub * 3));
+  CK(pl->o_cov.need(sizeof(double) * nsub * 25));
+  CK(pl->o_chi2.need(sizeof(double) * nsub));
+  CK(pl->o_rchi2.need(sizeof(double) * nsub));
+  CK(pl->o_snr.need(sizeof(double) * nsub));
+  CK(pl->o_nfev.need(sizeof(int) * nsub));
+  CK(pl->o_rc.need(sizeof(int) * nsub));
+  CK(pl->o_scales.need(sizeof(double) * nsc));
+  CK(pl->o_serrs.need(sizeof(double) * nsc));
+  CK(pl->o_csnr.need(sizeof(double) * nsc));
+  CK(pl->o_lag.need(sizeof(int) * nsub));
+  CK(pl->o_phig.need(sizeof(double) * nsub));
+
+  const int chunk = pick_chunk(pl, nsub);
+  const int G = rows_per_cta(pl, chunk);
+  const int rows_conc = std::max(1, 1024 / N);
+  const int gx = (nchan + G - 1) / G;
+  const int nparts = gx * rows_conc;
+  pl->stats.chunk = chunk;
+  CK(pl->X.need(sizeof(float2) * (size_t)chunk * nchan * N));
+  if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
+  const bool data_on_device = is_device_ptr(args->data);
+  const size_t sub_floats = (size_t)nchan * 2 * N;
+  if (!data_on_device)
+    for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need(sizeof(float) * (size_t)chunk * sub_floats));
+
+  SolverState st;
+  st.x = pl->st_x.as<double>(); st.xprev = pl->st_xprev.as<double>(); st.step = pl->st_step.as<double>();
+  st.fprev = pl->st_fprev.as<double>(); st.lam = pl->st_lam.as<double>(); st.iter = pl->st_iter.as<int>();
+  st.done = pl->st_done.as<int>();
+
+  cudaEvent_t ev_t0 = nullptr;
+  if (pl->timing) { ev_t0 = get_event(pl); CK(cudaEventRecord(ev_t0, pl->stream)); }
+
+  // ---- per-subint scalars ----------------------------------------------------------
+  {
+    PrepArgs p;
+    p.freqs = pl->freqs.as<double>(); p.mask = dmask; p.weights = dw; p.snrs = dsnrs; p.nu_fits_in = dnufits;
+    p.nu_fit = pl->nu_fit.as<double>(); p.nu_mean = pl->nu_mean.as<double>(); p.wsum = pl->wsum.as<double>();
+    p.nok = pl->nok.as<int>(); p.nsub = nsub; p.nchan = nchan; p.nu_fit_mode = args->nu_fit_mode;
+    k_prep<<<(nsub + 3) / 4, 128, 0, pl->stream>>>(p);
+    pl->stats.launches++;
+  }
+  if (!want_guess) {
+    k_init_state<<<(nsub + 127) / 128, 128, 0, pl->stream>>>(st, dinit, 0, nsub);
+    pl->stats.launches++;
+    CK(cudaMemsetAsync(pl->o_lag.p, 0xff, sizeof(int) * nsub, pl->stream));
+  }
+  const double2* table = nullptr;
+  if (want_guess && grid_table(pl, Ns, &table)) return -2;
+
+  // when the data live on the host: the first chunk's copy starts right away
+  const int nchunks = (nsub + chunk - 1) / chunk;
+  auto issue_copy = [&](int c) -> cudaError_t {
+    const int b = c & 1;
+    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(pl->data_stage[b].p, args->data + (size_t)s0 * sub_floats, sizeof(float) * ns * sub_floats,
+                        cudaMemcpyHostToDevice, pl->copy_stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(pl->ev_copy[b], pl->copy_stream);
+  };
+  if (!data_on_device) {
+    // the staging buffers are free at the start
+    CK(cudaEventRecord(pl->ev_free[0], pl->stream));
+    CK(cudaEventRecord(pl->ev_free[1], pl->stream));
+    CK(issue_copy(0));
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    const float* dchunk;
+    int s0_data;  // subint index offset to apply inside the data pointer
+    if (data_on_device) { dchunk = args->data; s0_data = s0; }
+    else {
+      if (c + 1 < nchunks) CK(issue_copy(c + 1));
+      CK(cudaStreamWaitEvent(pl->stream, pl->ev_copy[c & 1], 0));
+      // kernels index data with the global subint number: bias the base pointer
+      dchunk = pl->data_stage[c & 1].as<float>() - (size_t)s0 * sub_floats;
+      s0_data = s0;
+    }
+    (void)s0_data;
+    {
+      SpanGuard g(pl, SP_SPECTRA);
+      SpectraArgs a;
+      a.data = dchunk; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
+      a.pn = pl->pn.as<double>(); a.nu2 = pl->nu2.as<double>();
+      a.errs = derrs; a.mask = dmask; a.weights = dw; a.P = dP; a.DMg = ddmg; a.nu_mean = pl->nu_mean.as<double>();
+      a.X = pl->X.as<float2>(); a.partial = want_guess ? pl->partial.as<float2>() : nullptr;
+      a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
+      a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
+      if (fftp == 64) {
+        a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
+        DISPATCH_N(N, k_spectra<NN, double><<<dim3(gx, ns), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a));
+      } else {
+        a.twN = pl->twN32.p; a.tw2N = pl->tw2N32.p;
+        DISPATCH_N(N, k_spectra<NN, float><<<dim3(gx, ns), 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a));
+      }
+      pl->stats.launches++;
+    }
+    if (!data_on_device) CK(cudaEventRecord(pl->ev_free[c & 1], pl->stream));
+    if (want_guess) {
+      SpanGuard g(pl, SP_GUESS);
+      GuessArgs ga;
+      memset(&ga, 0, sizeof ga);
+      ga.partial = pl->partial.as<float2>(); ga.mconj = pl->mmean.as<float2>(); ga.nparts = nparts; ga.nmodel = 1;
+      ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
+      ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
+      ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
+      ga.init = nullptr;
+      k_guess<<<ns, 256, sizeof(double2) * N, pl->stream>>>(ga);
+      k_reset_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
+      pl->stats.launches += 2;
+    }
+    PassArgs pa;
+    pa.X = pl->X.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
+    pa.Ssn = pl->Ssn.as<double>(); pa.sigma = pl->sigma.as<double>(); pa.csum = pl->csum.as<double>(); pa.st = st;
+    pa.s0 = s0; pa.nchan = nchan; pa.N = N;
+    UpdateArgs ua;
+    memset(&ua, 0, sizeof ua);
+    ua.csum = pl->csum.as<double>(); ua.Ssn = pl->Ssn.as<double>(); ua.Sdn = pl->Sdn.as<double>(); ua.nu2 = pl->nu2.as<double>();
+    ua.freqs = pl->freqs.as<double>(); ua.P = dP; ua.nu_fit = pl->nu_fit.as<double>(); ua.nu_outs = dnuouts;
+    ua.nok = pl->nok.as<int>(); ua.st = st;
+    ua.params = pl->o_params.as<double>(); ua.param_errs = pl->o_perrs.as<double>(); ua.nu_out = pl->o_nuout.as<double>();
+    ua.cov = pl->o_cov.as<double>(); ua.chi2 = pl->o_chi2.as<double>(); ua.red_chi2 = pl->o_rchi2.as<double>();
+    ua.snr = pl->o_snr.as<double>(); ua.nfeval = pl->o_nfev.as<int>(); ua.rc = pl->o_rc.as<int>();
+    ua.scales = pl->o_scales.as<double>(); ua.scale_errs = pl->o_serrs.as<double>(); ua.channel_snrs = pl->o_csnr.as<double>();
+    ua.s0 = s0; ua.nchan = nchan; ua.nbin = 2 * N; ua.max_iter = max_iter; ua.semantics = args->semantics;
+    ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol;
+    for (int it = 0; it < n_launch_iter; ++it) {
+      {
+        SpanGuard g(pl, SP_PASS);
+        DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(pa));
+      }
+      {
+        SpanGuard g(pl, SP_UPDATE);
+        k_update2<<<ns, 128, 0, pl->stream>>>(ua);
+      }
+      pl->stats.launches += 2;
+      pl->stats.pass_launches++;
+    }
+  }
+  CK(cudaGetLastError());
+  cudaEvent_t ev_t1 = nullptr;
+  if (pl->timing) {
+    ev_t1 = get_event(pl);
+    CK(cudaEventRecord(ev_t1, pl->stream));
+    pl->spans.push_back({SP_TOTAL, ev_t0, ev_t1});
+  }
+
+  // ---- results -------------------------------------------------------------------------
+  if (copy_out(pl, out->params, pl->o_params.as<double>(), (size_t)nsub * 5)) return -2;
+  if (copy_out(pl, out->param_errs, pl->o_perrs.as<double>(), (size_t)nsub * 5)) return -2;
+  if (copy_out(pl, out->nu_out, pl->o_nuout.as<double>(), (size_t)nsub * 3)) return -2;
+  if (copy_out(pl, out->cov, pl->o_cov.as<double>(), (size_t)nsub * 25)) return -2;
+  if (copy_out(pl, out->chi2, pl->o_chi2.as<double>(), (size_t)nsub)) return -2;
+  if (copy_out(pl, out->red_chi2, pl->o_rchi2.as<double>(), (size_t)nsub)) return -2;
+  if (copy_out(pl, out->snr, pl->o_snr.as<double>(), (size_t)nsub)) return -2;
+  if (copy_out(pl, out->nfeval, pl->o_nfev.as<int>(), (size_t)nsub)) return -2;
+  if (copy_out(pl, out->return_code, pl->o_rc.as<int>(), (size_t)nsub)) return -2;
+  if (copy_out(pl, out->scales, pl->o_scales.as<double>(), nsc)) return -2;
+  if (copy_out(pl, out->scale_errs, pl->o_serrs.as<double>(), nsc)) return -2;
+  if (copy_out(pl, out->channel_snrs, pl->o_csnr.as<double>(), nsc)) return -2;
+  if (copy_out(pl, out->noise, pl->sigma.as<double>(), nsc)) return -2;
+  if (copy_out(pl, out->lag_index, pl->o_lag.as<int>(), (size_t)nsub)) return -2;
+  if (want_guess) { if (copy_out(pl, out->phi_guess, pl->o_phig.as<double>(), (size_t)nsub)) return -2; }
+  else if (out->phi_guess && dinit) {
+    // phi_guess = init[:,0]
+    CK(cudaMemcpy2DAsync(out->phi_guess, sizeof(double), dinit, 5 * sizeof(double), sizeof(double), nsub,
+                         is_device_ptr(out->phi_guess) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, pl->stream));
+  }
+  if (copy_out(pl, out->chan_sums, pl->csum.as<double>(), nsc * kNCsum)) return -2;
+  CK(cudaStreamSynchronize(pl->stream));
+  CK(cudaGetLastError());
+  stats_end(pl);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// batched 1-D FFTFIT, rotation, noise
+// ----------------------------------------------------------------------------
+template <typename T> static const void* tw1(pp_plan* pl) { return sizeof(T) == 8 ? pl->twN64.p : pl->twN32.p; }
+template <typename T> static const void* tw2(pp_plan* pl) { return sizeof(T) == 8 ? pl->tw2N64.p : pl->tw2N32.p; }
+
+static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spec, int conj, double* noise, int bits) {
+  const int N = pl->N;
+  RowsArgs a;
+  a.in = in; a.spec = spec; a.noise = noise; a.nrows = nrows; a.conj = conj;
+  if (bits == 64) {
+    a.twN = tw1<double>(pl); a.tw2N = tw2<double>(pl);
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rfft_rows<NN, double><<<(nrows + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+    });
+  } else {
+    a.twN = tw1<float>(pl); a.tw2N = tw2<float>(pl);
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rfft_rows<NN, float><<<(nrows + rows - 1) / rows, 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a);
+    });
+  }
+  pl->stats.launches++;
+  return 0;
+}
+
+extern "C" int pp_fit_phase_shift_batch(pp_plan_t* pl, const float* profiles, int32_t n, const float* models, int32_t nmodel,
+                                        const double* noise, int32_t Ns, const pp_pshift_out_t* out) {
+  if (!pl || !profiles || !models || !out) return fail(-1, "NULL argument");
+  if (n < 1) return fail(-1, "n must be >= 1");
+  if (nmodel != 1 && nmodel != n) return fail(-1, "nmodel must be 1 or n");
+  if (Ns <= 0) Ns = 100;
+  if (Ns < 2) return fail(-1, "Ns must be >= 2");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N;
+  const float *dprof, *dmod;
+  const double* dnoise;
+  if (stage_in(pl, pl->rot_in, profiles, (size_t)n * 2 * N, &dprof)) return -2;
+  if (stage_in(pl, pl->model_stage, models, (size_t)nmodel * 2 * N, &dmod)) return -2;
+  if (stage_in(pl, pl->in_noise, noise, (size_t)n, &dnoise)) return -2;
+  CK(pl->ps_spec.need(sizeof(float2) * (size_t)n * N));
+  CK(pl->ps_mspec.need(sizeof(float2) * (size_t)nmodel * N));
+  CK(pl->ps_phase.need(sizeof(double) * n)); CK(pl->ps_perr.need(sizeof(double) * n));
+  CK(pl->ps_scale.need(sizeof(double) * n)); CK(pl->ps_serr.need(sizeof(double) * n));
+  CK(pl->ps_snr.need(sizeof(double) * n)); CK(pl->ps_rchi2.need(sizeof(double) * n));
+  CK(pl->ps_lag.need(sizeof(int) * n));
+  const int bits = pl->fft_precision ? pl->fft_precision : 64;
+  if (launch_rfft_rows(pl, dprof, n, pl->ps_spec.as<float2>(), 0, nullptr, bits)) return -2;
+  if (launch_rfft_rows(pl, dmod, nmodel, pl->ps_mspec.as<float2>(), 1, nullptr, 64)) return -2;
+  const double2* table = nullptr;
+  if (grid_table(pl, Ns, &table)) return -2;
+  GuessArgs ga;
+  memset(&ga, 0, sizeof ga);
+  ga.partial = pl->ps_spec.as<float2>(); ga.mconj = pl->ps_mspec.as<float2>(); ga.nparts = 1; ga.nmodel = nmodel;
+  ga.N = N; ga.Ns = Ns; ga.wsum = nullptr; ga.noise = dnoise; ga.table = table; ga.s0 = 0;
+  ga.phase = pl->ps_phase.as<double>(); ga.phase_err = pl->ps_perr.as<double>(); ga.scale = pl->ps_scale.as<double>();
+  ga.scale_err = pl->ps_serr.as<double>(); ga.snr = pl->ps_snr.as<double>(); ga.red_chi2 = pl->ps_rchi2.as<double>();
+  ga.lag = pl->ps_lag.as<int>();
+  k_guess<<<n, 256, sizeof(double2) * N, pl->stream>>>(ga);
+  pl->stats.launches++;
+  CK(cudaGetLastError());
+  if (copy_out(pl, out->phase, pl->ps_phase.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->phase_err, pl->ps_perr.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->scale, pl->ps_scale.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->scale_err, pl->ps_serr.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->snr, pl->ps_snr.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->red_chi2, pl->ps_rchi2.as<double>(), (size_t)n)) return -2;
+  if (copy_out(pl, out->lag_index, pl->ps_lag.as<int>(), (size_t)n)) return -2;
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+extern "C" int pp_rotate_batch(pp_plan_t* pl, const float* in, float* outp, int32_t nsub, const double* phase, const double* DM,
+                               const double* P, const double* nu_ref) {
+  if (!pl || !in || !outp || !phase || !DM || !P || !nu_ref) return fail(-1, "NULL argument");
+  if (nsub < 1) return fail(-1, "nsub must be >= 1");
+  if (!pl->freqs_set) return fail(-1, "pp_set_model or pp_set_freqs must be called before pp_rotate_batch");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan;
+  const size_t tot = (size_t)nsub * nchan * 2 * N;
+  const float* din;
+  if (stage_in(pl, pl->rot_in, in, tot, &din)) return -2;
+  float* dout = outp;
+  const bool out_dev = is_device_ptr(outp);
+  if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  const double *dph, *ddm, *dP, *dnr;
+  if (stage_in(pl, pl->rot_phase, phase, (size_t)nsub, &dph)) return -2;
+  if (stage_in(pl, pl->rot_dm, DM, (size_t)nsub, &ddm)) return -2;
+  if (stage_in(pl, pl->rot_P, P, (size_t)nsub, &dP)) return -2;
+  if (stage_in(pl, pl->rot_nuref, nu_ref, (size_t)nsub, &dnr)) return -2;
+  RotateArgs a;
+  a.in = din; a.out = dout; a.phase = dph; a.DM = ddm; a.P = dP; a.nu_ref = dnr; a.nu2 = pl->nu2.as<double>();
+  a.nsub = nsub; a.nchan = nchan;
+  const long nrows = (long)nsub * nchan;
+  if (pl->fft_precision == 64) {
+    a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rotate<NN, double><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+    });
+  } else {
+    a.twN = pl->twN32.p; a.tw2N = pl->tw2N32.p;
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rotate<NN, float><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a);
+    });
+  }
+  pl->stats.launches++;
+  CK(cudaGetLastError());
+  if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+extern "C" int pp_get_noise_batch(pp_plan_t* pl, const float* data, int32_t nsub, double* noise_out) {
+  if (!pl || !data || !noise_out) return fail(-1, "NULL argument");
+  if (nsub < 1) return fail(-1, "nsub must be >= 1");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan;
+  const long nrows = (long)nsub * nchan;
+  const float* din;
+  if (stage_in(pl, pl->rot_in, data, (size_t)nrows * 2 * N, &din)) return -2;
+  CK(pl->ps_noise.need(sizeof(double) * nrows));
+  const int bits = pl->fft_precision ? pl->fft_precision : 64;
+  if (launch_rfft_rows(pl, din, (int)nrows, nullptr, 0, pl->ps_noise.as<double>(), bits)) return -2;
+  CK(cudaGetLastError());
+  if (copy_out(pl, noise_out, pl->ps_noise.as<double>(), (size_t)nrows)) return -2;
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}

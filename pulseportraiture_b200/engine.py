@@ -1,0 +1,222 @@
+"""Batch-first Python front end of the C ABI (one plan per device).
+
+``WidebandPlan`` is what the reference-compatible facade functions
+(``pplib.fit_portrait``, ``pptoaslib.fit_portrait_full``,
+``pplib.fit_phase_shift``, ``pptoas.GetTOAs``) are built on: they are the
+``nsub = 1`` views of these batched calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+_KEEP = "_keepalive"
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, dtype, keep, name, shape=None):
+    """Raw pointer of a numpy array / torch tensor (host or CUDA); None->NULL."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        want = {np.float32: torch.float32, np.float64: torch.float64,
+                np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+        if x.dtype != want:
+            raise TypeError("%s: expected torch dtype %s, got %s" % (name, want, x.dtype))
+        if not x.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+        if shape is not None and tuple(x.shape) != tuple(shape):
+            raise ValueError("%s: expected shape %s, got %s" % (name, shape, tuple(x.shape)))
+        keep.append(x)
+        return x.data_ptr()
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    keep.append(a)
+    return a.ctypes.data
+
+
+class WidebandPlan(object):
+    """Device plan for portraits of shape [nchan, nbin] (C ABI pp_plan_*)."""
+
+    def __init__(self, nchan, nbin, device=0, stream=None):
+        self._lib = _ffi.lib()
+        self._h = C.c_void_p()
+        _ffi.check(self._lib.pp_plan_create(int(nchan), int(nbin), int(device),
+                                            C.byref(self._h)), "pp_plan_create")
+        self.nchan, self.nbin, self.device = int(nchan), int(nbin), int(device)
+        self.freqs = None
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pp_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- configuration -------------------------------------------------------
+    def set_stream(self, stream):
+        """stream: torch.cuda.Stream, raw cudaStream_t int, or None."""
+        h = getattr(stream, "cuda_stream", stream)
+        _ffi.check(self._lib.pp_plan_set_stream(self._h, C.c_void_p(h or 0)),
+                   "pp_plan_set_stream")
+
+    def set_chunk(self, n):
+        _ffi.check(self._lib.pp_plan_set_chunk(self._h, int(n)), "pp_plan_set_chunk")
+
+    def set_fft_precision(self, bits):
+        """0 = automatic, 32 = float FFT, 64 = double FFT (data rows)."""
+        _ffi.check(self._lib.pp_plan_set_fft_precision(self._h, int(bits)),
+                   "pp_plan_set_fft_precision")
+
+    def set_freqs(self, freqs):
+        keep = []
+        fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",
+                  (self.nchan,))
+        _ffi.check(self._lib.pp_set_freqs(self._h, fp), "pp_set_freqs")
+        self.freqs = np.array(freqs, dtype=np.float64)
+
+    def enable_timing(self, on=True):
+        _ffi.check(self._lib.pp_plan_enable_timing(self._h, 1 if on else 0),
+                   "pp_plan_enable_timing")
+
+    def stats(self):
+        st = _ffi.Stats()
+        _ffi.check(self._lib.pp_get_stats(self._h, C.byref(st)), "pp_get_stats")
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    def set_model(self, model, freqs):
+        keep = []
+        mp = _ptr(model, np.float32, keep, "model", (self.nchan, self.nbin))
+        fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",
+                  (self.nchan,))
+        _ffi.check(self._lib.pp_set_model(self._h, mp, fp), "pp_set_model")
+        self.freqs = np.array(freqs, dtype=np.float64)
+
+    # ---- batched wideband fit ---------------------------------------------------
+    def fit_batch(self, data, P, errs=None, chan_mask=None, weights=None,
+                  init=None, DM_guess=None, snrs=None, nu_fits=None,
+                  nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
+                  log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
+                  tol=0.0, semantics="full", want_chan_sums=False, nsub=None):
+        """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
+        CUDA torch tensor).  Returns a dict of numpy arrays."""
+        keep = []
+        if nsub is None:
+            nsub = int(data.shape[0]) if hasattr(data, "shape") and len(data.shape) == 3 else 1
+        nchan, nbin = self.nchan, self.nbin
+        a = _ffi.FitArgs()
+        a.data = _ptr(data, np.float32, keep, "data", (nsub, nchan, nbin))
+        a.nsub = nsub
+        a.semantics = {"full": 0, "fit_portrait": 1}[semantics]
+        Parr = np.broadcast_to(np.asarray(P, dtype=np.float64), (nsub,)) \
+            if not _is_torch(P) else P
+        a.P = _ptr(Parr, np.float64, keep, "P", (nsub,))
+        a.errs = _ptr(errs, np.float64, keep, "errs", (nsub, nchan))
+        a.chan_mask = _ptr(chan_mask, np.uint8, keep, "chan_mask", (nsub, nchan))
+        a.weights = _ptr(weights, np.float64, keep, "weights", (nsub, nchan))
+        a.init = _ptr(init, np.float64, keep, "init", (nsub, 5))
+        a.DM_guess = _ptr(None if DM_guess is None else
+                          (DM_guess if _is_torch(DM_guess) else
+                           np.broadcast_to(np.asarray(DM_guess, dtype=np.float64), (nsub,))),
+                          np.float64, keep, "DM_guess", (nsub,))
+        a.snrs = _ptr(snrs, np.float64, keep, "snrs", (nsub, nchan))
+        a.nu_fits = _ptr(nu_fits, np.float64, keep, "nu_fits", (nsub, 3))
+        a.nu_fit_mode = int(nu_fit_mode)
+        a.nu_outs = _ptr(nu_outs, np.float64, keep, "nu_outs", (nsub, 3))
+        for i in range(5):
+            a.fit_flags[i] = 1 if fit_flags[i] else 0
+        a.log10_tau = 1 if log10_tau else 0
+        a.option = int(option)
+        a.is_toa = 1 if is_toa else 0
+        a.Ns = int(Ns)
+        a.max_iter = int(max_iter)
+        a.tol = float(tol)
+
+        res = {
+            "params": np.empty((nsub, 5)), "param_errs": np.empty((nsub, 5)),
+            "nu_out": np.empty((nsub, 3)), "cov": np.empty((nsub, 5, 5)),
+            "chi2": np.empty(nsub), "red_chi2": np.empty(nsub),
+            "snr": np.empty(nsub), "nfeval": np.empty(nsub, dtype=np.int32),
+            "return_code": np.empty(nsub, dtype=np.int32),
+            "scales": np.empty((nsub, nchan)), "scale_errs": np.empty((nsub, nchan)),
+            "channel_snrs": np.empty((nsub, nchan)), "noise": np.empty((nsub, nchan)),
+            "lag_index": np.empty(nsub, dtype=np.int32), "phi_guess": np.empty(nsub),
+        }
+        if want_chan_sums:
+            res["chan_sums"] = np.empty((nsub, nchan, 9))
+        o = _ffi.FitOut()
+        for k, v in res.items():
+            setattr(o, k, v.ctypes.data)
+        _ffi.check(self._lib.pp_fit_batch(self._h, C.byref(a), C.byref(o)),
+                   "pp_fit_batch")
+        del keep
+        return res
+
+    # ---- batched 1-D FFTFIT --------------------------------------------------------
+    def fit_phase_shift_batch(self, profiles, models, noise=None, Ns=100):
+        keep = []
+        n = int(profiles.shape[0])
+        nmodel = int(models.shape[0]) if len(models.shape) == 2 else 1
+        pp = _ptr(profiles, np.float32, keep, "profiles", (n, self.nbin))
+        mp = _ptr(models, np.float32, keep, "models", (nmodel, self.nbin))
+        nz = _ptr(noise, np.float64, keep, "noise", (n,))
+        res = {k: np.empty(n) for k in ("phase", "phase_err", "scale",
+                                        "scale_err", "snr", "red_chi2")}
+        res["lag_index"] = np.empty(n, dtype=np.int32)
+        o = _ffi.PShiftOut()
+        for k, v in res.items():
+            setattr(o, k, v.ctypes.data)
+        _ffi.check(self._lib.pp_fit_phase_shift_batch(self._h, pp, n, mp, nmodel,
+                                                      nz, int(Ns), C.byref(o)),
+                   "pp_fit_phase_shift_batch")
+        return res
+
+    # ---- batched rotation -------------------------------------------------------------
+    def rotate_batch(self, data, phase, DM, P, nu_ref, out=None):
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        if out is None:
+            if _is_torch(data):
+                import torch
+                out = torch.empty_like(data)
+            else:
+                out = np.empty((nsub, self.nchan, self.nbin), dtype=np.float32)
+        op = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        bc = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), (nsub,))  # noqa: E731
+        _ffi.check(self._lib.pp_rotate_batch(
+            self._h, ip, op, nsub,
+            _ptr(bc(phase), np.float64, keep, "phase"),
+            _ptr(bc(DM), np.float64, keep, "DM"),
+            _ptr(bc(P), np.float64, keep, "P"),
+            _ptr(bc(nu_ref), np.float64, keep, "nu_ref")), "pp_rotate_batch")
+        return out
+
+    def get_noise_batch(self, data):
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        out = np.empty((nsub, self.nchan))
+        _ffi.check(self._lib.pp_get_noise_batch(self._h, ip, nsub, out.ctypes.data),
+                   "pp_get_noise_batch")
+        return out

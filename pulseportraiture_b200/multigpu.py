@@ -1,0 +1,98 @@
+"""Sharding of independent subints across GPUs (no data-path collective).
+
+Every subint (and every archive) is fit independently (pptoas.py:247, 344), so
+the batch is split into contiguous ranges, one per GPU.  Two launch styles:
+
+* one process per GPU under ``torch.distributed`` (bench.py, large campaigns):
+  :func:`shard_range` + :func:`gather_results` (a host-side gather of the small
+  result arrays; the only collective, and not on the data path);
+* one host thread per GPU inside a single process (:class:`MultiGPUFitter`),
+  the style the Python facade uses for interactive sessions.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous [start, stop) of n items for ``rank`` of ``world`` (sizes
+    differ by at most one; earlier ranks take the remainder)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    base, rem = divmod(int(n), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_results(local, group=None, dst=0):
+    """Concatenate per-rank result dicts (numpy arrays, first axis = subint) on
+    rank ``dst`` in rank order.  Returns the merged dict on ``dst``, None
+    elsewhere.  Works with any torch.distributed backend (gloo on CPU, nccl)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object(local, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = {}
+    for k in bucket[0]:
+        out[k] = np.concatenate([np.asarray(b[k]) for b in bucket], axis=0)
+    return out
+
+
+class MultiGPUFitter(object):
+    """Fit one batch on several GPUs from one process: one plan, one stream and
+    one host thread per device; results are concatenated on the host."""
+
+    def __init__(self, nchan, nbin, devices):
+        from .engine import WidebandPlan
+        self.devices = list(devices)
+        self.plans = [WidebandPlan(nchan, nbin, d) for d in self.devices]
+
+    def set_model(self, model, freqs):
+        for p in self.plans:
+            p.set_model(model, freqs)
+
+    def close(self):
+        for p in self.plans:
+            p.close()
+
+    def fit_batch(self, data, P, **kw):
+        nsub = int(data.shape[0])
+        world = len(self.plans)
+        results = [None] * world
+        errors = [None] * world
+        P = np.broadcast_to(np.asarray(P, dtype=np.float64), (nsub,))
+
+        def slice_kw(a, b):
+            out = {}
+            for k, v in kw.items():
+                if hasattr(v, "shape") and len(getattr(v, "shape", ())) >= 1 \
+                        and v.shape[0] == nsub:
+                    out[k] = v[a:b]
+                else:
+                    out[k] = v
+            return out
+
+        def work(i):
+            a, b = shard_range(nsub, i, world)
+            if b <= a:
+                return
+            try:
+                results[i] = self.plans[i].fit_batch(data[a:b], P[a:b], **slice_kw(a, b))
+            except Exception as exc:  # noqa: BLE001
+                errors[i] = exc
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        parts = [r for r in results if r is not None]
+        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}

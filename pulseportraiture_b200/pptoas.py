@@ -1,0 +1,405 @@
+"""Reference-compatible ``pptoas.GetTOAs`` (pptoas.py:75-743) re-plumbed to
+batch: every archive's subints go to the GPU in one ``pp_fit_batch`` call.
+
+PSRCHIVE is not a dependency: an "archive" is the ``DataBunch`` that
+``pplib.load_data`` would return (field list pplib.py:2803-2813), given either
+directly or as an ``.npz`` file holding those fields (``save_databunch`` /
+``load_data`` below).  Epochs are two-part MJDs (:class:`MJD`).
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+
+from . import pplib
+from .pplib import DataBunch, read_model, gen_gaussian_portrait, scattering_alpha  # noqa: F401
+from .pplib import get_plan, _f32
+
+max_nfile = 999                                  # pptoas.py:18-23
+rm_baseline = bool(pplib.F0_fact)                # pptoas.py:25-29
+
+
+class MJD(object):
+    """Two-part MJD (integer day + fraction), the part of psrchive.MJD that
+    get_TOAs and write_TOAs use (in_days, intday, fracday, +)."""
+
+    def __init__(self, day=0, frac=0.0):
+        if frac == 0.0 and not float(day).is_integer():
+            frac, day = float(day) - np.floor(day), int(np.floor(day))
+        d = int(day) + int(np.floor(frac))
+        self._day, self._frac = d, float(frac - np.floor(frac))
+
+    def intday(self):
+        return self._day
+
+    def fracday(self):
+        return self._frac
+
+    def in_days(self):
+        return self._day + self._frac
+
+    def __add__(self, other):
+        if not isinstance(other, MJD):
+            other = MJD(0, float(other))
+        return MJD(self._day + other._day, self._frac + other._frac)
+
+    def __repr__(self):
+        return "MJD(%d + %.15f)" % (self._day, self._frac)
+
+
+class TOA:
+    """TOA attributes bundled together (pptoas.py:31-73)."""
+
+    def __init__(self, archive, frequency, MJD, TOA_error, telescope,
+                 telescope_code, DM=None, DM_error=None, flags={}):
+        self.archive = archive
+        self.frequency = frequency
+        self.MJD = MJD
+        self.TOA_error = TOA_error
+        self.telescope = telescope
+        self.telescope_code = telescope_code
+        self.DM = DM
+        self.DM_error = DM_error
+        self.flags = flags
+        for flag in flags.keys():
+            setattr(self, flag, flags[flag])
+
+
+_DB_FIELDS = ["backend", "backend_delay", "bw", "doppler_factors", "DM", "dmc",
+              "epochs", "filename", "freqs", "frontend", "integration_length",
+              "masks", "nbin", "nchan", "noise_stds", "npol", "nsub", "nu0",
+              "ok_ichans", "ok_isubs", "parallactic_angles", "phases", "Ps",
+              "SNRs", "source", "state", "subints", "subtimes", "telescope",
+              "telescope_code", "weights"]
+
+
+def save_databunch(path, data):
+    """Write the load_data field contract (pplib.py:2803-2813) to ``.npz``."""
+    out = {}
+    for k in _DB_FIELDS:
+        v = data[k]
+        if k == "epochs":
+            out["epochs_day"] = np.array([e.intday() for e in v])
+            out["epochs_frac"] = np.array([e.fracday() for e in v])
+        elif k == "ok_ichans":
+            m = np.zeros((data["nsub"], data["nchan"]), dtype=np.uint8)
+            for i, idx in enumerate(v):
+                m[i, np.asarray(idx, dtype=int)] = 1
+            out["ok_mask"] = m
+        else:
+            out[k] = np.asarray(v)
+    np.savez(path, **out)
+
+
+def load_data(filename, **kwargs):
+    """PSRCHIVE-free stand-in for pplib.load_data (pplib.py:2650-2814): reads
+    the same fields from an ``.npz`` written by :func:`save_databunch`."""
+    z = np.load(filename, allow_pickle=False)
+    d = {}
+    for k in z.files:
+        v = z[k]
+        d[k] = v.item() if v.shape == () else v
+    d["epochs"] = [MJD(int(a), float(b)) for a, b in zip(d.pop("epochs_day"), d.pop("epochs_frac"))]
+    m = d.pop("ok_mask")
+    d["ok_ichans"] = [np.where(row)[0] for row in m]
+    d["arch"] = None
+    d["filename"] = str(filename)
+    for k in ("backend", "frontend", "source", "state", "telescope", "telescope_code"):
+        d[k] = str(d[k])
+    return DataBunch(**d)
+
+
+def weighted_mean(data, errs=1.0):
+    """pplib.py:686-705."""
+    data = np.asarray(data, dtype=np.float64)
+    errs = np.ones(len(data)) * errs if np.isscalar(errs) else np.asarray(errs, dtype=np.float64)
+    iis = np.where(errs > 0.0)[0]
+    mean, sum_weights = np.average(data[iis], weights=errs[iis] ** -2.0, returned=True)
+    return mean, sum_weights ** -0.5
+
+
+class GetTOAs:
+    """Measure TOAs and DMs from wideband data (pptoas.py:75-743)."""
+
+    def __init__(self, datafiles, modelfile, quiet=False):
+        if isinstance(datafiles, (list, tuple)):
+            self.datafiles = list(datafiles)
+        elif isinstance(datafiles, str) and not datafiles.endswith(".npz"):
+            self.datafiles = [line.strip() for line in open(datafiles, "r").readlines()
+                              if line.strip()]             # metafile (pptoas.py:93-95)
+        else:
+            self.datafiles = [datafiles]
+        if len(self.datafiles) > max_nfile:
+            print("Too many archives.  See/change max_nfile(=%d) in pptoas.py." % max_nfile)
+            sys.exit()
+        self.is_FITS_model = False
+        self.modelfile = modelfile
+        for name in ("obs", "doppler_fs", "nu0s", "nu_fits", "nu_refs", "ok_idatafiles",
+                     "ok_isubs", "epochs", "MJDs", "Ps", "phis", "phi_errs", "TOAs",
+                     "TOA_errs", "DM0s", "DMs", "DM_errs", "DeltaDM_means", "DeltaDM_errs",
+                     "GMs", "GM_errs", "taus", "tau_errs", "alphas", "alpha_errs", "scales",
+                     "scale_errs", "snrs", "channel_snrs", "profile_fluxes",
+                     "profile_flux_errs", "fluxes", "flux_errs", "flux_freqs", "red_chi2s",
+                     "channel_red_chi2s", "covariances", "nfevals", "rcs", "fit_durations",
+                     "order", "TOA_list", "zap_channels"):
+            setattr(self, name, [])                         # pptoas.py:102-143
+        self.instrumental_response_dict = self.ird = {'DM': 0.0, 'wids': [], 'irf_types': []}
+        self.quiet = quiet
+
+    def _model_for(self, phases, freqs_row, P):
+        if isinstance(self.modelfile, np.ndarray):
+            self.model_name, self.ngauss = "array", 0
+            return self.modelfile
+        self.model_name, self.ngauss, model = read_model(self.modelfile, phases, freqs_row, P,
+                                                         quiet=True)
+        return model
+
+    def get_TOAs(self, datafile=None, tscrunch=False, nu_refs=None, DM0=None,
+                 bary=True, fit_DM=True, fit_GM=False, fit_scat=False,
+                 log10_tau=True, scat_guess=None, fix_alpha=False,
+                 print_phase=False, print_flux=False, print_parangle=False,
+                 add_instrumental_response=False, addtnl_toa_flags={},
+                 method='trust-ncg', bounds=None, nu_fits=None, show_plot=False,
+                 quiet=None):
+        """Measure wideband TOAs (pptoas.py:150-743).  Same keyword arguments
+        as the reference; results fill the attribute lists of the instance."""
+        if quiet is None:
+            quiet = self.quiet
+        if tscrunch or show_plot or add_instrumental_response:
+            raise NotImplementedError("tscrunch / show_plot / add_instrumental_response "
+                                      "need PSRCHIVE or matplotlib and are outside the hot path")
+        self.nfit = 1 + int(bool(fit_DM)) + int(bool(fit_GM)) + 2 * int(bool(fit_scat)) - \
+            int(bool(fix_alpha))
+        self.fit_phi, self.fit_DM, self.fit_GM = True, fit_DM, fit_GM
+        self.fit_tau = self.fit_alpha = fit_scat
+        if fit_scat:
+            self.fit_alpha = not fix_alpha
+        self.fit_flags = [int(self.fit_phi), int(self.fit_DM), int(self.fit_GM),
+                          int(self.fit_tau), int(self.fit_alpha)]
+        if not fit_scat:
+            log10_tau = False                               # pptoas.py:229-230
+        self.log10_tau = log10_tau
+        self.scat_guess, self.DM0, self.bary = scat_guess, DM0, bary
+        nu_ref_tuple, nu_fit_tuple = nu_refs, nu_fits
+        start = time.time()
+        datafiles = self.datafiles if datafile is None else [datafile]
+        for iarch, datafile in enumerate(datafiles):
+            try:
+                data = datafile if isinstance(datafile, dict) else load_data(datafile)
+            except (RuntimeError, IOError, OSError):
+                if not quiet:
+                    print("Cannot load_data(%s).  Skipping it." % datafile)
+                continue
+            if not len(data.ok_isubs):
+                if not quiet:
+                    print("No subints to fit for %s.  Skipping it." % data.filename)
+                continue
+            self.ok_idatafiles.append(iarch)
+            d = data
+            nsub, nchan, nbin = int(d.nsub), int(d.nchan), int(d.nbin)
+            ok_isubs = np.asarray(d.ok_isubs, dtype=int)
+            source = d.source if d.source is not None else "noname"  # noqa: F841
+            obs = DataBunch(telescope=d.telescope, backend=d.backend, frontend=d.frontend)
+            freqs = np.asarray(d.freqs, dtype=np.float64)
+            Ps = np.asarray(d.Ps, dtype=np.float64)
+            DM_stored = float(d.DM)
+            DM0_arch = DM_stored if self.DM0 is None else self.DM0
+            MJDs = np.array([e.in_days() for e in d.epochs], dtype=np.double)
+            if np.any(freqs != freqs[0]):
+                raise NotImplementedError("per-subint frequency tables")
+            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]])
+
+            mask = np.zeros((nsub, nchan), dtype=np.uint8)
+            for isub in ok_isubs:
+                mask[isub, np.asarray(d.ok_ichans[isub], dtype=int)] = 1
+            nok = mask.sum(axis=1)
+            subints = _f32(np.asarray(d.subints)[:, 0])
+            errs = np.ascontiguousarray(np.asarray(d.noise_stds)[:, 0], dtype=np.float64)
+            snrs = np.ascontiguousarray(np.asarray(d.SNRs)[:, 0], dtype=np.float64)
+            weights = np.ascontiguousarray(d.weights, dtype=np.float64)
+            if nu_fit_tuple is None:
+                nu_fits_in, mode = None, 1                 # guess_fit_freq, pptoas.py:402
+            else:
+                nu_fits_in = np.tile([nu_fit_tuple[0], nu_fit_tuple[0], nu_fit_tuple[-1]],
+                                     (nsub, 1)).astype(np.float64)
+                mode = 0
+            nu_outs_in = None
+            if nu_ref_tuple is not None:
+                nu_outs_in = np.full((nsub, 3), np.nan)
+                if nu_ref_tuple[0]:
+                    nu_outs_in[:, 0] = nu_outs_in[:, 1] = nu_ref_tuple[0]
+                if nu_ref_tuple[-1]:
+                    nu_outs_in[:, 2] = nu_ref_tuple[-1]
+                    if bary:
+                        nu_outs_in[:, 2] /= np.asarray(d.doppler_factors)
+            pl = get_plan(nchan, nbin)
+            pl.set_model(_f32(model), freqs[0])
+
+            # subints with a single usable channel are fit for phase only
+            # (pptoas.py:475-478); two channels drop GM (479-483)
+            groups = {}
+            for isub in ok_isubs:
+                if nok[isub] == 1:
+                    flags = (1, 0, 0, 0, 0)
+                elif nok[isub] == 2 and self.fit_DM and self.fit_GM:
+                    flags = tuple(self.fit_flags[:2] + [0] + self.fit_flags[3:])
+                else:
+                    flags = tuple(self.fit_flags)
+                groups.setdefault(flags, []).append(isub)
+            res = {}
+            fit_start = time.time()
+            for flags, isubs in groups.items():
+                idx = np.asarray(isubs, dtype=int)
+                r = pl.fit_batch(
+                    np.ascontiguousarray(subints[idx]), Ps[idx], errs=errs[idx],
+                    chan_mask=mask[idx], weights=weights[idx], DM_guess=np.full(len(idx), DM_stored),
+                    snrs=snrs[idx], nu_fits=None if nu_fits_in is None else nu_fits_in[idx],
+                    nu_fit_mode=mode, nu_outs=None if nu_outs_in is None else nu_outs_in[idx],
+                    fit_flags=flags, log10_tau=self.log10_tau, option=0, is_toa=True,
+                    Ns=100, semantics="full")
+                for j, isub in enumerate(idx):
+                    res[isub] = (flags, {k: v[j] for k, v in r.items()})
+            fit_duration = time.time() - fit_start
+
+            phis = np.zeros(nsub); phi_errs = np.zeros(nsub)
+            TOAs = np.zeros(nsub, dtype="object"); TOA_errs = np.zeros(nsub, dtype="object")
+            DMs = np.zeros(nsub); DM_errs = np.zeros(nsub)
+            GMs = np.zeros(nsub); GM_errs = np.zeros(nsub)
+            taus = np.zeros(nsub); tau_errs = np.zeros(nsub)
+            alphas = np.zeros(nsub); alpha_errs = np.zeros(nsub)
+            scales = np.zeros([nsub, nchan]); scale_errs = np.zeros([nsub, nchan])
+            snrs_out = np.zeros(nsub); channel_snrs = np.zeros([nsub, nchan])
+            profile_fluxes = np.zeros([nsub, nchan]); profile_flux_errs = np.zeros([nsub, nchan])
+            fluxes = np.zeros(nsub); flux_errs = np.zeros(nsub); flux_freqs = np.zeros(nsub)
+            red_chi2s = np.zeros(nsub)
+            covariances = np.zeros([nsub, self.nfit, self.nfit])
+            nfevals = np.zeros(nsub, dtype="int"); rcs = np.zeros(nsub, dtype="int")
+            nu_fits_arr = list(np.zeros([nsub, 3])); nu_refs_arr = list(np.zeros([nsub, 3]))
+            for isub in ok_isubs:
+                flags, r = res[isub]
+                okc = np.asarray(d.ok_ichans[isub], dtype=int)
+                freqsx = freqs[isub, okc]
+                P = Ps[isub]
+                phi, phi_err = r["params"][0], r["param_errs"][0]
+                DM, DM_err = r["params"][1], r["param_errs"][1]
+                GM, GM_err = r["params"][2], r["param_errs"][2]
+                # TOA (pptoas.py:528-531)
+                TOA_mjd = d.epochs[isub] + MJD(0, ((phi * P) + d.backend_delay) / (3600 * 24.))
+                TOA_err = phi_err * P * 1e6
+                # Doppler correction (pptoas.py:539-549)
+                if self.bary:
+                    df = np.asarray(d.doppler_factors)[isub]
+                    if flags[1]:
+                        DM *= df
+                    if flags[2]:
+                        GM *= df ** 3
+                else:
+                    df = 1.0
+                if print_flux:                              # pptoas.py:554-577
+                    means = np.asarray(model)[okc].mean(axis=1)
+                    profile_fluxes[isub, okc] = means * r["scales"][okc]
+                    profile_flux_errs[isub, okc] = abs(means) * r["scale_errs"][okc]
+                    fluxes[isub], flux_errs[isub] = weighted_mean(profile_fluxes[isub, okc],
+                                                                 profile_flux_errs[isub, okc])
+                    flux_freqs[isub], _ = weighted_mean(freqsx, profile_flux_errs[isub, okc])
+                nu_refs_arr[isub] = list(r["nu_out"])
+                phis[isub], phi_errs[isub] = phi, phi_err
+                TOAs[isub], TOA_errs[isub] = TOA_mjd, TOA_err
+                DMs[isub], DM_errs[isub] = DM, DM_err
+                GMs[isub], GM_errs[isub] = GM, GM_err
+                taus[isub], tau_errs[isub] = r["params"][3], r["param_errs"][3]
+                alphas[isub], alpha_errs[isub] = r["params"][4], r["param_errs"][4]
+                nfevals[isub], rcs[isub] = r["nfeval"], r["return_code"]
+                scales[isub, okc] = r["scales"][okc]
+                scale_errs[isub, okc] = r["scale_errs"][okc]
+                snrs_out[isub] = r["snr"]
+                channel_snrs[isub, okc] = r["channel_snrs"][okc]
+                ifit = np.where(flags)[0]
+                cm = r["cov"][np.ix_(ifit, ifit)]
+                if cm.shape == covariances[isub].shape:
+                    covariances[isub] = cm
+                else:                                       # pptoas.py:596-600
+                    for ii, a_ in enumerate(ifit):
+                        for jj, b_ in enumerate(ifit):
+                            if a_ < self.nfit and b_ < self.nfit:
+                                covariances[isub][a_, b_] = cm[ii, jj]
+                red_chi2s[isub] = r["red_chi2"]
+                toa_flags = {}                              # pptoas.py:604-651
+                DM_out, DM_err_out = (DM, DM_err) if flags[1] else (None, None)
+                if flags[2]:
+                    toa_flags['gm'], toa_flags['gm_err'] = GM, GM_err
+                toa_flags['be'] = d.backend
+                toa_flags['fe'] = d.frontend
+                toa_flags['f'] = d.frontend + "_" + d.backend
+                toa_flags['nbin'] = nbin
+                toa_flags['nch'] = nchan
+                toa_flags['nchx'] = len(freqsx)
+                toa_flags['bw'] = freqsx.max() - freqsx.min()
+                toa_flags['chbw'] = abs(d.bw) / nchan
+                toa_flags['subint'] = int(isub)
+                toa_flags['tobs'] = np.asarray(d.subtimes)[isub]
+                toa_flags['fratio'] = freqsx.max() / freqsx.min()
+                toa_flags['tmplt'] = self.modelfile if isinstance(self.modelfile, str) else "array"
+                toa_flags['snr'] = r["snr"]
+                if nu_ref_tuple is not None and nu_ref_tuple[0] is not None and np.all(flags[:2]):
+                    toa_flags['phi_DM_cov'] = cm[0, 1]
+                toa_flags['gof'] = r["red_chi2"]
+                if print_phase:
+                    toa_flags['phs'], toa_flags['phs_err'] = phi, phi_err
+                if print_flux:
+                    toa_flags['flux'] = fluxes[isub]
+                    toa_flags['flux_err'] = flux_errs[isub]
+                    toa_flags['flux_ref_freq'] = flux_freqs[isub]
+                if print_parangle:
+                    toa_flags['par_angle'] = np.asarray(d.parallactic_angles)[isub]
+                for k, v in addtnl_toa_flags.items():
+                    toa_flags[k] = v
+                self.TOA_list.append(TOA(d.filename, r["nu_out"][0], TOA_mjd, TOA_err,
+                                         d.telescope, d.telescope_code, DM_out, DM_err_out,
+                                         toa_flags))
+            # per-archive Delta-DM mean (pptoas.py:665-682)
+            DeltaDMs = DMs - DM0_arch
+            if np.all(DM_errs[ok_isubs]):
+                DM_weights = DM_errs[ok_isubs] ** -2
+            else:
+                DM_weights = np.ones(len(ok_isubs))
+            DeltaDM_mean, DeltaDM_var = np.average(DeltaDMs[ok_isubs], weights=DM_weights,
+                                                   returned=True)
+            DeltaDM_var = DeltaDM_var ** -1
+            if len(ok_isubs) > 1:
+                DeltaDM_var *= np.sum(((DeltaDMs[ok_isubs] - DeltaDM_mean) ** 2) * DM_weights) / \
+                    (len(ok_isubs) - 1)
+            DeltaDM_err = DeltaDM_var ** 0.5
+            self.order.append(d.filename); self.obs.append(obs)
+            self.doppler_fs.append(d.doppler_factors); self.nu0s.append(d.nu0)
+            self.nu_fits.append(nu_fits_arr); self.nu_refs.append(nu_refs_arr)
+            self.ok_isubs.append(ok_isubs); self.epochs.append(d.epochs)
+            self.MJDs.append(MJDs); self.Ps.append(Ps)
+            self.phis.append(phis); self.phi_errs.append(phi_errs)
+            self.TOAs.append(TOAs); self.TOA_errs.append(TOA_errs)
+            self.DM0s.append(DM0_arch); self.DMs.append(DMs); self.DM_errs.append(DM_errs)
+            self.DeltaDM_means.append(DeltaDM_mean); self.DeltaDM_errs.append(DeltaDM_err)
+            self.GMs.append(GMs); self.GM_errs.append(GM_errs)
+            self.taus.append(taus); self.tau_errs.append(tau_errs)
+            self.alphas.append(alphas); self.alpha_errs.append(alpha_errs)
+            self.scales.append(scales); self.scale_errs.append(scale_errs)
+            self.snrs.append(snrs_out); self.channel_snrs.append(channel_snrs)
+            self.profile_fluxes.append(profile_fluxes)
+            self.profile_flux_errs.append(profile_flux_errs)
+            self.fluxes.append(fluxes); self.flux_errs.append(flux_errs)
+            self.flux_freqs.append(flux_freqs)
+            self.covariances.append(covariances); self.red_chi2s.append(red_chi2s)
+            self.nfevals.append(nfevals); self.rcs.append(rcs)
+            self.fit_durations.append(fit_duration)
+            if not quiet:
+                print("--------------------------")
+                print(d.filename)
+                print("~%.4f sec/TOA" % (fit_duration / len(ok_isubs)))
+                print("Med. TOA error is %.3f us" % (np.median(phi_errs[ok_isubs]) * Ps.mean() * 1e6))
+        tot_duration = time.time() - start
+        if not quiet and len(self.ok_isubs):
+            print("--------------------------")
+            print("Total time: %.2f sec, ~%.4f sec/TOA" % (
+                tot_duration, tot_duration / (np.array(list(map(len, self.ok_isubs))).sum())))

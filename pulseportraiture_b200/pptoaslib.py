@@ -1,0 +1,79 @@
+"""Reference-compatible facade for ``pptoaslib.fit_portrait_full``
+(pptoaslib.py:928-1096) on top of the batched C ABI."""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+
+from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32,  # noqa: F401
+                    get_plan, scattering_times, scattering_portrait_FT)
+
+
+def fit_portrait_full(data_port, model_port, init_params, P, freqs,
+                      nu_fits=[None, None, None], nu_outs=[None, None, None],
+                      errs=None, fit_flags=[1, 1, 1, 1, 1],
+                      bounds=[(None, None), (None, None), (None, None),
+                              (None, None), (None, None)], log10_tau=True,
+                      option=0, sub_id=None, method='trust-ncg', is_toa=True,
+                      quiet=True):
+    """Fit phase, DM, GM, tau and alpha between data and model portraits.
+
+    Same arguments, units and DataBunch fields as pptoaslib.fit_portrait_full
+    (pptoaslib.py:928-1096).  ``method`` is accepted for compatibility; the
+    scipy minimisers are replaced by the on-device safeguarded Newton solver,
+    which converges to the same optimum (``return_code`` 0 = converged,
+    1 = max passes, 3 = non-finite objective).  ``bounds`` (TNC only in the
+    reference) must be unset.
+    """
+    if method == 'TNC':
+        _check_bounds(bounds)
+    elif method not in ('trust-ncg', 'Newton-CG'):
+        print("Method '%s' is not implemented." % method)
+        sys.exit()
+    data_port = np.asarray(data_port)
+    nchan, nbin = data_port.shape
+    freqs = np.asarray(freqs, dtype=np.float64)
+    pl = get_plan(nchan, nbin)
+    pl.set_model(_f32(model_port), freqs)
+    init = np.array(init_params, dtype=np.float64).reshape(1, 5)
+
+    def three(vals):
+        vals = list(vals)
+        if all(v is None for v in vals):
+            return None
+        return np.array([[np.nan if v is None else float(v) for v in vals]])
+
+    start = time.time()
+    r = pl.fit_batch(_f32(data_port)[None], P,
+                     errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],
+                     init=init, nu_fits=three(nu_fits), nu_outs=three(nu_outs),
+                     fit_flags=[1 if f else 0 for f in fit_flags],
+                     log10_tau=bool(log10_tau), option=int(option),
+                     is_toa=bool(is_toa), semantics="full")
+    duration = time.time() - start
+    rc = int(r["return_code"][0])
+    if rc not in (0, 1):
+        if sub_id is not None:
+            ii = sub_id[::-1].index("_")
+            isub, filename = sub_id[-ii:], sub_id[:-ii - 1]
+            sys.stderr.write("Fit 'failed' with return code %d: %s -- %s subint %s\n"
+                             % (rc, RCSTRINGS[str(rc)], filename, isub))
+        else:
+            sys.stderr.write("Fit 'failed' with return code %d -- %s" % (rc, RCSTRINGS[str(rc)]))
+    ifit = np.where(fit_flags)[0]
+    params = list(r["params"][0])
+    perr = r["param_errs"][0].copy()
+    cov = r["cov"][0][np.ix_(ifit, ifit)]
+    return DataBunch(params=params, param_errs=perr, phi=params[0],
+                     phi_err=perr[0], DM=params[1], DM_err=perr[1],
+                     GM=params[2], GM_err=perr[2], tau=params[3],
+                     tau_err=perr[3], alpha=params[4], alpha_err=perr[4],
+                     scales=r["scales"][0], scale_errs=r["scale_errs"][0],
+                     nu_DM=r["nu_out"][0, 0], nu_GM=r["nu_out"][0, 1],
+                     nu_tau=r["nu_out"][0, 2], covariance_matrix=cov,
+                     chi2=r["chi2"][0], red_chi2=r["red_chi2"][0],
+                     snr=r["snr"][0], channel_snrs=r["channel_snrs"][0],
+                     duration=duration, nfeval=int(r["nfeval"][0]),
+                     return_code=rc)

@@ -1,0 +1,104 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds for sm_100a,
+loads without a GPU, exports every symbol include/ppb200.h declares, its
+structs have the layout the ctypes binding assumes, and compute calls fail
+loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ppb200.h")
+
+
+@pytest.fixture(scope="module")
+def ffi():
+    from pulseportraiture_b200 import _ffi
+    _ffi.build()
+    return _ffi
+
+
+def header_functions():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(ffi):
+    L = ffi.lib()
+    declared = header_functions()
+    assert declared, "no functions parsed from the header"
+    for name in declared:
+        assert hasattr(L, name), "missing symbol " + name
+    assert sorted(ffi.SYMBOLS) == declared
+    assert L.pp_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(ffi, tmp_path):
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ppb200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(pp_fit_args_t), offsetof(pp_fit_args_t, nu_fit_mode),'
+                   'offsetof(pp_fit_args_t, fit_flags), offsetof(pp_fit_args_t, tol),'
+                   'sizeof(pp_fit_out_t), sizeof(pp_pshift_out_t), sizeof(pp_stats_t),'
+                   'offsetof(pp_stats_t, chunk));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(ffi.FitArgs), ffi.FitArgs.nu_fit_mode.offset, ffi.FitArgs.fit_flags.offset,
+            ffi.FitArgs.tol.offset, C.sizeof(ffi.FitOut), C.sizeof(ffi.PShiftOut),
+            C.sizeof(ffi.Stats), ffi.Stats.chunk.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback(ffi):
+    """Without a CUDA device plan creation must fail with a message; with one
+    (GPU box) it must succeed.  Either way nothing is computed on the CPU."""
+    L = ffi.lib()
+    h = C.c_void_p()
+    rc = L.pp_plan_create(8, 256, 0, C.byref(h))
+    if rc == 0:
+        L.pp_plan_destroy(h)
+    else:
+        assert rc < 0 and len(L.pp_last_error()) > 0
+    assert L.pp_plan_create(8, 1000, 0, C.byref(h)) < 0        # not a power of two
+    assert b"power of two" in L.pp_last_error()
+    assert L.pp_fit_batch(None, None, None) < 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pulseportraiture_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("pp_oracle-free", ""), f
+
+
+def test_host_helpers_match_oracle():
+    """Host-side (non-hot-path) helpers of the facade: model generator and
+    scalar transforms agree with the oracle's independent restatement."""
+    from pulseportraiture_b200 import pplib
+    from oracle import pp_oracle as orc
+    from tests import synth
+    freqs, model = synth.example_model(16, 256, 1500., 800.)
+    _, _, m2 = pplib.read_model(synth.GMODEL, pplib.get_bin_centers(256), freqs,
+                                synth.P_EXAMPLE, quiet=True)
+    assert np.allclose(m2, model, rtol=0, atol=1e-12)
+    assert pplib.guess_fit_freq(freqs) == pytest.approx(orc.guess_fit_freq(freqs), rel=1e-15)
+    for a in ((0.3, 2e-3, 1400., 1500.), (0.49, 5e-3, 1200., np.inf)):
+        assert pplib.phase_transform(*a, P=synth.P_EXAMPLE, mod=True) == \
+            pytest.approx(orc.phase_transform(*a, P=synth.P_EXAMPLE, mod=True), abs=1e-15)
+    name, code, nu_ref, ngauss, params, flags, alpha, fit_alpha = pplib.read_model(synth.GMODEL)
+    assert ngauss == 3 and code == "000" and nu_ref == 1300.0 and alpha == -4.0
+
+
+def test_mjd_arithmetic():
+    from pulseportraiture_b200.pptoas import MJD
+    t = MJD(55000, 0.75) + MJD(0, 0.5)
+    assert t.intday() == 55001 and abs(t.fracday() - 0.25) < 1e-15
+    assert abs((MJD(55000, 0.1) + 1e-9).in_days() - 55000.100000001) < 1e-9
