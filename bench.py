@@ -229,6 +229,8 @@ def run_ours(args):
     plan.set_model(model.astype(np.float32), freqs)
     if args.chunk:
         plan.set_chunk(args.chunk)
+    if args.fft:
+        plan.set_fft_precision(args.fft)
     data, phi_true, dDM_true = make_device_batch(model, freqs, nsub, 777 + rank, dev)
     torch.cuda.synchronize()
 
@@ -332,6 +334,7 @@ def run_ours(args):
                                        % nsub,
                            "l2": "inputs (%.1f GB) larger than L2" % (data.numel() * 4 / 1e9),
                            "tol_sigma": args.tol or 1e-3, "mean_passes": mean_pass,
+                           "fft_arith": {0: "auto", 32: "f32", 64: "f64"}[args.fft],
                            "converged": "%d/%d" % (ok, nsub),
                            "dDM_pull_rms": float(np.sqrt(np.mean(pull ** 2)))},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -351,6 +354,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nsub", type=int, default=10000, help="subints per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="subints per pipeline chunk (0=auto)")
+    ap.add_argument("--fft", type=int, default=0, help="FFT arithmetic: 0 auto, 32, 64")
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--max-iter", type=int, default=0)
     ap.add_argument("--e2e-nsub", type=int, default=1024)

@@ -1,0 +1,241 @@
+// Register-radix (8/4/2) Stockham FFT rows for the K1 hot kernel (k_spectra).
+//
+// A row of N complex points is owned by T = N/8 threads (a "row slot"); several
+// slots share one CTA and synchronise independently with named barriers, so a
+// slot that waits on its global loads does not stall the others.  Each pass
+// pulls R points per butterfly into registers, applies the twiddles, runs an
+// in-register DFT_R and writes the autosort permutation back IN PLACE (all
+// reads of a pass complete before its writes: one barrier in between), which
+// keeps the footprint at one padded buffer per slot.
+//
+// The radix plan covers N/2; the last radix-2 pass of the N-point transform is
+// fused into the real-FFT split (unpack), which saves one shared-memory round
+// trip: Z[k] = a[k] + w^k b[k], Z[k+N/2] = a[k] - w^k b[k].
+#pragma once
+#include "fft.cuh"
+
+namespace ppb {
+
+// 16-byte elements: pad one element every 8 so that a stride-8 (radix-8 output)
+// access pattern is conflict free.
+__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
+template <int N> struct Padded { static constexpr int value = N + (N >> 3); };
+
+__device__ __forceinline__ void bar_slot(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- 1-D bulk async copy (TMA) + mbarrier helpers ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both 16-byte aligned),
+// completion is signalled on `bar` as transaction bytes.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename F> __device__ __forceinline__ void dft4(cx<F>& v0, cx<F>& v1, cx<F>& v2, cx<F>& v3) {
+  const cx<F> a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = csub(v1, v3);
+  const cx<F> b3 = mk<F>(a3.y, -a3.x);  // -i a3
+  v0 = cadd(a0, a2); v1 = cadd(a1, b3); v2 = csub(a0, a2); v3 = csub(a1, b3);
+}
+
+// in-register forward DFT of R points, natural-order output
+template <int R, typename F> __device__ __forceinline__ void dftR(cx<F> (&v)[R]) {
+  if constexpr (R == 2) {
+    const cx<F> t = v[0];
+    v[0] = cadd(t, v[1]); v[1] = csub(t, v[1]);
+  } else if constexpr (R == 4) {
+    dft4(v[0], v[1], v[2], v[3]);
+  } else {
+    static_assert(R == 8, "radix");
+    dft4(v[0], v[2], v[4], v[6]);   // E_q -> v[2q]
+    dft4(v[1], v[3], v[5], v[7]);   // O_q -> v[2q+1]
+    const F h = F(0.70710678118654752440);
+    const cx<F> o0 = v[1];
+    const cx<F> o1 = mk<F>(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));    // * W8
+    const cx<F> o2 = mk<F>(v[5].y, -v[5].x);                                  // * W8^2 = -i
+    const cx<F> o3 = mk<F>(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));   // * W8^3
+    const cx<F> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+  }
+}
+
+// Radix plan for the first N/2 of the transform (the trailing radix-2 is fused
+// into the split).  kPlan[i] = radix of pass i, 0-terminated.
+template <int N> struct Plan8 {
+  // packed radices, 4 bits each, pass 0 in the low nibble
+  static constexpr unsigned code = N == 32 ? 0x44u : N == 64 ? 0x48u : N == 128 ? 0x88u : N == 256 ? 0x448u
+                                 : N == 512 ? 0x488u : N == 1024 ? 0x888u : 0x4488u;
+  static constexpr int n = N <= 128 ? 2 : (N <= 1024 ? 3 : 4);
+  __host__ __device__ static constexpr int radix(int i) { return (int)((code >> (4 * i)) & 0xFu); }
+};
+
+template <int N> struct Slot8 {
+  static constexpr int kT = N / 8;                     // threads per row slot
+  static constexpr int kSlots = 256 / kT;              // row slots per CTA of 256 threads
+  static constexpr int kPairs = (N / 2) / kT;          // = 4 split pairs per thread
+  static constexpr int kBufElems = Padded<N>::value;   // padded complex elements per slot
+  static_assert(kT >= 4 && kT <= 256, "slot size");
+};
+
+template <int N> __device__ __forceinline__ void slot_sync(int slot) {
+  if constexpr (Slot8<N>::kT >= 32) bar_slot(1 + slot, Slot8<N>::kT);
+  else __syncwarp();
+}
+
+// Twiddle tables: per pass one base factor w1[k] = e^{-2 pi i k/(Ns R)}, k < Ns
+// (its powers w^2..w^{R-1} are formed in registers: shared-memory bandwidth, not
+// the FP64 pipe, bounds this kernel), then the N/2+1 split factors
+// e^{-2 pi i p/(2N)}; the factors of the fused last radix-2 pass are their
+// squares.
+template <int N> struct TwLayout {
+  using P = Plan8<N>;
+  __host__ __device__ static constexpr int ns(int i) { int v = 1; for (int q = 0; q < i; ++q) v *= P::radix(q); return v; }
+  __host__ __device__ static constexpr int off(int i) { int o = 0; for (int q = 1; q < i; ++q) o += ns(q); return o; }
+  static constexpr int kPassTotal = off(P::n);
+  static constexpr int kSplitOff = kPassTotal;              // e^{-2 pi i p/(2N)}, p <= N/2
+  static constexpr int kTotal = kSplitOff + N / 2 + 1;
+};
+
+template <typename F> __device__ __forceinline__ cx<F> csqr(cx<F> a) {
+  return mk<F>(fma(a.x, a.x, -a.y * a.y), F(2) * a.x * a.y);
+}
+
+// One in-place pass of radix R.  First pass: inputs come from `g` (the staged
+// packed real row viewed as float2, shared memory) and carry no twiddles.
+template <int N, int R, typename F, typename Hook>
+__device__ __forceinline__ void pass8(cx<F>* __restrict__ buf, const cx<F>* __restrict__ twp, int t, int slot, int Ns,
+                                      const float2* __restrict__ g, bool gvalid, Hook hook) {
+  constexpr int T = Slot8<N>::kT;
+  constexpr int NB = N / R;       // butterflies per pass
+  constexpr int PER = NB / T;     // butterflies per thread (R=8:1, 4:2, 2:4)
+  static_assert(PER >= 1, "plan");
+  cx<F> v[PER][R];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = t + i * T;
+    if (g != nullptr) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float2 x = gvalid ? g[j + r * NB] : make_float2(0.f, 0.f);
+        v[i][r] = mk<F>((F)x.x, (F)x.y);
+      }
+    } else {
+      const int k = j & (Ns - 1);
+      cx<F> w[R];
+      w[1] = twp[k];
+      if constexpr (R >= 4) { w[2] = csqr(w[1]); w[3] = cmul(w[2], w[1]); }
+      if constexpr (R >= 8) { w[4] = csqr(w[2]); w[5] = cmul(w[4], w[1]); w[6] = csqr(w[3]); w[7] = cmul(w[4], w[3]); }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cx<F> x = buf[phys(j + r * NB)];
+        if (r > 0) x = cmul(x, w[r]);
+        v[i][r] = x;
+      }
+    }
+  }
+  slot_sync<N>(slot);   // every read of this pass (and of the previous row's split) is done
+  hook();               // issue independent global loads here: they overlap the butterflies
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = t + i * T;
+    const int k = j & (Ns - 1);
+    dftR<R, F>(v[i]);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[phys(j0 + r * Ns)] = v[i][r];
+  }
+  slot_sync<N>(slot);
+}
+
+// All passes of Plan8<N>: afterwards buf holds the input of the fused last
+// radix-2 pass (a = buf[0:N/2], b = buf[N/2:N], both through phys()).
+// `after_first_reads` runs right after the first pass has pulled the staged row
+// into registers (the staging buffer may then be refilled); `in_last_pass` runs
+// inside the last pass, after its reads and before its butterflies.
+template <int N, typename F, typename Fn, typename Fn2>
+__device__ __forceinline__ void fft8_rows(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, int t, int slot,
+                                          const float2* __restrict__ g, bool gvalid, Fn after_first_reads,
+                                          Fn2 in_last_pass) {
+  using P = Plan8<N>;
+  using L = TwLayout<N>;
+  auto nop = []() {};
+  pass8<N, P::radix(0), F>(buf, tw, t, slot, 1, g, gvalid, nop);
+  after_first_reads();
+  if constexpr (P::n == 2) {
+    constexpr int o = L::off(1), ns = L::ns(1);
+    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+  } else {
+    constexpr int o = L::off(1), ns = L::ns(1);
+    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, nullptr, false, nop);
+  }
+  if constexpr (P::n == 3) {
+    constexpr int o = L::off(2), ns = L::ns(2);
+    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+  } else if constexpr (P::n > 3) {
+    constexpr int o = L::off(2), ns = L::ns(2);
+    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, nullptr, false, nop);
+  }
+  if constexpr (P::n == 4) {
+    constexpr int o = L::off(3), ns = L::ns(3);
+    pass8<N, P::radix(3), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+  }
+}
+
+// Fused last radix-2 pass + real-FFT split for the pair (p, N-p), 1 <= p <= N/2.
+template <int N, typename F>
+__device__ __forceinline__ void split_pair8(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, int p, cx<F>& dp,
+                                            cx<F>& dq) {
+  constexpr int H = N / 2;
+  const cx<F> w2 = tw[TwLayout<N>::kSplitOff + p];    // e^{-2 pi i p/(2N)}
+  cx<F> zp, zq;
+  if (p < H) {
+    const cx<F> wn = csqr(w2);                        // e^{-2 pi i p/N}
+    const cx<F> a = buf[phys(p)], b = cmul(wn, buf[phys(p + H)]);
+    zp = cadd(a, b);                                  // Z[p]
+    const int m = H - p;                              // N - p = H + m ; e^{-2 pi i m/N} = -conj(wn)
+    const cx<F> a2 = buf[phys(m)], b2 = cmul(mk<F>(-wn.x, wn.y), buf[phys(m + H)]);
+    zq = csub(a2, b2);                                // Z[N-p]
+  } else {
+    zp = csub(buf[phys(0)], buf[phys(H)]);            // Z[N/2] (self paired)
+    zq = zp;
+  }
+  const cx<F> zc = cconj(zq);
+  const cx<F> E = mk<F>(F(0.5) * (zp.x + zc.x), F(0.5) * (zp.y + zc.y));
+  const cx<F> D = mk<F>(F(0.5) * (zp.x - zc.x), F(0.5) * (zp.y - zc.y));
+  const cx<F> O = mk<F>(D.y, -D.x);
+  const cx<F> tt = cmul(w2, O);
+  dp = cadd(E, tt);
+  dq = cconj(csub(E, tt));
+}
+
+// Z[0] = a[0] + b[0]: returns (DC, Nyquist) = (Re+Im, Re-Im) of Z[0]
+template <int N, typename F>
+__device__ __forceinline__ void split_dc8(const cx<F>* __restrict__ buf, F& dc, F& ny) {
+  const cx<F> z0 = cadd(buf[phys(0)], buf[phys(N / 2)]);
+  dc = z0.x + z0.y;
+  ny = z0.x - z0.y;
+}
+
+}  // namespace ppb

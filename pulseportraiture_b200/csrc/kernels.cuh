@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "fft.cuh"
+#include "fft8.cuh"
 
 namespace ppb {
 
@@ -226,12 +227,12 @@ __global__ void k_prep(PrepArgs a) {
 }
 
 // ----------------------------------------------------------------------------
-// k_spectra: K1 + K2.  grid = (ceil(nchan/G), subints in chunk), 256 threads.
-// T = arithmetic type of the FFT (float or double); storage of X is float2.
+// k_spectra: K1 + K2.  grid = (ceil(nchan/G), subints in chunk), 256 threads =
+// Slot8<N>::kSlots row slots of N/8 threads.  The FFT runs in double (see
+// DESIGN.md "precision"); X is stored as float2.
 // ----------------------------------------------------------------------------
 struct SpectraArgs {
   const float* data;         // [nsub,nchan,2N], global subint index
-  const cx<float>* mconj32;  // [nchan,N]
   const cx<double>* mconj64; // [nchan,N]
   const double* pn;          // [nchan]
   const double* nu2;         // [nchan] nu^-2
@@ -246,34 +247,36 @@ struct SpectraArgs {
   double* sigma;             // [nsub,nchan] out
   double* Ssn;               // [nsub,nchan] out: p_n / sigma_F^2 (0 = channel unused)
   double* Sdn;               // [nsub,nchan] out
-  const void* twN;           // cx<T>[N]
-  const void* tw2N;          // cx<T>[N/2+1]
+  const cx<double>* tw8;     // [TwLayout<N>::kTotal] per-pass twiddle tables
   int s0;                    // first global subint of the chunk
   int nchan, G, nparts;
 };
 
-template <int N, typename T>
-__global__ void __launch_bounds__(256) k_spectra(SpectraArgs a) {
-  using G = RowGeom<N>;
+template <int N>
+__global__ void __launch_bounds__(256, (N >= 2048 ? 1 : 2)) k_spectra(SpectraArgs a) {
+  using S8 = Slot8<N>;
+  using L = TwLayout<N>;
+  using F = double;
+  constexpr int T = S8::kT, NS = S8::kSlots, NPAIR = S8::kPairs, NACC = 2 * NPAIR + 1;
+  constexpr unsigned kRowBytes = 2 * N * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
-  cx<T>* tw2N = twN + N;
-  cx<T>* bufs = tw2N + (N / 2 + 2);
-  __shared__ double red[2][8];
-  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
-  {
-    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.twN);
-    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.tw2N);
-    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
-    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
-  }
-  cx<T>* bufA = bufs + (size_t)r * 2 * N;
-  cx<T>* bufB = bufA + N;
+  cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [L::kTotal] (+pad)
+  cx<F>* bufs = tw + ((L::kTotal + 1) & ~1);                            // [NS][kBufElems]
+  float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * S8::kBufElems);  // [NS][2][2N]
+  __shared__ double red[NS][(T >= 32 ? T / 32 : 1)][2];
+  __shared__ __align__(8) unsigned long long mbar[NS][2];
+  const int tid = threadIdx.x, slot = tid / T, t = tid % T;
+  for (int i = tid; i < L::kTotal; i += 256) tw[i] = a.tw8[i];
+  if (t == 0) { mbar_init(&mbar[slot][0], 1); mbar_init(&mbar[slot][1], 1); }
+  mbar_fence_init();
+  __syncthreads();
+  cx<F>* buf = bufs + (size_t)slot * S8::kBufElems;
+  float* stage = stage_all + (size_t)slot * 2 * (2 * N);
 
   const int sl = blockIdx.y, s = a.s0 + sl;
   const int ch_begin = blockIdx.x * a.G;
   const int ch_end = min(ch_begin + a.G, a.nchan);
-  const int nsteps = (a.G + G::kRows - 1) / G::kRows;
+  const int nsteps = (a.G + NS - 1) / NS;
   constexpr int kc = (3 * (N + 1)) / 4;           // int(0.75*nharm), pplib.py:2244
   constexpr int ntop = N + 1 - kc;
   const bool want_guess = a.partial != nullptr;
@@ -282,153 +285,139 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraArgs a) {
   const double numean = a.nu_mean[s];
   const double numean2 = 1.0 / (numean * numean);
 
-  float2 acc[2 * G::kPairs + 1];
+  float2 acc[NACC];
 #pragma unroll
-  for (int i = 0; i < 2 * G::kPairs + 1; ++i) acc[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < NACC; ++i) acc[i] = make_float2(0.f, 0.f);
 
-  auto row_used = [&](int ch) -> bool {
-    if (ch >= ch_end) return false;
+  auto row_used = [&](int step) -> bool {
+    const int ch = ch_begin + step * NS + slot;
+    if (step >= nsteps || ch >= ch_end) return false;
     return a.mask ? (a.mask[(size_t)s * a.nchan + ch] != 0) : true;
   };
-  float4 pre[G::kLoads];
-  {
-    const int ch = ch_begin + r;
-    const bool u = row_used(ch);
-    const float4* src = reinterpret_cast<const float4*>(a.data + ((size_t)s * a.nchan + (u ? ch : 0)) * 2 * N);
-#pragma unroll
-    for (int m = 0; m < G::kLoads; ++m) pre[m] = u ? __ldg(src + t_row + m * G::kTRow) : make_float4(0, 0, 0, 0);
-  }
-  for (int step = 0; step < nsteps; ++step) {
-    const int ch = ch_begin + step * G::kRows + r;
-    const bool inrange = ch < ch_end;
-    bool used = row_used(ch);
-#pragma unroll
-    for (int m = 0; m < G::kLoads; ++m) {
-      const int i4 = t_row + m * G::kTRow;
-      bufA[2 * i4] = mk<T>((T)pre[m].x, (T)pre[m].y);
-      bufA[2 * i4 + 1] = mk<T>((T)pre[m].z, (T)pre[m].w);
+  // TMA producer (one thread per slot): bulk-copy the raw row into the staging buffer
+  auto fetch = [&](int step) {
+    if (t == 0 && row_used(step)) {
+      const int ch = ch_begin + step * NS + slot;
+      unsigned long long* bar = &mbar[slot][step & 1];
+      mbar_expect_tx(bar, kRowBytes);
+      bulk_g2s(stage + (size_t)(step & 1) * 2 * N, a.data + ((size_t)s * a.nchan + ch) * 2 * N, kRowBytes, bar);
     }
-    if (step + 1 < nsteps) {  // prefetch the next row while this one is transformed
-      const int chn = ch + G::kRows;
-      const bool u = row_used(chn);
-      const float4* src = reinterpret_cast<const float4*>(a.data + ((size_t)s * a.nchan + (u ? chn : 0)) * 2 * N);
-#pragma unroll
-      for (int m = 0; m < G::kLoads; ++m) pre[m] = u ? __ldg(src + t_row + m * G::kTRow) : make_float4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  };
+  fetch(0);
+  fetch(1);
+  unsigned ph0 = 0u, ph1 = 0u;
 
-    // ---- half spectrum of this thread's harmonics -------------------------
-    cx<T> d[2 * G::kPairs + 1];
-    T s_all = 0, s_top = 0;
+  for (int step = 0; step < nsteps; ++step) {
+    const int ch = ch_begin + step * NS + slot;
+    const bool inrange = ch < ch_end;
+    const bool used = row_used(step);
+    if (used) {
+      if (step & 1) { mbar_wait(&mbar[slot][1], ph1); ph1 ^= 1u; }
+      else { mbar_wait(&mbar[slot][0], ph0); ph0 ^= 1u; }
+    }
+    const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
+    // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
+    // FFT pass so that their latency hides behind its butterflies
+    const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
+    cx<F> mcv[NACC];
+    auto load_mc = [&]() {
+      if (used && a.X != nullptr) {
 #pragma unroll
-    for (int i = 0; i < G::kPairs; ++i) {
-      const int p = t_row + 1 + i * G::kTRow;
-      d[2 * i] = mk<T>(0, 0);
-      d[2 * i + 1] = mk<T>(0, 0);
-      if (p <= N / 2) {
-        unpack_pair<T>(Z, tw2N, N, p, d[2 * i], d[2 * i + 1]);
-        const T pw = d[2 * i].x * d[2 * i].x + d[2 * i].y * d[2 * i].y;
-        s_all += pw;
-        if (p >= kc) s_top += pw;
-        if (p < N / 2) {
-          const T qw = d[2 * i + 1].x * d[2 * i + 1].x + d[2 * i + 1].y * d[2 * i + 1].y;
-          s_all += qw;
-          if (N - p >= kc) s_top += qw;
-        } else {
-          d[2 * i + 1] = mk<T>(0, 0);
+        for (int i = 0; i < NPAIR; ++i) {
+          const int p = t + 1 + i * T;
+          mcv[2 * i] = mc[p];
+          mcv[2 * i + 1] = (p < N / 2) ? mc[N - p] : mk<F>(0.0, 0.0);
         }
+        mcv[2 * NPAIR] = mc[0];
+      }
+    };
+    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); }, load_mc);
+
+    // ---- split + power sums; X and the guess accumulators need no sigma ------------
+    const size_t xo = ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
+    const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
+    const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
+    double s_all = 0.0, s_top = 0.0;
+    auto emit = [&](int k, cx<F> d, cx<F> mval, float2& ac) {
+      const double pw = d.x * d.x + d.y * d.y;
+      s_all += pw;
+      if (k >= kc) s_top += pw;
+      const int sl_k = (k == N) ? 0 : k;
+      if (a.X != nullptr && inrange) {
+        float2 xv = make_float2(0.f, 0.f);
+        if (used) {
+          const cx<F> pr = cmul(d, mval);
+          xv = make_float2((float)pr.x, (float)pr.y);
+        }
+        a.X[xo + sl_k] = xv;
+      }
+      if (wgt != 0.f) {
+        float vx = (float)d.x, vy = (float)d.y;
+        if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
+          double c, sn;
+          cis2pi((double)k * shift, c, sn);
+          const float cf = (float)c, sf = (float)sn;
+          const float tx = vx * cf - vy * sf;
+          vy = vx * sf + vy * cf; vx = tx;
+        }
+        ac.x = fmaf(wgt, vx, ac.x);
+        ac.y = fmaf(wgt, vy, ac.y);
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < NPAIR; ++i) {
+      const int p = t + 1 + i * T;
+      cx<F> dp, dq;
+      split_pair8<N, F>(buf, tw, p, dp, dq);
+      emit(p, dp, mcv[2 * i], acc[2 * i]);
+      if (p < N / 2) emit(N - p, dq, mcv[2 * i + 1], acc[2 * i + 1]);
+    }
+    if (t == 0) {
+      F dc, ny;
+      split_dc8<N, F>(buf, dc, ny);
+      emit(N, mk<F>(ny, 0.0), mcv[2 * NPAIR], acc[2 * NPAIR]);
+    }
+    // ---- row-slot reduction of the two power sums ---------------------------------
+    if constexpr (T >= 32) {
+      s_all = warp_sum(s_all); s_top = warp_sum(s_top);
+      if constexpr (T > 32) {
+        if ((tid & 31) == 0) { red[slot][t >> 5][0] = s_all; red[slot][t >> 5][1] = s_top; }
+        slot_sync<N>(slot);
+        double sa = 0.0, st = 0.0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) { sa += red[slot][w][0]; st += red[slot][w][1]; }
+        s_all = sa; s_top = st;
+      }
+    } else {
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) {
+        s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
+        s_top += __shfl_xor_sync(0xffffffffu, s_top, o);
       }
     }
-    d[2 * G::kPairs] = mk<T>(0, 0);
-    if (t_row == 0) {
-      const T ny = Z[0].x - Z[0].y;
-      d[2 * G::kPairs] = mk<T>(ny, 0);
-      s_all += ny * ny;
-      s_top += ny * ny;
-    }
-    // ---- row-slot reduction of the two power sums ---------------------------
-    double v_all = s_all, v_top = s_top;
-#pragma unroll
-    for (int o = (G::kTRow < 32 ? G::kTRow : 32) / 2; o > 0; o >>= 1) {
-      v_all += __shfl_xor_sync(0xffffffffu, v_all, o);
-      v_top += __shfl_xor_sync(0xffffffffu, v_top, o);
-    }
-    if (G::kTRow > 32) {
-      if ((tid & 31) == 0) { red[0][tid >> 5] = v_all; red[1][tid >> 5] = v_top; }
-      __syncthreads();
-      double sa = 0.0, st = 0.0;
-#pragma unroll
-      for (int w = 0; w < G::kTRow / 32; ++w) { sa += red[0][r * (G::kTRow / 32) + w]; st += red[1][r * (G::kTRow / 32) + w]; }
-      v_all = sa; v_top = st;
-    }
-    // ---- noise, Sd, S --------------------------------------------------------
-    double sig;
-    if (a.errs) sig = used ? a.errs[(size_t)s * a.nchan + ch] : 0.0;
-    else sig = sqrt(v_top / ((double)(2 * N) * (double)ntop));       // pplib.py:2243-2245
-    const double sF2 = sig * sig * (double)N;                         // sigma^2 * nbin/2
-    if (!(sF2 > 0.0) || !(sF2 < 1e300)) used = false;
-    if (inrange && t_row == 0) {
+    // ---- noise, Sd, S ------------------------------------------------------------------
+    if (inrange && t == 0) {
+      double sig;
+      if (a.errs) sig = used ? a.errs[(size_t)s * a.nchan + ch] : 0.0;
+      else sig = sqrt(s_top / ((double)(2 * N) * (double)ntop));       // pplib.py:2243-2245
+      const double sF2 = sig * sig * (double)N;                         // sigma^2 * nbin/2
+      const bool ok = used && (sF2 > 0.0) && (sF2 < 1e300);
       const size_t o = (size_t)s * a.nchan + ch;
-      a.sigma[o] = used ? sig : 0.0;
-      a.Ssn[o] = used ? a.pn[ch] / sF2 : 0.0;
-      a.Sdn[o] = used ? v_all / sF2 : 0.0;
+      a.sigma[o] = ok ? sig : 0.0;
+      a.Ssn[o] = ok ? a.pn[ch] / sF2 : 0.0;
+      a.Sdn[o] = ok ? s_all / sF2 : 0.0;
     }
-    // ---- cross spectrum + guess accumulation ---------------------------------
-    if (inrange) {
-      float2* xr = a.X ? a.X + ((size_t)sl * a.nchan + ch) * N : nullptr;
-      const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
-      const double shift = Dfac != 0.0 ? Dfac * (a.nu2[ch] - numean2) : 0.0;
-#pragma unroll
-      for (int i = 0; i < 2 * G::kPairs + 1; ++i) {
-        const int ip = i >> 1;
-        const int p = t_row + 1 + ip * G::kTRow;
-        int k;  // harmonic index of d[i]
-        bool live;
-        if (i == 2 * G::kPairs) { k = N; live = (t_row == 0); }
-        else if ((i & 1) == 0) { k = p; live = p <= N / 2; }
-        else { k = N - p; live = p < N / 2; }
-        if (!live) continue;
-        const int slot = (k == N) ? 0 : k;
-        if (xr) {
-          float2 xv = make_float2(0.f, 0.f);
-          if (used) {
-            cx<T> m;
-            if constexpr (sizeof(T) == 8) m = a.mconj64[(size_t)ch * N + slot];
-            else m = a.mconj32[(size_t)ch * N + slot];
-            const cx<T> pr = cmul(d[i], m);
-            xv = make_float2((float)pr.x, (float)pr.y);
-          }
-          xr[slot] = xv;
-        }
-        if (wgt != 0.f) {
-          float2 v = make_float2((float)d[i].x, (float)d[i].y);
-          if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
-            double c, sn;
-            cis2pi((double)k * shift, c, sn);
-            const float cf = (float)c, sf = (float)sn;
-            v = make_float2(v.x * cf - v.y * sf, v.x * sf + v.y * cf);
-          }
-          acc[i].x = fmaf(wgt, v.x, acc[i].x);
-          acc[i].y = fmaf(wgt, v.y, acc[i].y);
-        }
-      }
-    }
-    __syncthreads();  // bufA/bufB are rewritten by the next step
   }
   if (want_guess) {
-    const int part = blockIdx.x * G::kRows + r;
+    const int part = blockIdx.x * NS + slot;
     float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
 #pragma unroll
-    for (int i = 0; i < 2 * G::kPairs + 1; ++i) {
-      const int ip = i >> 1;
-      const int p = t_row + 1 + ip * G::kTRow;
-      int k; bool live;
-      if (i == 2 * G::kPairs) { k = N; live = (t_row == 0); }
-      else if ((i & 1) == 0) { k = p; live = p <= N / 2; }
-      else { k = N - p; live = p < N / 2; }
-      if (live) pr[(k == N) ? 0 : k] = acc[i];
+    for (int i = 0; i < NPAIR; ++i) {
+      const int p = t + 1 + i * T;
+      pr[(p == N) ? 0 : p] = acc[2 * i];
+      if (p < N / 2) pr[N - p] = acc[2 * i + 1];
     }
+    if (t == 0) pr[0] = acc[2 * NPAIR];
   }
 }
 

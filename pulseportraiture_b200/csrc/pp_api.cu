@@ -67,7 +67,7 @@ struct pp_plan {
   int l2_bytes = 0, sm_count = 0;
   bool model_set = false;
   // tables + model
-  DBuf twN32, tw2N32, twN64, tw2N64, freqs, nu2, mconj32, mconj64, mpow, pn, mmean, model_stage;
+  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, mconj32, mconj64, mpow, pn, mmean, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
@@ -184,12 +184,37 @@ template <int N, typename T> static size_t fft_smem_bytes() {
     default: return fail(-1, "unsupported nbin %d", 2 * (Nval)); \
   }
 
+template <int N> static size_t spectra_smem_bytes() {
+  return (size_t)(((TwLayout<N>::kTotal + 1) & ~1) + Slot8<N>::kSlots * Slot8<N>::kBufElems) * sizeof(cx<double>) +
+         (size_t)Slot8<N>::kSlots * 2 * (2 * N) * sizeof(float);
+}
+
+// per-pass twiddle tables in the layout of TwLayout<N> (fft8.cuh)
+template <int N> static void build_tw8(std::vector<double2>& out) {
+  using P = Plan8<N>;
+  using L = TwLayout<N>;
+  out.assign(L::kTotal, make_double2(0.0, 0.0));
+  auto root = [](long num, long den) {   // e^{-2 pi i num/den} with exact quadrant values
+    num %= den;
+    if (num == 0) return make_double2(1.0, 0.0);
+    if (4 * num == den) return make_double2(0.0, -1.0);
+    if (2 * num == den) return make_double2(-1.0, 0.0);
+    if (4 * num == 3 * den) return make_double2(0.0, 1.0);
+    const double a = -2.0 * M_PI * (double)num / (double)den;
+    return make_double2(cos(a), sin(a));
+  };
+  for (int i = 1; i < P::n; ++i) {
+    const int Ns = L::ns(i), R = P::radix(i);
+    for (int k = 0; k < Ns; ++k) out[L::off(i) + k] = root((long)k, (long)Ns * R);
+  }
+  for (int p2 = 0; p2 <= N / 2; ++p2) out[L::kSplitOff + p2] = root(p2, 2L * N);
+}
+
 template <int N> static cudaError_t setup_attrs() {
   const int b32 = (int)fft_smem_bytes<N, float>(), b64 = (int)fft_smem_bytes<N, double>();
   cudaError_t e;
 #define SET_(fn, bytes) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (e != cudaSuccess) return e;
-  SET_((k_spectra<N, float>), b32)
-  SET_((k_spectra<N, double>), b64)
+  SET_((k_spectra<N>), (int)spectra_smem_bytes<N>())
   SET_((k_model<N>), b64)
   SET_((k_rfft_rows<N, float>), b32)
   SET_((k_rfft_rows<N, double>), b64)
@@ -255,6 +280,10 @@ extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_pl
     cudaError_t e = cudaSuccess;
     DISPATCH_N(N, e = setup_attrs<NN>());
     CK(e);
+    std::vector<double2> t8;
+    DISPATCH_N(N, build_tw8<NN>(t8));
+    CK(pl->tw8.need(t8.size() * sizeof(double2)));
+    CK(cudaMemcpy(pl->tw8.p, t8.data(), t8.size() * sizeof(double2), cudaMemcpyHostToDevice));
   }
   *out = pl;
   return 0;
@@ -264,7 +293,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -391,14 +420,15 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
 }
 
 // FFT arithmetic for the data rows.  A float FFT has ~1e-7 relative error per
-// harmonic; when the noise level is *measured* from the top quarter of the
-// power spectrum (nbin/8 harmonics) that error scales the whole chi^2 of the
-// channel.  Estimated relative chi^2 error ~ 6e-7 / sqrt(nchan * nbin / 8):
-// use double below 2^20 samples per portrait, float above (and always float
-// when the caller supplies the noise).
+// harmonic, which is harmless for the fitted parameters (<1e-5 sigma) but not
+// for chi^2 of SMALL portraits: the measured noise level (mean of nbin/8
+// harmonic powers) scales the whole chi^2 of a channel, and the data power Sd
+// is dominated by a few strong harmonics per channel, so neither averages down
+// below 1e-8 relative unless nchan*nbin is large.  Automatic choice: double
+// below 2^20 samples per portrait, float from there on ("precision").
 static int pick_fft_precision(pp_plan* pl, bool noise_measured) {
+  (void)noise_measured;
   if (pl->fft_precision) return pl->fft_precision;
-  if (!noise_measured) return 32;
   return ((long)pl->nchan * pl->nbin < (1L << 20)) ? 64 : 32;
 }
 
@@ -417,7 +447,7 @@ static int pick_chunk(pp_plan* pl, int nsub) {
 
 static int rows_per_cta(pp_plan* pl, int chunk) {
   // rows per k_spectra CTA: aim at >= 4 CTAs per SM per launch, multiple of kRows
-  const int rows_conc = std::max(1, 1024 / pl->N);
+  const int rows_conc = 256 / (pl->N / 8);
   long total_rows = (long)chunk * pl->nchan;
   long target_ctas = 4L * pl->sm_count;
   long g = std::max(1L, total_rows / target_ctas);
@@ -444,7 +474,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (Ns < 2) return fail(-1, "Ns must be >= 2");
   const int max_iter = args->max_iter > 0 ? args->max_iter : (args->max_iter < 0 ? -1 : 8);
   const int n_launch_iter = max_iter < 0 ? 1 : max_iter;
-  const int fftp = pick_fft_precision(pl, args->errs == nullptr);
+
   const double tol = args->tol > 0 ? args->tol : 1e-3;
   const size_t nsc = (size_t)nsub * nchan;
 
@@ -495,13 +525,15 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   const int chunk = pick_chunk(pl, nsub);
   const int G = rows_per_cta(pl, chunk);
-  const int rows_conc = std::max(1, 1024 / N);
+  const int rows_conc = 256 / (N / 8);
   const int gx = (nchan + G - 1) / G;
   const int nparts = gx * rows_conc;
   pl->stats.chunk = chunk;
   CK(pl->X.need(sizeof(float2) * (size_t)chunk * nchan * N));
   if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
   const bool data_on_device = is_device_ptr(args->data);
+  if (data_on_device && (reinterpret_cast<uintptr_t>(args->data) & 15))
+    return fail(-1, "device data pointer must be 16-byte aligned");
   const size_t sub_floats = (size_t)nchan * 2 * N;
   if (!data_on_device)
     for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need(sizeof(float) * (size_t)chunk * sub_floats));
@@ -566,19 +598,14 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     {
       SpanGuard g(pl, SP_SPECTRA);
       SpectraArgs a;
-      a.data = dchunk; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
+      a.data = dchunk; a.mconj64 = pl->mconj64.as<cx<double>>();
       a.pn = pl->pn.as<double>(); a.nu2 = pl->nu2.as<double>();
       a.errs = derrs; a.mask = dmask; a.weights = dw; a.P = dP; a.DMg = ddmg; a.nu_mean = pl->nu_mean.as<double>();
       a.X = pl->X.as<float2>(); a.partial = want_guess ? pl->partial.as<float2>() : nullptr;
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
+      a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      if (fftp == 64) {
-        a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
-        DISPATCH_N(N, k_spectra<NN, double><<<dim3(gx, ns), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a));
-      } else {
-        a.twN = pl->twN32.p; a.tw2N = pl->tw2N32.p;
-        DISPATCH_N(N, k_spectra<NN, float><<<dim3(gx, ns), 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a));
-      }
+      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), 256, spectra_smem_bytes<NN>(), pl->stream>>>(a));
       pl->stats.launches++;
     }
     if (!data_on_device) CK(cudaEventRecord(pl->ev_free[c & 1], pl->stream));
