@@ -177,6 +177,11 @@ typedef struct {
 int pp_plan_enable_timing(pp_plan_t* plan, int32_t on);
 int pp_get_stats(pp_plan_t* plan, pp_stats_t* stats);
 
+/* Page-locked host memory for result / input buffers (makes the D2H / H2D
+ * copies of pp_fit_batch asynchronous and full-speed). */
+void* pp_host_alloc(uint64_t bytes);
+void pp_host_free(void* p);
+
 const char* pp_last_error(void);
 int pp_abi_version(void);
 

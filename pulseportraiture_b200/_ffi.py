@@ -24,7 +24,8 @@ SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
            "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_set_freqs",
            "pp_set_model", "pp_fit_batch",
            "pp_fit_phase_shift_batch", "pp_rotate_batch", "pp_get_noise_batch",
-           "pp_plan_enable_timing", "pp_get_stats", "pp_last_error",
+           "pp_plan_enable_timing", "pp_get_stats", "pp_host_alloc",
+           "pp_host_free", "pp_last_error",
            "pp_abi_version"]
 
 
@@ -147,6 +148,10 @@ def lib():
     L.pp_plan_enable_timing.restype = C.c_int
     L.pp_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.pp_get_stats.restype = C.c_int
+    L.pp_host_alloc.argtypes = [C.c_uint64]
+    L.pp_host_alloc.restype = C.c_void_p
+    L.pp_host_free.argtypes = [vp]
+    L.pp_host_free.restype = None
     L.pp_last_error.argtypes = []
     L.pp_last_error.restype = C.c_char_p
     L.pp_abi_version.argtypes = []

@@ -591,8 +591,16 @@ struct PassArgs {
   int s0, nchan, N;
 };
 
+// streaming 16-byte load: read-only path, do not keep in L1
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 template <int N>
-__global__ void __launch_bounds__(256) k_pass2(PassArgs a) {
+__global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
   const int sl = blockIdx.y, s = a.s0 + sl;
   if (a.st.done[s]) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -618,10 +626,10 @@ __global__ void __launch_bounds__(256) k_pass2(PassArgs a) {
     cis2pi(16.0 * theta, cw, sw);
     double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
     constexpr int NJ = N / 16;
-#pragma unroll 4
-    for (int j = 0; j < NJ; ++j) {
-      float4 v = __ldg(row + j * 8 + l8);
-      if (j == 0 && l8 == 0) { v.x = 0.f; v.y = 0.f; }  // slot 0 is handled below
+    constexpr int U = NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1);   // loads kept in flight per buffer
+    constexpr int NG = NJ / U;                                 // groups (even)
+    auto consume = [&](float4 v, bool first) {
+      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; }          // slot 0 is handled below
       const double xr0 = v.x, xi0 = v.y, xr1 = v.z, xi1 = v.w;
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
       const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
@@ -632,6 +640,23 @@ __global__ void __launch_bounds__(256) k_pass2(PassArgs a) {
       const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
       const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
       k0 += 16.0; k1 += 16.0;
+    };
+    // software pipeline: the next group's loads are in flight while this one is consumed
+    float4 qa[U], qb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + u * 8 + l8);
+#pragma unroll 1
+    for (int gI = 0; gI < NG; gI += 2) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + ((gI + 1) * U + u) * 8 + l8);
+#pragma unroll
+      for (int u = 0; u < U; ++u) consume(qa[u], gI == 0 && u == 0);
+      if (gI + 2 < NG) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + ((gI + 2) * U + u) * 8 + l8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) consume(qb[u], false);
     }
     if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xn = __ldg(reinterpret_cast<const float2*>(row));

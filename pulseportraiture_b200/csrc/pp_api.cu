@@ -39,6 +39,17 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* pp_last_error(void) { return g_err.c_str(); }
+
+extern "C" void* pp_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    fail(-2, "cudaHostAlloc(%llu) failed", (unsigned long long)bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int pp_abi_version(void) { return PPB200_ABI_VERSION; }
 
 // ----------------------------------------------------------------------------
@@ -437,12 +448,13 @@ static int pick_fft_precision(pp_plan* pl, bool noise_measured) {
 // ----------------------------------------------------------------------------
 static int pick_chunk(pp_plan* pl, int nsub) {
   if (pl->chunk_req > 0) return std::min(pl->chunk_req, nsub);
-  // keep a chunk's cross-spectra (8 N nchan bytes per subint) within ~40% of L2
+  // Streaming mode: chunks large enough that every launch fills the GPU many
+  // times over (launch latency and the serial FFTFIT-guess tail amortised);
+  // the cross-spectrum scratch (8 N nchan bytes per subint) is capped at 8 GiB.
   const double per = 8.0 * pl->N * (double)pl->nchan;
-  int c = (int)floor(0.4 * (double)pl->l2_bytes / per);
-  c = std::max(c, 4);
-  // at least ~2 waves of CTAs for the pass kernel
-  return std::min(c, nsub);
+  long c = (long)floor(8.0 * 1073741824.0 / per);
+  c = std::max(c, 64L);
+  return (int)std::min<long>(c, nsub);
 }
 
 static int rows_per_cta(pp_plan* pl, int chunk) {

@@ -43,6 +43,34 @@ def _ptr(x, dtype, keep, name, shape=None):
     return a.ctypes.data
 
 
+class PinnedPool(object):
+    """Named page-locked host arrays (pp_host_alloc), grown on demand."""
+
+    def __init__(self, lib):
+        self._lib, self._bufs = lib, {}
+
+    def array(self, name, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ent = self._bufs.get(name)
+        if ent is None or ent[1] < nbytes:
+            if ent is not None:
+                self._lib.pp_host_free(C.c_void_p(ent[0]))
+            cap = max(nbytes, 64)
+            ptr = self._lib.pp_host_alloc(cap)
+            if not ptr:
+                raise _ffi.PPError("pp_host_alloc(%d) failed" % cap)
+            ent = (ptr, cap)
+            self._bufs[name] = ent
+        raw = (C.c_char * nbytes).from_address(ent[0])
+        return np.frombuffer(raw, dtype=dtype).reshape(shape)
+
+    def close(self):
+        for ptr, _ in self._bufs.values():
+            self._lib.pp_host_free(C.c_void_p(ptr))
+        self._bufs = {}
+
+
 class WidebandPlan(object):
     """Device plan for portraits of shape [nchan, nbin] (C ABI pp_plan_*)."""
 
@@ -53,10 +81,13 @@ class WidebandPlan(object):
                                             C.byref(self._h)), "pp_plan_create")
         self.nchan, self.nbin, self.device = int(nchan), int(nbin), int(device)
         self.freqs = None
+        self._pool = PinnedPool(self._lib)
         if stream is not None:
             self.set_stream(stream)
 
     def close(self):
+        if getattr(self, "_pool", None) is not None:
+            self._pool.close()
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pp_plan_destroy(self._h)
             self._h = C.c_void_p()
@@ -117,9 +148,13 @@ class WidebandPlan(object):
                   init=None, DM_guess=None, snrs=None, nu_fits=None,
                   nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
                   log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
-                  tol=0.0, semantics="full", want_chan_sums=False, nsub=None):
+                  tol=0.0, semantics="full", want_chan_sums=False, nsub=None,
+                  pinned_results=False):
         """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
-        CUDA torch tensor).  Returns a dict of numpy arrays."""
+        CUDA torch tensor).  Returns a dict of numpy arrays.
+
+        pinned_results=True returns views of plan-owned page-locked buffers
+        (full-speed D2H); they are overwritten by the next call on this plan."""
         keep = []
         if nsub is None:
             nsub = int(data.shape[0]) if hasattr(data, "shape") and len(data.shape) == 3 else 1
@@ -152,18 +187,22 @@ class WidebandPlan(object):
         a.max_iter = int(max_iter)
         a.tol = float(tol)
 
-        res = {
-            "params": np.empty((nsub, 5)), "param_errs": np.empty((nsub, 5)),
-            "nu_out": np.empty((nsub, 3)), "cov": np.empty((nsub, 5, 5)),
-            "chi2": np.empty(nsub), "red_chi2": np.empty(nsub),
-            "snr": np.empty(nsub), "nfeval": np.empty(nsub, dtype=np.int32),
-            "return_code": np.empty(nsub, dtype=np.int32),
-            "scales": np.empty((nsub, nchan)), "scale_errs": np.empty((nsub, nchan)),
-            "channel_snrs": np.empty((nsub, nchan)), "noise": np.empty((nsub, nchan)),
-            "lag_index": np.empty(nsub, dtype=np.int32), "phi_guess": np.empty(nsub),
+        spec = {
+            "params": ((nsub, 5), np.float64), "param_errs": ((nsub, 5), np.float64),
+            "nu_out": ((nsub, 3), np.float64), "cov": ((nsub, 5, 5), np.float64),
+            "chi2": ((nsub,), np.float64), "red_chi2": ((nsub,), np.float64),
+            "snr": ((nsub,), np.float64), "nfeval": ((nsub,), np.int32),
+            "return_code": ((nsub,), np.int32),
+            "scales": ((nsub, nchan), np.float64), "scale_errs": ((nsub, nchan), np.float64),
+            "channel_snrs": ((nsub, nchan), np.float64), "noise": ((nsub, nchan), np.float64),
+            "lag_index": ((nsub,), np.int32), "phi_guess": ((nsub,), np.float64),
         }
         if want_chan_sums:
-            res["chan_sums"] = np.empty((nsub, nchan, 9))
+            spec["chan_sums"] = ((nsub, nchan, 9), np.float64)
+        if pinned_results:
+            res = {k: self._pool.array(k, sh, dt) for k, (sh, dt) in spec.items()}
+        else:
+            res = {k: np.empty(sh, dtype=dt) for k, (sh, dt) in spec.items()}
         o = _ffi.FitOut()
         for k, v in res.items():
             setattr(o, k, v.ctypes.data)
