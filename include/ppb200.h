@@ -104,6 +104,9 @@ typedef struct {
   int32_t Ns;               /* FFTFIT grid size (pplib.py:2054), default 100   */
   int32_t max_iter;         /* Newton passes per subint (0 = default)          */
   double tol;               /* convergence: |step| < tol * 1-sigma (0=default) */
+  const double* scat_guess; /* [nsub,2] with init==NULL: tau start value [rot,
+                               linear] at nu_fit_tau and alpha start value
+                               (pptoas.py:427-452); NULL = 0, 0                */
 } pp_fit_args_t;
 
 typedef struct {

@@ -82,6 +82,7 @@ class FitArgs(C.Structure):
         ("Ns", C.c_int32),
         ("max_iter", C.c_int32),
         ("tol", C.c_double),
+        ("scat_guess", C.c_void_p),
     ]
 
 

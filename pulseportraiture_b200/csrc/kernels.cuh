@@ -29,6 +29,11 @@ namespace ppb {
 constexpr double kDconst = 1.0 / 0.000241;  // pplib.py:48-51
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 constexpr int kNCsum = 9;                   // per-channel sums kept per subint
+// The first kLoK slots of every X row also keep the float32 rounding residual
+// ("lo" part): the low harmonics carry almost all of |X|^2, so their float
+// quantisation dominates the error of C_n (5.7e-9 rms of chi^2 on a 32x256
+// portrait); with 64 lo slots it drops to ~2e-11 for +64/N traffic.
+template <int N> struct LoK { static constexpr int value = N < 64 ? N : 64; };
 
 // ----------------------------------------------------------------------------
 // small device helpers
@@ -83,7 +88,7 @@ struct ModelArgs {
   const float* model;   // [nchan, 2N]
   cx<float>* mconj32;   // [nchan, N] conj(m), slot layout
   cx<double>* mconj64;  // [nchan, N]
-  float* mpow;          // [nchan, N] |m|^2, slot layout
+  double* mpow;         // [nchan, N] |m|^2, slot layout
   double* pn;           // [nchan]
   const cx<double>* twN;
   const cx<double>* tw2N;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256) k_model(ModelArgs a) {
     if (valid) {
       a.mconj64[ro + slot] = cconj(d);
       a.mconj32[ro + slot] = mk<float>((float)d.x, (float)(-d.y));
-      a.mpow[ro + slot] = (float)pw;
+      a.mpow[ro + slot] = pw;
     }
   };
 #pragma unroll
@@ -243,6 +248,7 @@ struct SpectraArgs {
   const double* DMg;         // [nsub] or null
   const double* nu_mean;     // [nsub]
   float2* X;                 // [chunk,nchan,N]  (null: do not store)
+  float2* Xlo;               // [chunk,nchan,LoK<N>] float32 residuals of the first slots
   float2* partial;           // [chunk,nparts,N] (null: no guess)
   double* sigma;             // [nsub,nchan] out
   double* Ssn;               // [nsub,nchan] out: p_n / sigma_F^2 (0 = channel unused)
@@ -344,12 +350,14 @@ __global__ void __launch_bounds__(256, (N >= 2048 ? 1 : 2)) k_spectra(SpectraArg
       if (k >= kc) s_top += pw;
       const int sl_k = (k == N) ? 0 : k;
       if (a.X != nullptr && inrange) {
-        float2 xv = make_float2(0.f, 0.f);
+        float2 xv = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
         if (used) {
           const cx<F> pr = cmul(d, mval);
           xv = make_float2((float)pr.x, (float)pr.y);
+          xl = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
         }
         a.X[xo + sl_k] = xv;
+        if (sl_k < LoK<N>::value) a.Xlo[((size_t)sl * a.nchan + ch) * LoK<N>::value + sl_k] = xl;
       }
       if (wgt != 0.f) {
         float vx = (float)d.x, vy = (float)d.y;
@@ -442,6 +450,8 @@ struct GuessArgs {
   const double* nu_mean;   // [nsub]
   const double* nu_fit;    // [nsub,3]
   const double* init;      // [nsub,5] or null: template for GM,tau,alpha start values
+  const double* scat;      // [nsub,2] tau_guess [rot, linear] and alpha_guess, or null
+  int log10_tau, fit_scat;
 };
 
 __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
@@ -457,6 +467,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   const double inv_w = a.wsum ? 1.0 / a.wsum[ig] : 1.0;
   const float2* mc = a.mconj + (size_t)(a.nmodel > 1 ? il : 0) * N;
   double v[3] = {0.0, 0.0, 0.0};  // sum |d|^2, sum |m|^2, top-quarter power
+  const double tau_g = (a.scat && a.fit_scat) ? a.scat[(size_t)ig * 2] : 0.0;
   for (int i = tid; i < N; i += 256) {
     float sx = 0.f, sy = 0.f;
     for (int q = 0; q < a.nparts; ++q) {
@@ -464,12 +475,17 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       sx += t.x; sy += t.y;
     }
     const double dx = (double)sx * inv_w, dy = (double)sy * inv_w;
-    const float2 m = mc[i];
-    Y[i] = make_double2(dx * m.x - dy * m.y, dx * m.y + dy * m.x);
+    const int k = (i == 0) ? N : i;
+    double mx = mc[i].x, my = mc[i].y;
+    if (tau_g != 0.0) {   // scattered mean model (pptoas.py:444-447): conj(m B) = conj(m) conj(B)
+      const double b = kTwoPi * (double)k * tau_g, q = 1.0 / (1.0 + b * b);
+      const double tx = mx * q - my * (b * q);
+      my = mx * (b * q) + my * q; mx = tx;
+    }
+    Y[i] = make_double2(dx * mx - dy * my, dx * my + dy * mx);
     const double pw = dx * dx + dy * dy;
     v[0] += pw;
-    v[1] += (double)m.x * m.x + (double)m.y * m.y;
-    const int k = (i == 0) ? N : i;
+    v[1] += mx * mx + my * my;
     if (k >= kc) v[2] += pw;
   }
   block_sum<3, 256>(v, sh);
@@ -558,6 +574,11 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       xs[2] = a.init ? a.init[(size_t)ig * 5 + 2] : 0.0;
       xs[3] = a.init ? a.init[(size_t)ig * 5 + 3] : 0.0;
       xs[4] = a.init ? a.init[(size_t)ig * 5 + 4] : 0.0;
+      if (a.scat) {                                  // pptoas.py:427-452
+        double tg = a.scat[(size_t)ig * 2];
+        if (a.log10_tau) { if (tg == 0.0) tg = 1.0 / (double)(2 * N); tg = log10(tg); }
+        xs[3] = tg; xs[4] = a.scat[(size_t)ig * 2 + 1];
+      }
     }
   }
 }
@@ -581,6 +602,7 @@ struct SolverState {
 // ----------------------------------------------------------------------------
 struct PassArgs {
   const float2* X;         // [chunk,nchan,N]
+  const float2* Xlo;       // [chunk,nchan,LoK<N>]
   const double* nu2;       // [nchan]
   const double* P;         // [nsub]
   const double* nu_fit;    // [nsub,3]
@@ -602,7 +624,7 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 template <int N>
 __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
   const int sl = blockIdx.y, s = a.s0 + sl;
-  if (a.st.done[s]) return;
+  if (a.st.done[s] == 1) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int sub = lane >> 3, l8 = lane & 7;
   const int ch = blockIdx.x * 32 + w * 4 + sub;
@@ -628,9 +650,13 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
     constexpr int NJ = N / 16;
     constexpr int U = NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1);   // loads kept in flight per buffer
     constexpr int NG = NJ / U;                                 // groups (even)
-    auto consume = [&](float4 v, bool first) {
-      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; }          // slot 0 is handled below
-      const double xr0 = v.x, xi0 = v.y, xr1 = v.z, xi1 = v.w;
+    constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
+    const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
+    auto lo_of = [&](int j) { return j < KJ ? ld_stream(lorow + j * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f); };
+    auto consume = [&](float4 v, float4 lo, bool first) {
+      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
+      const double xr0 = (double)v.x + (double)lo.x, xi0 = (double)v.y + (double)lo.y;
+      const double xr1 = (double)v.z + (double)lo.z, xi1 = (double)v.w + (double)lo.w;
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
       const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
       C += re0 + re1;
@@ -650,20 +676,22 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
 #pragma unroll
       for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + ((gI + 1) * U + u) * 8 + l8);
 #pragma unroll
-      for (int u = 0; u < U; ++u) consume(qa[u], gI == 0 && u == 0);
+      for (int u = 0; u < U; ++u) consume(qa[u], lo_of(gI * U + u), gI == 0 && u == 0);
       if (gI + 2 < NG) {
 #pragma unroll
         for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + ((gI + 2) * U + u) * 8 + l8);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) consume(qb[u], false);
+      for (int u = 0; u < U; ++u) consume(qb[u], lo_of((gI + 1) * U + u), false);
     }
     if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
-      const float2 xn = __ldg(reinterpret_cast<const float2*>(row));
+      const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
+      const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
+      const double xnx = (double)xh.x + (double)xl.x, xny = (double)xh.y + (double)xl.y;
       double cn, sn;
       cis2pi((double)N * theta, cn, sn);
-      const double re = (double)xn.x * cn - (double)xn.y * sn;
-      const double im = (double)xn.x * sn + (double)xn.y * cn;
+      const double re = xnx * cn - xny * sn;
+      const double im = xnx * sn + xny * cn;
       C += re; C1 = fma((double)N, im, C1); C2 = fma((double)N * (double)N, re, C2);
     }
   }
@@ -917,12 +945,666 @@ __global__ void k_init_state(SolverState st, const double* init, int s0, int n) 
   st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
 }
 
+// number of subints of [s0, s0+n) that are not finished yet
+__global__ void k_count_running(SolverState st, int s0, int n, int* out) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (st.done[s0 + i] != 1);
+  atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = cnt;
+}
+
 __global__ void k_reset_state(SolverState st, int s0, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = s0 + i;
   for (int q = 0; q < 5; ++q) { st.xprev[(size_t)s * 5 + q] = st.x[(size_t)s * 5 + q]; st.step[(size_t)s * 5 + q] = 0.0; }
   st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+}
+
+// ----------------------------------------------------------------------------
+// k_pass5: K3 for (phi, DM, GM, tau, alpha) -- pptoaslib.py:181-523.
+// Per channel the nine primitive sums with respect to (theta_n, tau_n):
+//   C, C_th, C_thth, C_t, C_tt, C_tht  (Cdbp* family, 424-523)
+//   S, S_t, S_tt                        (Sbp* family, 390-422)
+// with B_nk = 1/(1 + i w tau_n), w = 2 pi k (pplib.py:4080-4095),
+// dB/dtau_n = -i w B^2, d2B/dtau_n^2 = -2 w^2 B^3 (== B(B-1)/tau_n, 2B(B-1)^2/tau_n^2;
+// pptoaslib.py:318-356).  Same lane mapping as k_pass2.
+// ----------------------------------------------------------------------------
+struct Pass5Args {
+  const float2* X;         // [chunk,nchan,N]
+  const float2* Xlo;       // [chunk,nchan,LoK<N>]
+  const double* mpow;      // [nchan,N] |m|^2 (slot layout, double: S_n must not carry float rounding)
+  const double* nu2;       // [nchan]
+  const double* freqs;     // [nchan]
+  const double* P;         // [nsub]
+  const double* nu_fit;    // [nsub,3]
+  const double* Ssn;       // [nsub,nchan] (0 => unused channel)
+  const double* sigma;     // [nsub,nchan]
+  double* csum;            // [nsub,nchan,kNCsum]
+  SolverState st;
+  int s0, nchan, log10_tau;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
+  const int sl = blockIdx.y, s = a.s0 + sl;
+  if (a.st.done[s] == 1) return;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int sub = lane >> 3, l8 = lane & 7;
+  const int ch = blockIdx.x * 32 + w * 4 + sub;
+  const bool inrange = ch < a.nchan;
+  const int chc = inrange ? ch : a.nchan - 1;
+  const bool used = inrange && a.Ssn[(size_t)s * a.nchan + chc] > 0.0;
+
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double taun = 0.0;
+  if (used) {
+    const double* x = a.st.x + (size_t)s * 5;
+    const double P = a.P[s];
+    const double nD = a.nu_fit[(size_t)s * 3 + 0], nG = a.nu_fit[(size_t)s * 3 + 1], nT = a.nu_fit[(size_t)s * 3 + 2];
+    const double n2 = a.nu2[ch];
+    const double gD = kDconst * (n2 - 1.0 / (nD * nD)) / P;                       // pptoaslib.py:206
+    const double gG = kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P;  // :207
+    double theta = x[0] + x[1] * gD + x[2] * gG;
+    theta -= rint(theta);
+    const double tau = a.log10_tau ? pow(10.0, x[3]) : x[3];
+    taun = tau * pow(a.freqs[ch] / nT, x[4]);                                      // pplib.py:4049-4053
+    const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
+    const double2* mrow = reinterpret_cast<const double2*>(a.mpow + (size_t)ch * N);
+    double c0, s0, c1, s1, cw, sw;
+    cis2pi((double)(2 * l8) * theta, c0, s0);
+    cis2pi((double)(2 * l8 + 1) * theta, c1, s1);
+    cis2pi(16.0 * theta, cw, sw);
+    double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
+    const double wt = kTwoPi * taun;   // b = k * wt
+    auto element = [&](double xr, double xi, double m, double c, double sn, double k) {
+      const double zr = xr * c - xi * sn, zi = xr * sn + xi * c;      // X e^{i psi}
+      const double b = k * wt;
+      const double q = 1.0 / fma(b, b, 1.0);                          // |B|^2
+      const double br = q, bi = b * q;                                // conj(B)
+      const double a1r = zr * br - zi * bi, a1i = zr * bi + zi * br;  // Z conjB
+      const double a2r = a1r * br - a1i * bi, a2i = a1r * bi + a1i * br;
+      const double a3r = a2r * br - a2i * bi;
+      const double k2 = k * k;
+      acc[0] += a1r;
+      acc[1] = fma(k, a1i, acc[1]);
+      acc[2] = fma(k2, a1r, acc[2]);
+      acc[3] = fma(k, a2i, acc[3]);
+      acc[4] = fma(k2, a3r, acc[4]);
+      acc[5] = fma(k2, a2r, acc[5]);
+      const double qm = q * m;
+      const double k2q2m = k2 * q * qm;
+      acc[6] += qm;
+      acc[7] += k2q2m;
+      acc[8] = fma(k2q2m, fma(4.0 * b * b, q, -1.0), acc[8]);
+    };
+    constexpr int NJ = N / 16;
+    constexpr int KJ = LoK<N>::value / 16;
+    const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
+#pragma unroll 2
+    for (int j = 0; j < NJ; ++j) {
+      float4 v = ld_stream(row + j * 8 + l8);
+      const float4 lo = j < KJ ? ld_stream(lorow + j * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const double2 mm = __ldg(mrow + j * 8 + l8);
+      const bool z = (j == 0 && l8 == 0);
+      element(z ? 0.0 : (double)v.x + (double)lo.x, z ? 0.0 : (double)v.y + (double)lo.y, z ? 0.0 : mm.x, c0, s0, k0);
+      element((double)v.z + (double)lo.z, (double)v.w + (double)lo.w, mm.y, c1, s1, k1);
+      const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
+      const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
+      k0 += 16.0; k1 += 16.0;
+    }
+    if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
+      const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
+      const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
+      const double mn = __ldg(a.mpow + (size_t)ch * N);
+      double cn, sn;
+      cis2pi((double)N * theta, cn, sn);
+      element((double)xh.x + (double)xl.x, (double)xh.y + (double)xl.y, mn, cn, sn, (double)N);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (inrange && l8 == 0) {
+    double* o = a.csum + ((size_t)s * a.nchan + ch) * kNCsum;
+    if (used) {
+      const double sg = a.sigma[(size_t)s * a.nchan + ch];
+      const double isF2 = 1.0 / (sg * sg * (double)N);
+      const double p2 = kTwoPi * kTwoPi;
+      o[0] = acc[0] * isF2;                        // C
+      o[1] = -kTwoPi * acc[1] * isF2;              // C_th   = -sum w Im(A1)
+      o[2] = -p2 * acc[2] * isF2;                  // C_thth = -sum w^2 Re(A1)
+      o[3] = -kTwoPi * acc[3] * isF2;              // C_t    = -sum w Im(A2)
+      o[4] = -2.0 * p2 * acc[4] * isF2;            // C_tt   = -2 sum w^2 Re(A3)
+      o[5] = -p2 * acc[5] * isF2;                  // C_tht  = -sum w^2 Re(A2)
+      o[6] = acc[6] * isF2;                        // S      = sum |B|^2 M
+      o[7] = -2.0 * taun * p2 * acc[7] * isF2;     // S_t    = -2 tau_n sum w^2 q^2 M
+      o[8] = 2.0 * p2 * acc[8] * isF2;             // S_tt   = sum 2 w^2 q^2 (4 b^2 q - 1) M
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) o[i] = 0.0;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// small dense helpers for k_update5 (n <= 5, row-major 5x5 storage)
+// ----------------------------------------------------------------------------
+__device__ inline bool chol5(const double* A, int n, double* L) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * 5 + j];
+      for (int k = 0; k < j; ++k) s -= L[i * 5 + k] * L[j * 5 + k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i * 5 + i] = sqrt(s);
+      } else L[i * 5 + j] = s / L[j * 5 + j];
+    }
+  return true;
+}
+__device__ inline void chol5_solve(const double* L, int n, const double* b, double* x) {
+  double y[5];
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i * 5 + k] * y[k];
+    y[i] = s / L[i * 5 + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < n; ++k) s -= L[k * 5 + i] * x[k];
+    x[i] = s / L[i * 5 + i];
+  }
+}
+__device__ inline void chol5_inverse(const double* L, int n, double* Inv) {
+  for (int c = 0; c < n; ++c) {
+    double e[5] = {0, 0, 0, 0, 0}, x[5];
+    e[c] = 1.0;
+    chol5_solve(L, n, e, x);
+    for (int r = 0; r < n; ++r) Inv[r * 5 + c] = x[r];
+  }
+}
+
+// Real positive roots of sum_i c[i] x^(deg-i) (np.roots convention), Aberth iteration in
+// complex double; returns the count written to out[].
+__device__ inline int real_pos_roots(const double* c_in, int deg_in, double* out) {
+  double c[8];
+  int deg = deg_in, off = 0;
+  while (deg > 0 && c_in[off] == 0.0) { ++off; --deg; }   // strip leading zeros
+  if (deg <= 0) return 0;
+  for (int i = 0; i <= deg; ++i) c[i] = c_in[off + i] / c_in[off];
+  double zr[8], zi[8];
+  double rad = 0.0;
+  for (int i = 1; i <= deg; ++i) rad = fmax(rad, pow(fabs(c[i]), 1.0 / i));
+  rad = rad > 0 ? 2.0 * rad : 1.0;
+  for (int i = 0; i < deg; ++i) { double sn, cs; sincospi(2.0 * (i + 0.35) / deg, &sn, &cs); zr[i] = 0.6 * rad * cs; zi[i] = 0.6 * rad * sn; }
+  for (int it = 0; it < 200; ++it) {
+    double change = 0.0;
+    for (int i = 0; i < deg; ++i) {
+      double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;   // Horner p and p'
+      for (int k = 1; k <= deg; ++k) {
+        const double ndr = dr * zr[i] - di * zi[i] + pr, ndi = dr * zi[i] + di * zr[i] + pi;
+        dr = ndr; di = ndi;
+        const double npr = pr * zr[i] - pi * zi[i] + c[k], npi = pr * zi[i] + pi * zr[i];
+        pr = npr; pi = npi;
+      }
+      const double dd = dr * dr + di * di;
+      if (dd == 0.0) continue;
+      double nr = (pr * dr + pi * di) / dd, ni = (pi * dr - pr * di) / dd;  // p/p'
+      double sr = 0.0, si = 0.0;
+      for (int j = 0; j < deg; ++j) if (j != i) {
+        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
+        const double e2 = er * er + ei * ei;
+        if (e2 > 0) { sr += er / e2; si -= ei / e2; }
+      }
+      const double qr = 1.0 - (nr * sr - ni * si), qi = -(nr * si + ni * sr);
+      const double q2 = qr * qr + qi * qi;
+      if (q2 == 0.0) continue;
+      const double wr = (nr * qr + ni * qi) / q2, wi = (ni * qr - nr * qi) / q2;
+      zr[i] -= wr; zi[i] -= wi;
+      change = fmax(change, fabs(wr) + fabs(wi));
+    }
+    if (change < 1e-15 * rad) break;
+  }
+  int n = 0;
+  for (int i = 0; i < deg; ++i)
+    if (fabs(zi[i]) <= 1e-9 * fabs(zr[i]) && zr[i] > 0.0) out[n++] = zr[i];
+  return n;
+}
+
+// ----------------------------------------------------------------------------
+// k_update5: K3' for the general fit: chain rule to the five global parameters,
+// gradient / Hessian (pptoaslib.py:544-643), safeguarded Newton on the fitted
+// subset, and -- once converged and re-evaluated at the final point -- the
+// epilogue: get_nu_zeros (733-906), re-referencing (1040-1065), covariance with
+// the amplitude block (645-731 in closed form), scales, snr, chi2 (1069-1085).
+// ----------------------------------------------------------------------------
+struct Update5Args {
+  const double* csum; const double* Sdn; const double* nu2; const double* freqs; const double* P;
+  const double* nu_fit; const double* nu_outs; const int* nok;
+  SolverState st;
+  double* params; double* param_errs; double* nu_out; double* cov; double* chi2; double* red_chi2;
+  double* snr; int* nfeval; int* rc; double* scales; double* scale_errs; double* channel_snrs;
+  int s0, nchan, nbin, max_iter, log10_tau, option, is_toa;
+  int flags[5];
+  double tol;
+};
+
+struct ChanJ {   // per-channel Jacobians of (theta_n, tau_n) w.r.t. the five parameters
+  double Jth[3], Jt[2], Ktt, Kta, Kaa, lnf, taun;
+};
+
+__device__ __forceinline__ ChanJ chan_jac(double nu, double n2, double P, double nD, double nG, double nT, double tau_lin,
+                                          double alpha, int log10_tau) {
+  ChanJ j;
+  j.Jth[0] = 1.0;
+  j.Jth[1] = kDconst * (n2 - 1.0 / (nD * nD)) / P;                           // pptoaslib.py:222
+  j.Jth[2] = kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P;  // :223
+  j.lnf = log(nu / nT);
+  j.taun = tau_lin * pow(nu / nT, alpha);
+  const double ln10 = 2.302585092994045684;
+  if (log10_tau) {                                                            // :246-274
+    j.Jt[0] = ln10 * j.taun; j.Ktt = ln10 * j.Jt[0]; j.Kta = ln10 * j.lnf * j.taun;
+  } else {
+    j.Jt[0] = tau_lin != 0.0 ? j.taun / tau_lin : 0.0; j.Ktt = 0.0;
+    j.Kta = tau_lin != 0.0 ? j.lnf * j.taun / tau_lin : 0.0;
+  }
+  j.Jt[1] = j.lnf * j.taun;
+  j.Kaa = j.lnf * j.Jt[1];
+  return j;
+}
+
+// first derivatives of C_n, S_n w.r.t. the five parameters
+__device__ __forceinline__ void chan_first(const double* c, const ChanJ& j, double* dC, double* dS) {
+  dC[0] = c[1] * j.Jth[0]; dC[1] = c[1] * j.Jth[1]; dC[2] = c[1] * j.Jth[2];
+  dC[3] = c[3] * j.Jt[0]; dC[4] = c[3] * j.Jt[1];
+  dS[0] = dS[1] = dS[2] = 0.0; dS[3] = c[7] * j.Jt[0]; dS[4] = c[7] * j.Jt[1];
+}
+__device__ __forceinline__ double chan_d2C(const double* c, const ChanJ& j, int a, int b) {
+  if (a > b) { const int t = a; a = b; b = t; }
+  if (b < 3) return c[2] * j.Jth[a] * j.Jth[b];
+  if (a < 3) return c[5] * j.Jth[a] * j.Jt[b - 3];
+  const double K = (a == 3 && b == 3) ? j.Ktt : ((a == 3) ? j.Kta : j.Kaa);
+  return c[4] * j.Jt[a - 3] * j.Jt[b - 3] + c[3] * K;
+}
+__device__ __forceinline__ double chan_d2S(const double* c, const ChanJ& j, int a, int b) {
+  if (a > b) { const int t = a; a = b; b = t; }
+  if (a < 3) return 0.0;
+  const double K = (a == 3 && b == 3) ? j.Ktt : ((a == 3) ? j.Kta : j.Kaa);
+  return c[8] * j.Jt[a - 3] * j.Jt[b - 3] + c[7] * K;
+}
+// per-channel profile-likelihood Hessian entry (pptoaslib.py:624-628, written without 1/C)
+__device__ __forceinline__ double chan_H(double C, double S, double d2C, double d2S, double dCa, double dCb, double dSa,
+                                         double dSb) {
+  const double iS = 1.0 / S;
+  return -2.0 * (C * d2C * iS - 0.5 * C * C * d2S * iS * iS + dCa * dCb * iS + C * C * dSa * dSb * iS * iS * iS -
+                 C * (dCa * dSb + dSa * dCb) * iS * iS);
+}
+
+__global__ void __launch_bounds__(128) k_update5(Update5Args a) {
+  const int s = a.s0 + blockIdx.x;
+  const int state = a.st.done[s];
+  if (state == 1) return;
+  __shared__ double sh[24 * 4];
+  __shared__ double bc[48];
+  const int tid = threadIdx.x, nchan = a.nchan;
+  const double* cs = a.csum + (size_t)s * nchan * kNCsum;
+  const double P = a.P[s];
+  const double nD = a.nu_fit[(size_t)s * 3], nG = a.nu_fit[(size_t)s * 3 + 1], nT = a.nu_fit[(size_t)s * 3 + 2];
+  double* x = a.st.x + (size_t)s * 5;
+  double* xp = a.st.xprev + (size_t)s * 5;
+  double* stp = a.st.step + (size_t)s * 5;
+  const double tau_lin = a.log10_tau ? pow(10.0, x[3]) : x[3];
+  const double alpha = x[4];
+  // mirror of the reference: with all tau_n == 0 the scattering derivatives are zero
+  // (pptoaslib.py:325-330, 341-356)
+  const bool scat_on = tau_lin != 0.0;
+  int fl[5];
+  int nfit = 0, idx[5];
+  for (int i = 0; i < 5; ++i) { fl[i] = a.flags[i]; if (fl[i]) idx[nfit++] = i; }
+
+  if (state == 0) {
+    // ---- f, gradient, Hessian --------------------------------------------------------
+    double v[23];
+    for (int i = 0; i < 23; ++i) v[i] = 0.0;   // f, g[5], H upper [15], Sd, spare
+    double gmax1 = 0.0, gmax2 = 0.0;
+    for (int n = tid; n < nchan; n += 128) {
+      double c[9];
+      for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+      const double S = c[6];
+      if (!(S > 0.0)) continue;
+      if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+      double dC[5], dS[5];
+      chan_first(c, j, dC, dS);
+      const double C = c[0];
+      v[0] -= C * C / S;
+      for (int i = 0; i < 5; ++i) v[1 + i] += (-2.0 * C * dC[i] / S + C * C * dS[i] / (S * S)) * fl[i];  // :572
+      int q = 6;
+      for (int i = 0; i < 5; ++i)
+        for (int k = i; k < 5; ++k, ++q)
+          v[q] += chan_H(C, S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * fl[i] * fl[k];
+      v[21] += a.Sdn[(size_t)s * nchan + n];
+      gmax1 = fmax(gmax1, fabs(j.Jth[1]));
+      gmax2 = fmax(gmax2, fabs(j.Jth[2]));
+    }
+    block_sum<23, 128>(v, sh);
+    double gm[2] = {gmax1, gmax2};
+    for (int o = 16; o > 0; o >>= 1) { gm[0] = fmax(gm[0], __shfl_xor_sync(0xffffffffu, gm[0], o)); gm[1] = fmax(gm[1], __shfl_xor_sync(0xffffffffu, gm[1], o)); }
+    __syncthreads();
+    if ((tid & 31) == 0) { sh[tid >> 5] = gm[0]; sh[8 + (tid >> 5)] = gm[1]; }
+    __syncthreads();
+    gmax1 = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3]));
+    gmax2 = fmax(fmax(sh[8], sh[9]), fmax(sh[10], sh[11]));
+    if (tid == 0) {
+      const int it = a.st.iter[s] + 1;
+      a.st.iter[s] = it;
+      const double f = v[0];
+      int action = 0;   // 0 continue, 1 go to final evaluation at x, 2 finish now (failure)
+      int rc = 0;
+      if (!(f == f) || fabs(f) > 1e300) { action = 2; rc = 3; }
+      else if (a.max_iter < 0) { action = 3; rc = 0; }          // evaluate-only: epilogue at x now
+      else if (it > 1 && f > a.st.fprev[s] + 1e-12 * fabs(a.st.fprev[s])) {
+        const double lam = a.st.lam[s] * 0.25;
+        a.st.lam[s] = lam;
+        if (it >= a.max_iter || lam < 1e-6) { action = 3; rc = 1; }
+        else for (int i = 0; i < 5; ++i) x[i] = xp[i] + lam * stp[i];
+      } else {
+        double H[25], g[5], L[25], d[5] = {0, 0, 0, 0, 0}, dr[5];
+        int q = 6;
+        double Hf[25];
+        for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) { Hf[i * 5 + k] = v[q]; Hf[k * 5 + i] = v[q]; }
+        for (int i = 0; i < nfit; ++i) { g[i] = v[1 + idx[i]]; for (int k = 0; k < nfit; ++k) H[i * 5 + k] = Hf[idx[i] * 5 + idx[k]]; }
+        bool pd = chol5(H, nfit, L);
+        double Inv[25];
+        if (pd) {
+          double mg[5];
+          for (int i = 0; i < nfit; ++i) mg[i] = -g[i];
+          chol5_solve(L, nfit, mg, dr);
+          chol5_inverse(L, nfit, Inv);
+        } else {
+          // Levenberg damping until positive definite
+          double lamd = 0.0;
+          for (int i = 0; i < nfit; ++i) lamd = fmax(lamd, fabs(H[i * 5 + i]));
+          lamd *= 1e-3;
+          bool ok = false;
+          for (int tr = 0; tr < 40 && !ok; ++tr) {
+            double Hd[25];
+            for (int i = 0; i < nfit; ++i) for (int k = 0; k < nfit; ++k) Hd[i * 5 + k] = H[i * 5 + k] + (i == k ? lamd : 0.0);
+            ok = chol5(Hd, nfit, L);
+            lamd *= 4.0;
+          }
+          if (ok) { double mg[5]; for (int i = 0; i < nfit; ++i) mg[i] = -g[i]; chol5_solve(L, nfit, mg, dr); }
+          else for (int i = 0; i < nfit; ++i) dr[i] = -g[i] / (fabs(H[i * 5 + i]) + 1e-300);
+        }
+        for (int i = 0; i < nfit; ++i) d[idx[i]] = dr[i];
+        // step limits: rotation of any channel <= 0.1 turn, log10(tau) <= 0.5, alpha <= 1,
+        // linear tau: at most halve / grow by its own size
+        double sc = 1.0;
+        const double rot = fabs(d[0]) + fabs(d[1]) * gmax1 + fabs(d[2]) * gmax2;
+        if (rot > 0.1) sc = fmin(sc, 0.1 / rot);
+        if (a.log10_tau) { if (fabs(d[3]) > 0.5) sc = fmin(sc, 0.5 / fabs(d[3])); }
+        else if (fl[3] && x[3] > 0.0 && fabs(d[3]) > 0.5 * x[3]) sc = fmin(sc, 0.5 * x[3] / fabs(d[3]));
+        if (fabs(d[4]) > 1.0) sc = fmin(sc, 1.0 / fabs(d[4]));
+        for (int i = 0; i < 5; ++i) d[i] *= sc;
+        bool conv = pd && sc == 1.0;
+        if (conv) for (int i = 0; i < nfit; ++i) {
+          const double sg = sqrt(2.0 * Inv[i * 5 + i]);     // 1-sigma from inv(H/2)
+          if (!(fabs(dr[i]) <= a.tol * sg)) conv = false;
+        }
+        for (int i = 0; i < 5; ++i) { xp[i] = x[i]; stp[i] = d[i]; }
+        a.st.fprev[s] = f;
+        a.st.lam[s] = 1.0;
+        for (int i = 0; i < 5; ++i) x[i] += d[i];
+        if (conv) { action = 1; rc = 0; }
+        else if (it >= a.max_iter) { action = 1; rc = 1; }
+      }
+      if (action == 1) a.st.done[s] = 2;   // one more pass at the final point, then the epilogue
+      bc[0] = (double)action; bc[1] = (double)rc;
+      if (action == 1 || action == 2 || action == 3) a.rc[s] = rc;
+      if (action == 2) {                    // non-finite objective: report what we have
+        double* po = a.params + (size_t)s * 5;
+        for (int i = 0; i < 5; ++i) po[i] = x[i];
+        a.nfeval[s] = it; a.st.done[s] = 1;
+      }
+    }
+    __syncthreads();
+    if ((int)bc[0] != 3) return;   // 3: run the epilogue right now with the sums at x
+  }
+
+  // ======================= epilogue: sums in csum are at the final x =======================
+  const double K1 = kDconst / P, K2 = kDconst * kDconst / P;
+  // ---- get_nu_zeros (pptoaslib.py:733-906) at the fit reference frequencies ----------------
+  int zfl[5];
+  for (int i = 0; i < 5; ++i) zfl[i] = fl[i];
+  if (fl[0] && fl[1] && fl[2] && fl[3] && fl[4]) zfl[2] = 0;      // [1,1,1,1,1] -> formulas of [1,1,0,1,1] (:893-901)
+  double u[24];
+  for (int i = 0; i < 24; ++i) u[i] = 0.0;
+  // u[0..14]: for j=0..4: sum h_th(j), sum nu^-2 h_th(j), sum nu^-4 h_th(j)
+  // u[15..20]: for j in {0,1,3}: sum h_ln(j), sum ln(nu) h_ln(j) ; u[21]: f ; u[22]: Sd ; u[23]: snr^2
+  for (int n = tid; n < nchan; n += 128) {
+    double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    const double S = c[6];
+    if (!(S > 0.0)) continue;
+    if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+    double dC[5], dS[5];
+    chan_first(c, j, dC, dS);
+    const double C = c[0], n2 = a.nu2[n], lnnu = log(a.freqs[n]);
+    for (int p = 0; p < 5; ++p) {
+      // Hessian row w.r.t. theta_n (= Hn[DM,p]/gDM_n etc.): d2C[theta,p], no S-dependence on theta
+      const double d2 = (p < 3) ? c[2] * j.Jth[p] : c[5] * j.Jt[p - 3];
+      const double h = chan_H(C, S, d2, 0.0, c[1], dC[p], 0.0, dS[p]) * zfl[p];
+      u[3 * p] += h; u[3 * p + 1] += n2 * h; u[3 * p + 2] += n2 * n2 * h;
+    }
+    {
+      // Hessian row w.r.t. alpha divided by ln(nu_n/nu_tau): d/dalpha = lnf * tau_n d/dtau_n
+      const double Cta = c[3] * j.taun, Sta = c[7] * j.taun;
+      const double k10 = a.log10_tau ? 2.302585092994045684 * j.taun : (tau_lin != 0.0 ? j.taun / tau_lin : 0.0);
+      const int ps[3] = {0, 1, 3};
+      for (int q = 0; q < 3; ++q) {
+        const int p = ps[q];
+        double d2C, d2S;
+        if (p < 3) { d2C = c[5] * j.Jth[p] * j.taun; d2S = 0.0; }
+        else { d2C = c[4] * j.taun * j.Jt[0] + c[3] * k10; d2S = c[8] * j.taun * j.Jt[0] + c[7] * k10; }
+        const double h = chan_H(C, S, d2C, d2S, Cta, dC[p], Sta, dS[p]) * zfl[p];
+        u[15 + 2 * q] += h; u[16 + 2 * q] += lnnu * h;
+      }
+    }
+    u[21] -= C * C / S;
+    u[22] += a.Sdn[(size_t)s * nchan + n];
+    u[23] += C * C / S;
+  }
+  block_sum<24, 128>(u, sh);
+  // full Hessian at the fit frequencies (needed by some nu_zero formulas)
+  double hv[15];
+  for (int i = 0; i < 15; ++i) hv[i] = 0.0;
+  double fmean = 0.0;
+  for (int n = tid; n < nchan; n += 128) {
+    double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    const double S = c[6];
+    if (!(S > 0.0)) continue;
+    if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+    double dC[5], dS[5];
+    chan_first(c, j, dC, dS);
+    int q = 0;
+    for (int i = 0; i < 5; ++i)
+      for (int k = i; k < 5; ++k, ++q)
+        hv[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * zfl[i] * zfl[k];
+    fmean += a.freqs[n];
+  }
+  block_sum<15, 128>(hv, sh);
+  double fm[1] = {fmean};
+  block_sum<1, 128>(fm, sh);
+  if (tid == 0) {
+    double Hz[25];
+    int q = 0;
+    for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) { Hz[i * 5 + k] = hv[q]; Hz[k * 5 + i] = hv[q]; }
+    double nzD = nD, nzG = nG, nzT = nT;
+    const int code = fl[0] * 16 + fl[1] * 8 + fl[2] * 4 + fl[3] * 2 + fl[4];
+    const double fbar = fm[0] / (double)a.nok[s];
+    auto th = [&](int p, int m) { return u[3 * p + m]; };          // m: 0 sum, 1 nu^-2, 2 nu^-4
+    auto ln = [&](int q2, int m) { return u[15 + 2 * q2 + m]; };    // q2: 0 phi, 1 DM, 2 tau
+    if (code == 0b11000) {                                          // :746-752
+      nzD = pow(th(0, 1) / th(0, 0), -0.5);
+    } else if (code == 0b10100) {                                   // :753-760
+      nzG = pow(th(0, 2) / th(0, 0), -0.25);
+    } else if (code == 0b00011) {                                   // :761-767
+      nzT = exp(ln(2, 1) / ln(2, 0));
+    } else if (code == 0b11010) {                                   // :768-778
+      const double H13 = Hz[3 * 5 + 0], H33 = Hz[3 * 5 + 3];
+      nzD = pow((H13 * th(3, 1) - H33 * th(0, 1)) / (H13 * th(3, 0) - H33 * th(0, 0)), -0.5);
+    } else if (code == 0b11011 || code == 0b11111) {                // :813-836 (and 893-901)
+      // reduced indices (phi, DM, tau, alpha) = (0,1,3,4)
+      const double H11 = Hz[0], H22 = Hz[6], H33 = Hz[18], H44 = Hz[24];
+      const double H12 = Hz[1], H13 = Hz[3], H14 = Hz[4], H23 = Hz[8], H34 = Hz[19];
+      (void)H22;
+      const double c1 = H34 * H34 - H33 * H44, c2 = H13 * H44 - H14 * H34, c3 = H14 * H33 - H13 * H34;
+      nzD = pow((c1 * th(0, 1) + c2 * th(3, 1) + c3 * th(4, 1)) / (c1 * th(0, 0) + c2 * th(3, 0) + c3 * th(4, 0)), -0.5);
+      const double e1 = H13 * H22 - H12 * H23, e2 = H11 * H23 - H12 * H13, e3 = H12 * H12 - H11 * H22;
+      nzT = exp((e1 * ln(0, 1) + e2 * ln(1, 1) + e3 * ln(2, 1)) / (e1 * ln(0, 0) + e2 * ln(1, 0) + e3 * ln(2, 0)));
+    } else if (code == 0b11100 && (a.option == 0 || a.option == 1)) {   // :779-812
+      double A, B, C_, D, E, F, G, Hh;
+      if (a.option == 0) { A = th(0, 2); B = th(0, 0); C_ = th(2, 1); D = th(2, 0); E = th(2, 2); F = th(2, 0); G = th(0, 1); Hh = th(0, 0); }
+      else { A = th(0, 2); B = th(0, 0); C_ = th(1, 1); D = th(1, 0); E = th(1, 2); F = th(1, 0); G = th(0, 1); Hh = th(0, 0); }
+      const double cf[7] = {A * C_ - E * G, 0.0, E * Hh - A * D, 0.0, F * G - B * C_, 0.0, B * D - F * Hh};
+      double r[8];
+      const int nr = real_pos_roots(cf, 6, r);
+      if (nr > 0) { double best = r[0]; for (int i = 1; i < nr; ++i) if (fabs(fbar - r[i]) < fabs(fbar - best)) best = r[i]; nzD = nzG = best; }
+    } else if (code == 0b11110 && (a.option == 0 || a.option == 1)) {   // :837-892
+      const double cD = K1, cG = K2;
+      const double H14 = Hz[3 * 5 + 0], H44 = Hz[3 * 5 + 3];
+      double cf[6]; int deg;
+      if (a.option == 0) {
+        const double A = cG * th(3, 2), a_ = cG * th(3, 0), B = cD * th(0, 1), b_ = cD * th(0, 0), C_ = cG * th(0, 2), c_ = cG * th(0, 0);
+        const double D = cD * th(2, 1), d_ = cD * th(2, 0), E = cG * th(2, 2), e_ = cG * th(2, 0), F = cD * th(3, 1), f_ = cD * th(3, 0);
+        cf[0] = A * A * B + H44 * C_ * D + H14 * E * F - H44 * B * E - A * C_ * F - H14 * A * D;
+        cf[1] = -A * A * b_ - H44 * C_ * d_ - H14 * E * f_ + H44 * b_ * E + A * C_ * f_ + H14 * A * d_;
+        cf[2] = -2 * A * a_ * B - H44 * c_ * D - H14 * e_ * F + H44 * B * e_ + (A * c_ + a_ * C_) * F + H14 * a_ * D;
+        cf[3] = 2 * A * a_ * b_ + H44 * c_ * d_ + H14 * e_ * f_ - H44 * b_ * e_ - (A * c_ + a_ * C_) * f_ - H14 * a_ * d_;
+        cf[4] = a_ * a_ * B - a_ * c_ * F;
+        cf[5] = -a_ * a_ * b_ + a_ * c_ * f_;
+        deg = 5;
+      } else {
+        const double A = cD * th(3, 1), a_ = cD * th(3, 0), B = cG * th(0, 2), b_ = cG * th(0, 0), C_ = cD * th(0, 1), c_ = cD * th(0, 0);
+        const double D = cG * th(1, 2), d_ = cG * th(1, 0), E = cD * th(1, 1), e_ = cD * th(1, 0), F = cG * th(3, 2), f_ = cG * th(3, 0);
+        cf[0] = A * A * B + H44 * C_ * D + H14 * E * F - H44 * B * E - A * C_ * F - H14 * A * D;
+        cf[1] = -2 * A * a_ * B - H44 * c_ * D - H14 * e_ * F + H44 * B * e_ + (A * c_ + a_ * C_) * F + H14 * a_ * D;
+        cf[2] = -(A * A * b_ - a_ * a_ * B) - H44 * C_ * d_ - H14 * E * f_ + H44 * b_ * E + (A * C_ * f_ - a_ * c_ * F) + H14 * A * d_;
+        cf[3] = 2 * A * a_ * b_ + H44 * c_ * d_ + H14 * e_ * f_ - H44 * b_ * e_ - (A * c_ + a_ * C_) * f_ - H14 * a_ * d_;
+        cf[4] = -a_ * a_ * b_ + a_ * c_ * f_;
+        deg = 4;
+      }
+      double r[8];
+      const int nr = real_pos_roots(cf, deg, r);
+      if (nr > 0) {
+        double best = sqrt(r[0]);
+        for (int i = 1; i < nr; ++i) if (fabs(fbar - sqrt(r[i])) < fabs(fbar - best)) best = sqrt(r[i]);
+        nzD = nzG = best;
+      }
+    }
+    // requested output frequencies (NaN = zero-covariance value)          :1040-1050
+    double noD = a.nu_outs ? a.nu_outs[(size_t)s * 3] : CUDART_NAN;
+    double noG = a.nu_outs ? a.nu_outs[(size_t)s * 3 + 1] : CUDART_NAN;
+    double noT = a.nu_outs ? a.nu_outs[(size_t)s * 3 + 2] : CUDART_NAN;
+    if (!(noD == noD)) noD = nzD;
+    if (!(noG == noG)) noG = nzG;
+    if (!(noT == noT)) noT = nzT;
+    if (a.is_toa) { if (fl[1]) noG = noD; else if (fl[2]) noD = noG; }
+    bc[2] = noD; bc[3] = noG; bc[4] = noT;
+  }
+  __syncthreads();
+  const double noD = bc[2], noG = bc[3], noT = bc[4];
+  // ---- re-reference phi and tau (pptoaslib.py:1052-1065) -----------------------------------
+  const double tau_out_lin = tau_lin * pow(noT / nT, alpha);
+  // ---- Hessian at the output frequencies, covariance incl. amplitudes (645-731) -------------
+  double ho[15];
+  for (int i = 0; i < 15; ++i) ho[i] = 0.0;
+  for (int n = tid; n < nchan; n += 128) {
+    double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    const double S = c[6];
+    if (!(S > 0.0)) continue;
+    if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha, a.log10_tau);
+    double dC[5], dS[5];
+    chan_first(c, j, dC, dS);
+    int q = 0;
+    for (int i = 0; i < 5; ++i)
+      for (int k = i; k < 5; ++k, ++q)
+        ho[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * fl[i] * fl[k];
+  }
+  block_sum<15, 128>(ho, sh);
+  if (tid == 0) {
+    double Hf[25], H[25], L[25], Inv[25];
+    int q = 0;
+    for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) { Hf[i * 5 + k] = ho[q]; Hf[k * 5 + i] = ho[q]; }
+    for (int i = 0; i < nfit; ++i) for (int k = 0; k < nfit; ++k) H[i * 5 + k] = Hf[idx[i] * 5 + idx[k]];
+    bool ok = chol5(H, nfit, L);
+    for (int i = 0; i < 25; ++i) Inv[i] = CUDART_NAN;
+    if (ok) chol5_inverse(L, nfit, Inv);
+    for (int i = 0; i < 25; ++i) bc[8 + i] = Inv[i];   // X^-1 = inv(H_out) over the fitted subset
+  }
+  __syncthreads();
+  double Xinv[25];
+  for (int i = 0; i < 25; ++i) Xinv[i] = bc[8 + i];
+  for (int n = tid; n < nchan; n += 128) {
+    double c[9];
+    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    const double S = c[6];
+    const size_t o = (size_t)s * nchan + n;
+    double sc = 0.0, se = 0.0, csn = 0.0;
+    if (S > 0.0) {
+      if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha, a.log10_tau);
+      double dC[5], dS[5];
+      chan_first(c, j, dC, dS);
+      sc = c[0] / S;                                               // :688
+      csn = sc * sqrt(S);                                          // :1081
+      double U[5];
+      for (int i = 0; i < nfit; ++i) U[i] = -2.0 * (dC[idx[i]] - sc * dS[idx[i]]);   // :690, 715
+      double qf = 0.0;
+      for (int i = 0; i < nfit; ++i) for (int k = 0; k < nfit; ++k) qf += U[i] * Xinv[i * 5 + k] * U[k];
+      se = sqrt(1.0 / S + qf / (2.0 * S * S));                     // diag(2 LR), :721-724
+    }
+    if (a.scales) a.scales[o] = sc;
+    if (a.scale_errs) a.scale_errs[o] = se;
+    if (a.channel_snrs) a.channel_snrs[o] = csn;
+  }
+  if (tid == 0) {
+    const double phi_inf = x[0] - K1 * x[1] / (nD * nD) - K2 * x[2] / (nG * nG * nG * nG);   // :1052-1053
+    double phi_out = phi_inf + K1 * x[1] / (noD * noD) + K2 * x[2] / (noG * noG * noG * noG);
+    phi_out = wrap_phase(phi_out);
+    double* po = a.params + (size_t)s * 5;
+    po[0] = phi_out; po[1] = x[1]; po[2] = x[2];
+    po[3] = a.log10_tau ? log10(tau_out_lin) : tau_out_lin;
+    po[4] = x[4];
+    double* pe = a.param_errs + (size_t)s * 5;
+    double* cv = a.cov + (size_t)s * 25;
+    for (int i = 0; i < 5; ++i) pe[i] = 0.0;
+    for (int i = 0; i < 25; ++i) cv[i] = 0.0;
+    for (int i = 0; i < nfit; ++i) {
+      pe[idx[i]] = sqrt(2.0 * Xinv[i * 5 + i]);
+      for (int k = 0; k < nfit; ++k) cv[idx[i] * 5 + idx[k]] = 2.0 * Xinv[i * 5 + k];
+    }
+    double* no = a.nu_out + (size_t)s * 3;
+    no[0] = noD; no[1] = noG; no[2] = noT;
+    const int nok = a.nok[s];
+    const double chi2 = u[22] + u[21];
+    a.chi2[s] = chi2;
+    a.red_chi2[s] = chi2 / ((double)nok * a.nbin - (double)(nfit + nok));
+    a.snr[s] = sqrt(u[23]);
+    a.nfeval[s] = a.st.iter[s] + (state == 2 ? 1 : 0);
+    a.st.done[s] = 1;
+  }
 }
 
 // ----------------------------------------------------------------------------

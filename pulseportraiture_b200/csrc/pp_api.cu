@@ -84,14 +84,14 @@ struct pp_plan {
   // FFTFIT grid tables keyed by Ns
   std::vector<std::pair<int, DBuf>> grid_tables;
   // per-batch staging of small inputs and per-subint / per-channel workspace
-  DBuf in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
+  DBuf running, in_scat, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
   DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
   DBuf ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
       rot_phase, rot_dm, rot_P, rot_nuref;
   // chunk-sized
-  DBuf X, partial, data_stage[2];
+  DBuf X, Xlo, partial, data_stage[2];
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -304,7 +304,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -312,7 +312,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
                  &pl->Ssn, &pl->Sdn, &pl->csum, &pl->st_x, &pl->st_xprev, &pl->st_step, &pl->st_fprev, &pl->st_lam,
                  &pl->st_iter, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
                  &pl->o_snr, &pl->o_nfev, &pl->o_rc, &pl->o_scales, &pl->o_serrs, &pl->o_csnr, &pl->o_lag, &pl->o_phig,
-                 &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->X,
+                 &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->X, &pl->Xlo,
                  &pl->partial, &pl->data_stage[0], &pl->data_stage[1]};
   for (DBuf* b : all) b->release();
   for (auto& gt : pl->grid_tables) gt.second.release();
@@ -411,12 +411,12 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   if (set_freqs_impl(pl, freqs)) return -2;
   CK(pl->mconj32.need(sizeof(float2) * (size_t)nchan * N));
   CK(pl->mconj64.need(sizeof(double2) * (size_t)nchan * N));
-  CK(pl->mpow.need(sizeof(float) * (size_t)nchan * N));
+  CK(pl->mpow.need(sizeof(double) * (size_t)nchan * N));
   CK(pl->pn.need(sizeof(double) * nchan));
   CK(pl->mmean.need(sizeof(float2) * N));
   ModelArgs a;
   a.model = dmodel; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
-  a.mpow = pl->mpow.as<float>(); a.pn = pl->pn.as<double>();
+  a.mpow = pl->mpow.as<double>(); a.pn = pl->pn.as<double>();
   a.twN = pl->twN64.as<cx<double>>(); a.tw2N = pl->tw2N64.as<cx<double>>(); a.nchan = nchan;
   DISPATCH_N(N, {
     const int rows = RowGeom<NN>::kRows;
@@ -475,23 +475,32 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (!args->data || !args->P) return fail(-1, "data and P are required");
   if (args->nsub < 1) return fail(-1, "nsub must be >= 1");
   const uint8_t* ff = args->fit_flags;
-  if (ff[2] || ff[3] || ff[4])
-    return fail(-3, "fit_flags [%d,%d,%d,%d,%d]: GM/tau/alpha fits are not built in this library version", ff[0], ff[1],
-                ff[2], ff[3], ff[4]);
-  if (!ff[0] && !ff[1]) return fail(-1, "nothing to fit");
+  if (!ff[0] && !ff[1] && !ff[2] && !ff[3] && !ff[4]) return fail(-1, "nothing to fit");
+  // The (phi, DM) kernels apply when GM, tau, alpha are neither fit nor non-zero.
+  bool general = ff[2] || ff[3] || ff[4] || args->log10_tau;
+  if (!general && args->init) {
+    if (is_device_ptr(args->init)) general = true;   // cannot inspect cheaply: take the general path
+    else
+      for (int i = 0; i < args->nsub && !general; ++i)
+        if (args->init[(size_t)i * 5 + 2] != 0.0 || args->init[(size_t)i * 5 + 3] != 0.0) general = true;
+  }
+  if (!general && args->scat_guess) general = true;
+  if (general && args->semantics == PP_SEM_FIT_PORTRAIT)
+    return fail(-1, "PP_SEM_FIT_PORTRAIT is defined for the (phi, DM) fit only");
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int nsub = args->nsub, nchan = pl->nchan, N = pl->N;
   const int Ns = args->Ns > 0 ? args->Ns : 100;
   if (Ns < 2) return fail(-1, "Ns must be >= 2");
-  const int max_iter = args->max_iter > 0 ? args->max_iter : (args->max_iter < 0 ? -1 : 8);
-  const int n_launch_iter = max_iter < 0 ? 1 : max_iter;
+  const int dflt_iter = general ? 40 : 8;
+  const int max_iter = args->max_iter > 0 ? args->max_iter : (args->max_iter < 0 ? -1 : dflt_iter);
+  const int n_launch_iter = max_iter < 0 ? 1 : (general ? max_iter + 1 : max_iter);
 
   const double tol = args->tol > 0 ? args->tol : 1e-3;
   const size_t nsc = (size_t)nsub * nchan;
 
   // ---- stage small inputs ------------------------------------------------------
-  const double *dP, *derrs, *dw, *dinit, *ddmg, *dsnrs, *dnufits, *dnuouts;
+  const double *dP, *derrs, *dw, *dinit, *ddmg, *dsnrs, *dnufits, *dnuouts, *dscat;
   const uint8_t* dmask;
   if (stage_in(pl, pl->in_P, args->P, (size_t)nsub, &dP)) return -2;
   if (stage_in(pl, pl->in_errs, args->errs, nsc, &derrs)) return -2;
@@ -502,6 +511,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (stage_in(pl, pl->in_snrs, args->snrs, nsc, &dsnrs)) return -2;
   if (stage_in(pl, pl->in_nufits, args->nu_fits, (size_t)nsub * 3, &dnufits)) return -2;
   if (stage_in(pl, pl->in_nuouts, args->nu_outs, (size_t)nsub * 3, &dnuouts)) return -2;
+  if (stage_in(pl, pl->in_scat, args->scat_guess, (size_t)nsub * 2, &dscat)) return -2;
   const bool want_guess = (args->init == nullptr);
 
   // ---- workspace -------------------------------------------------------------------
@@ -534,6 +544,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->o_csnr.need(sizeof(double) * nsc));
   CK(pl->o_lag.need(sizeof(int) * nsub));
   CK(pl->o_phig.need(sizeof(double) * nsub));
+  CK(pl->running.need(sizeof(int)));
 
   const int chunk = pick_chunk(pl, nsub);
   const int G = rows_per_cta(pl, chunk);
@@ -542,6 +553,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   const int nparts = gx * rows_conc;
   pl->stats.chunk = chunk;
   CK(pl->X.need(sizeof(float2) * (size_t)chunk * nchan * N));
+  CK(pl->Xlo.need(sizeof(float2) * (size_t)chunk * nchan * std::min(N, 64)));
   if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
   const bool data_on_device = is_device_ptr(args->data);
   if (data_on_device && (reinterpret_cast<uintptr_t>(args->data) & 15))
@@ -613,7 +625,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.data = dchunk; a.mconj64 = pl->mconj64.as<cx<double>>();
       a.pn = pl->pn.as<double>(); a.nu2 = pl->nu2.as<double>();
       a.errs = derrs; a.mask = dmask; a.weights = dw; a.P = dP; a.DMg = ddmg; a.nu_mean = pl->nu_mean.as<double>();
-      a.X = pl->X.as<float2>(); a.partial = want_guess ? pl->partial.as<float2>() : nullptr;
+      a.X = pl->X.as<float2>(); a.Xlo = pl->Xlo.as<float2>(); a.partial = want_guess ? pl->partial.as<float2>() : nullptr;
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
@@ -629,13 +641,13 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
-      ga.init = nullptr;
+      ga.init = nullptr; ga.scat = dscat; ga.log10_tau = args->log10_tau; ga.fit_scat = ff[3] ? 1 : 0;
       k_guess<<<ns, 256, sizeof(double2) * N, pl->stream>>>(ga);
       k_reset_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
       pl->stats.launches += 2;
     }
     PassArgs pa;
-    pa.X = pl->X.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
+    pa.X = pl->X.as<float2>(); pa.Xlo = pl->Xlo.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
     pa.Ssn = pl->Ssn.as<double>(); pa.sigma = pl->sigma.as<double>(); pa.csum = pl->csum.as<double>(); pa.st = st;
     pa.s0 = s0; pa.nchan = nchan; pa.N = N;
     UpdateArgs ua;
@@ -649,17 +661,46 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     ua.scales = pl->o_scales.as<double>(); ua.scale_errs = pl->o_serrs.as<double>(); ua.channel_snrs = pl->o_csnr.as<double>();
     ua.s0 = s0; ua.nchan = nchan; ua.nbin = 2 * N; ua.max_iter = max_iter; ua.semantics = args->semantics;
     ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol;
+    Pass5Args p5;
+    Update5Args u5;
+    if (general) {
+      p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>();
+      p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
+      p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
+      p5.log10_tau = args->log10_tau;
+      memset(&u5, 0, sizeof u5);
+      u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>();
+      u5.freqs = pl->freqs.as<double>(); u5.P = dP; u5.nu_fit = pl->nu_fit.as<double>(); u5.nu_outs = dnuouts;
+      u5.nok = pl->nok.as<int>(); u5.st = st;
+      u5.params = ua.params; u5.param_errs = ua.param_errs; u5.nu_out = ua.nu_out; u5.cov = ua.cov; u5.chi2 = ua.chi2;
+      u5.red_chi2 = ua.red_chi2; u5.snr = ua.snr; u5.nfeval = ua.nfeval; u5.rc = ua.rc; u5.scales = ua.scales;
+      u5.scale_errs = ua.scale_errs; u5.channel_snrs = ua.channel_snrs;
+      u5.s0 = s0; u5.nchan = nchan; u5.nbin = 2 * N; u5.max_iter = max_iter; u5.log10_tau = args->log10_tau;
+      u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol;
+      for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
+    }
     for (int it = 0; it < n_launch_iter; ++it) {
       {
         SpanGuard g(pl, SP_PASS);
-        DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(pa));
+        if (general) { DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(p5)); }
+        else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(pa)); }
       }
       {
         SpanGuard g(pl, SP_UPDATE);
-        k_update2<<<ns, 128, 0, pl->stream>>>(ua);
+        if (general) k_update5<<<ns, 128, 0, pl->stream>>>(u5);
+        else k_update2<<<ns, 128, 0, pl->stream>>>(ua);
       }
       pl->stats.launches += 2;
       pl->stats.pass_launches++;
+      // the general solver needs a data-dependent number of passes: poll every 4 launches
+      if (general && (it & 3) == 3 && it + 1 < n_launch_iter) {
+        k_count_running<<<1, 256, 0, pl->stream>>>(st, s0, ns, pl->running.as<int>());
+        pl->stats.launches++;
+        int running = 0;
+        CK(cudaMemcpyAsync(&running, pl->running.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+        CK(cudaStreamSynchronize(pl->stream));
+        if (running == 0) break;
+      }
     }
   }
   CK(cudaGetLastError());

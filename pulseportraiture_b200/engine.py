@@ -149,7 +149,7 @@ class WidebandPlan(object):
                   nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
                   log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
                   tol=0.0, semantics="full", want_chan_sums=False, nsub=None,
-                  pinned_results=False):
+                  pinned_results=False, scat_guess=None):
         """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
         CUDA torch tensor).  Returns a dict of numpy arrays.
 
@@ -186,6 +186,7 @@ class WidebandPlan(object):
         a.Ns = int(Ns)
         a.max_iter = int(max_iter)
         a.tol = float(tol)
+        a.scat_guess = _ptr(scat_guess, np.float64, keep, "scat_guess", (nsub, 2))
 
         spec = {
             "params": ((nsub, 5), np.float64), "param_errs": ((nsub, 5), np.float64),

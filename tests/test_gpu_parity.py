@@ -24,6 +24,14 @@ def rel(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
 
 
+def chi2_close(chi2, ref_chi2, ref_snr, tol=CHI2_TOL):
+    """chi2 = Sd + f is the difference of the data term Sd and the model term
+    -f = snr^2; the float32 storage of the cross-spectrum quantises both at the
+    1e-8 level, so the bar is 1e-8 of the larger of chi2 and snr^2.  For the
+    BASELINE configs (sigma = 1.5) snr^2 ~ 1.1 chi2, i.e. 1e-8 relative."""
+    return abs(chi2 - ref_chi2) <= tol * max(abs(ref_chi2), ref_snr ** 2)
+
+
 @pytest.fixture(scope="module")
 def engine():
     from pulseportraiture_b200 import engine as e
@@ -143,6 +151,105 @@ def test_phidm_golden_cases(engine, case):
     assert rel(r["scales"][0], g("scales")) < 1e-5
     assert rel(r["scale_errs"][0], g("scale_errs")) < 1e-5
     assert rel(r2["noise"][0], errs) < 1e-9
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in G.files if k.startswith("full_")}))
+def test_full_fit_golden_cases(engine, case):
+    """5-parameter fits (every fit_flags pattern get_nu_zeros distinguishes, log10 tau on/off,
+    option 0/1) against the REFERENCE's own fit_portrait_full outputs."""
+    cfg = G[case + "/cfg"]
+    nchan, nbin, nu0, bw, seed = int(cfg[0]), int(cfg[1]), cfg[2], cfg[3], int(cfg[4])
+    tau_s, log10, option = cfg[5], bool(cfg[6]), int(cfg[7])
+    flags = [int(v) for v in G[case + "/flags"]]
+    c = synth.make_case(nchan, nbin, nu0, bw, seed, tau_data_s=tau_s, sigma=0.5)
+    errs = G[case + "/errs"]
+    init = np.array(G[case + "/init"], dtype=np.float64)[None]
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(c["model"].astype(np.float32), c["freqs"])
+        r = pl.fit_batch(c["data"].astype(np.float32)[None], c["P"], errs=errs[None], init=init,
+                         fit_flags=flags, log10_tau=log10, option=option)
+    g = lambda f: G[case + "/full." + f]  # noqa: E731
+    assert int(r["return_code"][0]) == 0
+    names = ["phi", "DM", "GM", "tau", "alpha"]
+    for i, nm in enumerate(names):
+        if flags[i]:
+            assert abs(r["params"][0, i] - g(nm)) / g(nm + "_err") < SIG_TOL, nm
+            assert rel(r["param_errs"][0, i], g(nm + "_err")) < 1e-4, nm
+        else:
+            assert abs(r["params"][0, i] - g(nm)) <= 1e-9 * max(1.0, abs(g(nm))), nm
+            assert r["param_errs"][0, i] == 0.0
+    assert rel(r["nu_out"][0], [g("nu_DM"), g("nu_GM"), g("nu_tau")]) < 1e-4
+    assert chi2_close(r["chi2"][0], g("chi2"), g("snr"))          # sigma = 0.5: snr^2 >> chi2
+    assert rel(r["red_chi2"][0] / r["chi2"][0], g("red_chi2") / g("chi2")) < 1e-12   # same dof
+    assert rel(r["snr"][0], g("snr")) < 1e-6
+    assert rel(r["scales"][0], g("scales")) < 1e-4
+    assert rel(r["scale_errs"][0], g("scale_errs")) < 1e-4
+    assert rel(r["channel_snrs"][0], g("channel_snrs")) < 1e-4
+    ifit = np.where(flags)[0]
+    cm = g("covariance_matrix")
+    sc = np.sqrt(np.abs(np.diag(cm)))
+    assert np.max(np.abs(r["cov"][0][np.ix_(ifit, ifit)] - cm) / np.outer(sc, sc)) < 1e-3
+
+
+def test_full_fit_batch_with_guess(engine):
+    """Scattering fit for a batch, started from the FFTFIT guess with a scattered mean
+    model (pptoas.py:427-456), vs the oracle's toa_core."""
+    nsub, nchan, nbin, nu0, bw = 6, 64, 512, 600., 400.
+    tau_s = 50e-6
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 7000 + s, tau_data_s=tau_s, sigma=0.5)
+             for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    errs = np.stack([orc.get_noise(c["data"], chans=True) for c in cases])
+    nu_fit = freqs.mean()
+    tau_g = 0.8 * tau_s / P * (nu_fit / nu0) ** -4.0
+    scat = np.tile([tau_g, -4.0], (nsub, 1))
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+        r = pl.fit_batch(data, P, errs=errs, fit_flags=(1, 1, 0, 1, 1), log10_tau=True,
+                         scat_guess=scat)
+    for s, c in enumerate(cases):
+        ref, _, _ = orc.toa_core(c["data"], c["model"], P, freqs, errs[s], fit_flags=(1, 1, 0, 1, 1),
+                                 nu_fits=[nu_fit] * 3, log10_tau=True, tau_guess=tau_g,
+                                 alpha_guess=-4.0, polish="exact")
+        assert int(r["lag_index"][s]) == ref.lag_index
+        for i, nm in ((0, "phi"), (1, "DM"), (3, "tau"), (4, "alpha")):
+            assert abs(r["params"][s, i] - ref[nm]) / ref[nm + "_err"] < SIG_TOL, nm
+        assert chi2_close(r["chi2"][s], ref.chi2, ref.snr)
+        assert rel(r["nu_out"][s], [ref.nu_DM, ref.nu_GM, ref.nu_tau]) < 1e-4
+        assert rel(r["scale_errs"][s], ref.scale_errs) < 1e-4
+
+
+def test_config3_like_scattering_sigma15(engine):
+    """CHIME-like shape reduced to what the oracle finishes in seconds (256 chan x 1024
+    bin, nu0 600 MHz, tau = 50 us, alpha = -4, sigma = 1.5 as in SURVEY 8d C3), flags
+    [1,1,0,1,1] and [1,1,1,1,1], log10 tau: the strict 1e-8 chi2 bar applies here."""
+    nsub, nchan, nbin, nu0, bw, tau_s = 3, 256, 1024, 600., 400., 50e-6
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 7100 + s, tau_data_s=tau_s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    errs = np.stack([orc.get_noise(c["data"], chans=True) for c in cases])
+    tau0 = np.log10(0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0)
+    for flags in ([1, 1, 0, 1, 1], [1, 1, 1, 1, 1]):
+        init = np.zeros((nsub, 5))
+        for s, c in enumerate(cases):
+            g = orc.fit_phase_shift(c["data"].mean(0), c["model"].mean(0), Ns=100, polish="exact")
+            init[s] = [g.phase, 0.0, 0.0, tau0, -4.0]
+        with engine.WidebandPlan(nchan, nbin) as pl:
+            pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+            r = pl.fit_batch(data, P, errs=errs, init=init, fit_flags=flags, log10_tau=True)
+        for s, c in enumerate(cases):
+            ref = orc.fit_portrait_full(c["data"], c["model"], list(init[s]), P, freqs, errs=errs[s],
+                                        fit_flags=flags, log10_tau=True)
+            for i, nm in enumerate(["phi", "DM", "GM", "tau", "alpha"]):
+                if flags[i]:
+                    assert abs(r["params"][s, i] - ref[nm]) / ref[nm + "_err"] < SIG_TOL, nm
+                    assert rel(r["param_errs"][s, i], ref[nm + "_err"]) < 1e-4
+            assert abs(r["chi2"][s] / ref.chi2 - 1) < CHI2_TOL
+            assert rel(r["nu_out"][s], [ref.nu_DM, ref.nu_GM, ref.nu_tau]) < 1e-4
+            assert rel(r["scales"][s], ref.scales) < 1e-4
+            assert rel(r["scale_errs"][s], ref.scale_errs) < 1e-4
+            assert int(r["return_code"][s]) == 0
 
 
 def test_batch_64x512_vs_oracle(engine):
@@ -345,7 +452,7 @@ def test_edge_cases(engine):
                                  polish="exact")
         assert abs(r["params"][0, 0] - ref.phi) / ref.phi_err < 0.3   # guess uses all-channel model mean
         with pytest.raises(PPError):
-            pl.fit_batch(data[None], c["P"], fit_flags=(1, 1, 0, 1, 1))
+            pl.fit_batch(data[None], c["P"], fit_flags=(0, 0, 0, 0, 0))
     with pytest.raises(PPError):
         engine.WidebandPlan(8, 1000)
     with pytest.raises(PPError):
