@@ -16,10 +16,12 @@
 
 namespace ppb {
 
-// 16-byte elements: pad one element every 8 so that a stride-8 (radix-8 output)
-// access pattern is conflict free.
-__device__ __forceinline__ int phys(int i) { return i + (i >> 3); }
-template <int N> struct Padded { static constexpr int value = N + (N >> 3); };
+// 16-byte elements, 8 per 128-byte bank row: XOR-swizzle the position inside a
+// group of 8 with the group index, so that a stride-8 (radix-8 output) pattern
+// hits 8 different bank groups while contiguous runs stay inside whole rows
+// (no padding gaps: a warp reading 32 consecutive elements costs 4 wavefronts).
+__device__ __forceinline__ int phys(int i) { return i ^ ((i >> 3) & 7); }
+template <int N> struct Padded { static constexpr int value = N; };
 
 __device__ __forceinline__ void bar_slot(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -28,6 +28,9 @@ namespace ppb {
 
 constexpr double kDconst = 1.0 / 0.000241;  // pplib.py:48-51
 constexpr double kTwoPi = 6.283185307179586476925286766559;
+#ifndef PP_SPECTRA_MINB
+#define PP_SPECTRA_MINB 2
+#endif
 constexpr int kNCsum = 9;                   // per-channel sums kept per subint
 // The first kLoK slots of every X row also keep the float32 rounding residual
 // ("lo" part): the low harmonics carry almost all of |X|^2, so their float
@@ -259,7 +262,7 @@ struct SpectraArgs {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256, (N >= 2048 ? 1 : 2)) k_spectra(SpectraArgs a) {
+__global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spectra(SpectraArgs a) {
   using S8 = Slot8<N>;
   using L = TwLayout<N>;
   using F = double;
