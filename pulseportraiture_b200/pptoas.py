@@ -80,6 +80,8 @@ def save_databunch(path, data):
     out = {}
     for k in _DB_FIELDS:
         v = data[k]
+        if v is None:
+            continue
         if k == "epochs":
             out["epochs_day"] = np.array([e.intday() for e in v])
             out["epochs_frac"] = np.array([e.fracday() for e in v])
@@ -105,9 +107,11 @@ def load_data(filename, **kwargs):
     m = d.pop("ok_mask")
     d["ok_ichans"] = [np.where(row)[0] for row in m]
     d["arch"] = None
+    for k in _DB_FIELDS:
+        d.setdefault(k, None)
     d["filename"] = str(filename)
     for k in ("backend", "frontend", "source", "state", "telescope", "telescope_code"):
-        d[k] = str(d[k])
+        d[k] = None if d[k] is None else str(d[k])
     return DataBunch(**d)
 
 
@@ -148,13 +152,21 @@ class GetTOAs:
         self.instrumental_response_dict = self.ird = {'DM': 0.0, 'wids': [], 'irf_types': []}
         self.quiet = quiet
 
-    def _model_for(self, phases, freqs_row, P):
+    def _model_for(self, phases, freqs_row, P, fit_scat=False):
         if isinstance(self.modelfile, np.ndarray):
             self.model_name, self.ngauss = "array", 0
             return self.modelfile
-        self.model_name, self.ngauss, model = read_model(self.modelfile, phases, freqs_row, P,
-                                                         quiet=True)
-        return model
+        if not fit_scat:
+            self.model_name, self.ngauss, model = read_model(self.modelfile, phases, freqs_row, P,
+                                                             quiet=True)
+            return model
+        # scattering is fit: use the unscattered portrait (pptoas.py:364-375)
+        (self.model_name, self.model_code, self.model_nu_ref, self.ngauss, self.gparams,
+         model_fit_flags, self.alpha, model_fit_alpha) = read_model(self.modelfile, quiet=True)
+        unscat_params = np.copy(self.gparams)
+        unscat_params[1] = 0.0
+        return gen_gaussian_portrait(self.model_code, unscat_params, 0.0, phases, freqs_row,
+                                     self.model_nu_ref)
 
     def get_TOAs(self, datafile=None, tscrunch=False, nu_refs=None, DM0=None,
                  bary=True, fit_DM=True, fit_GM=False, fit_scat=False,
@@ -209,7 +221,7 @@ class GetTOAs:
             MJDs = np.array([e.in_days() for e in d.epochs], dtype=np.double)
             if np.any(freqs != freqs[0]):
                 raise NotImplementedError("per-subint frequency tables")
-            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]])
+            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]], fit_scat)
 
             mask = np.zeros((nsub, nchan), dtype=np.uint8)
             for isub in ok_isubs:
@@ -219,7 +231,15 @@ class GetTOAs:
             errs = np.ascontiguousarray(np.asarray(d.noise_stds)[:, 0], dtype=np.float64)
             snrs = np.ascontiguousarray(np.asarray(d.SNRs)[:, 0], dtype=np.float64)
             weights = np.ascontiguousarray(d.weights, dtype=np.float64)
-            if nu_fit_tuple is None:
+            if nu_fit_tuple is None and fit_scat:
+                # the scattering start value needs nu_fit_tau on the host (pptoas.py:402, 431-441)
+                nu_fits_in = np.zeros((nsub, 3))
+                for isub in ok_isubs:
+                    okc = np.asarray(d.ok_ichans[isub], dtype=int)
+                    nu_fits_in[isub, :] = pplib.guess_fit_freq(freqs[isub, okc], snrs[isub, okc])
+                nu_fits_in[nu_fits_in[:, 0] == 0] = freqs[0].mean()
+                mode = 0
+            elif nu_fit_tuple is None:
                 nu_fits_in, mode = None, 1                 # guess_fit_freq, pptoas.py:402
             else:
                 nu_fits_in = np.tile([nu_fit_tuple[0], nu_fit_tuple[0], nu_fit_tuple[-1]],
@@ -234,6 +254,22 @@ class GetTOAs:
                     nu_outs_in[:, 2] = nu_ref_tuple[-1]
                     if bary:
                         nu_outs_in[:, 2] /= np.asarray(d.doppler_factors)
+            scat_in = None
+            if fit_scat:                                    # pptoas.py:427-441
+                scat_in = np.zeros((nsub, 2))
+                for isub in ok_isubs:
+                    if self.scat_guess is not None:
+                        tau_guess_s, tau_guess_ref, alpha_guess = self.scat_guess
+                        tau_guess = (tau_guess_s / Ps[isub]) * \
+                            (nu_fits_in[isub, 2] / tau_guess_ref) ** alpha_guess
+                    else:
+                        alpha_guess = getattr(self, "alpha", scattering_alpha)
+                        if hasattr(self, "gparams"):
+                            tau_guess = (self.gparams[1] / Ps[isub]) * \
+                                (nu_fits_in[isub, 2] / self.model_nu_ref) ** alpha_guess
+                        else:
+                            tau_guess = 0.0
+                    scat_in[isub] = [tau_guess, alpha_guess]
             pl = get_plan(nchan, nbin)
             pl.set_model(_f32(model), freqs[0])
 
@@ -258,7 +294,8 @@ class GetTOAs:
                     snrs=snrs[idx], nu_fits=None if nu_fits_in is None else nu_fits_in[idx],
                     nu_fit_mode=mode, nu_outs=None if nu_outs_in is None else nu_outs_in[idx],
                     fit_flags=flags, log10_tau=self.log10_tau, option=0, is_toa=True,
-                    Ns=100, semantics="full")
+                    Ns=100, semantics="full",
+                    scat_guess=None if scat_in is None else scat_in[idx])
                 for j, isub in enumerate(idx):
                     res[isub] = (flags, {k: v[j] for k, v in r.items()})
             fit_duration = time.time() - fit_start
@@ -330,6 +367,19 @@ class GetTOAs:
                 DM_out, DM_err_out = (DM, DM_err) if flags[1] else (None, None)
                 if flags[2]:
                     toa_flags['gm'], toa_flags['gm_err'] = GM, GM_err
+                if flags[3]:                                # pptoas.py:611-624
+                    tau_r, tau_e = r["params"][3], r["param_errs"][3]
+                    if self.log10_tau:
+                        toa_flags['scat_time'] = 10 ** tau_r * P / df * 1e6
+                        toa_flags['log10_scat_time'] = tau_r + np.log10(P / df)
+                        toa_flags['log10_scat_time_err'] = tau_e
+                    else:
+                        toa_flags['scat_time'] = tau_r * P / df * 1e6
+                        toa_flags['scat_time_err'] = tau_e * P / df * 1e6
+                    toa_flags['scat_ref_freq'] = r["nu_out"][2] * df
+                    toa_flags['scat_ind'] = r["params"][4]
+                if flags[4]:
+                    toa_flags['scat_ind_err'] = r["param_errs"][4]
                 toa_flags['be'] = d.backend
                 toa_flags['fe'] = d.frontend
                 toa_flags['f'] = d.frontend + "_" + d.backend

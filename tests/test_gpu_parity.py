@@ -457,3 +457,97 @@ def test_edge_cases(engine):
         engine.WidebandPlan(8, 1000)
     with pytest.raises(PPError):
         engine.WidebandPlan(8, 8192)
+
+
+def _fake_archive(nsub, nchan, nbin, seed0, DM_stored=0.0, tau_s=0.0, nu0=1500., bw=800., sigma=1.5):
+    """The load_data field contract (pplib.py:2803-2813) filled with synthetic subints."""
+    from pulseportraiture_b200.pptoas import MJD
+    from pulseportraiture_b200.pplib import DataBunch
+    rng = np.random.RandomState(seed0)
+    cases = [synth.make_case(nchan, nbin, nu0, bw, seed0 + s, dDM=DM_stored + rng.normal(3e-4, 2e-4),
+                             tau_data_s=tau_s, sigma=sigma) for s in range(nsub)]
+    freqs = np.tile(cases[0]["freqs"], (nsub, 1))
+    subints = np.stack([c["data"] for c in cases])[:, None]
+    noise = np.stack([orc.get_noise(c["data"], chans=True) for c in cases])[:, None]
+    ok_ichans = []
+    for s in range(nsub):
+        ok = np.ones(nchan, bool)
+        ok[rng.choice(nchan, size=3, replace=False)] = False
+        ok_ichans.append(np.where(ok)[0])
+    return DataBunch(
+        arch=None, backend="GUPPI", backend_delay=2.0e-6, bw=bw, doppler_factors=1.0 + 1e-4 * rng.randn(nsub),
+        DM=DM_stored, dmc=0, epochs=[MJD(56000 + s, 0.25 + 0.01 * s) for s in range(nsub)],
+        filename="fake_%d.npz" % seed0, flux_prof=None, freqs=freqs, frontend="Rcvr_800",
+        integration_length=nsub * 60.0, masks=None, nbin=nbin, nchan=nchan, noise_stds=noise, npol=1,
+        nsub=nsub, nu0=nu0, ok_ichans=ok_ichans, ok_isubs=np.arange(nsub), parallactic_angles=np.zeros(nsub),
+        phases=orc.get_bin_centers(nbin), prof=None, prof_noise=None, prof_SNR=None,
+        Ps=np.full(nsub, cases[0]["P"]), SNRs=np.tile(np.linspace(5., 20., nchan), (nsub, 1))[:, None],
+        source="J1234-5678", state="Intensity", subints=subints, subtimes=np.full(nsub, 60.0),
+        telescope="GBT", telescope_code="1", weights=np.ones((nsub, nchan))), cases
+
+
+def test_gettoas_facade_matches_reference_flow(tmp_path):
+    """pptoas.GetTOAs.get_TOAs with the reference's arguments on a synthetic archive (also through
+    the .npz provider): every subint vs the oracle's restatement of pptoas.py:384-486, plus the TOA
+    arithmetic (528-531), Doppler correction (539-549) and the per-archive DeltaDM mean (665-682)."""
+    from pulseportraiture_b200 import pptoas
+    data, cases = _fake_archive(5, 32, 512, 8000, DM_stored=2.5e-3)
+    path = str(tmp_path / "fake.npz")
+    pptoas.save_databunch(path, data)
+    for datafiles in (data, path):
+        gt = pptoas.GetTOAs([datafiles] if isinstance(datafiles, dict) else datafiles, synth.GMODEL, quiet=True)
+        gt.get_TOAs(DM0=2.5e-3, print_phase=True)
+        assert len(gt.TOA_list) == 5
+        DMs_ref, DMerrs_ref = [], []
+        for s, c in enumerate(cases):
+            ok = data.ok_ichans[s]
+            ref, _, _ = orc.toa_core(c["data"][ok], c["model"][ok], c["P"], c["freqs"][ok],
+                                     data.noise_stds[s, 0, ok], weights=data.weights[s, ok],
+                                     SNRs=data.SNRs[s, 0, ok], DM_stored=2.5e-3, polish="exact")
+            df = data.doppler_factors[s]
+            assert abs(gt.phis[0][s] - ref.phi) / ref.phi_err < SIG_TOL
+            assert abs(gt.DMs[0][s] - ref.DM * df) / ref.DM_err < SIG_TOL
+            assert rel(gt.DM_errs[0][s], ref.DM_err) < 1e-4
+            assert rel(gt.red_chi2s[0][s], ref.red_chi2) < CHI2_TOL
+            assert rel(gt.nu_refs[0][s][0], ref.nu_DM) < 1e-4
+            assert rel(gt.scales[0][s][ok], ref.scales) < 1e-4
+            toa = gt.TOA_list[s]
+            t_ref = data.epochs[s].in_days() + (ref.phi * c["P"] + data.backend_delay) / 86400.0
+            assert abs(toa.MJD.in_days() - t_ref) < 1e-9
+            assert abs(toa.TOA_error - ref.phi_err * c["P"] * 1e6) < 1e-4 * toa.TOA_error
+            assert toa.flags["nchx"] == len(ok) and toa.flags["be"] == "GUPPI"
+            assert abs(toa.flags["phs"] - ref.phi) / ref.phi_err < SIG_TOL
+            DMs_ref.append(ref.DM * df); DMerrs_ref.append(ref.DM_err)
+        DMs_ref, DMerrs_ref = np.array(DMs_ref), np.array(DMerrs_ref)
+        w = DMerrs_ref ** -2
+        mean = np.average(DMs_ref - 2.5e-3, weights=w)
+        var = (1.0 / w.sum()) * np.sum((DMs_ref - 2.5e-3 - mean) ** 2 * w) / 4
+        assert abs(gt.DeltaDM_means[0] - mean) < 1e-3 * var ** 0.5
+        assert rel(gt.DeltaDM_errs[0], var ** 0.5) < 1e-3
+
+
+def test_gettoas_scattering_fit():
+    """fit_scat=True through the facade: scat_guess handling (pptoas.py:427-452), unscattered model,
+    log10 tau, TOA flags."""
+    from pulseportraiture_b200 import pptoas
+    tau_s = 50e-6
+    data, cases = _fake_archive(3, 64, 512, 8100, tau_s=tau_s, nu0=600., bw=400., sigma=0.5)
+    for s in range(3):
+        data.ok_ichans[s] = np.arange(64)
+    gt = pptoas.GetTOAs([data], synth.GMODEL, quiet=True)
+    gt.get_TOAs(fit_scat=True, log10_tau=True, scat_guess=(0.8 * tau_s, 600., -4.0), bary=False)
+    for s, c in enumerate(cases):
+        nu_fit = orc.guess_fit_freq(c["freqs"], data.SNRs[s, 0])
+        tau_g = (0.8 * tau_s / c["P"]) * (nu_fit / 600.) ** -4.0
+        ref, _, _ = orc.toa_core(c["data"], c["model"], c["P"], c["freqs"], data.noise_stds[s, 0],
+                                 SNRs=data.SNRs[s, 0], fit_flags=(1, 1, 0, 1, 1), log10_tau=True,
+                                 tau_guess=tau_g, alpha_guess=-4.0, polish="exact")
+        assert abs(gt.phis[0][s] - ref.phi) / ref.phi_err < SIG_TOL
+        assert abs(gt.taus[0][s] - ref.tau) / ref.tau_err < SIG_TOL
+        assert abs(gt.alphas[0][s] - ref.alpha) / ref.alpha_err < SIG_TOL
+        fl = gt.TOA_list[s].flags
+        assert abs(fl["scat_time"] - 10 ** ref.tau * c["P"] * 1e6) < 1e-3 * fl["scat_time"]
+        assert abs(fl["scat_ref_freq"] - ref.nu_tau) < 1e-3
+        # the injected scattering time is recovered (50 us at 600 MHz)
+        tau_600 = 10 ** ref.tau * (600. / ref.nu_tau) ** ref.alpha * c["P"]
+        assert abs(tau_600 - tau_s) < 6 * ref.tau_err * np.log(10) * tau_s + 0.3 * tau_s
