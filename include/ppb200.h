@@ -158,6 +158,23 @@ int pp_rotate_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
                     const double* phase, const double* DM, const double* P,
                     const double* nu_ref);
 
+/* Same with the nu^-4 ("GM") delay term: replaces pptoaslib.rotate_portrait_full
+ * (pptoaslib.py:52-81).  GM / nu_GM may be NULL (= pp_rotate_batch). */
+int pp_rotate_full_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
+                         const double* phase, const double* DM, const double* GM,
+                         const double* P, const double* nu_DM, const double* nu_GM);
+
+/* ---- align-and-accumulate (ppalign inner loop) ---------------------------------
+ * Replaces the per-subint accumulation of ppalign.align_archives
+ * (ppalign.py:202-208): aligned[n] = sum_s weights[s,n] * rotate_data(data[s,n],
+ * phase_s, DM_s, P_s, freqs, nu_ref_s), accumulated in the Fourier domain in
+ * double; rows with weight <= 0 are skipped.  aligned: [nchan,nbin] float64
+ * (not normalised), wsum: [nchan] float64. */
+int pp_align_accumulate(pp_plan_t* plan, const float* data, int32_t nsub,
+                        const double* phase, const double* DM, const double* P,
+                        const double* nu_ref, const double* weights,
+                        double* aligned, double* wsum);
+
 /* ---- per-channel noise -----------------------------------------------------
  * Replaces pplib.get_noise(data, chans=True) (pplib.py:2227-2245). */
 int pp_get_noise_batch(pp_plan_t* plan, const float* data, int32_t nsub,

@@ -242,6 +242,7 @@ __global__ void k_prep(PrepArgs a) {
 struct SpectraArgs {
   const float* data;         // [nsub,nchan,2N], global subint index
   const cx<double>* mconj64; // [nchan,N]
+  const cx<float>* mconj32;  // [nchan,N]
   const double* pn;          // [nchan]
   const double* nu2;         // [nchan] nu^-2
   const double* errs;        // [nsub,nchan] or null
@@ -327,17 +328,34 @@ __global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spec
     const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
     // FFT pass so that their latency hides behind its butterflies
+    // Slots >= LoK carry no lo part: float product and float conj(model) suffice there (kMix:
+    // for N >= 512 the lo slots are only this thread's first harmonic of pair 0 and slot 0).
+    constexpr bool kMix = (T >= 64);
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
-    cx<F> mcv[NACC];
+    const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
+    cx<F> mc64[kMix ? 2 : NACC];
+    cx<float> mc32[kMix ? NACC : 1];
     auto load_mc = [&]() {
       if (used && a.X != nullptr) {
+        if constexpr (kMix) {
+          mc64[0] = mc[t + 1];
+          mc64[1] = mc[0];
 #pragma unroll
-        for (int i = 0; i < NPAIR; ++i) {
-          const int p = t + 1 + i * T;
-          mcv[2 * i] = mc[p];
-          mcv[2 * i + 1] = (p < N / 2) ? mc[N - p] : mk<F>(0.0, 0.0);
+          for (int i = 0; i < NPAIR; ++i) {
+            const int p = t + 1 + i * T;
+            mc32[2 * i] = mcf[p];
+            mc32[2 * i + 1] = mcf[(p < N / 2) ? N - p : p];
+          }
+          mc32[2 * NPAIR] = mcf[0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NPAIR; ++i) {
+            const int p = t + 1 + i * T;
+            mc64[2 * i] = mc[p];
+            mc64[2 * i + 1] = (p < N / 2) ? mc[N - p] : mk<F>(0.0, 0.0);
+          }
+          mc64[2 * NPAIR] = mc[0];
         }
-        mcv[2 * NPAIR] = mc[0];
       }
     };
     fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); }, load_mc);
@@ -347,23 +365,34 @@ __global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spec
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
     double s_all = 0.0, s_top = 0.0;
-    auto emit = [&](int k, cx<F> d, cx<F> mval, float2& ac) {
+    auto emit = [&](int k, cx<F> d, int idx, float2& ac) {
       const double pw = d.x * d.x + d.y * d.y;
       s_all += pw;
       if (k >= kc) s_top += pw;
       const int sl_k = (k == N) ? 0 : k;
+      const float dfx = (float)d.x, dfy = (float)d.y;
       if (a.X != nullptr && inrange) {
-        float2 xv = make_float2(0.f, 0.f), xl = make_float2(0.f, 0.f);
-        if (used) {
-          const cx<F> pr = cmul(d, mval);
-          xv = make_float2((float)pr.x, (float)pr.y);
-          xl = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
+        float2 xv = make_float2(0.f, 0.f);
+        if (kMix && sl_k >= LoK<N>::value) {
+          if (used) {
+            const cx<float> m = mc32[kMix ? idx : 0];
+            xv = make_float2(fmaf(dfx, m.x, -dfy * m.y), fmaf(dfx, m.y, dfy * m.x));
+          }
+          a.X[xo + sl_k] = xv;
+        } else {
+          float2 xl = make_float2(0.f, 0.f);
+          if (used) {
+            const cx<F> mval = kMix ? mc64[idx == 0 ? 0 : 1] : mc64[kMix ? 0 : idx];
+            const cx<F> pr = cmul(d, mval);
+            xv = make_float2((float)pr.x, (float)pr.y);
+            xl = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
+          }
+          a.X[xo + sl_k] = xv;
+          if (sl_k < LoK<N>::value) a.Xlo[((size_t)sl * a.nchan + ch) * LoK<N>::value + sl_k] = xl;
         }
-        a.X[xo + sl_k] = xv;
-        if (sl_k < LoK<N>::value) a.Xlo[((size_t)sl * a.nchan + ch) * LoK<N>::value + sl_k] = xl;
       }
       if (wgt != 0.f) {
-        float vx = (float)d.x, vy = (float)d.y;
+        float vx = dfx, vy = dfy;
         if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
           double c, sn;
           cis2pi((double)k * shift, c, sn);
@@ -380,13 +409,13 @@ __global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spec
       const int p = t + 1 + i * T;
       cx<F> dp, dq;
       split_pair8<N, F>(buf, tw, p, dp, dq);
-      emit(p, dp, mcv[2 * i], acc[2 * i]);
-      if (p < N / 2) emit(N - p, dq, mcv[2 * i + 1], acc[2 * i + 1]);
+      emit(p, dp, 2 * i, acc[2 * i]);
+      if (p < N / 2) emit(N - p, dq, 2 * i + 1, acc[2 * i + 1]);
     }
     if (t == 0) {
       F dc, ny;
       split_dc8<N, F>(buf, dc, ny);
-      emit(N, mk<F>(ny, 0.0), mcv[2 * NPAIR], acc[2 * NPAIR]);
+      emit(N, mk<F>(ny, 0.0), 2 * NPAIR, acc[2 * NPAIR]);
     }
     // ---- row-slot reduction of the two power sums ---------------------------------
     if constexpr (T >= 32) {
@@ -1699,11 +1728,32 @@ struct RotateArgs {
   const double* DM;     // [nsub]
   const double* P;      // [nsub]
   const double* nu_ref; // [nsub]
+  const double* GM;     // [nsub] or null (pptoaslib.rotate_portrait_full, pptoaslib.py:52-81)
+  const double* nu_GM;  // [nsub] or null
   const double* nu2;    // [nchan]
   const void* twN;
   const void* tw2N;
   int nsub, nchan;
 };
+
+// theta_n = phase + Dconst DM (nu^-2 - nu_ref^-2)/P + Dconst^2 GM (nu^-4 - nu_GM^-4)/P
+__device__ __forceinline__ double rot_theta(const RotateArgs& a, int s, int ch) {
+  double theta = a.phase[s];
+  const double dm = a.DM[s];
+  const double n2 = a.nu2[ch];
+  if (dm != 0.0) {
+    const double nr = a.nu_ref[s];
+    theta += kDconst * dm / a.P[s] * (n2 - 1.0 / (nr * nr));   // pplib.py:2381-2411
+  }
+  if (a.GM) {
+    const double gm = a.GM[s];
+    if (gm != 0.0) {
+      const double ng = a.nu_GM[s];
+      theta += kDconst * kDconst * gm / a.P[s] * (n2 * n2 - 1.0 / (ng * ng * ng * ng));   // pptoaslib.py:207
+    }
+  }
+  return theta - rint(theta);
+}
 
 template <int N, typename T>
 __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
@@ -1737,14 +1787,7 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
   __syncthreads();
   cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
   cx<T>* other = (Z == bufA) ? bufB : bufA;
-  // theta_n = phase + Dconst*DM/P*(nu_n^-2 - nu_ref^-2)  (pplib.py:2381-2411)
-  double theta = a.phase[s];
-  const double dm = a.DM[s];
-  if (dm != 0.0) {
-    const double nr = a.nu_ref[s];
-    theta += kDconst * dm / a.P[s] * (a.nu2[ch] - 1.0 / (nr * nr));
-  }
-  theta -= rint(theta);
+  const double theta = rot_theta(a, s, ch);
 #pragma unroll
   for (int i = 0; i < G::kPairs; ++i) {
     const int p = t_row + 1 + i * G::kTRow;
@@ -1784,6 +1827,111 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
       const cx<T> y0 = Y[2 * i4], y1 = Y[2 * i4 + 1];
       dst[i4] = make_float4((float)(y0.x * sc), (float)(-y0.y * sc), (float)(y1.x * sc), (float)(-y1.y * sc));
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_align_accum: K5, the inner loop of ppalign.align_archives (ppalign.py:160-213):
+// aligned[n] = sum_s w_sn * rotate(data_sn, phi_s, DM_s), accumulated in the
+// Fourier domain in double and inverse transformed once per channel.  One row
+// slot per channel, looping over the subints.
+// ----------------------------------------------------------------------------
+struct AlignArgs {
+  RotateArgs r;            // in = data [nsub,nchan,2N]; out unused
+  const double* weights;   // [nsub,nchan] (scales / sigma^2, ppalign.py:202); <= 0 skips the row
+  double* aligned;         // [nchan,2N] sum (not normalised)
+  double* wsum;            // [nchan] sum of the weights used
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) k_align_accum(AlignArgs a) {
+  using G = RowGeom<N>;
+  using T = double;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  {
+    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.r.twN);
+    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.r.tw2N);
+    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
+    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
+  }
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+  const int ch = blockIdx.x * G::kRows + r;
+  const bool valid = ch < a.r.nchan;
+  const int chc = valid ? ch : 0;
+  cx<T> accp[G::kPairs], accq[G::kPairs];
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) { accp[i] = mk<T>(0, 0); accq[i] = mk<T>(0, 0); }
+  T acc0 = 0, accN = 0, wtot = 0;
+  for (int s = 0; s < a.r.nsub; ++s) {
+    const double w = valid ? a.weights[(size_t)s * a.r.nchan + chc] : 0.0;
+    const bool use = w > 0.0;
+    const float4* src = reinterpret_cast<const float4*>(a.r.in + ((size_t)s * a.r.nchan + chc) * 2 * N);
+    __syncthreads();   // previous iteration's reads of the buffers are done
+#pragma unroll
+    for (int m = 0; m < G::kLoads; ++m) {
+      const int i4 = t_row + m * G::kTRow;
+      const float4 v = use ? __ldg(src + i4) : make_float4(0, 0, 0, 0);
+      bufA[2 * i4] = mk<T>((T)v.x, (T)v.y);
+      bufA[2 * i4 + 1] = mk<T>((T)v.z, (T)v.w);
+    }
+    __syncthreads();
+    cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+    if (use) {
+      const double theta = rot_theta(a.r, s, chc);
+#pragma unroll
+      for (int i = 0; i < G::kPairs; ++i) {
+        const int p = t_row + 1 + i * G::kTRow;
+        if (p <= N / 2) {
+          cx<T> dp, dq;
+          unpack_pair<T>(Z, tw2N, N, p, dp, dq);
+          double c, sn;
+          cis2pi((double)p * theta, c, sn);
+          dp = cmul(dp, mk<T>(c * w, sn * w));
+          accp[i] = cadd(accp[i], dp);
+          if (p < N / 2) {
+            cis2pi((double)(N - p) * theta, c, sn);
+            dq = cmul(dq, mk<T>(c * w, sn * w));
+            accq[i] = cadd(accq[i], dq);
+          }
+        }
+      }
+      if (t_row == 0) {
+        double c, sn;
+        cis2pi((double)N * theta, c, sn);
+        acc0 += w * (Z[0].x + Z[0].y);
+        accN += w * (Z[0].x - Z[0].y) * c;
+        wtot += w;
+      }
+    }
+  }
+  __syncthreads();
+  // pack the accumulated half spectrum and inverse transform (conj / FFT / conj / N)
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) {
+    const int p = t_row + 1 + i * G::kTRow;
+    if (p <= N / 2) {
+      cx<T> zp, zq;
+      pack_pair<T>(accp[i], (p < N / 2) ? accq[i] : accp[i], tw2N[p], zp, zq);
+      bufA[p] = cconj(zp);
+      if (p < N / 2) bufA[N - p] = cconj(zq);
+    }
+  }
+  if (t_row == 0) bufA[0] = mk<T>(T(0.5) * (acc0 + accN), -T(0.5) * (acc0 - accN));
+  __syncthreads();
+  cx<T>* Y = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  if (valid) {
+    double* dst = a.aligned + (size_t)ch * 2 * N;
+    const T sc = T(1) / T(N);
+    for (int j = t_row; j < N; j += G::kTRow) {
+      dst[2 * j] = Y[j].x * sc;
+      dst[2 * j + 1] = -Y[j].y * sc;
+    }
+    if (t_row == 0) a.wsum[ch] = wtot;
   }
 }
 

@@ -232,7 +232,26 @@ class WidebandPlan(object):
         return res
 
     # ---- batched rotation -------------------------------------------------------------
-    def rotate_batch(self, data, phase, DM, P, nu_ref, out=None):
+    def align_accumulate(self, data, phase, DM, P, nu_ref, weights):
+        """sum_s weights[s,n] * rotate(data[s,n], phase_s, DM_s) (ppalign.py:202-208).
+        Returns (aligned[nchan,nbin] float64 un-normalised, wsum[nchan])."""
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        bc = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), (nsub,))  # noqa: E731
+        aligned = np.empty((self.nchan, self.nbin))
+        wsum = np.empty(self.nchan)
+        _ffi.check(self._lib.pp_align_accumulate(
+            self._h, ip, nsub, _ptr(bc(phase), np.float64, keep, "phase"),
+            _ptr(bc(DM), np.float64, keep, "DM"), _ptr(bc(P), np.float64, keep, "P"),
+            _ptr(bc(nu_ref), np.float64, keep, "nu_ref"),
+            _ptr(weights, np.float64, keep, "weights", (nsub, self.nchan)),
+            aligned.ctypes.data, wsum.ctypes.data), "pp_align_accumulate")
+        return aligned, wsum
+
+    def rotate_batch(self, data, phase, DM, P, nu_ref, out=None, GM=None, nu_GM=None):
+        if GM is not None:
+            return self._rotate_full(data, phase, DM, GM, P, nu_ref, nu_GM, out)
         keep = []
         nsub = int(data.shape[0])
         ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
@@ -250,6 +269,25 @@ class WidebandPlan(object):
             _ptr(bc(DM), np.float64, keep, "DM"),
             _ptr(bc(P), np.float64, keep, "P"),
             _ptr(bc(nu_ref), np.float64, keep, "nu_ref")), "pp_rotate_batch")
+        return out
+
+    def _rotate_full(self, data, phase, DM, GM, P, nu_DM, nu_GM, out=None):
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        if out is None:
+            if _is_torch(data):
+                import torch
+                out = torch.empty_like(data)
+            else:
+                out = np.empty((nsub, self.nchan, self.nbin), dtype=np.float32)
+        op = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        bc = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), (nsub,))  # noqa: E731
+        _ffi.check(self._lib.pp_rotate_full_batch(
+            self._h, ip, op, nsub, _ptr(bc(phase), np.float64, keep, "phase"),
+            _ptr(bc(DM), np.float64, keep, "DM"), _ptr(bc(GM), np.float64, keep, "GM"),
+            _ptr(bc(P), np.float64, keep, "P"), _ptr(bc(nu_DM), np.float64, keep, "nu_DM"),
+            _ptr(bc(nu_GM), np.float64, keep, "nu_GM")), "pp_rotate_full_batch")
         return out
 
     def get_noise_batch(self, data):

@@ -209,6 +209,8 @@ class GetTOAs:
                     print("No subints to fit for %s.  Skipping it." % data.filename)
                 continue
             self.ok_idatafiles.append(iarch)
+            self._archives = getattr(self, "_archives", {})
+            self._archives[iarch] = data
             d = data
             nsub, nchan, nbin = int(d.nsub), int(d.nchan), int(d.nbin)
             ok_isubs = np.asarray(d.ok_isubs, dtype=int)
@@ -272,6 +274,8 @@ class GetTOAs:
                     scat_in[isub] = [tau_guess, alpha_guess]
             pl = get_plan(nchan, nbin)
             pl.set_model(_f32(model), freqs[0])
+            self._models = getattr(self, "_models", {})
+            self._models[iarch] = np.asarray(model, dtype=np.float64)
 
             # subints with a single usable channel are fit for phase only
             # (pptoas.py:475-478); two channels drop GM (479-483)
@@ -448,8 +452,68 @@ class GetTOAs:
                 print(d.filename)
                 print("~%.4f sec/TOA" % (fit_duration / len(ok_isubs)))
                 print("Med. TOA error is %.3f us" % (np.median(phi_errs[ok_isubs]) * Ps.mean() * 1e6))
+        self._models = getattr(self, "_models", {})
         tot_duration = time.time() - start
         if not quiet and len(self.ok_isubs):
             print("--------------------------")
             print("Total time: %.2f sec, ~%.4f sec/TOA" % (
                 tot_duration, tot_duration / (np.array(list(map(len, self.ok_isubs))).sum())))
+
+    def get_channels_to_zap(self, SNR_threshold=8.0, rchi2_threshold=1.3, iterate=True,
+                            show=False):
+        """Flag channels by per-channel reduced chi-squared and S/N (pptoas.py:1208-1285).
+        NB: get_TOAs(...) needs to have been called first.  The data are rotated onto the
+        model with the fitted parameters on the device (show_fit, pptoas.py:1398-1399);
+        the per-channel residual sums are host arithmetic."""
+        if show:
+            raise NotImplementedError("plots need matplotlib")
+        from .pplib import scattering_portrait_FT, scattering_times
+        for k, iarch in enumerate(self.ok_idatafiles):
+            d, model0 = self._archives[iarch], self._models[iarch]
+            nchan, nbin = int(d.nchan), int(d.nbin)
+            pl = get_plan(nchan, nbin)
+            freqs = np.asarray(d.freqs, dtype=np.float64)
+            pl.set_freqs(freqs[0])
+            ok_isubs = np.asarray(self.ok_isubs[k], dtype=int)
+            phi, DM, GM = self.phis[k][ok_isubs], self.DMs[k][ok_isubs].copy(), self.GMs[k][ok_isubs].copy()
+            if self.bary:                                   # back to the fitted values (1353-1355)
+                df = np.asarray(self.doppler_fs[k])[ok_isubs]
+                DM /= df
+                GM /= df ** 3
+            nus = np.array([self.nu_refs[k][i] for i in ok_isubs], dtype=np.float64)
+            rot = pl.rotate_batch(_f32(np.asarray(d.subints)[ok_isubs, 0]), phi, DM,
+                                  np.asarray(d.Ps)[ok_isubs], nus[:, 0], GM=GM, nu_GM=nus[:, 1])
+            channel_red_chi2s, zap_channels = [], []
+            for j, isub in enumerate(ok_isubs):
+                ok_ichans = np.asarray(d.ok_ichans[isub], dtype=int)
+                model = model0
+                if self.taus[k][isub] != 0.0:               # 1388-1394
+                    tau = 10 ** self.taus[k][isub] if self.log10_tau else self.taus[k][isub]
+                    taus = scattering_times(tau, self.alphas[k][isub], freqs[isub], nus[j, 2])
+                    model = np.fft.irfft(scattering_portrait_FT(taus, nbin) *
+                                         np.fft.rfft(model0, axis=1), axis=1)
+                model_scaled = self.scales[k][isub][:, None] * model
+                noise = np.asarray(d.noise_stds)[isub, 0]
+                csnr = self.channel_snrs[k][isub]
+                thr = (SNR_threshold ** 2.0 / len(ok_ichans)) ** 0.5
+                red, bad = [], []
+                for c in ok_ichans:
+                    rc2 = np.sum(((rot[j, c] - model_scaled[c]) / noise[c]) ** 2.0) / (nbin - 2)
+                    red.append(rc2)
+                    if rc2 > rchi2_threshold or np.isnan(rc2):
+                        bad.append(int(c))
+                    elif SNR_threshold and csnr[c] < thr:
+                        bad.append(int(c))
+                if iterate and SNR_threshold and len(bad):  # 1262-1277
+                    old_len, added_new = len(bad), True
+                    while added_new and (len(ok_ichans) - len(bad)):
+                        thr = (SNR_threshold ** 2.0 / (len(ok_ichans) - len(bad))) ** 0.5
+                        for c in ok_ichans:
+                            if int(c) not in bad and csnr[c] < thr:
+                                bad.append(int(c))
+                        added_new = bool(len(bad) - old_len)
+                        old_len = len(bad)
+                channel_red_chi2s.append(red)
+                zap_channels.append(bad)
+            self.channel_red_chi2s.append(channel_red_chi2s)
+            self.zap_channels.append(zap_channels)

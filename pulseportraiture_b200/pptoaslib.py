@@ -77,3 +77,32 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
                      snr=r["snr"][0], channel_snrs=r["channel_snrs"][0],
                      duration=duration, nfeval=int(r["nfeval"][0]),
                      return_code=rc)
+
+
+def rotate_portrait_full(port, phi, DM, GM, freqs, nu_DM=np.inf, nu_GM=np.inf, P=None):
+    """Rotate / dedisperse a portrait including the nu**-4 term (pptoaslib.py:52-81)."""
+    port = np.asarray(port)
+    nchan, nbin = port.shape
+    if P is None:
+        P = 1.0
+    big = lambda v: 1e300 if np.isinf(v) else float(v)  # noqa: E731
+    pl = get_plan(nchan, nbin)
+    pl.set_freqs(np.asarray(freqs, dtype=np.float64))
+    out = pl.rotate_batch(_f32(port)[None], phi, DM, P, big(nu_DM), GM=GM, nu_GM=big(nu_GM))
+    return out[0].astype(np.float64)
+
+
+def get_scales_full(params, data_port, model_port, P, freqs, nu_DM, nu_GM, nu_tau, log10_tau,
+                    errs=None):
+    """Maximum-likelihood per-channel amplitudes at given parameters
+    (pptoaslib.py:908-926; takes time-domain portraits instead of their FFTs)."""
+    data_port = np.asarray(data_port)
+    nchan, nbin = data_port.shape
+    pl = get_plan(nchan, nbin)
+    pl.set_model(_f32(model_port), np.asarray(freqs, dtype=np.float64))
+    nus = np.array([[nu_DM, nu_GM, nu_tau]], dtype=np.float64)
+    r = pl.fit_batch(_f32(data_port)[None], P,
+                     errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],
+                     init=np.array(params, dtype=np.float64).reshape(1, 5), nu_fits=nus, nu_outs=nus,
+                     fit_flags=(1, 1, 1, 1, 1), log10_tau=bool(log10_tau), max_iter=-1)
+    return r["scales"][0]

@@ -1,0 +1,137 @@
+"""GPU tests of the 'next' rows of SURVEY 8(f): the ppalign inner loop (rotate-accumulate,
+iterated template) and the zap scans, against compositions of oracle functions."""
+import numpy as np
+import pytest
+
+from oracle import pp_oracle as orc
+from tests import synth
+from tests.test_gpu_parity import _fake_archive, rel, SIG_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_rotate_full(port, phi, DM, GM, freqs, nu_DM, nu_GM, P):
+    """pptoaslib.rotate_portrait_full (pptoaslib.py:52-81) restated with numpy."""
+    FT = np.fft.rfft(port, axis=-1)
+    k = np.arange(FT.shape[-1])
+    th = phi + orc.Dconst * DM * (freqs ** -2 - nu_DM ** -2) / P + \
+        orc.Dconst ** 2 * GM * (freqs ** -4 - nu_GM ** -4) / P
+    return np.fft.irfft(FT * np.exp(2.0j * np.pi * np.outer(th, k)), axis=-1)
+
+
+def test_rotate_portrait_full_and_scales_full():
+    from pulseportraiture_b200 import pptoaslib
+    c = synth.make_case(32, 512, 600., 400., 9001, tau_data_s=50e-6, sigma=0.5)
+    data, model, freqs, P = c["data"], c["model"], c["freqs"], c["P"]
+    out = pptoaslib.rotate_portrait_full(data, 0.21, 1.5e-3, 2.0e-7, freqs, 650., 620., P)
+    ref = oracle_rotate_full(data, 0.21, 1.5e-3, 2.0e-7, freqs, 650., 620., P)
+    assert np.max(np.abs(out - ref)) < 2e-5 * np.max(np.abs(ref))
+    params = [0.1, 2e-4, 1e-8, np.log10(3e-3), -4.2]
+    errs = orc.get_noise(data, chans=True)
+    sc = pptoaslib.get_scales_full(params, data, model, P, freqs, 610., 590., 600., True, errs=errs)
+    dFT, mFT = orc._spectra(data, model)
+    prob = orc._FullProblem(dFT, mFT, errs * np.sqrt(256.), P, freqs, 610., 590., 600.,
+                            [1, 1, 1, 1, 1], True)
+    pr = prob.primitives(params, order=0)
+    assert rel(sc, pr["C"] / pr["S"]) < 1e-6
+
+
+def test_align_accumulate_vs_oracle():
+    from pulseportraiture_b200.engine import WidebandPlan
+    nsub, nchan, nbin = 7, 48, 1024
+    rng = np.random.RandomState(3)
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 9100 + s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    phi, DM = rng.uniform(-0.5, 0.5, nsub), rng.normal(0, 1e-3, nsub)
+    nu_ref = rng.uniform(1200., 1800., nsub)
+    w = rng.uniform(0.5, 2.0, (nsub, nchan))
+    w[2, 5] = 0.0
+    w[4, :] = 0.0
+    with WidebandPlan(nchan, nbin) as pl:
+        pl.set_freqs(freqs)
+        acc, wsum = pl.align_accumulate(data, phi, DM, P, nu_ref, w)
+    ref = np.zeros((nchan, nbin))
+    for s in range(nsub):
+        ref += w[s][:, None] * orc.rotate_data(data[s].astype(np.float64), phi[s], DM[s], P, freqs, nu_ref[s])
+    assert rel(wsum, w.sum(axis=0)) < 1e-14
+    assert np.max(np.abs(acc - ref)) < 1e-9 * np.max(np.abs(ref))
+
+
+def _oracle_align(archive, cases, template, fit_dm, niter):
+    """ppalign.py:113-213 restated with oracle functions (exact FFTFIT polish)."""
+    nsub, nchan, nbin = archive.nsub, archive.nchan, archive.nbin
+    for _ in range(niter):
+        aligned = np.zeros((nchan, nbin))
+        tot = np.zeros(nchan)
+        for s in range(nsub):
+            ok = np.asarray(archive.ok_ichans[s])
+            c = cases[s]
+            port, model, freqs = c["data"][ok], template[ok], c["freqs"][ok]
+            errs = archive.noise_stds[s, 0, ok]
+            nu_fit = orc.guess_fit_freq(freqs, archive.SNRs[s, 0, ok])
+            rot_port = orc.rotate_data(port, 0.0, archive.DM, c["P"], freqs, nu_fit)
+            g = orc.fit_phase_shift(np.average(rot_port, axis=0, weights=archive.weights[s, ok]),
+                                    model.mean(axis=0), Ns=nbin, polish="exact")
+            r = orc.fit_portrait_full(port, model, [g.phase, archive.DM, 0, 0, 0], c["P"], freqs,
+                                      [nu_fit] * 3, [None] * 3, errs, [1, int(fit_dm), 0, 0, 0],
+                                      log10_tau=False)
+            w = r.scales / errs ** 2
+            aligned[ok] += w[:, None] * orc.rotate_data(port, r.phi, r.DM, c["P"], freqs, r.nu_DM)
+            tot[ok] += w
+        good = tot > 0
+        aligned[good] /= tot[good, None]
+        template = aligned
+    return template, tot
+
+
+def test_align_archives_two_iterations():
+    """Config-5 style loop at a size the oracle finishes in seconds."""
+    from pulseportraiture_b200 import ppalign
+    archive, cases = _fake_archive(6, 32, 256, 9200, DM_stored=0.0)
+    # the initial template is a noisy, slightly wrong model (a smoothed single subint)
+    tmpl0 = orc.rotate_data(cases[0]["model"], 0.013)
+    out = ppalign.align_archives([archive], tmpl0, fit_dm=True, niter=2, quiet=True)
+    ref, tot = _oracle_align(archive, cases, tmpl0, True, 2)
+    assert rel(out.weights, tot) < 1e-4
+    assert np.max(np.abs(out.port - ref)) < 2e-5 * np.max(np.abs(ref))
+    # 'place' and 'norm' options run and do what they say
+    # (the reference's 1e-4-wide delta is only non-zero when `place` is within 20 sigma of a bin
+    # centre, pplib.py:805-806: use a bin centre)
+    place = 128.5 / 256.0
+    out2 = ppalign.align_archives([archive], tmpl0, niter=1, norm="max", place=place, quiet=True)
+    assert np.allclose(out2.port.max(axis=1)[out2.weights > 0], 1.0, atol=0.15)   # rotated after norm
+    assert abs((np.argmax(out2.port.mean(axis=0)) + 0.5) / 256.0 - place) < 0.02
+
+
+def test_zap_scans():
+    from pulseportraiture_b200 import pptoas, ppzap
+    archive, cases = _fake_archive(3, 32, 512, 9300)
+    # RFI: channel 7 of subint 1 gets extra noise after the noise levels were measured
+    rng = np.random.RandomState(1)
+    archive.subints[1, 0, 7] += rng.normal(0, 3.0, 512)
+    for s in range(3):
+        archive.ok_ichans[s] = np.arange(32)
+    gt = pptoas.GetTOAs([archive], synth.GMODEL, quiet=True)
+    gt.get_TOAs(bary=False)
+    gt.get_channels_to_zap(SNR_threshold=0.0, rchi2_threshold=2.0)
+    assert gt.zap_channels[0][1] == [7] and gt.zap_channels[0][0] == [] and gt.zap_channels[0][2] == []
+    # per-channel reduced chi2 vs the time-domain restatement (pptoas.py:1398-1401, pplib.py:727-750)
+    s = 1
+    r = gt
+    port = orc.rotate_data(archive.subints[s, 0], r.phis[0][s], r.DMs[0][s], archive.Ps[s],
+                           cases[s]["freqs"], r.nu_refs[0][s][0])
+    model = cases[s]["model"]      # float32-rounded model, as the device saw it
+    red = np.sum(((port - r.scales[0][s][:, None] * model) / archive.noise_stds[s, 0][:, None]) ** 2,
+                 axis=1) / 510.
+    assert rel(np.array(gt.channel_red_chi2s[0][s]), red) < 1e-4
+    # median / sigma noise zapping (ppzap.py:18-48)
+    archive.noise_stds[2, 0, [3, 20]] *= 8.0
+    z = ppzap.get_zap_channels(archive, nstd=3)
+    assert z[2] == [3, 20] and z[0] == []
+    # S/N cut with iteration
+    gt2 = pptoas.GetTOAs([archive], synth.GMODEL, quiet=True)
+    gt2.get_TOAs(bary=False)
+    thr = 1.05 * np.sqrt(32) * np.sort(gt2.channel_snrs[0][0])[2]
+    gt2.get_channels_to_zap(SNR_threshold=thr, rchi2_threshold=1e9, iterate=False)
+    assert len(gt2.zap_channels[0][0]) == 3
