@@ -93,9 +93,13 @@ template <int N> struct Plan8 {
   __host__ __device__ static constexpr int radix(int i) { return (int)((code >> (4 * i)) & 0xFu); }
 };
 
+#ifndef PP_SPECTRA_THREADS
+#define PP_SPECTRA_THREADS 128
+#endif
 template <int N> struct Slot8 {
   static constexpr int kT = N / 8;                     // threads per row slot
-  static constexpr int kSlots = 256 / kT;              // row slots per CTA of 256 threads
+  static constexpr int kSlots = (PP_SPECTRA_THREADS / kT) > 0 ? (PP_SPECTRA_THREADS / kT) : 1;  // row slots per CTA
+  static constexpr int kThreads = kSlots * kT;         // CTA size
   static constexpr int kPairs = (N / 2) / kT;          // = 4 split pairs per thread
   static constexpr int kBufElems = Padded<N>::value;   // padded complex elements per slot
   static_assert(kT >= 4 && kT <= 256, "slot size");

@@ -29,7 +29,7 @@ namespace ppb {
 constexpr double kDconst = 1.0 / 0.000241;  // pplib.py:48-51
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 #ifndef PP_SPECTRA_MINB
-#define PP_SPECTRA_MINB 2
+#define PP_SPECTRA_MINB 5
 #endif
 constexpr int kNCsum = 9;                   // per-channel sums kept per subint
 // The first kLoK slots of every X row also keep the float32 rounding residual
@@ -263,7 +263,7 @@ struct SpectraArgs {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spectra(SpectraArgs a) {
+__global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spectra(SpectraArgs a) {
   using S8 = Slot8<N>;
   using L = TwLayout<N>;
   using F = double;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spec
   __shared__ double red[NS][(T >= 32 ? T / 32 : 1)][2];
   __shared__ __align__(8) unsigned long long mbar[NS][2];
   const int tid = threadIdx.x, slot = tid / T, t = tid % T;
-  for (int i = tid; i < L::kTotal; i += 256) tw[i] = a.tw8[i];
+  for (int i = tid; i < L::kTotal; i += S8::kThreads) tw[i] = a.tw8[i];
   if (t == 0) { mbar_init(&mbar[slot][0], 1); mbar_init(&mbar[slot][1], 1); }
   mbar_fence_init();
   __syncthreads();

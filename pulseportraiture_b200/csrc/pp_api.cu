@@ -460,7 +460,7 @@ static int pick_chunk(pp_plan* pl, int nsub) {
 
 static int rows_per_cta(pp_plan* pl, int chunk) {
   // rows per k_spectra CTA: aim at >= 4 CTAs per SM per launch, multiple of kRows
-  const int rows_conc = 256 / (pl->N / 8);
+  const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (pl->N / 8));
   long total_rows = (long)chunk * pl->nchan;
   long target_ctas = 4L * pl->sm_count;
   long g = std::max(1L, total_rows / target_ctas);
@@ -552,7 +552,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   const int chunk = pick_chunk(pl, nsub);
   const int G = rows_per_cta(pl, chunk);
-  const int rows_conc = 256 / (N / 8);
+  const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (N / 8));
   const int gx = (nchan + G - 1) / G;
   const int nparts = gx * rows_conc;
   pl->stats.chunk = chunk;
@@ -633,7 +633,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), 256, spectra_smem_bytes<NN>(), pl->stream>>>(a));
+      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), Slot8<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
       pl->stats.launches++;
     }
     if (!data_on_device) CK(cudaEventRecord(pl->ev_free[c & 1], pl->stream));
