@@ -459,15 +459,14 @@ static int pick_chunk(pp_plan* pl, int nsub) {
 }
 
 static int rows_per_cta(pp_plan* pl, int chunk) {
-  // rows per k_spectra CTA: aim at >= 4 CTAs per SM per launch, multiple of kRows
+  // Channel rows handled by one k_spectra CTA.  It fixes how the partial profile spectra of
+  // the FFTFIT guess are grouped, so it must NOT depend on the batch or chunk size (results
+  // are bit-identical for any chunking): a function of nchan only, ~16 CTAs per subint.
+  (void)chunk;
   const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (pl->N / 8));
-  long total_rows = (long)chunk * pl->nchan;
-  long target_ctas = 4L * pl->sm_count;
-  long g = std::max(1L, total_rows / target_ctas);
-  g = std::min<long>(g, 32);
+  int g = std::max(rows_conc, std::min(32, pl->nchan / 16));
   g = ((g + rows_conc - 1) / rows_conc) * rows_conc;
-  g = std::min<long>(g, ((pl->nchan + rows_conc - 1) / rows_conc) * rows_conc);
-  return (int)g;
+  return g;
 }
 
 extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_fit_out_t* out) {

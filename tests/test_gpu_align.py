@@ -132,6 +132,7 @@ def test_zap_scans():
     # S/N cut with iteration
     gt2 = pptoas.GetTOAs([archive], synth.GMODEL, quiet=True)
     gt2.get_TOAs(bary=False)
-    thr = 1.05 * np.sqrt(32) * np.sort(gt2.channel_snrs[0][0])[2]
+    srt = np.sort(gt2.channel_snrs[0][0])
+    thr = np.sqrt(32) * 0.5 * (srt[2] + srt[3])
     gt2.get_channels_to_zap(SNR_threshold=thr, rchi2_threshold=1e9, iterate=False)
     assert len(gt2.zap_channels[0][0]) == 3
