@@ -1056,7 +1056,11 @@ __global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
     auto element = [&](double xr, double xi, double m, double c, double sn, double k) {
       const double zr = xr * c - xi * sn, zi = xr * sn + xi * c;      // X e^{i psi}
       const double b = k * wt;
-      const double q = 1.0 / fma(b, b, 1.0);                          // |B|^2
+      const double b2 = b * b, den = b2 + 1.0;
+      double q;                                                       // |B|^2 = 1/(1 + b^2)
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));         // ~20 bits, then two Newton steps
+      q = q * fma(-den, q, 2.0);
+      q = q * fma(-den, q, 2.0);
       const double br = q, bi = b * q;                                // conj(B)
       const double a1r = zr * br - zi * bi, a1i = zr * bi + zi * br;  // Z conjB
       const double a2r = a1r * br - a1i * bi, a2i = a1r * bi + a1i * br;
@@ -1072,7 +1076,7 @@ __global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
       const double k2q2m = k2 * q * qm;
       acc[6] += qm;
       acc[7] += k2q2m;
-      acc[8] = fma(k2q2m, fma(4.0 * b * b, q, -1.0), acc[8]);
+      acc[8] = fma(k2q2m, fma(4.0 * b2, q, -1.0), acc[8]);
     };
     constexpr int NJ = N / 16;
     constexpr int KJ = LoK<N>::value / 16;

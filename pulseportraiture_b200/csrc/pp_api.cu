@@ -94,6 +94,7 @@ struct pp_plan {
   DBuf X, Xlo, partial, data_stage[2];
   // timing
   bool timing = false;
+  std::vector<cudaEvent_t> ev_chunk;   // "chunk finished" events for the overlapped result copies
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   struct Span { int kind; cudaEvent_t a, b; };
@@ -173,6 +174,14 @@ static int copy_out(pp_plan* pl, T* dst, const T* dev, size_t n) {
   if (!dst) return 0;
   CK(cudaMemcpyAsync(dst, dev, n * sizeof(T), is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                      pl->stream));
+  return 0;
+}
+
+template <typename T>
+static int copy_out_at(cudaStream_t st, T* dst, const T* dev, size_t off, size_t n) {
+  if (!dst || n == 0) return 0;
+  CK(cudaMemcpyAsync(dst + off, dev + off, n * sizeof(T),
+                     is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
@@ -318,6 +327,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   for (DBuf* b : all) b->release();
   for (auto& gt : pl->grid_tables) gt.second.release();
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_chunk) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(pl->ev_copy[i]); cudaEventDestroy(pl->ev_free[i]); }
   cudaStreamDestroy(pl->own_stream);
   cudaStreamDestroy(pl->copy_stream);
@@ -707,6 +717,34 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
         if (running == 0) break;
       }
     }
+    // results of this chunk go back on the copy stream while the next chunk computes
+    {
+      while ((int)pl->ev_chunk.size() <= c) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        pl->ev_chunk.push_back(e);
+      }
+      CK(cudaEventRecord(pl->ev_chunk[c], pl->stream));
+      CK(cudaStreamWaitEvent(pl->copy_stream, pl->ev_chunk[c], 0));
+      cudaStream_t cs = pl->copy_stream;
+      const size_t o1 = (size_t)s0, n1 = (size_t)ns, oc = (size_t)s0 * nchan, ncn = (size_t)ns * nchan;
+      if (copy_out_at(cs, out->params, pl->o_params.as<double>(), o1 * 5, n1 * 5)) return -2;
+      if (copy_out_at(cs, out->param_errs, pl->o_perrs.as<double>(), o1 * 5, n1 * 5)) return -2;
+      if (copy_out_at(cs, out->nu_out, pl->o_nuout.as<double>(), o1 * 3, n1 * 3)) return -2;
+      if (copy_out_at(cs, out->cov, pl->o_cov.as<double>(), o1 * 25, n1 * 25)) return -2;
+      if (copy_out_at(cs, out->chi2, pl->o_chi2.as<double>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->red_chi2, pl->o_rchi2.as<double>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->snr, pl->o_snr.as<double>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->nfeval, pl->o_nfev.as<int>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->return_code, pl->o_rc.as<int>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->scales, pl->o_scales.as<double>(), oc, ncn)) return -2;
+      if (copy_out_at(cs, out->scale_errs, pl->o_serrs.as<double>(), oc, ncn)) return -2;
+      if (copy_out_at(cs, out->channel_snrs, pl->o_csnr.as<double>(), oc, ncn)) return -2;
+      if (copy_out_at(cs, out->noise, pl->sigma.as<double>(), oc, ncn)) return -2;
+      if (copy_out_at(cs, out->lag_index, pl->o_lag.as<int>(), o1, n1)) return -2;
+      if (want_guess && copy_out_at(cs, out->phi_guess, pl->o_phig.as<double>(), o1, n1)) return -2;
+      if (copy_out_at(cs, out->chan_sums, pl->csum.as<double>(), oc * kNCsum, ncn * kNCsum)) return -2;
+    }
   }
   CK(cudaGetLastError());
   cudaEvent_t ev_t1 = nullptr;
@@ -716,28 +754,13 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     pl->spans.push_back({SP_TOTAL, ev_t0, ev_t1});
   }
 
-  // ---- results -------------------------------------------------------------------------
-  if (copy_out(pl, out->params, pl->o_params.as<double>(), (size_t)nsub * 5)) return -2;
-  if (copy_out(pl, out->param_errs, pl->o_perrs.as<double>(), (size_t)nsub * 5)) return -2;
-  if (copy_out(pl, out->nu_out, pl->o_nuout.as<double>(), (size_t)nsub * 3)) return -2;
-  if (copy_out(pl, out->cov, pl->o_cov.as<double>(), (size_t)nsub * 25)) return -2;
-  if (copy_out(pl, out->chi2, pl->o_chi2.as<double>(), (size_t)nsub)) return -2;
-  if (copy_out(pl, out->red_chi2, pl->o_rchi2.as<double>(), (size_t)nsub)) return -2;
-  if (copy_out(pl, out->snr, pl->o_snr.as<double>(), (size_t)nsub)) return -2;
-  if (copy_out(pl, out->nfeval, pl->o_nfev.as<int>(), (size_t)nsub)) return -2;
-  if (copy_out(pl, out->return_code, pl->o_rc.as<int>(), (size_t)nsub)) return -2;
-  if (copy_out(pl, out->scales, pl->o_scales.as<double>(), nsc)) return -2;
-  if (copy_out(pl, out->scale_errs, pl->o_serrs.as<double>(), nsc)) return -2;
-  if (copy_out(pl, out->channel_snrs, pl->o_csnr.as<double>(), nsc)) return -2;
-  if (copy_out(pl, out->noise, pl->sigma.as<double>(), nsc)) return -2;
-  if (copy_out(pl, out->lag_index, pl->o_lag.as<int>(), (size_t)nsub)) return -2;
-  if (want_guess) { if (copy_out(pl, out->phi_guess, pl->o_phig.as<double>(), (size_t)nsub)) return -2; }
-  else if (out->phi_guess && dinit) {
+  // ---- results (per-chunk copies were queued on the copy stream) -------------------------
+  if (!want_guess && out->phi_guess && dinit) {
     // phi_guess = init[:,0]
     CK(cudaMemcpy2DAsync(out->phi_guess, sizeof(double), dinit, 5 * sizeof(double), sizeof(double), nsub,
                          is_device_ptr(out->phi_guess) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, pl->stream));
   }
-  if (copy_out(pl, out->chan_sums, pl->csum.as<double>(), nsc * kNCsum)) return -2;
+  CK(cudaStreamSynchronize(pl->copy_stream));
   CK(cudaStreamSynchronize(pl->stream));
   CK(cudaGetLastError());
   stats_end(pl);
