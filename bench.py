@@ -347,7 +347,7 @@ def run_ours(args):
                 "value": value, "unit": "TOAs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 storage/FFT, f64 phasors+accumulators", "data": "synthetic",
+                "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "phi+DM batch fit, 512 chan x 2048 bin x %d subints per GPU "
                                        "(config 2), FFTFIT guess + Newton solve, noise measured"
                                        % nsub,

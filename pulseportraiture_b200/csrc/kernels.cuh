@@ -468,6 +468,7 @@ struct GuessArgs {
   const float2* partial;   // [n, nparts, N] spectra to be summed (slot layout)
   const float2* mconj;     // [nmodel, N] conj(model spectrum)
   int nparts, nmodel, N, Ns;
+  double polish_tol;       // stop the exact polish when |dx| < polish_tol [rot]
   const double* wsum;      // [n] divisor of the partial sum, or null (=1)
   const double* noise;     // [n] time-domain sigma or null (measure from spectrum)
   const double2* table;    // [Ns-1] e^{2 pi i m/(Ns-1)}
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       double xn = (C2 > 0.0) ? x - C1 / C2 : CUDART_NAN;
       if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
       bc[0] = xn; bc[1] = lo; bc[2] = hi;
-      bc[3] = (fabs(xn - x) < 1e-14 || C1 == 0.0) ? 1.0 : 0.0;
+      bc[3] = (fabs(xn - x) < a.polish_tol || C1 == 0.0) ? 1.0 : 0.0;
     }
     __syncthreads();
     const bool stop = bc[3] != 0.0;

@@ -654,6 +654,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
+      ga.polish_tol = 1e-9;   // a start value: the Newton solver refines it
       ga.init = nullptr; ga.scat = dscat; ga.log10_tau = args->log10_tau; ga.fit_scat = ff[3] ? 1 : 0;
       k_guess<<<ns, 256, sizeof(double2) * N, pl->stream>>>(ga);
       k_reset_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
@@ -823,7 +824,7 @@ extern "C" int pp_fit_phase_shift_batch(pp_plan_t* pl, const float* profiles, in
   GuessArgs ga;
   memset(&ga, 0, sizeof ga);
   ga.partial = pl->ps_spec.as<float2>(); ga.mconj = pl->ps_mspec.as<float2>(); ga.nparts = 1; ga.nmodel = nmodel;
-  ga.N = N; ga.Ns = Ns; ga.wsum = nullptr; ga.noise = dnoise; ga.table = table; ga.s0 = 0;
+  ga.N = N; ga.Ns = Ns; ga.wsum = nullptr; ga.noise = dnoise; ga.table = table; ga.s0 = 0; ga.polish_tol = 1e-14;
   ga.phase = pl->ps_phase.as<double>(); ga.phase_err = pl->ps_perr.as<double>(); ga.scale = pl->ps_scale.as<double>();
   ga.scale_err = pl->ps_serr.as<double>(); ga.snr = pl->ps_snr.as<double>(); ga.red_chi2 = pl->ps_rchi2.as<double>();
   ga.lag = pl->ps_lag.as<int>();
