@@ -100,7 +100,7 @@ template <int N> struct Slot8 {
   static constexpr int kT = N / 8;                     // threads per row slot
   static constexpr int kSlots = (PP_SPECTRA_THREADS / kT) > 0 ? (PP_SPECTRA_THREADS / kT) : 1;  // row slots per CTA
   static constexpr int kThreads = kSlots * kT;         // CTA size
-  static constexpr int kPairs = (N / 2) / kT;          // = 4 split pairs per thread
+  static constexpr int kQuads = (N / 4) / kT;          // = 2 split quads (4 harmonics each) per thread
   static constexpr int kBufElems = Padded<N>::value;   // padded complex elements per slot
   static_assert(kT >= 4 && kT <= 256, "slot size");
 };
@@ -209,39 +209,59 @@ __device__ __forceinline__ void fft8_rows(cx<F>* __restrict__ buf, const cx<F>* 
   }
 }
 
-// Fused last radix-2 pass + real-FFT split for the pair (p, N-p), 1 <= p <= N/2.
-template <int N, typename F>
-__device__ __forceinline__ void split_pair8(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, int p, cx<F>& dp,
-                                            cx<F>& dq) {
-  constexpr int H = N / 2;
-  const cx<F> w2 = tw[TwLayout<N>::kSplitOff + p];    // e^{-2 pi i p/(2N)}
-  cx<F> zp, zq;
-  if (p < H) {
-    const cx<F> wn = csqr(w2);                        // e^{-2 pi i p/N}
-    const cx<F> a = buf[phys(p)], b = cmul(wn, buf[phys(p + H)]);
-    zp = cadd(a, b);                                  // Z[p]
-    const int m = H - p;                              // N - p = H + m ; e^{-2 pi i m/N} = -conj(wn)
-    const cx<F> a2 = buf[phys(m)], b2 = cmul(mk<F>(-wn.x, wn.y), buf[phys(m + H)]);
-    zq = csub(a2, b2);                                // Z[N-p]
-  } else {
-    zp = csub(buf[phys(0)], buf[phys(H)]);            // Z[N/2] (self paired)
-    zq = zp;
-  }
+// Real-FFT split of one conjugate pair: from Z[k], Z[N-k] of the packed complex
+// transform to the real-series harmonics d[k] and d[N-k]; w = e^{-2 pi i k/(2N)}.
+template <typename F>
+__device__ __forceinline__ void real_pair(cx<F> zp, cx<F> zq, cx<F> w, cx<F>& dp, cx<F>& dq) {
   const cx<F> zc = cconj(zq);
   const cx<F> E = mk<F>(F(0.5) * (zp.x + zc.x), F(0.5) * (zp.y + zc.y));
   const cx<F> D = mk<F>(F(0.5) * (zp.x - zc.x), F(0.5) * (zp.y - zc.y));
   const cx<F> O = mk<F>(D.y, -D.x);
-  const cx<F> tt = cmul(w2, O);
+  const cx<F> tt = cmul(w, O);
   dp = cadd(E, tt);
   dq = cconj(csub(E, tt));
 }
 
-// Z[0] = a[0] + b[0]: returns (DC, Nyquist) = (Re+Im, Re-Im) of Z[0]
+// Fused last radix-2 pass + real-FFT split, four harmonics per call so that every
+// element of the buffer is read exactly once per row.  With H = N/2, a = buf[0:H],
+// b = buf[H:N] and 1 <= p < N/4 the inputs a[p], b[p], a[H-p], b[H-p] give
+// Z[p], Z[p+H], Z[H-p], Z[N-p], i.e. the two conjugate pairs (p, N-p) and
+// (H-p, H+p):  d[0..3] = harmonics p, N-p, H-p, H+p.
 template <int N, typename F>
-__device__ __forceinline__ void split_dc8(const cx<F>* __restrict__ buf, F& dc, F& ny) {
-  const cx<F> z0 = cadd(buf[phys(0)], buf[phys(N / 2)]);
-  dc = z0.x + z0.y;
-  ny = z0.x - z0.y;
+__device__ __forceinline__ void split_quad8(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, int p,
+                                            cx<F> (&d)[4]) {
+  constexpr int H = N / 2;
+  const cx<F> w2 = tw[TwLayout<N>::kSplitOff + p];    // e^{-2 pi i p/(2N)}
+  const cx<F> A1 = buf[phys(p)], B1 = buf[phys(p + H)], A2 = buf[phys(H - p)], B2 = buf[phys(N - p)];
+  const cx<F> wn = csqr(w2);                          // e^{-2 pi i p/N}; e^{-2 pi i (H-p)/N} = -conj(wn)
+  const cx<F> wb1 = cmul(wn, B1), wb2 = cmul(cconj(wn), B2);
+  const cx<F> Zp = cadd(A1, wb1), ZpH = csub(A1, wb1);   // Z[p], Z[p+H]
+  const cx<F> Zq = csub(A2, wb2), ZqH = cadd(A2, wb2);   // Z[H-p], Z[N-p]
+  real_pair(Zp, ZqH, w2, d[0], d[1]);
+  real_pair(Zq, ZpH, mk<F>(-w2.y, -w2.x), d[2], d[3]);   // e^{-2 pi i (H-p)/(2N)} = -i conj(w2)
+}
+
+// The p = 0 quad: a[0], b[0] give Z[0] (DC and Nyquist of the real series) and the
+// self-paired Z[H]; a[N/4], b[N/4] give the pair (N/4, 3N/4).
+// d[0..3] = harmonics H, N (Nyquist, real), N/4, 3N/4; returns the DC term.
+template <int N, typename F>
+__device__ __forceinline__ F split_quad0(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, cx<F> (&d)[4]) {
+  constexpr int H = N / 2, Q = N / 4;
+  const cx<F> A1 = buf[phys(0)], B1 = buf[phys(H)], A2 = buf[phys(Q)], B2 = buf[phys(H + Q)];
+  const cx<F> z0 = cadd(A1, B1), zh = csub(A1, B1);
+  cx<F> unused;
+  real_pair(zh, zh, tw[TwLayout<N>::kSplitOff + H], d[0], unused);
+  d[1] = mk<F>(z0.x - z0.y, F(0));
+  const cx<F> wb = mk<F>(B2.y, -B2.x);                // e^{-2 pi i Q/N} = -i
+  real_pair(cadd(A2, wb), csub(A2, wb), tw[TwLayout<N>::kSplitOff + Q], d[2], d[3]);
+  return z0.x + z0.y;
+}
+
+// harmonic number of output `which` (0..3) of the quad p (see split_quad8 / split_quad0)
+template <int N> __device__ __forceinline__ int quad_harmonic(int p, int which) {
+  constexpr int H = N / 2;
+  if (p == 0) return which == 0 ? H : which == 1 ? N : which == 2 ? N / 4 : 3 * (N / 4);
+  return which == 0 ? p : which == 1 ? N - p : which == 2 ? H - p : H + p;
 }
 
 }  // namespace ppb

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
   using S8 = Slot8<N>;
   using L = TwLayout<N>;
   using F = double;
-  constexpr int T = S8::kT, NS = S8::kSlots, NPAIR = S8::kPairs, NACC = 2 * NPAIR + 1;
+  constexpr int T = S8::kT, NS = S8::kSlots, NQUAD = S8::kQuads, NACC = 4 * NQUAD;
   constexpr unsigned kRowBytes = 2 * N * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [L::kTotal] (+pad)
@@ -329,32 +329,24 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
     // FFT pass so that their latency hides behind its butterflies
     // Slots >= LoK carry no lo part: float product and float conj(model) suffice there (kMix:
-    // for N >= 512 the lo slots are only this thread's first harmonic of pair 0 and slot 0).
+    // for N >= 512 the only lo slot a thread can own is slot t, its first output).
+    // Output idx = 4 i + which of quad p = t + i T is harmonic quad_harmonic<N>(p, which).
     constexpr bool kMix = (T >= 64);
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
     const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
-    cx<F> mc64[kMix ? 2 : NACC];
+    cx<F> mc64[kMix ? 1 : NACC];
     cx<float> mc32[kMix ? NACC : 1];
     auto load_mc = [&]() {
       if (used && a.X != nullptr) {
-        if constexpr (kMix) {
-          mc64[0] = mc[t + 1];
-          mc64[1] = mc[0];
+        if constexpr (kMix) mc64[0] = mc[t];
 #pragma unroll
-          for (int i = 0; i < NPAIR; ++i) {
-            const int p = t + 1 + i * T;
-            mc32[2 * i] = mcf[p];
-            mc32[2 * i + 1] = mcf[(p < N / 2) ? N - p : p];
-          }
-          mc32[2 * NPAIR] = mcf[0];
-        } else {
+        for (int i = 0; i < NQUAD; ++i) {
 #pragma unroll
-          for (int i = 0; i < NPAIR; ++i) {
-            const int p = t + 1 + i * T;
-            mc64[2 * i] = mc[p];
-            mc64[2 * i + 1] = (p < N / 2) ? mc[N - p] : mk<F>(0.0, 0.0);
+          for (int q = 0; q < 4; ++q) {
+            const int k = quad_harmonic<N>(t + i * T, q);
+            if constexpr (kMix) mc32[4 * i + q] = mcf[k == N ? 0 : k];
+            else mc64[4 * i + q] = mc[k == N ? 0 : k];
           }
-          mc64[2 * NPAIR] = mc[0];
         }
       }
     };
@@ -382,7 +374,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
         } else {
           float2 xl = make_float2(0.f, 0.f);
           if (used) {
-            const cx<F> mval = kMix ? mc64[idx == 0 ? 0 : 1] : mc64[kMix ? 0 : idx];
+            const cx<F> mval = mc64[kMix ? 0 : idx];
             const cx<F> pr = cmul(d, mval);
             xv = make_float2((float)pr.x, (float)pr.y);
             xl = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
@@ -405,17 +397,13 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
       }
     };
 #pragma unroll
-    for (int i = 0; i < NPAIR; ++i) {
-      const int p = t + 1 + i * T;
-      cx<F> dp, dq;
-      split_pair8<N, F>(buf, tw, p, dp, dq);
-      emit(p, dp, 2 * i, acc[2 * i]);
-      if (p < N / 2) emit(N - p, dq, 2 * i + 1, acc[2 * i + 1]);
-    }
-    if (t == 0) {
-      F dc, ny;
-      split_dc8<N, F>(buf, dc, ny);
-      emit(N, mk<F>(ny, 0.0), 2 * NPAIR, acc[2 * NPAIR]);
+    for (int i = 0; i < NQUAD; ++i) {
+      const int p = t + i * T;
+      cx<F> d[4];
+      if (i > 0 || p != 0) split_quad8<N, F>(buf, tw, p, d);
+      else split_quad0<N, F>(buf, tw, d);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) emit(quad_harmonic<N>(p, q), d[q], 4 * i + q, acc[4 * i + q]);
     }
     // ---- row-slot reduction of the two power sums ---------------------------------
     if constexpr (T >= 32) {
@@ -452,12 +440,13 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     const int part = blockIdx.x * NS + slot;
     float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
 #pragma unroll
-    for (int i = 0; i < NPAIR; ++i) {
-      const int p = t + 1 + i * T;
-      pr[(p == N) ? 0 : p] = acc[2 * i];
-      if (p < N / 2) pr[N - p] = acc[2 * i + 1];
+    for (int i = 0; i < NQUAD; ++i) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = quad_harmonic<N>(t + i * T, q);
+        pr[k == N ? 0 : k] = acc[4 * i + q];
+      }
     }
-    if (t == 0) pr[0] = acc[2 * NPAIR];
   }
 }
 
