@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
   float2 acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = make_float2(0.f, 0.f);
+  double keep_all = 0.0, keep_top = 0.0;
 
   auto row_used = [&](int step) -> bool {
     const int ch = ch_begin + step * NS + slot;
@@ -350,12 +351,13 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
         }
       }
     };
-    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); }, load_mc);
-
-    // ---- split + power sums; X and the guess accumulators need no sigma ------------
+    // per-row scalars: loaded before the transform so that their latency is hidden
     const size_t xo = ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
+    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); }, load_mc);
+
+    // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
     auto emit = [&](int k, cx<F> d, int idx, float2& ac) {
       const double pw = d.x * d.x + d.y * d.y;
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
       const float dfx = (float)d.x, dfy = (float)d.y;
       if (a.X != nullptr && inrange) {
         float2 xv = make_float2(0.f, 0.f);
-        if (kMix && sl_k >= LoK<N>::value) {
+        if (kMix && (idx >= 2 || sl_k >= LoK<N>::value)) {
           if (used) {
             const cx<float> m = mc32[kMix ? idx : 0];
             xv = make_float2(fmaf(dfx, m.x, -dfy * m.y), fmaf(dfx, m.y, dfy * m.x));
@@ -423,17 +425,25 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
         s_top += __shfl_xor_sync(0xffffffffu, s_top, o);
       }
     }
-    // ---- noise, Sd, S ------------------------------------------------------------------
-    if (inrange && t == 0) {
-      double sig;
-      if (a.errs) sig = used ? a.errs[(size_t)s * a.nchan + ch] : 0.0;
-      else sig = sqrt(s_top / ((double)(2 * N) * (double)ntop));       // pplib.py:2243-2245
-      const double sF2 = sig * sig * (double)N;                         // sigma^2 * nbin/2
-      const bool ok = used && (sF2 > 0.0) && (sF2 < 1e300);
-      const size_t o = (size_t)s * a.nchan + ch;
-      a.sigma[o] = ok ? sig : 0.0;
-      a.Ssn[o] = ok ? a.pn[ch] / sF2 : 0.0;
-      a.Sdn[o] = ok ? s_all / sF2 : 0.0;
+    // ---- noise, Sd, S: thread (step mod T) keeps the sums of this row and the slot
+    // finalises T rows at a time, one row per thread (sqrt and two divisions off the
+    // per-row critical path) -------------------------------------------------------------
+    if ((step % T) == t) { keep_all = s_all; keep_top = s_top; }
+    if (((step + 1) % T) == 0 || step + 1 == nsteps) {
+      const int fstep = step - (step % T) + t;        // the row this thread finalises
+      const int fch = ch_begin + fstep * NS + slot;
+      if (fstep <= step && fch < ch_end) {
+        const bool fused = row_used(fstep);
+        double sig;
+        if (a.errs) sig = fused ? a.errs[(size_t)s * a.nchan + fch] : 0.0;
+        else sig = sqrt(keep_top / ((double)(2 * N) * (double)ntop));      // pplib.py:2243-2245
+        const double sF2 = sig * sig * (double)N;                           // sigma^2 * nbin/2
+        const bool ok = fused && (sF2 > 0.0) && (sF2 < 1e300);
+        const size_t o = (size_t)s * a.nchan + fch;
+        a.sigma[o] = ok ? sig : 0.0;
+        a.Ssn[o] = ok ? a.pn[fch] / sF2 : 0.0;
+        a.Sdn[o] = ok ? keep_all / sF2 : 0.0;
+      }
     }
   }
   if (want_guess) {
