@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
   cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [L::kTotal] (+pad)
   cx<F>* bufs = tw + ((L::kTotal + 1) & ~1);                            // [NS][kBufElems]
   float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * S8::kBufElems);  // [NS][2][2N]
-  __shared__ double red[NS][(T >= 32 ? T / 32 : 1)][2];
+  __shared__ double red[2][NS][(T >= 32 ? T / 32 : 1)][2];   // per-warp power sums, by row parity
   __shared__ __align__(8) unsigned long long mbar[NS][2];
   const int tid = threadIdx.x, slot = tid / T, t = tid % T;
   for (int i = tid; i < L::kTotal; i += S8::kThreads) tw[i] = a.tw8[i];
@@ -299,6 +299,17 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = make_float2(0.f, 0.f);
   double keep_all = 0.0, keep_top = 0.0;
+  // thread r of a slot collects the power sums of row r (T > 32: from the per-warp totals)
+  auto latch = [&](int r) {
+    if constexpr (T > 32) {
+      if (r == t) {
+        double sa = 0.0, st = 0.0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) { sa += red[r & 1][slot][w][0]; st += red[r & 1][slot][w][1]; }
+        keep_all = sa; keep_top = st;
+      }
+    }
+  };
 
   auto row_used = [&](int step) -> bool {
     const int ch = ch_begin + step * NS + slot;
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     const size_t xo = ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
-    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); }, load_mc);
+    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); latch(step - 1); }, load_mc);
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
@@ -407,43 +418,36 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
 #pragma unroll
       for (int q = 0; q < 4; ++q) emit(quad_harmonic<N>(p, q), d[q], 4 * i + q, acc[4 * i + q]);
     }
-    // ---- row-slot reduction of the two power sums ---------------------------------
-    if constexpr (T >= 32) {
+    // ---- power sums of the row: warp totals go to shared memory (by row parity); thread
+    // `step` of the slot picks them up after the next barrier (inside the next transform)
+    if constexpr (T > 32) {
       s_all = warp_sum(s_all); s_top = warp_sum(s_top);
-      if constexpr (T > 32) {
-        if ((tid & 31) == 0) { red[slot][t >> 5][0] = s_all; red[slot][t >> 5][1] = s_top; }
-        slot_sync<N>(slot);
-        double sa = 0.0, st = 0.0;
-#pragma unroll
-        for (int w = 0; w < T / 32; ++w) { sa += red[slot][w][0]; st += red[slot][w][1]; }
-        s_all = sa; s_top = st;
-      }
+      if ((tid & 31) == 0) { red[step & 1][slot][t >> 5][0] = s_all; red[step & 1][slot][t >> 5][1] = s_top; }
     } else {
 #pragma unroll
       for (int o = T / 2; o > 0; o >>= 1) {
         s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
         s_top += __shfl_xor_sync(0xffffffffu, s_top, o);
       }
+      if (step == t) { keep_all = s_all; keep_top = s_top; }
     }
-    // ---- noise, Sd, S: thread (step mod T) keeps the sums of this row and the slot
-    // finalises T rows at a time, one row per thread (sqrt and two divisions off the
-    // per-row critical path) -------------------------------------------------------------
-    if ((step % T) == t) { keep_all = s_all; keep_top = s_top; }
-    if (((step + 1) % T) == 0 || step + 1 == nsteps) {
-      const int fstep = step - (step % T) + t;        // the row this thread finalises
-      const int fch = ch_begin + fstep * NS + slot;
-      if (fstep <= step && fch < ch_end) {
-        const bool fused = row_used(fstep);
-        double sig;
-        if (a.errs) sig = fused ? a.errs[(size_t)s * a.nchan + fch] : 0.0;
-        else sig = sqrt(keep_top / ((double)(2 * N) * (double)ntop));      // pplib.py:2243-2245
-        const double sF2 = sig * sig * (double)N;                           // sigma^2 * nbin/2
-        const bool ok = fused && (sF2 > 0.0) && (sF2 < 1e300);
-        const size_t o = (size_t)s * a.nchan + fch;
-        a.sigma[o] = ok ? sig : 0.0;
-        a.Ssn[o] = ok ? a.pn[fch] / sF2 : 0.0;
-        a.Sdn[o] = ok ? keep_all / sF2 : 0.0;
-      }
+  }
+  // ---- noise, Sd, S: one row per thread (the host keeps nsteps <= T), so that the sqrt and
+  // the two divisions are off the per-row critical path ------------------------------------
+  if constexpr (T > 32) { slot_sync<N>(slot); latch(nsteps - 1); }
+  {
+    const int fch = ch_begin + t * NS + slot;
+    if (t < nsteps && fch < ch_end) {
+      const bool fused = row_used(t);
+      double sig;
+      if (a.errs) sig = fused ? a.errs[(size_t)s * a.nchan + fch] : 0.0;
+      else sig = sqrt(keep_top / ((double)(2 * N) * (double)ntop));      // pplib.py:2243-2245
+      const double sF2 = sig * sig * (double)N;                           // sigma^2 * nbin/2
+      const bool ok = fused && (sF2 > 0.0) && (sF2 < 1e300);
+      const size_t o = (size_t)s * a.nchan + fch;
+      a.sigma[o] = ok ? sig : 0.0;
+      a.Ssn[o] = ok ? a.pn[fch] / sF2 : 0.0;
+      a.Sdn[o] = ok ? keep_all / sF2 : 0.0;
     }
   }
   if (want_guess) {

@@ -476,6 +476,7 @@ static int rows_per_cta(pp_plan* pl, int chunk) {
   const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (pl->N / 8));
   int g = std::max(rows_conc, std::min(32, pl->nchan / 16));
   g = ((g + rows_conc - 1) / rows_conc) * rows_conc;
+  // k_spectra finalises one row per thread of a row slot: rows per slot <= N/8 (32 <= 128 here)
   return g;
 }
 
