@@ -242,26 +242,21 @@ __device__ __forceinline__ void split_quad8(const cx<F>* __restrict__ buf, const
 }
 
 // The p = 0 quad: a[0], b[0] give Z[0] (DC and Nyquist of the real series) and the
-// self-paired Z[H]; a[N/4], b[N/4] give the pair (N/4, 3N/4).
-// d[0..3] = harmonics H, N (Nyquist, real), N/4, 3N/4; returns the DC term.
+// self-paired Z[H]; a[N/4], b[N/4] give the pair (N/4, 3N/4).  The outputs are ordered
+// so that they resemble the general quad (slot p = 0 first, a top-quarter harmonic
+// second): d[0..3] = harmonics N (Nyquist, real; stored in slot 0), 3N/4, H, N/4.
+// Returns the DC term.
 template <int N, typename F>
 __device__ __forceinline__ F split_quad0(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, cx<F> (&d)[4]) {
   constexpr int H = N / 2, Q = N / 4;
   const cx<F> A1 = buf[phys(0)], B1 = buf[phys(H)], A2 = buf[phys(Q)], B2 = buf[phys(H + Q)];
   const cx<F> z0 = cadd(A1, B1), zh = csub(A1, B1);
   cx<F> unused;
-  real_pair(zh, zh, tw[TwLayout<N>::kSplitOff + H], d[0], unused);
-  d[1] = mk<F>(z0.x - z0.y, F(0));
+  real_pair(zh, zh, tw[TwLayout<N>::kSplitOff + H], d[2], unused);
+  d[0] = mk<F>(z0.x - z0.y, F(0));
   const cx<F> wb = mk<F>(B2.y, -B2.x);                // e^{-2 pi i Q/N} = -i
-  real_pair(cadd(A2, wb), csub(A2, wb), tw[TwLayout<N>::kSplitOff + Q], d[2], d[3]);
+  real_pair(cadd(A2, wb), csub(A2, wb), tw[TwLayout<N>::kSplitOff + Q], d[3], d[1]);
   return z0.x + z0.y;
-}
-
-// harmonic number of output `which` (0..3) of the quad p (see split_quad8 / split_quad0)
-template <int N> __device__ __forceinline__ int quad_harmonic(int p, int which) {
-  constexpr int H = N / 2;
-  if (p == 0) return which == 0 ? H : which == 1 ? N : which == 2 ? N / 4 : 3 * (N / 4);
-  return which == 0 ? p : which == 1 ? N - p : which == 2 ? H - p : H + p;
 }
 
 }  // namespace ppb

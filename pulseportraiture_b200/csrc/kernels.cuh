@@ -339,68 +339,84 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     }
     const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
-    // FFT pass so that their latency hides behind its butterflies
+    // FFT pass so that their latency hides behind its butterflies.
+    // Output q of quad i (p = t + i T) lives in slot p, N-p, N/2-p, N/2+p (q = 0..3); the
+    // p = 0 quad of thread 0 holds slot 0 (Nyquist), 3N/4, N/2, N/4 instead (split_quad0).
     // Slots >= LoK carry no lo part: float product and float conj(model) suffice there (kMix:
-    // for N >= 512 the only lo slot a thread can own is slot t, its first output).
-    // Output idx = 4 i + which of quad p = t + i T is harmonic quad_harmonic<N>(p, which).
+    // for N >= 512 the only lo slot a thread can own is slot t, output 0 of quad 0).
     constexpr bool kMix = (T >= 64);
+    constexpr int kLo = LoK<N>::value;
+    static_assert(kc == 3 * (N / 4), "top-quarter rule below");
+    const bool first = (t == 0);
+    auto slot_of = [&](int i, int q) -> int {
+      const int p = t + i * T;
+      if (q == 0) return p;
+      if (q == 2) return N / 2 - p;
+      if (q == 1) return (i == 0 && first) ? 3 * (N / 4) : N - p;
+      return (i == 0 && first) ? N / 4 : N / 2 + p;
+    };
+    const bool doX = a.X != nullptr && inrange;
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
     const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
     cx<F> mc64[kMix ? 1 : NACC];
     cx<float> mc32[kMix ? NACC : 1];
     auto load_mc = [&]() {
-      if (used && a.X != nullptr) {
+      if (doX && used) {
         if constexpr (kMix) mc64[0] = mc[t];
 #pragma unroll
         for (int i = 0; i < NQUAD; ++i) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int k = quad_harmonic<N>(t + i * T, q);
-            if constexpr (kMix) mc32[4 * i + q] = mcf[k == N ? 0 : k];
-            else mc64[4 * i + q] = mc[k == N ? 0 : k];
+            if constexpr (kMix) mc32[4 * i + q] = mcf[slot_of(i, q)];
+            else mc64[4 * i + q] = mc[slot_of(i, q)];
           }
+        }
+      } else {   // unused rows store zeros
+        if constexpr (kMix) mc64[0] = mk<F>(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+          if constexpr (kMix) mc32[i] = mk<float>(0.f, 0.f);
+          else mc64[i] = mk<F>(0.0, 0.0);
         }
       }
     };
     // per-row scalars: loaded before the transform so that their latency is hidden
-    const size_t xo = ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
+    float2* const Xrow = a.X + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
+    float2* const Xlorow = a.Xlo + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * kLo;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
     fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); latch(step - 1); }, load_mc);
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
-    auto emit = [&](int k, cx<F> d, int idx, float2& ac) {
+    auto emit = [&](cx<F> d, const int i, const int q, float2& ac) {
+      const int idx = 4 * i + q;
       const double pw = d.x * d.x + d.y * d.y;
       s_all += pw;
-      if (k >= kc) s_top += pw;
-      const int sl_k = (k == N) ? 0 : k;
+      // harmonics >= kc = 3N/4: output 1 of every quad, and the Nyquist term
+      if (q == 1 || (q == 0 && i == 0 && first)) s_top += pw;
       const float dfx = (float)d.x, dfy = (float)d.y;
-      if (a.X != nullptr && inrange) {
-        float2 xv = make_float2(0.f, 0.f);
-        if (kMix && (idx >= 2 || sl_k >= LoK<N>::value)) {
-          if (used) {
-            const cx<float> m = mc32[kMix ? idx : 0];
-            xv = make_float2(fmaf(dfx, m.x, -dfy * m.y), fmaf(dfx, m.y, dfy * m.x));
-          }
-          a.X[xo + sl_k] = xv;
+      if (doX) {
+        const int sk = slot_of(i, q);
+        bool lo;
+        if constexpr (kMix) lo = (i == 0 && q == 0) && (t < kLo);
+        else lo = true;
+        if (!lo) {
+          const cx<float> m = mc32[kMix ? idx : 0];
+          Xrow[sk] = make_float2(fmaf(dfx, m.x, -dfy * m.y), fmaf(dfx, m.y, dfy * m.x));
         } else {
-          float2 xl = make_float2(0.f, 0.f);
-          if (used) {
-            const cx<F> mval = mc64[kMix ? 0 : idx];
-            const cx<F> pr = cmul(d, mval);
-            xv = make_float2((float)pr.x, (float)pr.y);
-            xl = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
-          }
-          a.X[xo + sl_k] = xv;
-          if (sl_k < LoK<N>::value) a.Xlo[((size_t)sl * a.nchan + ch) * LoK<N>::value + sl_k] = xl;
+          const cx<F> pr = cmul(d, mc64[kMix ? 0 : idx]);
+          const float2 xv = make_float2((float)pr.x, (float)pr.y);
+          Xrow[sk] = xv;
+          if (kMix || sk < kLo) Xlorow[sk] = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
         }
       }
-      if (wgt != 0.f) {
+      if (want_guess) {
         float vx = dfx, vy = dfy;
         if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
+          const int sk = slot_of(i, q);
           double c, sn;
-          cis2pi((double)k * shift, c, sn);
+          cis2pi((double)(sk == 0 ? N : sk) * shift, c, sn);
           const float cf = (float)c, sf = (float)sn;
           const float tx = vx * cf - vy * sf;
           vy = vx * sf + vy * cf; vx = tx;
@@ -411,12 +427,11 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     };
 #pragma unroll
     for (int i = 0; i < NQUAD; ++i) {
-      const int p = t + i * T;
       cx<F> d[4];
-      if (i > 0 || p != 0) split_quad8<N, F>(buf, tw, p, d);
+      if (i > 0 || !first) split_quad8<N, F>(buf, tw, t + i * T, d);
       else split_quad0<N, F>(buf, tw, d);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) emit(quad_harmonic<N>(p, q), d[q], 4 * i + q, acc[4 * i + q]);
+      for (int q = 0; q < 4; ++q) emit(d[q], i, q, acc[4 * i + q]);
     }
     // ---- power sums of the row: warp totals go to shared memory (by row parity); thread
     // `step` of the slot picks them up after the next barrier (inside the next transform)
@@ -453,13 +468,14 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
   if (want_guess) {
     const int part = blockIdx.x * NS + slot;
     float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
+    const bool first = (t == 0);
 #pragma unroll
     for (int i = 0; i < NQUAD; ++i) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = quad_harmonic<N>(t + i * T, q);
-        pr[k == N ? 0 : k] = acc[4 * i + q];
-      }
+      const int p = t + i * T;
+      pr[p] = acc[4 * i];
+      pr[(i == 0 && first) ? 3 * (N / 4) : N - p] = acc[4 * i + 1];
+      pr[N / 2 - p] = acc[4 * i + 2];
+      pr[(i == 0 && first) ? N / 4 : N / 2 + p] = acc[4 * i + 3];
     }
   }
 }
