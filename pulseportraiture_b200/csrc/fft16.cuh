@@ -1,0 +1,131 @@
+// Radix-16 register butterflies for the N = 1024 row transform of k_spectra:
+// 1024 = 16 * 16 * 4, two shared-memory passes of 64 threads (16 points per
+// thread) and a last radix-4 pass fused into the real-FFT split.  Compared with
+// the radix-8 plan (8 * 8 * 8 * 2) one full shared-memory round trip per row
+// disappears; shared-memory bandwidth is what bounds the radix-8 passes.
+#pragma once
+#include "fft8.cuh"
+
+namespace ppb {
+
+// 16 B elements: the radix-16 passes read stride-64 / write stride-16 (pass 1) and
+// stride-16 within 256 (pass 2); XOR the column with bits 4..6 of the position.
+__device__ __forceinline__ int phys16(int i) { return i ^ ((i >> 4) & 7); }
+
+template <typename F> __device__ __forceinline__ cx<F> mul_c(cx<F> a, F c, F s) {   // a * (c - i s)
+  return mk<F>(fma(a.x, c, a.y * s), fma(a.y, c, -a.x * s));
+}
+
+// In-register forward DFT of 16 points.  Input natural order; output X[k] is left
+// in v[(k >> 2) + 4 (k & 3)] (read it through dft16_at()).
+template <typename F> __device__ __forceinline__ void dft16(cx<F> (&v)[16]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) dft4(v[r], v[r + 4], v[r + 8], v[r + 12]);   // A_r[q] -> v[r + 4q]
+  const F h = F(0.70710678118654752440), c1 = F(0.92387953251128675613), s1 = F(0.38268343236508977173);
+  // v[r + 4q] *= W16^(r q)
+  v[5] = mul_c(v[5], c1, s1);                                        // W16^1
+  v[6] = mk<F>(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));        // W16^2
+  v[7] = mul_c(v[7], s1, c1);                                        // W16^3
+  v[9] = mk<F>(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));        // W16^2
+  v[10] = mk<F>(v[10].y, -v[10].x);                                  // W16^4 = -i
+  v[11] = mk<F>(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y));  // W16^6
+  v[13] = mul_c(v[13], s1, c1);                                      // W16^3
+  v[14] = mk<F>(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y));  // W16^6
+  v[15] = mul_c(v[15], -c1, -s1);                                    // W16^9 = -c1 + i s1
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dft4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);  // X[q + 4s] -> v[s + 4q]
+}
+__host__ __device__ constexpr int dft16_at(int k) { return (k >> 2) + 4 * (k & 3); }
+
+// v[r] *= w^r, r = 1..15
+template <typename F> __device__ __forceinline__ void twiddle16(cx<F> (&v)[16], cx<F> w1) {
+  const cx<F> w2 = csqr(w1), w3 = cmul(w2, w1), w4 = csqr(w2);
+  v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+  v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+  const cx<F> w8 = csqr(w4);
+  v[8] = cmul(v[8], w8);
+  v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+  const cx<F> w12 = cmul(w8, w4);
+  v[12] = cmul(v[12], w12);
+  v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+}
+
+// The two radix-16 passes of a 1024-point row, 64 threads (t = 0..63), in place in
+// `buf` (phys16 layout).  `g`: the staged packed real row as float2; `tw16`: 16
+// factors e^{-2 pi i k/256}.  sync(): barrier over the 64 threads of the row.
+// Afterwards buf[p + 256 c] (c = 0..3, p < 256) is the input of the last radix-4 pass.
+template <typename F, typename Sync, typename Fn, typename Fn2>
+__device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw16, int t,
+                                               const float2* __restrict__ g, bool gvalid, Sync sync,
+                                               Fn after_first_reads, Fn2 in_last_pass) {
+  cx<F> v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 x = gvalid ? g[t + 64 * r] : make_float2(0.f, 0.f);
+    v[r] = mk<F>((F)x.x, (F)x.y);
+  }
+  sync();   // staged row consumed; the previous row's split reads of buf are done
+  after_first_reads();
+  dft16(v);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) buf[phys16(16 * t + k)] = v[dft16_at(k)];
+  sync();
+  const int k = t & 15;
+  const cx<F> w1 = tw16[k];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = buf[phys16(t + 64 * r)];
+  sync();
+  in_last_pass();
+  twiddle16(v, w1);
+  dft16(v);
+  const int j0 = (t - k) * 16 + k;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) buf[phys16(j0 + 16 * r)] = v[dft16_at(r)];
+  sync();
+}
+
+// Last radix-4 pass fused with the real-FFT split (N = 1024).  The butterflies p and
+// 256 - p (1 <= p <= 127) give Z[p + 256 j] and Z[256 - p + 256 j], i.e. the four
+// conjugate pairs (p + 256 j, N - p - 256 j): d[2j] = harmonic p + 256 j,
+// d[2j + 1] = harmonic N - p - 256 j.  w2s[p] = e^{-2 pi i p/2048}, p <= 128.
+template <typename F>
+__device__ __forceinline__ void split_oct16(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ w2s, int p, cx<F> (&d)[8]) {
+  const F h = F(0.70710678118654752440);
+  const cx<F> w2 = w2s[p];
+  cx<F> a0 = buf[phys16(p)], a1 = buf[phys16(p + 256)], a2 = buf[phys16(p + 512)], a3 = buf[phys16(p + 768)];
+  cx<F> b0 = buf[phys16(256 - p)], b1 = buf[phys16(512 - p)], b2 = buf[phys16(768 - p)], b3 = buf[phys16(1024 - p)];
+  const cx<F> wn1 = csqr(w2), wn2 = csqr(wn1), wn3 = cmul(wn1, wn2);     // e^{-2 pi i c p/N}
+  a1 = cmul(a1, wn1); a2 = cmul(a2, wn2); a3 = cmul(a3, wn3);
+  dft4(a0, a1, a2, a3);                                                  // Z[p + 256 j]
+  // e^{-2 pi i c (256 - p)/N} = (-i)^c conj(wn_c)
+  b1 = cmul(b1, mk<F>(-wn1.y, -wn1.x)); b2 = cmul(b2, mk<F>(-wn2.x, wn2.y)); b3 = cmul(b3, mk<F>(wn3.y, wn3.x));
+  dft4(b0, b1, b2, b3);                                                  // Z[256 - p + 256 j]
+  // split factors e^{-2 pi i (p + 256 j)/2048} = w2 W8^j
+  real_pair(a0, b3, w2, d[0], d[1]);
+  real_pair(a1, b2, mk<F>(h * (w2.x + w2.y), h * (w2.y - w2.x)), d[2], d[3]);
+  real_pair(a2, b1, mk<F>(w2.y, -w2.x), d[4], d[5]);
+  real_pair(a3, b0, mk<F>(h * (w2.y - w2.x), -h * (w2.x + w2.y)), d[6], d[7]);
+}
+
+// The special unit: butterflies p = 0 and p = 128.  d[0] = Nyquist (real, slot 0),
+// d[2], d[4], d[6] = harmonics 256, 512, 768; d[1], d[3], d[5], d[7] = 896, 640, 384, 128.
+template <typename F>
+__device__ __forceinline__ void split_oct0(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ w2s, cx<F> (&d)[8]) {
+  const F h = F(0.70710678118654752440);
+  cx<F> a0 = buf[phys16(0)], a1 = buf[phys16(256)], a2 = buf[phys16(512)], a3 = buf[phys16(768)];
+  cx<F> b0 = buf[phys16(128)], b1 = buf[phys16(384)], b2 = buf[phys16(640)], b3 = buf[phys16(896)];
+  dft4(a0, a1, a2, a3);                                                  // Z[0], Z[256], Z[512], Z[768]
+  b1 = mk<F>(h * (b1.x + b1.y), h * (b1.y - b1.x));                      // W8^1
+  b2 = mk<F>(b2.y, -b2.x);                                               // W8^2
+  b3 = mk<F>(h * (b3.y - b3.x), -h * (b3.x + b3.y));                     // W8^3
+  dft4(b0, b1, b2, b3);                                                  // Z[128], Z[384], Z[640], Z[896]
+  cx<F> unused;
+  d[0] = mk<F>(a0.x - a0.y, F(0));
+  real_pair(a1, a3, mk<F>(h, -h), d[2], d[6]);                           // e^{-2 pi i 256/2048}
+  real_pair(a2, a2, mk<F>(F(0), F(-1)), d[4], unused);
+  const cx<F> w = w2s[128];                                              // e^{-2 pi i 128/2048}
+  real_pair(b0, b3, w, d[7], d[1]);
+  real_pair(b1, b2, mk<F>(h * (w.x + w.y), h * (w.y - w.x)), d[5], d[3]);
+}
+
+}  // namespace ppb

@@ -22,7 +22,7 @@
 #include <stdint.h>
 
 #include "fft.cuh"
-#include "fft8.cuh"
+#include "spectra_plan.cuh"
 
 namespace ppb {
 
@@ -73,6 +73,15 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* >= NV *
 __device__ __forceinline__ void cis2pi(double x, double& c, double& s) {
   x -= rint(x);
   sincospi(2.0 * x, &s, &c);
+}
+
+// (vx + i vy) e^{2 pi i x}, out of line: the rarely used DM_guess rotation of k_spectra
+// would otherwise put one double sincospi per harmonic into its hot loop's code.
+__device__ __noinline__ float2 rot2pi(float vx, float vy, double x) {
+  double c, sn;
+  cis2pi(x, c, sn);
+  const float cf = (float)c, sf = (float)sn;
+  return make_float2(vx * cf - vy * sf, vx * sf + vy * cf);
 }
 
 __device__ __forceinline__ double wrap_phase(double phi) {
@@ -262,25 +271,24 @@ struct SpectraArgs {
   int nchan, G, nparts;
 };
 
-template <int N>
-__global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTRA_MINB)) k_spectra(SpectraArgs a) {
-  using S8 = Slot8<N>;
-  using L = TwLayout<N>;
+template <int N, class PL = SpecPlan<N>>
+__global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(SpectraArgs a) {
   using F = double;
-  constexpr int T = S8::kT, NS = S8::kSlots, NQUAD = S8::kQuads, NACC = 4 * NQUAD;
+  constexpr int T = PL::kT, NS = PL::kSlots, NUNIT = PL::kUnits, NOUT = PL::kOut, NACC = NUNIT * NOUT;
+  static_assert(NACC * T == N, "every harmonic slot has one owner");
   constexpr unsigned kRowBytes = 2 * N * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [L::kTotal] (+pad)
-  cx<F>* bufs = tw + ((L::kTotal + 1) & ~1);                            // [NS][kBufElems]
-  float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * S8::kBufElems);  // [NS][2][2N]
+  cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [PL::kTwTotal] (+pad)
+  cx<F>* bufs = tw + ((PL::kTwTotal + 1) & ~1);                         // [NS][N]
+  float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * N);   // [NS][2][2N]
   __shared__ double red[2][NS][(T >= 32 ? T / 32 : 1)][2];   // per-warp power sums, by row parity
   __shared__ __align__(8) unsigned long long mbar[NS][2];
   const int tid = threadIdx.x, slot = tid / T, t = tid % T;
-  for (int i = tid; i < L::kTotal; i += S8::kThreads) tw[i] = a.tw8[i];
+  for (int i = tid; i < PL::kTwTotal; i += PL::kThreads) tw[i] = a.tw8[i];
   if (t == 0) { mbar_init(&mbar[slot][0], 1); mbar_init(&mbar[slot][1], 1); }
   mbar_fence_init();
   __syncthreads();
-  cx<F>* buf = bufs + (size_t)slot * S8::kBufElems;
+  cx<F>* buf = bufs + (size_t)slot * N;
   float* stage = stage_all + (size_t)slot * 2 * (2 * N);
 
   const int sl = blockIdx.y, s = a.s0 + sl;
@@ -339,22 +347,15 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     }
     const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
-    // FFT pass so that their latency hides behind its butterflies.
-    // Output q of quad i (p = t + i T) lives in slot p, N-p, N/2-p, N/2+p (q = 0..3); the
-    // p = 0 quad of thread 0 holds slot 0 (Nyquist), 3N/4, N/2, N/4 instead (split_quad0).
+    // FFT pass so that their latency hides behind its butterflies.  Output q of unit i
+    // lives in slot PL::slot_of(t, i, q, first) (spectra_plan.cuh).
     // Slots >= LoK carry no lo part: float product and float conj(model) suffice there (kMix:
-    // for N >= 512 the only lo slot a thread can own is slot t, output 0 of quad 0).
+    // for N >= 512 the only lo slot a thread can own is slot t, output 0 of unit 0).
     constexpr bool kMix = (T >= 64);
     constexpr int kLo = LoK<N>::value;
-    static_assert(kc == 3 * (N / 4), "top-quarter rule below");
+    static_assert(kc == 3 * (N / 4), "PL::top() assumes the top quarter starts at 3N/4");
     const bool first = (t == 0);
-    auto slot_of = [&](int i, int q) -> int {
-      const int p = t + i * T;
-      if (q == 0) return p;
-      if (q == 2) return N / 2 - p;
-      if (q == 1) return (i == 0 && first) ? 3 * (N / 4) : N - p;
-      return (i == 0 && first) ? N / 4 : N / 2 + p;
-    };
+    auto slot_of = [&](int i, int q) -> int { return PL::slot_of(t, i, q, first); };
     const bool doX = a.X != nullptr && inrange;
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
     const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
@@ -364,11 +365,11 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
       if (doX && used) {
         if constexpr (kMix) mc64[0] = mc[t];
 #pragma unroll
-        for (int i = 0; i < NQUAD; ++i) {
+        for (int i = 0; i < NUNIT; ++i) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if constexpr (kMix) mc32[4 * i + q] = mcf[slot_of(i, q)];
-            else mc64[4 * i + q] = mc[slot_of(i, q)];
+          for (int q = 0; q < NOUT; ++q) {
+            if constexpr (kMix) mc32[NOUT * i + q] = mcf[slot_of(i, q)];
+            else mc64[NOUT * i + q] = mc[slot_of(i, q)];
           }
         }
       } else {   // unused rows store zeros
@@ -385,16 +386,15 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     float2* const Xlorow = a.Xlo + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * kLo;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
-    fft8_rows<N, F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); latch(step - 1); }, load_mc);
+    PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); latch(step - 1); }, load_mc);
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
     auto emit = [&](cx<F> d, const int i, const int q, float2& ac) {
-      const int idx = 4 * i + q;
+      const int idx = NOUT * i + q;
       const double pw = d.x * d.x + d.y * d.y;
       s_all += pw;
-      // harmonics >= kc = 3N/4: output 1 of every quad, and the Nyquist term
-      if (q == 1 || (q == 0 && i == 0 && first)) s_top += pw;
+      if (PL::top(i, q, first)) s_top += pw;      // harmonics >= kc = 3N/4
       const float dfx = (float)d.x, dfy = (float)d.y;
       if (doX) {
         const int sk = slot_of(i, q);
@@ -415,23 +415,19 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
         float vx = dfx, vy = dfy;
         if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
           const int sk = slot_of(i, q);
-          double c, sn;
-          cis2pi((double)(sk == 0 ? N : sk) * shift, c, sn);
-          const float cf = (float)c, sf = (float)sn;
-          const float tx = vx * cf - vy * sf;
-          vy = vx * sf + vy * cf; vx = tx;
+          const float2 r = rot2pi(vx, vy, (double)(sk == 0 ? N : sk) * shift);
+          vx = r.x; vy = r.y;
         }
         ac.x = fmaf(wgt, vx, ac.x);
         ac.y = fmaf(wgt, vy, ac.y);
       }
     };
 #pragma unroll
-    for (int i = 0; i < NQUAD; ++i) {
-      cx<F> d[4];
-      if (i > 0 || !first) split_quad8<N, F>(buf, tw, t + i * T, d);
-      else split_quad0<N, F>(buf, tw, d);
+    for (int i = 0; i < NUNIT; ++i) {
+      cx<F> d[NOUT];
+      PL::template split<F>(buf, tw, t, i, first, d);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) emit(d[q], i, q, acc[4 * i + q]);
+      for (int q = 0; q < NOUT; ++q) emit(d[q], i, q, acc[NOUT * i + q]);
     }
     // ---- power sums of the row: warp totals go to shared memory (by row parity); thread
     // `step` of the slot picks them up after the next barrier (inside the next transform)
@@ -449,7 +445,7 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
   }
   // ---- noise, Sd, S: one row per thread (the host keeps nsteps <= T), so that the sqrt and
   // the two divisions are off the per-row critical path ------------------------------------
-  if constexpr (T > 32) { slot_sync<N>(slot); latch(nsteps - 1); }
+  if constexpr (T > 32) { PL::sync(slot); latch(nsteps - 1); }
   {
     const int fch = ch_begin + t * NS + slot;
     if (t < nsteps && fch < ch_end) {
@@ -470,12 +466,9 @@ __global__ void __launch_bounds__(Slot8<N>::kThreads, (N >= 2048 ? 1 : PP_SPECTR
     float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
     const bool first = (t == 0);
 #pragma unroll
-    for (int i = 0; i < NQUAD; ++i) {
-      const int p = t + i * T;
-      pr[p] = acc[4 * i];
-      pr[(i == 0 && first) ? 3 * (N / 4) : N - p] = acc[4 * i + 1];
-      pr[N / 2 - p] = acc[4 * i + 2];
-      pr[(i == 0 && first) ? N / 4 : N / 2 + p] = acc[4 * i + 3];
+    for (int i = 0; i < NUNIT; ++i) {
+#pragma unroll
+      for (int q = 0; q < NOUT; ++q) pr[PL::slot_of(t, i, q, first)] = acc[NOUT * i + q];
     }
   }
 }

@@ -205,24 +205,52 @@ template <int N, typename T> static size_t fft_smem_bytes() {
   }
 
 template <int N> static size_t spectra_smem_bytes() {
-  return (size_t)(((TwLayout<N>::kTotal + 1) & ~1) + Slot8<N>::kSlots * Slot8<N>::kBufElems) * sizeof(cx<double>) +
-         (size_t)Slot8<N>::kSlots * 2 * (2 * N) * sizeof(float);
+  using PL = SpecPlan<N>;
+  return (size_t)(((PL::kTwTotal + 1) & ~1) + PL::kSlots * N) * sizeof(cx<double>) +
+         (size_t)PL::kSlots * 2 * (2 * N) * sizeof(float);
+}
+// row slots per k_spectra CTA for this nbin
+static int spectra_slots(int N) {
+  switch (N) {
+    case 32: return SpecPlan<32>::kSlots;
+    case 64: return SpecPlan<64>::kSlots;
+    case 128: return SpecPlan<128>::kSlots;
+    case 256: return SpecPlan<256>::kSlots;
+    case 512: return SpecPlan<512>::kSlots;
+    case 1024: return SpecPlan<1024>::kSlots;
+    default: return SpecPlan<2048>::kSlots;
+  }
 }
 
+static double2 unit_root(long num, long den) {   // e^{-2 pi i num/den} with exact quadrant values
+  num %= den;
+  if (num == 0) return make_double2(1.0, 0.0);
+  if (4 * num == den) return make_double2(0.0, -1.0);
+  if (2 * num == den) return make_double2(-1.0, 0.0);
+  if (4 * num == 3 * den) return make_double2(0.0, 1.0);
+  const double a = -2.0 * M_PI * (double)num / (double)den;
+  return make_double2(cos(a), sin(a));
+}
+// twiddle tables of the row-transform plan (spectra_plan.cuh)
+template <class PL> struct TwBuilder;
+template <> struct TwBuilder<SpecPlan16> {
+  static void build(std::vector<double2>& out) {
+    out.assign(SpecPlan16::kTwTotal, make_double2(0.0, 0.0));
+    for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
+    for (int p2 = 0; p2 <= 128; ++p2) out[SpecPlan16::kSplitOff + p2] = unit_root(p2, 2048);
+  }
+};
+template <int N> static void build_tw8_impl(std::vector<double2>& out);
+template <int N> struct TwBuilder<SpecPlan8<N>> {
+  static void build(std::vector<double2>& out) { build_tw8_impl<N>(out); }
+};
+template <int N> static void build_tw8(std::vector<double2>& out) { TwBuilder<SpecPlan<N>>::build(out); }
 // per-pass twiddle tables in the layout of TwLayout<N> (fft8.cuh)
-template <int N> static void build_tw8(std::vector<double2>& out) {
+template <int N> static void build_tw8_impl(std::vector<double2>& out) {
   using P = Plan8<N>;
   using L = TwLayout<N>;
   out.assign(L::kTotal, make_double2(0.0, 0.0));
-  auto root = [](long num, long den) {   // e^{-2 pi i num/den} with exact quadrant values
-    num %= den;
-    if (num == 0) return make_double2(1.0, 0.0);
-    if (4 * num == den) return make_double2(0.0, -1.0);
-    if (2 * num == den) return make_double2(-1.0, 0.0);
-    if (4 * num == 3 * den) return make_double2(0.0, 1.0);
-    const double a = -2.0 * M_PI * (double)num / (double)den;
-    return make_double2(cos(a), sin(a));
-  };
+  auto root = unit_root;
   for (int i = 1; i < P::n; ++i) {
     const int Ns = L::ns(i), R = P::radix(i);
     for (int k = 0; k < Ns; ++k) out[L::off(i) + k] = root((long)k, (long)Ns * R);
@@ -473,7 +501,7 @@ static int rows_per_cta(pp_plan* pl, int chunk) {
   // the FFTFIT guess are grouped, so it must NOT depend on the batch or chunk size (results
   // are bit-identical for any chunking): a function of nchan only, ~16 CTAs per subint.
   (void)chunk;
-  const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (pl->N / 8));
+  const int rows_conc = spectra_slots(pl->N);
   int g = std::max(rows_conc, std::min(32, pl->nchan / 16));
   g = ((g + rows_conc - 1) / rows_conc) * rows_conc;
   // k_spectra finalises one row per thread of a row slot: rows per slot <= N/8 (32 <= 128 here)
@@ -562,7 +590,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   const int chunk = pick_chunk(pl, nsub);
   const int G = rows_per_cta(pl, chunk);
-  const int rows_conc = std::max(1, PP_SPECTRA_THREADS / (N / 8));
+  const int rows_conc = spectra_slots(N);
   const int gx = (nchan + G - 1) / G;
   const int nparts = gx * rows_conc;
   pl->stats.chunk = chunk;
@@ -643,7 +671,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), Slot8<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
+      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
       pl->stats.launches++;
     }
     if (!data_on_device) CK(cudaEventRecord(pl->ev_free[c & 1], pl->stream));
