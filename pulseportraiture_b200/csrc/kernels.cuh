@@ -390,44 +390,50 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
-    auto emit = [&](cx<F> d, const int i, const int q, float2& ac) {
-      const int idx = NOUT * i + q;
-      const double pw = d.x * d.x + d.y * d.y;
-      s_all += pw;
-      if (PL::top(i, q, first)) s_top += pw;      // harmonics >= kc = 3N/4
-      const float dfx = (float)d.x, dfy = (float)d.y;
-      if (doX) {
-        const int sk = slot_of(i, q);
-        bool lo;
-        if constexpr (kMix) lo = (i == 0 && q == 0) && (t < kLo);
-        else lo = true;
-        if (!lo) {
-          const cx<float> m = mc32[kMix ? idx : 0];
-          Xrow[sk] = make_float2(fmaf(dfx, m.x, -dfy * m.y), fmaf(dfx, m.y, dfy * m.x));
-        } else {
-          const cx<F> pr = cmul(d, mc64[kMix ? 0 : idx]);
-          const float2 xv = make_float2((float)pr.x, (float)pr.y);
-          Xrow[sk] = xv;
-          if (kMix || sk < kLo) Xlorow[sk] = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
-        }
-      }
-      if (want_guess) {
-        float vx = dfx, vy = dfy;
-        if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422)
-          const int sk = slot_of(i, q);
-          const float2 r = rot2pi(vx, vy, (double)(sk == 0 ? N : sk) * shift);
-          vx = r.x; vy = r.y;
-        }
-        ac.x = fmaf(wgt, vx, ac.x);
-        ac.y = fmaf(wgt, vy, ac.y);
-      }
-    };
 #pragma unroll
     for (int i = 0; i < NUNIT; ++i) {
       cx<F> d[NOUT];
       PL::template split<F>(buf, tw, t, i, first, d);
+      float vx[NOUT], vy[NOUT];
 #pragma unroll
-      for (int q = 0; q < NOUT; ++q) emit(d[q], i, q, acc[NOUT * i + q]);
+      for (int q = 0; q < NOUT; ++q) {
+        const double pw = d[q].x * d[q].x + d[q].y * d[q].y;
+        s_all += pw;
+        if (PL::top(i, q, first)) s_top += pw;      // harmonics >= kc = 3N/4
+        vx[q] = (float)d[q].x; vy[q] = (float)d[q].y;
+      }
+      if (doX) {        // uniform over the row
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) {
+          const int idx = NOUT * i + q;
+          const int sk = slot_of(i, q);
+          bool lo;
+          if constexpr (kMix) lo = (i == 0 && q == 0) && (t < kLo);
+          else lo = true;
+          if (!lo) {
+            const cx<float> m = mc32[kMix ? idx : 0];
+            Xrow[sk] = make_float2(fmaf(vx[q], m.x, -vy[q] * m.y), fmaf(vx[q], m.y, vy[q] * m.x));
+          } else {
+            const cx<F> pr = cmul(d[q], mc64[kMix ? 0 : idx]);
+            const float2 xv = make_float2((float)pr.x, (float)pr.y);
+            Xrow[sk] = xv;
+            if (kMix || sk < kLo) Xlorow[sk] = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
+          }
+        }
+      }
+      if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422); uniform, rare
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) {
+          const int sk = slot_of(i, q);
+          const float2 r = rot2pi(vx[q], vy[q], (double)(sk == 0 ? N : sk) * shift);
+          vx[q] = r.x; vy[q] = r.y;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NOUT; ++q) {   // wgt = 0 when no guess is wanted or the row is unused
+        acc[NOUT * i + q].x = fmaf(wgt, vx[q], acc[NOUT * i + q].x);
+        acc[NOUT * i + q].y = fmaf(wgt, vy[q], acc[NOUT * i + q].y);
+      }
     }
     // ---- power sums of the row: warp totals go to shared memory (by row parity); thread
     // `step` of the slot picks them up after the next barrier (inside the next transform)
