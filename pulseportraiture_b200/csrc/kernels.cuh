@@ -703,11 +703,8 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
     constexpr int NG = NJ / U;                                 // groups (even)
     constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
-    auto lo_of = [&](int j) { return j < KJ ? ld_stream(lorow + j * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f); };
-    auto consume = [&](float4 v, float4 lo, bool first) {
-      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
-      const double xr0 = (double)v.x + (double)lo.x, xi0 = (double)v.y + (double)lo.y;
-      const double xr1 = (double)v.z + (double)lo.z, xi1 = (double)v.w + (double)lo.w;
+    static_assert(KJ <= U || KJ == NJ, "lo parts sit in the first group, or everywhere (N <= 64)");
+    auto accum = [&](double xr0, double xi0, double xr1, double xi1) {
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
       const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
       C += re0 + re1;
@@ -718,22 +715,55 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
       const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
       k0 += 16.0; k1 += 16.0;
     };
+    auto consume = [&](float4 v) { accum((double)v.x, (double)v.y, (double)v.z, (double)v.w); };
+    // the first KJ iterations carry the float32 residuals of the low harmonics
+    auto consume_lo = [&](float4 v, float4 lo, bool first) {
+      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
+      accum((double)v.x + (double)lo.x, (double)v.y + (double)lo.y, (double)v.z + (double)lo.z, (double)v.w + (double)lo.w);
+    };
     // software pipeline: the next group's loads are in flight while this one is consumed
-    float4 qa[U], qb[U];
+    float4 qa[U], qb[U], ql[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + u * 8 + l8);
-#pragma unroll 1
-    for (int gI = 0; gI < NG; gI += 2) {
+    for (int u = 0; u < U; ++u) {
+      qa[u] = ld_stream(row + u * 8 + l8);
+      ql[u] = u < KJ ? ld_stream(lorow + u * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if constexpr (KJ == NJ) {     // N <= 64: every iteration has a lo part
 #pragma unroll
-      for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + ((gI + 1) * U + u) * 8 + l8);
+      for (int j = 0; j < NJ; ++j)
+        consume_lo(ld_stream(row + j * 8 + l8), ld_stream(lorow + j * 8 + l8), j == 0);
+    } else if constexpr (NG == 1) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) consume(qa[u], lo_of(gI * U + u), gI == 0 && u == 0);
-      if (gI + 2 < NG) {
+      for (int u = 0; u < U; ++u) consume_lo(qa[u], ql[u], u == 0);
+    } else {
+      // first pair of groups, peeled: only group 0 has lo parts
 #pragma unroll
-        for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + ((gI + 2) * U + u) * 8 + l8);
+      for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + (U + u) * 8 + l8);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < KJ) consume_lo(qa[u], ql[u], u == 0);
+        else if (u == 0) consume_lo(qa[u], make_float4(0.f, 0.f, 0.f, 0.f), true);
+        else consume(qa[u]);
+      }
+      if (2 < NG) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + (2 * U + u) * 8 + l8);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) consume(qb[u], lo_of((gI + 1) * U + u), false);
+      for (int u = 0; u < U; ++u) consume(qb[u]);
+#pragma unroll 1
+      for (int gI = 2; gI < NG; gI += 2) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + ((gI + 1) * U + u) * 8 + l8);
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(qa[u]);
+        if (gI + 2 < NG) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + ((gI + 2) * U + u) * 8 + l8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) consume(qb[u]);
+      }
     }
     if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
