@@ -550,13 +550,18 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   double bv = CUDART_INF;
   int bi = 0x7fffffff;
   for (int j = w; j < a.Ns; j += 8) {
+    // e^{2 pi i k phi_j} = e^{-i pi k} e^{2 pi i (k j mod M)/M}; a lane's harmonics k = lane + 32 m all
+    // have the parity of the lane (the Nyquist term k = N in slot 0 is even, like lane 0)
     double acc = 0.0;
+    const int stepi = (32 * j) % M;
+    int idx = (lane == 0) ? (int)(((long long)N * j) % M) : (lane * j) % M;
     for (int i = lane; i < N; i += 32) {
-      const int k = (i == 0) ? N : i;
-      const double2 t = a.table[(int)(((long long)k * j) % M)];
-      const double re = Y[i].x * t.x - Y[i].y * t.y;
-      acc += (k & 1) ? -re : re;  // e^{-i pi k}
+      const double2 t = a.table[idx];
+      acc += Y[i].x * t.x - Y[i].y * t.y;
+      idx = (i == 0) ? stepi : idx + stepi;      // slot 0 held k = N; next is k = 32
+      if (idx >= M) idx -= M;
     }
+    if (lane & 1) acc = -acc;
     acc = warp_sum(acc);
     const double cj = -acc / err2;
     if (cj < bv) { bv = cj; bi = j; }  // j ascending: first index wins ties
@@ -600,9 +605,10 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
     }
     __syncthreads();
     const bool stop = bc[3] != 0.0;
-    if (!stop) { x = bc[0]; lo = bc[1]; hi = bc[2]; }
+    const double xn = bc[0];
+    if (!stop) { x = xn; lo = bc[1]; hi = bc[2]; }
     __syncthreads();
-    if (stop) break;
+    if (stop) { if (a.x) x = xn; break; }   // start value of the solver: take the last (tiny) step too
   }
   if (tid == 0) {
     const double fmin = C0;

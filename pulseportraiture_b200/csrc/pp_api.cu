@@ -683,7 +683,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
-      ga.polish_tol = 1e-9;   // a start value: the Newton solver refines it
+      ga.polish_tol = 1e-6;   // a start value (the last step is still applied): the Newton solver refines it
       ga.init = nullptr; ga.scat = dscat; ga.log10_tau = args->log10_tau; ga.fit_scat = ff[3] ? 1 : 0;
       k_guess<<<ns, 256, sizeof(double2) * N, pl->stream>>>(ga);
       k_reset_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
