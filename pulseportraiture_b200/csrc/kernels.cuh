@@ -698,17 +698,38 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
     double theta = phi + DM * g;               // pplib.py:1319-1320
     theta -= rint(theta);
     const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
-    // element (j, e): complex index 16 j + 2 l8 + e, harmonic k = index (slot 0 = Nyquist)
-    double c0, s0, c1, s1, cw, sw;
-    cis2pi((double)(2 * l8) * theta, c0, s0);
-    cis2pi((double)(2 * l8 + 1) * theta, c1, s1);
-    cis2pi(16.0 * theta, cw, sw);
-    double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
     constexpr int NJ = N / 16;
     constexpr int U = NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1);   // loads kept in flight per buffer
     constexpr int NG = NJ / U;                                 // groups (even)
     constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
+    // the first loads go out before the phasor set-up so that its latency is hidden
+    float4 qa[U], qb[U], ql[U];
+    if constexpr (KJ != NJ) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        qa[u] = ld_stream(row + u * 8 + l8);
+        ql[u] = u < KJ ? ld_stream(lorow + u * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // element (j, e): complex index 16 j + 2 l8 + e, harmonic k = index (slot 0 = Nyquist).
+    // Phasors e^{2 pi i k theta} for k = 2 l8, 2 l8 + 1 and the step 16 from one sincospi and
+    // repeated squaring (phase error ~1e-15 rad, far inside the chi^2 tolerance).
+    double c0, s0, c1, s1, cw, sw;
+    cx<double> e1, e2, e4, e8, e16;
+    cis2pi(theta, e1.x, e1.y);
+    e2 = csqr(e1); e4 = csqr(e2); e8 = csqr(e4); e16 = csqr(e8);
+    {
+      cx<double> z = mk<double>(1.0, 0.0);
+      if (l8 & 1) z = e2;
+      if (l8 & 2) z = cmul(z, e4);
+      if (l8 & 4) z = cmul(z, e8);
+      c0 = z.x; s0 = z.y;
+      const cx<double> z1 = cmul(z, e1);
+      c1 = z1.x; s1 = z1.y;
+      cw = e16.x; sw = e16.y;
+    }
+    double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
     static_assert(KJ <= U || KJ == NJ, "lo parts sit in the first group, or everywhere (N <= 64)");
     auto accum = [&](double xr0, double xi0, double xr1, double xi1) {
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
@@ -728,12 +749,6 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
       accum((double)v.x + (double)lo.x, (double)v.y + (double)lo.y, (double)v.z + (double)lo.z, (double)v.w + (double)lo.w);
     };
     // software pipeline: the next group's loads are in flight while this one is consumed
-    float4 qa[U], qb[U], ql[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      qa[u] = ld_stream(row + u * 8 + l8);
-      ql[u] = u < KJ ? ld_stream(lorow + u * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     if constexpr (KJ == NJ) {     // N <= 64: every iteration has a lo part
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
@@ -775,8 +790,10 @@ __global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
       const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
       const double xnx = (double)xh.x + (double)xl.x, xny = (double)xh.y + (double)xl.y;
-      double cn, sn;
-      cis2pi((double)N * theta, cn, sn);
+      cx<double> en = e16;          // e^{2 pi i N theta} = (e^{2 pi i 16 theta})^(N/16)
+#pragma unroll
+      for (int q = 16; q < N; q *= 2) en = csqr(en);
+      const double cn = en.x, sn = en.y;
       const double re = xnx * cn - xny * sn;
       const double im = xnx * sn + xny * cn;
       C += re; C1 = fma((double)N, im, C1); C2 = fma((double)N * (double)N, re, C2);
