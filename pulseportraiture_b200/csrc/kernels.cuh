@@ -678,8 +678,11 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return v;
 }
 
+#ifndef PP_PASS2_MINB
+#define PP_PASS2_MINB 3
+#endif
 template <int N>
-__global__ void __launch_bounds__(256, 3) k_pass2(PassArgs a) {
+__global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
   const int sl = blockIdx.y, s = a.s0 + sl;
   if (a.st.done[s] == 1) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
