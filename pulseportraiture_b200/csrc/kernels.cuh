@@ -1087,6 +1087,7 @@ struct Pass5Args {
   const double* mpow;      // [nchan,N] |m|^2 (slot layout, double: S_n must not carry float rounding)
   const double* nu2;       // [nchan]
   const double* freqs;     // [nchan]
+  const double* lgf;       // [nchan] log2(freqs)
   const double* P;         // [nsub]
   const double* nu_fit;    // [nsub,3]
   const double* Ssn;       // [nsub,nchan] (0 => unused channel)
@@ -1118,14 +1119,28 @@ __global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
     const double gG = kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P;  // :207
     double theta = x[0] + x[1] * gD + x[2] * gG;
     theta -= rint(theta);
-    const double tau = a.log10_tau ? pow(10.0, x[3]) : x[3];
-    taun = tau * pow(a.freqs[ch] / nT, x[4]);                                      // pplib.py:4049-4053
+    // tau_n = tau (nu_n/nu_tau)^alpha (pplib.py:4049-4053) as one exp2: log2(nu_n) is tabulated
+    {
+      const double lr = x[4] * (a.lgf[ch] - log2(nT));
+      taun = a.log10_tau ? exp2(fma(x[3], 3.3219280948873623479, lr)) : x[3] * exp2(lr);
+    }
     const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
     const double2* mrow = reinterpret_cast<const double2*>(a.mpow + (size_t)ch * N);
+    // phasors for k = 2 l8, 2 l8 + 1 and the step 16 from one sincospi by repeated squaring (as k_pass2)
     double c0, s0, c1, s1, cw, sw;
-    cis2pi((double)(2 * l8) * theta, c0, s0);
-    cis2pi((double)(2 * l8 + 1) * theta, c1, s1);
-    cis2pi(16.0 * theta, cw, sw);
+    cx<double> e1, e2, e4, e8, e16;
+    cis2pi(theta, e1.x, e1.y);
+    e2 = csqr(e1); e4 = csqr(e2); e8 = csqr(e4); e16 = csqr(e8);
+    {
+      cx<double> z = mk<double>(1.0, 0.0);
+      if (l8 & 1) z = e2;
+      if (l8 & 2) z = cmul(z, e4);
+      if (l8 & 4) z = cmul(z, e8);
+      c0 = z.x; s0 = z.y;
+      const cx<double> z1 = cmul(z, e1);
+      c1 = z1.x; s1 = z1.y;
+      cw = e16.x; sw = e16.y;
+    }
     double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
     const double wt = kTwoPi * taun;   // b = k * wt
     auto element = [&](double xr, double xi, double m, double c, double sn, double k) {
@@ -1156,25 +1171,38 @@ __global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
     constexpr int NJ = N / 16;
     constexpr int KJ = LoK<N>::value / 16;
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
-#pragma unroll 2
-    for (int j = 0; j < NJ; ++j) {
-      float4 v = ld_stream(row + j * 8 + l8);
-      const float4 lo = j < KJ ? ld_stream(lorow + j * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto advance = [&]() {
+      const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
+      const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
+      k0 += 16.0; k1 += 16.0;
+    };
+    // the first KJ iterations carry the float32 residuals of the low harmonics
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      const float4 v = ld_stream(row + j * 8 + l8);
+      const float4 lo = ld_stream(lorow + j * 8 + l8);
       const double2 mm = __ldg(mrow + j * 8 + l8);
       const bool z = (j == 0 && l8 == 0);
       element(z ? 0.0 : (double)v.x + (double)lo.x, z ? 0.0 : (double)v.y + (double)lo.y, z ? 0.0 : mm.x, c0, s0, k0);
       element((double)v.z + (double)lo.z, (double)v.w + (double)lo.w, mm.y, c1, s1, k1);
-      const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
-      const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
-      k0 += 16.0; k1 += 16.0;
+      advance();
+    }
+#pragma unroll 2
+    for (int j = KJ; j < NJ; ++j) {
+      const float4 v = ld_stream(row + j * 8 + l8);
+      const double2 mm = __ldg(mrow + j * 8 + l8);
+      element((double)v.x, (double)v.y, mm.x, c0, s0, k0);
+      element((double)v.z, (double)v.w, mm.y, c1, s1, k1);
+      advance();
     }
     if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
       const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
       const double mn = __ldg(a.mpow + (size_t)ch * N);
-      double cn, sn;
-      cis2pi((double)N * theta, cn, sn);
-      element((double)xh.x + (double)xl.x, (double)xh.y + (double)xl.y, mn, cn, sn, (double)N);
+      cx<double> en = e16;          // e^{2 pi i N theta} = (e^{2 pi i 16 theta})^(N/16)
+#pragma unroll
+      for (int q = 16; q < N; q *= 2) en = csqr(en);
+      element((double)xh.x + (double)xl.x, (double)xh.y + (double)xl.y, mn, en.x, en.y, (double)N);
     }
   }
 #pragma unroll

@@ -78,7 +78,7 @@ struct pp_plan {
   int l2_bytes = 0, sm_count = 0;
   bool model_set = false;
   // tables + model
-  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, mconj32, mconj64, mpow, pn, mmean, model_stage;
+  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, mconj32, mconj64, mpow, pn, mmean, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
@@ -342,7 +342,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -411,17 +411,20 @@ static int grid_table(pp_plan* pl, int Ns, const double2** out) {
 // ----------------------------------------------------------------------------
 static int set_freqs_impl(pp_plan* pl, const double* freqs) {
   const int nchan = pl->nchan;
-  std::vector<double> hf(nchan), hn2(nchan);
+  std::vector<double> hf(nchan), hn2(nchan), hlg(nchan);
   if (is_device_ptr(freqs)) CK(cudaMemcpy(hf.data(), freqs, sizeof(double) * nchan, cudaMemcpyDeviceToHost));
   else memcpy(hf.data(), freqs, sizeof(double) * nchan);
   for (int n = 0; n < nchan; ++n) {
     if (!(hf[n] > 0.0)) return fail(-1, "freqs[%d] = %g is not positive", n, hf[n]);
     hn2[n] = 1.0 / (hf[n] * hf[n]);
+    hlg[n] = log2(hf[n]);
   }
   CK(pl->freqs.need(sizeof(double) * nchan));
   CK(pl->nu2.need(sizeof(double) * nchan));
   CK(cudaMemcpyAsync(pl->freqs.p, hf.data(), sizeof(double) * nchan, cudaMemcpyHostToDevice, pl->stream));
   CK(cudaMemcpyAsync(pl->nu2.p, hn2.data(), sizeof(double) * nchan, cudaMemcpyHostToDevice, pl->stream));
+  CK(pl->lgf.need(sizeof(double) * nchan));
+  CK(cudaMemcpyAsync(pl->lgf.p, hlg.data(), sizeof(double) * nchan, cudaMemcpyHostToDevice, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));  // hf/hn2 are stack-owned
   pl->freqs_set = true;
   return 0;
@@ -707,7 +710,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     Pass5Args p5;
     Update5Args u5;
     if (general) {
-      p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>();
+      p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>(); p5.lgf = pl->lgf.as<double>();
       p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
       p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
       p5.log10_tau = args->log10_tau;
