@@ -175,6 +175,20 @@ int pp_align_accumulate(pp_plan_t* plan, const float* data, int32_t nsub,
                         const double* nu_ref, const double* weights,
                         double* aligned, double* wsum);
 
+/* Evolving-Gaussian model portrait generated on the device: replaces
+ * pplib.gen_gaussian_portrait (pplib.py:853-930) with evolve_parameter
+ * (pplib.py:996-1046), gaussian_profile (pplib.py:770-825) and the analytic
+ * scattering of pplib.py:4049-4095; what read_model (pplib.py:2867-2953) calls
+ * per archive / per subint (pptoas.py:356-379).
+ *   model_code  three characters '0' (power law) / '1' (linear) for loc, wid, amp
+ *   params      HOST [2 + 6*ngauss]: DC, tau [bin], then per component
+ *               loc, m_loc, wid, m_wid, amp, m_amp  (as read from a .gmodel file)
+ *   out         float [nchan, nbin], host or device; frequencies from pp_set_freqs.
+ * The result can be handed to pp_set_model without leaving the device. */
+int pp_gen_gaussian_portrait(pp_plan_t* plan, const char* model_code,
+                             const double* params, int32_t ngauss,
+                             double scattering_index, double nu_ref, float* out);
+
 /* ---- per-channel noise -----------------------------------------------------
  * Replaces pplib.get_noise(data, chans=True) (pplib.py:2227-2245). */
 int pp_get_noise_batch(pp_plan_t* plan, const float* data, int32_t nsub,

@@ -1825,6 +1825,83 @@ __global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
 }
 
 // ----------------------------------------------------------------------------
+// k_gauss_model: evolving-Gaussian model portrait (gen_gaussian_portrait,
+// pplib.py:853-930) with evolve_parameter (996-1046) and gaussian_profile
+// (770-825, norm=False).  One CTA per channel.  Scattering (params[1] != 0) is
+// applied afterwards by k_rotate with the taus written here.
+// ----------------------------------------------------------------------------
+struct GaussModelArgs {
+  const double* params;   // [2 + 6 ngauss]: DC, tau [bin], (loc, m_loc, wid, m_wid, amp, m_amp) per component
+  const double* freqs;    // [nchan]
+  float* out;             // [nchan, nbin]
+  double* taus;           // [nchan] out: (tau/nbin) (nu/nu_ref)^alpha [rot]
+  double nu_ref, alpha;
+  int ngauss, nchan, nbin;
+  int code_loc, code_wid, code_amp;   // 0 power law, 1 linear
+};
+
+__device__ __forceinline__ double evolve_param(double f, double nu_ref, double p, double m, int code) {
+  if (code == 0) return exp((log(f) - log(nu_ref)) * m + log(p));   // pplib.py:1034-1037
+  return (f - nu_ref) * m + p;                                       // pplib.py:1038-1041
+}
+
+constexpr int kMaxGauss = 64;
+
+__global__ void __launch_bounds__(256) k_gauss_model(GaussModelArgs a) {
+  __shared__ double g_mean[kMaxGauss], g_isig[kMaxGauss], g_amp[kMaxGauss];
+  const int ch = blockIdx.x, tid = threadIdx.x, nbin = a.nbin;
+  const double f = a.freqs[ch];
+  // bin centres: np.linspace(lo + d/(2 nbin), hi - d/(2 nbin), nbin) (pplib.py:671-684)
+  const double x_lo = 1.0 / (2.0 * nbin), x_hi = 1.0 - 1.0 / (2.0 * nbin);
+  const double dx = nbin > 1 ? (x_hi - x_lo) / (double)(nbin - 1) : 0.0;
+  auto xbin = [&](int i) { return i == nbin - 1 ? x_hi : x_lo + (double)i * dx; };
+  auto wrapx = [&](double x, double mean) {   // pplib.py:805-808
+    if (mean < 0.5) return x > mean + 0.5 ? x - 1.0 : x;
+    return x < mean - 0.5 ? x + 1.0 : x;
+  };
+  for (int g = tid; g < a.ngauss; g += 256) {
+    const double* q = a.params + 2 + 6 * g;
+    const double loc = evolve_param(f, a.nu_ref, q[0], q[1], a.code_loc);
+    const double wid = evolve_param(f, a.nu_ref, q[2], q[3], a.code_wid);
+    const double amp = evolve_param(f, a.nu_ref, q[4], q[5], a.code_amp);
+    double mean = 0.0, isig = 0.0, scale = 0.0;
+    if (wid > 0.0) {
+      const double sigma = wid / (2.0 * sqrt(2.0 * log(2.0)));
+      mean = loc - floor(loc);                      // loc % 1
+      isig = 1.0 / sigma;
+      // the peak bin (argmax of the profile = smallest |z|, first index on ties) fixes the
+      // amplitude: value exp(-0.5 ((x[ipk] - loc)/sigma)^2) at the peak bin (pplib.py:820-823)
+      int i0 = (int)floor(mean * nbin);
+      double best = CUDART_INF; int ipk = -1;
+      for (int d = -1; d <= 1; ++d) {
+        const int i = ((i0 + d) % nbin + nbin) % nbin;
+        const double z = fabs((wrapx(xbin(i), mean) - mean) * isig);
+        if (z < best || (z == best && i < ipk)) { best = z; ipk = i; }
+      }
+      if (best < 20.0) {
+        const double xp = wrapx(xbin(ipk), mean);
+        const double zl = (xp - loc) * isig;
+        scale = amp * exp(-0.5 * zl * zl) / exp(-0.5 * best * best);
+      }
+    }
+    g_mean[g] = mean; g_isig[g] = isig; g_amp[g] = scale;
+  }
+  if (tid == 0) a.taus[ch] = (a.params[1] / (double)nbin) * pow(f / a.nu_ref, a.alpha);   // pplib.py:4049-4053
+  __syncthreads();
+  const double dc = a.params[0];
+  for (int i = tid; i < nbin; i += 256) {
+    const double x = xbin(i);
+    double v = dc;
+    for (int g = 0; g < a.ngauss; ++g) {
+      if (g_amp[g] == 0.0) continue;
+      const double z = (wrapx(x, g_mean[g]) - g_mean[g]) * g_isig[g];
+      if (fabs(z) < 20.0) v += g_amp[g] * exp(-0.5 * z * z);
+    }
+    a.out[(size_t)ch * nbin + i] = (float)v;
+  }
+}
+
+// ----------------------------------------------------------------------------
 // k_rotate: rfft -> multiply harmonic k by e^{2 pi i k theta} -> irfft
 // (pplib.py:2338-2460).  One row-slot per channel row; rows = nsub*nchan.
 // ----------------------------------------------------------------------------
@@ -1838,10 +1915,19 @@ struct RotateArgs {
   const double* GM;     // [nsub] or null (pptoaslib.rotate_portrait_full, pptoaslib.py:52-81)
   const double* nu_GM;  // [nsub] or null
   const double* nu2;    // [nchan]
+  const double* taus;   // [nchan] scattering times [rot] or null: multiply harmonic k by 1/(1 + 2 pi i k tau_n)
+                        // (scattering_portrait_FT, pplib.py:4080-4095)
   const void* twN;
   const void* tw2N;
   int nsub, nchan;
 };
+
+// (c + i s) / (1 + i b): the rotation phasor times the scattering kernel B_nk
+__device__ __forceinline__ void scatter_factor(double& c, double& s, double b) {
+  const double q = 1.0 / (1.0 + b * b);
+  const double cr = (c + s * b) * q, ci = (s - c * b) * q;
+  c = cr; s = ci;
+}
 
 // theta_n = phase + Dconst DM (nu^-2 - nu_ref^-2)/P + Dconst^2 GM (nu^-4 - nu_GM^-4)/P
 __device__ __forceinline__ double rot_theta(const RotateArgs& a, int s, int ch) {
@@ -1895,6 +1981,7 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
   cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
   cx<T>* other = (Z == bufA) ? bufB : bufA;
   const double theta = rot_theta(a, s, ch);
+  const double wtau = a.taus ? kTwoPi * a.taus[ch] : 0.0;
 #pragma unroll
   for (int i = 0; i < G::kPairs; ++i) {
     const int p = t_row + 1 + i * G::kTRow;
@@ -1903,9 +1990,11 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
       unpack_pair<T>(Z, tw2N, N, p, dp, dq);
       double c, sn;
       cis2pi((double)p * theta, c, sn);
+      if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)p);
       dp = cmul(dp, mk<T>((T)c, (T)sn));
       if (p < N / 2) {
         cis2pi((double)(N - p) * theta, c, sn);
+        if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)(N - p));
         dq = cmul(dq, mk<T>((T)c, (T)sn));
       } else {
         dq = dp;
@@ -1920,6 +2009,7 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
     const T d0 = Z[0].x + Z[0].y;
     double c, sn;
     cis2pi((double)N * theta, c, sn);
+    if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)N);
     const T dN = (Z[0].x - Z[0].y) * (T)c;   // irfft keeps the real part of the Nyquist term
     Z[0] = mk<T>(T(0.5) * (d0 + dN), -T(0.5) * (d0 - dN));
   }

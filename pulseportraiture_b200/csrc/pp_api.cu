@@ -78,7 +78,7 @@ struct pp_plan {
   int l2_bytes = 0, sm_count = 0;
   bool model_set = false;
   // tables + model
-  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, mconj32, mconj64, mpow, pn, mmean, model_stage;
+  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
@@ -342,7 +342,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -899,7 +899,7 @@ extern "C" int pp_rotate_full_batch(pp_plan_t* pl, const float* in, float* outp,
   if (stage_in(pl, pl->rot_nugm, nu_GM, (size_t)nsub, &dng)) return -2;
   RotateArgs a;
   a.in = din; a.out = dout; a.phase = dph; a.DM = ddm; a.P = dP; a.nu_ref = dnr; a.GM = dgm; a.nu_GM = dng;
-  a.nu2 = pl->nu2.as<double>(); a.nsub = nsub; a.nchan = nchan;
+  a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.nsub = nsub; a.nchan = nchan;
   const long nrows = (long)nsub * nchan;
   if (pl->fft_precision == 64) {
     a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
@@ -947,7 +947,7 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   CK(pl->al_wsum.need(sizeof(double) * nchan));
   AlignArgs a;
   a.r.in = din; a.r.out = nullptr; a.r.phase = dph; a.r.DM = ddm; a.r.P = dP; a.r.nu_ref = dnr; a.r.GM = nullptr;
-  a.r.nu_GM = nullptr; a.r.nu2 = pl->nu2.as<double>(); a.r.twN = pl->twN64.p; a.r.tw2N = pl->tw2N64.p;
+  a.r.nu_GM = nullptr; a.r.taus = nullptr; a.r.nu2 = pl->nu2.as<double>(); a.r.twN = pl->twN64.p; a.r.tw2N = pl->tw2N64.p;
   a.r.nsub = nsub; a.r.nchan = nchan;
   a.weights = dw; a.aligned = pl->al_out.as<double>(); a.wsum = pl->al_wsum.as<double>();
   DISPATCH_N(N, {
@@ -958,6 +958,58 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   CK(cudaGetLastError());
   if (copy_out(pl, aligned, pl->al_out.as<double>(), (size_t)nchan * 2 * N)) return -2;
   if (copy_out(pl, wsum, pl->al_wsum.as<double>(), (size_t)nchan)) return -2;
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, const double* params, int32_t ngauss,
+                                        double scattering_index, double nu_ref, float* outp) {
+  if (!pl || !model_code || !params || !outp) return fail(-1, "NULL argument");
+  if (ngauss < 0 || ngauss > kMaxGauss) return fail(-1, "ngauss must be in [0, %d]", kMaxGauss);
+  if (strlen(model_code) < 3) return fail(-1, "model_code needs three characters (loc, wid, amp)");
+  for (int i = 0; i < 3; ++i)
+    if (model_code[i] != '0' && model_code[i] != '1') return fail(-1, "model_code digit %d must be '0' or '1'", i);
+  if (!(nu_ref > 0.0)) return fail(-1, "nu_ref must be positive");
+  if (!pl->freqs_set) return fail(-1, "pp_set_freqs must be called before pp_gen_gaussian_portrait");
+  if (is_device_ptr(params)) return fail(-1, "params must be a host array");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan;
+  const size_t np = 2 + 6 * (size_t)ngauss, tot = (size_t)nchan * 2 * N;
+  CK(pl->gm_params.need(sizeof(double) * np));
+  CK(pl->gm_taus.need(sizeof(double) * nchan));
+  CK(cudaMemcpyAsync(pl->gm_params.p, params, sizeof(double) * np, cudaMemcpyHostToDevice, pl->stream));
+  float* dout = outp;
+  const bool out_dev = is_device_ptr(outp);
+  if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  GaussModelArgs g;
+  g.params = pl->gm_params.as<double>(); g.freqs = pl->freqs.as<double>(); g.out = dout; g.taus = pl->gm_taus.as<double>();
+  g.nu_ref = nu_ref; g.alpha = scattering_index; g.ngauss = ngauss; g.nchan = nchan; g.nbin = 2 * N;
+  g.code_loc = model_code[0] - '0'; g.code_wid = model_code[1] - '0'; g.code_amp = model_code[2] - '0';
+  k_gauss_model<<<nchan, 256, 0, pl->stream>>>(g);
+  pl->stats.launches++;
+  if (params[1] != 0.0) {   // scattering: rfft, times 1/(1 + 2 pi i k tau_n), irfft (pplib.py:921-927), in place
+    if (!pl->gm_zero.p) {
+      const double z = 0.0, o = 1.0;
+      CK(pl->gm_zero.need(sizeof(double)));
+      CK(pl->gm_one.need(sizeof(double)));
+      CK(cudaMemcpyAsync(pl->gm_zero.p, &z, sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+      CK(cudaMemcpyAsync(pl->gm_one.p, &o, sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+      CK(cudaStreamSynchronize(pl->stream));
+    }
+    RotateArgs a;
+    a.in = dout; a.out = dout; a.phase = pl->gm_zero.as<double>(); a.DM = pl->gm_zero.as<double>();
+    a.P = pl->gm_one.as<double>(); a.nu_ref = pl->gm_one.as<double>(); a.GM = nullptr; a.nu_GM = nullptr;
+    a.nu2 = pl->nu2.as<double>(); a.taus = pl->gm_taus.as<double>(); a.nsub = 1; a.nchan = nchan;
+    a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rotate<NN, double><<<(unsigned)((nchan + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+    });
+    pl->stats.launches++;
+  }
+  CK(cudaGetLastError());
+  if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));
   return 0;
 }

@@ -249,6 +249,28 @@ class WidebandPlan(object):
             aligned.ctypes.data, wsum.ctypes.data), "pp_align_accumulate")
         return aligned, wsum
 
+    def gen_gaussian_portrait(self, model_code, params, scattering_index, nu_ref, out=None, device_out=False):
+        """Evolving-Gaussian model portrait on the device (pplib.py:853-930) for the plan's
+        frequencies (set_freqs first).  ``params`` = [DC, tau_bin, (loc, m_loc, wid, m_wid, amp,
+        m_amp) * ngauss].  Returns float32 [nchan, nbin]: a numpy array, or a torch CUDA
+        tensor with ``device_out=True`` (ready for set_model without a host round trip)."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 1 or (params.size - 2) % 6:
+            raise ValueError("params must have 2 + 6*ngauss entries")
+        ngauss = (params.size - 2) // 6
+        if out is None:
+            if device_out:
+                import torch
+                out = torch.empty((self.nchan, self.nbin), dtype=torch.float32,
+                                  device=torch.device("cuda", self.device))
+            else:
+                out = np.empty((self.nchan, self.nbin), dtype=np.float32)
+        op = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        _ffi.check(self._lib.pp_gen_gaussian_portrait(
+            self._h, str(model_code).encode("ascii"), params.ctypes.data, int(ngauss),
+            float(scattering_index), float(nu_ref), op), "pp_gen_gaussian_portrait")
+        return out
+
     def rotate_batch(self, data, phase, DM, P, nu_ref, out=None, GM=None, nu_GM=None):
         if GM is not None:
             return self._rotate_full(data, phase, DM, GM, P, nu_ref, nu_GM, out)

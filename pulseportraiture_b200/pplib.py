@@ -342,10 +342,26 @@ def gen_gaussian_portrait(model_code, params, scattering_index, phases, freqs,
     return gport
 
 
-def read_model(modelfile, phases=None, freqs=None, P=None, quiet=False):
+def gen_gaussian_portrait_device(model_code, params, scattering_index, phases, freqs,
+                                 nu_ref, join_ichans=[], P=None):
+    """gen_gaussian_portrait (pplib.py:853-930) evaluated by the CUDA kernel
+    ``k_gauss_model`` (+ the scattering multiply of ``k_rotate``): the per-archive /
+    per-subint model build of pptoas.py:356-379.  ``phases`` must be the bin centres
+    of get_bin_centers(nbin).  Returns float64 [nchan, nbin] (float32 precision)."""
+    if len(join_ichans):
+        raise NotImplementedError("join parameters are a ppgauss feature")
+    nbin, nchan = len(phases), len(freqs)
+    if not np.allclose(phases, get_bin_centers(nbin), rtol=0, atol=1e-12):
+        raise ValueError("the device generator works on get_bin_centers(nbin)")
+    pl = get_plan(nchan, nbin)
+    pl.set_freqs(np.asarray(freqs, dtype=np.float64))
+    return pl.gen_gaussian_portrait(model_code, params, scattering_index, nu_ref).astype(np.float64)
+
+
+def read_model(modelfile, phases=None, freqs=None, P=None, quiet=False, device=False):
     """Read a ``.gmodel`` file (pplib.py:2867-2953).  Without phases/freqs
     returns (name, code, nu_ref, ngauss, params, fit_flags, alpha, fit_alpha);
-    otherwise (name, ngauss, model)."""
+    otherwise (name, ngauss, model).  ``device=True`` builds the portrait on the GPU."""
     read_only = phases is None and freqs is None
     comps = []
     modelname, model_code, nu_ref = "", default_model, None
@@ -390,7 +406,8 @@ def read_model(modelfile, phases=None, freqs=None, P=None, quiet=False):
             print("Need period P for non-zero scattering value TAU.")
             return 0
         params[1] *= nbin / P
-    model = gen_gaussian_portrait(model_code, params, alpha, phases, freqs, nu_ref)
+    gen = gen_gaussian_portrait_device if device else gen_gaussian_portrait
+    model = gen(model_code, params, alpha, phases, freqs, nu_ref)
     if not quiet:
         print("Model Name: %s" % modelname)
         print("Made %d component model with %d profile bins," % (ngauss, nbin))

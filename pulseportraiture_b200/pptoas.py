@@ -158,15 +158,15 @@ class GetTOAs:
             return self.modelfile
         if not fit_scat:
             self.model_name, self.ngauss, model = read_model(self.modelfile, phases, freqs_row, P,
-                                                             quiet=True)
+                                                             quiet=True, device=True)
             return model
         # scattering is fit: use the unscattered portrait (pptoas.py:364-375)
         (self.model_name, self.model_code, self.model_nu_ref, self.ngauss, self.gparams,
          model_fit_flags, self.alpha, model_fit_alpha) = read_model(self.modelfile, quiet=True)
         unscat_params = np.copy(self.gparams)
         unscat_params[1] = 0.0
-        return gen_gaussian_portrait(self.model_code, unscat_params, 0.0, phases, freqs_row,
-                                     self.model_nu_ref)
+        return pplib.gen_gaussian_portrait_device(self.model_code, unscat_params, 0.0, phases,
+                                                  freqs_row, self.model_nu_ref)
 
     def get_TOAs(self, datafile=None, tscrunch=False, nu_refs=None, DM0=None,
                  bary=True, fit_DM=True, fit_GM=False, fit_scat=False,
