@@ -282,6 +282,29 @@ def test_batch_64x512_vs_oracle(engine):
     print("worst chi2 rel dev over 64 subints: %.2e" % worst)
 
 
+@pytest.mark.parametrize("nbin", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_every_supported_nbin(engine, nbin):
+    """Every row-transform plan (nbin 64 ... 4096), with channel counts that do not fill
+    the last k_spectra CTA / k_pass2 warp (ragged), two-parameter and five-parameter fits."""
+    nchan, nsub = 13, 3
+    sigma = 1.5 if nbin >= 512 else 0.4
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 8800 + 10 * nbin + s, sigma=sigma) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), cases[0]["freqs"])
+        r = pl.fit_batch(data, cases[0]["P"])
+        noise = pl.get_noise_batch(data)
+    for s, c in enumerate(cases):
+        errs = orc.get_noise(c["data"], chans=True)
+        assert rel(noise[s], errs) < 1e-12
+        ref, _, _ = orc.toa_core(c["data"], c["model"], c["P"], c["freqs"], errs, polish="exact")
+        assert int(r["lag_index"][s]) == ref.lag_index
+        assert abs(r["params"][s, 0] - ref.phi) / ref.phi_err < SIG_TOL
+        assert abs(r["params"][s, 1] - ref.DM) / ref.DM_err < SIG_TOL
+        assert chi2_close(r["chi2"][s], ref.chi2, ref.snr)
+        assert rel(r["scales"][s], ref.scales) < 1e-5
+
+
 def test_config2_subset_512x2048(engine):
     """BASELINE config 2 shape (512 chan x 2048 bin): parity subset vs oracle."""
     nsub, nchan, nbin = 12, 512, 2048
