@@ -182,6 +182,27 @@ __global__ void k_model_mean(const cx<double>* __restrict__ mconj, float2* __res
   mmean[i] = make_float2((float)(sx / nchan), (float)(sy / nchan));
 }
 
+// mean of conj(m) over the USED channels of each subint (modelx.mean(axis=0) with
+// modelx = model[ok_ichans], pptoas.py:446, 454): grid (ceil(N/128), subints in chunk).
+__global__ void k_model_mean_masked(const cx<double>* __restrict__ mconj, const uint8_t* __restrict__ mask,
+                                    const float2* __restrict__ mmean_all, float2* __restrict__ out, int s0, int nchan,
+                                    int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sl = blockIdx.y;
+  if (i >= N) return;
+  const uint8_t* m = mask + (size_t)(s0 + sl) * nchan;
+  double sx = 0.0, sy = 0.0;
+  int cnt = 0;
+  for (int n = 0; n < nchan; ++n) {
+    if (m[n]) {
+      const cx<double> v = mconj[(size_t)n * N + i];
+      sx += v.x; sy += v.y; ++cnt;
+    }
+  }
+  // nothing masked: bit-identical to the all-channel mean; nothing used: keep it finite
+  out[(size_t)sl * N + i] = (cnt == nchan || cnt == 0) ? mmean_all[i] : make_float2((float)(sx / cnt), (float)(sy / cnt));
+}
+
 // ----------------------------------------------------------------------------
 // k_prep: one warp per subint.
 // ----------------------------------------------------------------------------

@@ -78,7 +78,7 @@ struct pp_plan {
   int l2_bytes = 0, sm_count = 0;
   bool model_set = false;
   // tables + model
-  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, model_stage;
+  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, mmean_sub, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
@@ -343,7 +343,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
   DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
-                 &pl->pn, &pl->mmean, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
+                 &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
                  &pl->in_nuouts, &pl->in_noise, &pl->in_models, &pl->nu_fit, &pl->nu_mean, &pl->wsum, &pl->nok, &pl->sigma,
@@ -683,6 +683,14 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       GuessArgs ga;
       memset(&ga, 0, sizeof ga);
       ga.partial = pl->partial.as<float2>(); ga.mconj = pl->mmean.as<float2>(); ga.nparts = nparts; ga.nmodel = 1;
+      if (dmask) {   // the guess template is the mean model over the subint's usable channels (pptoas.py:446, 454)
+        CK(pl->mmean_sub.need(sizeof(float2) * (size_t)chunk * N));
+        k_model_mean_masked<<<dim3((N + 127) / 128, ns), 128, 0, pl->stream>>>(
+            pl->mconj64.as<cx<double>>(), dmask, pl->mmean.as<float2>(), pl->mmean_sub.as<float2>(), s0, nchan, N);
+        pl->stats.launches++;
+        ga.mconj = pl->mmean_sub.as<float2>();
+        ga.nmodel = 2;   // > 1: one template per subint of the chunk
+      }
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();

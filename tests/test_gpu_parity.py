@@ -353,6 +353,13 @@ def test_masks_errs_dmguess_nufit_modes(engine):
             c["data"][ok], c["model"][ok], c["P"], c["freqs"][ok], errs[s][ok],
             weights=weights[s][ok], SNRs=snrs[s][ok], DM_stored=2.5e-3, polish="exact")
         assert int(r["lag_index"][s]) == res.lag_index
+        # the guess itself: weighted mean of the usable channels, dedispersed with DM_guess about
+        # their mean frequency, against the mean model of the SAME channels (pptoas.py:421-456)
+        fok = c["freqs"][ok]
+        prof = np.average(orc.rotate_data(c["data"][ok], 0.0, 2.5e-3, c["P"], fok, fok.mean()), axis=0,
+                          weights=weights[s][ok])
+        g = orc.fit_phase_shift(prof, c["model"][ok].mean(axis=0), Ns=100, polish="exact")
+        assert abs(r["phi_guess"][s] - g.phase) < 2e-2 * g.phase_err
         assert abs(r["params"][s, 0] - res.phi) / res.phi_err < SIG_TOL
         assert abs(r["params"][s, 1] - res.DM) / res.DM_err < SIG_TOL
         assert abs(r["chi2"][s] / res.chi2 - 1) < CHI2_TOL
