@@ -9,9 +9,10 @@
 //
 // The arithmetic type T is float or double.  numpy's float64 rfft is what the
 // reference computes; a float FFT carries ~1e-7 relative error per harmonic,
-// which matters only for the *measured* noise level of small portraits (the
-// mean of nbin/8 harmonic powers scales the whole chi^2), so the host picks
-// double there (pp_api.cu: pick_fft_precision) and float for large portraits.
+// which is enough to move chi^2 by more than the 1e-8 bar, so the fit path
+// (k_spectra, fft8.cuh / fft16.cuh) always runs in double; the float
+// instantiation of these radix-4 rows serves rotation and noise helpers when
+// the caller asks for it (pp_plan_set_fft_precision).
 //
 // Twiddles come from tables computed on the host in double precision:
 // twN[j] = e^{-2 pi i j/N}, tw2N[k] = e^{-2 pi i k/(2N)}, k = 0..N/2.

@@ -265,9 +265,11 @@ __global__ void k_prep(PrepArgs a) {
 }
 
 // ----------------------------------------------------------------------------
-// k_spectra: K1 + K2.  grid = (ceil(nchan/G), subints in chunk), 256 threads =
-// Slot8<N>::kSlots row slots of N/8 threads.  The FFT runs in double (see
-// DESIGN.md "precision"); X is stored as float2.
+// k_spectra: K1 + K2.  grid = (ceil(nchan/G), subints in chunk); a CTA holds
+// PL::kSlots row slots of PL::kT threads and walks G channel rows (row plan PL:
+// spectra_plan.cuh).  Rows arrive by TMA bulk copies into a double-buffered
+// staging area; the FFT runs in double (DESIGN.md "precision"); X is stored as
+// float2 plus the float32 residual of the first LoK slots.
 // ----------------------------------------------------------------------------
 struct SpectraArgs {
   const float* data;         // [nsub,nchan,2N], global subint index

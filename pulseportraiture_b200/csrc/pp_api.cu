@@ -472,19 +472,6 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   return 0;
 }
 
-// FFT arithmetic for the data rows.  A float FFT has ~1e-7 relative error per
-// harmonic, which is harmless for the fitted parameters (<1e-5 sigma) but not
-// for chi^2 of SMALL portraits: the measured noise level (mean of nbin/8
-// harmonic powers) scales the whole chi^2 of a channel, and the data power Sd
-// is dominated by a few strong harmonics per channel, so neither averages down
-// below 1e-8 relative unless nchan*nbin is large.  Automatic choice: double
-// below 2^20 samples per portrait, float from there on ("precision").
-static int pick_fft_precision(pp_plan* pl, bool noise_measured) {
-  (void)noise_measured;
-  if (pl->fft_precision) return pl->fft_precision;
-  return ((long)pl->nchan * pl->nbin < (1L << 20)) ? 64 : 32;
-}
-
 // ----------------------------------------------------------------------------
 // fit
 // ----------------------------------------------------------------------------
@@ -654,16 +641,13 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   for (int c = 0; c < nchunks; ++c) {
     const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
     const float* dchunk;
-    int s0_data;  // subint index offset to apply inside the data pointer
-    if (data_on_device) { dchunk = args->data; s0_data = s0; }
+    if (data_on_device) dchunk = args->data;
     else {
       if (c + 1 < nchunks) CK(issue_copy(c + 1));
       CK(cudaStreamWaitEvent(pl->stream, pl->ev_copy[c & 1], 0));
       // kernels index data with the global subint number: bias the base pointer
       dchunk = pl->data_stage[c & 1].as<float>() - (size_t)s0 * sub_floats;
-      s0_data = s0;
     }
-    (void)s0_data;
     {
       SpanGuard g(pl, SP_SPECTRA);
       SpectraArgs a;
