@@ -694,9 +694,12 @@ struct PassArgs {
 };
 
 // streaming 16-byte load: read-only path, do not keep in L1
+#ifndef PP_LD_STREAM_QUAL
+#define PP_LD_STREAM_QUAL "ld.global.nc.L1::no_allocate.v4.f32"
+#endif
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile(PP_LD_STREAM_QUAL " {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
@@ -725,7 +728,10 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     theta -= rint(theta);
     const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
     constexpr int NJ = N / 16;
-    constexpr int U = NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1);   // loads kept in flight per buffer
+#ifndef PP_PASS2_U
+#define PP_PASS2_U 4
+#endif
+    constexpr int U = NJ >= 2 * PP_PASS2_U ? PP_PASS2_U : (NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1));   // loads kept in flight per buffer
     constexpr int NG = NJ / U;                                 // groups (even)
     constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
