@@ -101,10 +101,12 @@ __device__ __forceinline__ void split_oct16(const cx<F>* __restrict__ buf, const
   b1 = cmul(b1, mk<F>(-wn1.y, -wn1.x)); b2 = cmul(b2, mk<F>(-wn2.x, wn2.y)); b3 = cmul(b3, mk<F>(wn3.y, wn3.x));
   dft4(b0, b1, b2, b3);                                                  // Z[256 - p + 256 j]
   // split factors e^{-2 pi i (p + 256 j)/2048} = w2 W8^j
-  real_pair(a0, b3, w2, d[0], d[1]);
-  real_pair(a1, b2, mk<F>(h * (w2.x + w2.y), h * (w2.y - w2.x)), d[2], d[3]);
-  real_pair(a2, b1, mk<F>(w2.y, -w2.x), d[4], d[5]);
-  real_pair(a3, b0, mk<F>(h * (w2.y - w2.x), -h * (w2.x + w2.y)), d[6], d[7]);
+  const F hh = F(0.5) * h;
+  const cx<F> wh = chalf(w2);
+  real_pair_h(a0, b3, wh, d[0], d[1]);
+  real_pair_h(a1, b2, mk<F>(hh * (w2.x + w2.y), hh * (w2.y - w2.x)), d[2], d[3]);
+  real_pair_h(a2, b1, mk<F>(wh.y, -wh.x), d[4], d[5]);
+  real_pair_h(a3, b0, mk<F>(hh * (w2.y - w2.x), -hh * (w2.x + w2.y)), d[6], d[7]);
 }
 
 // The special unit: butterflies p = 0 and p = 128.  d[0] = Nyquist (real, slot 0),
@@ -121,11 +123,12 @@ __device__ __forceinline__ void split_oct0(const cx<F>* __restrict__ buf, const 
   dft4(b0, b1, b2, b3);                                                  // Z[128], Z[384], Z[640], Z[896]
   cx<F> unused;
   d[0] = mk<F>(a0.x - a0.y, F(0));
-  real_pair(a1, a3, mk<F>(h, -h), d[2], d[6]);                           // e^{-2 pi i 256/2048}
-  real_pair(a2, a2, mk<F>(F(0), F(-1)), d[4], unused);
+  const F hh = F(0.5) * h;
+  real_pair_h(a1, a3, mk<F>(hh, -hh), d[2], d[6]);                       // e^{-2 pi i 256/2048} / 2
+  real_pair_h(a2, a2, mk<F>(F(0), F(-0.5)), d[4], unused);
   const cx<F> w = w2s[128];                                              // e^{-2 pi i 128/2048}
-  real_pair(b0, b3, w, d[7], d[1]);
-  real_pair(b1, b2, mk<F>(h * (w.x + w.y), h * (w.y - w.x)), d[5], d[3]);
+  real_pair_h(b0, b3, chalf(w), d[7], d[1]);
+  real_pair_h(b1, b2, mk<F>(hh * (w.x + w.y), hh * (w.y - w.x)), d[5], d[3]);
 }
 
 }  // namespace ppb

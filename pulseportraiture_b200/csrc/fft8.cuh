@@ -210,17 +210,18 @@ __device__ __forceinline__ void fft8_rows(cx<F>* __restrict__ buf, const cx<F>* 
 }
 
 // Real-FFT split of one conjugate pair: from Z[k], Z[N-k] of the packed complex
-// transform to the real-series harmonics d[k] and d[N-k]; w = e^{-2 pi i k/(2N)}.
+// transform to the real-series harmonics d[k] and d[N-k].  wh = 0.5 e^{-2 pi i k/(2N)}:
+// with the halved factor the 1/2 of E = (Z[k] + conj Z[N-k])/2 rides on the final
+// FMAs (12 instead of 16 operations, same roundings as the textbook form).
 template <typename F>
-__device__ __forceinline__ void real_pair(cx<F> zp, cx<F> zq, cx<F> w, cx<F>& dp, cx<F>& dq) {
-  const cx<F> zc = cconj(zq);
-  const cx<F> E = mk<F>(F(0.5) * (zp.x + zc.x), F(0.5) * (zp.y + zc.y));
-  const cx<F> D = mk<F>(F(0.5) * (zp.x - zc.x), F(0.5) * (zp.y - zc.y));
-  const cx<F> O = mk<F>(D.y, -D.x);
-  const cx<F> tt = cmul(w, O);
-  dp = cadd(E, tt);
-  dq = cconj(csub(E, tt));
+__device__ __forceinline__ void real_pair_h(cx<F> zp, cx<F> zq, cx<F> wh, cx<F>& dp, cx<F>& dq) {
+  const cx<F> E2 = mk<F>(zp.x + zq.x, zp.y - zq.y);      // 2 E   = Z[k] + conj(Z[N-k])
+  const cx<F> O2 = mk<F>(zp.y + zq.y, zq.x - zp.x);      // 2 O   = -i (Z[k] - conj(Z[N-k]))
+  const cx<F> tt = cmul(wh, O2);                          // w O
+  dp = mk<F>(fma(F(0.5), E2.x, tt.x), fma(F(0.5), E2.y, tt.y));
+  dq = mk<F>(fma(F(0.5), E2.x, -tt.x), fma(F(-0.5), E2.y, tt.y));
 }
+template <typename F> __device__ __forceinline__ cx<F> chalf(cx<F> a) { return mk<F>(F(0.5) * a.x, F(0.5) * a.y); }
 
 // Fused last radix-2 pass + real-FFT split, four harmonics per call so that every
 // element of the buffer is read exactly once per row.  With H = N/2, a = buf[0:H],
@@ -237,8 +238,9 @@ __device__ __forceinline__ void split_quad8(const cx<F>* __restrict__ buf, const
   const cx<F> wb1 = cmul(wn, B1), wb2 = cmul(cconj(wn), B2);
   const cx<F> Zp = cadd(A1, wb1), ZpH = csub(A1, wb1);   // Z[p], Z[p+H]
   const cx<F> Zq = csub(A2, wb2), ZqH = cadd(A2, wb2);   // Z[H-p], Z[N-p]
-  real_pair(Zp, ZqH, w2, d[0], d[1]);
-  real_pair(Zq, ZpH, mk<F>(-w2.y, -w2.x), d[2], d[3]);   // e^{-2 pi i (H-p)/(2N)} = -i conj(w2)
+  const cx<F> wh = chalf(w2);
+  real_pair_h(Zp, ZqH, wh, d[0], d[1]);
+  real_pair_h(Zq, ZpH, mk<F>(-wh.y, -wh.x), d[2], d[3]);   // e^{-2 pi i (H-p)/(2N)} = -i conj(w2)
 }
 
 // The p = 0 quad: a[0], b[0] give Z[0] (DC and Nyquist of the real series) and the
@@ -252,10 +254,10 @@ __device__ __forceinline__ F split_quad0(const cx<F>* __restrict__ buf, const cx
   const cx<F> A1 = buf[phys(0)], B1 = buf[phys(H)], A2 = buf[phys(Q)], B2 = buf[phys(H + Q)];
   const cx<F> z0 = cadd(A1, B1), zh = csub(A1, B1);
   cx<F> unused;
-  real_pair(zh, zh, tw[TwLayout<N>::kSplitOff + H], d[2], unused);
+  real_pair_h(zh, zh, chalf(tw[TwLayout<N>::kSplitOff + H]), d[2], unused);
   d[0] = mk<F>(z0.x - z0.y, F(0));
   const cx<F> wb = mk<F>(B2.y, -B2.x);                // e^{-2 pi i Q/N} = -i
-  real_pair(cadd(A2, wb), csub(A2, wb), tw[TwLayout<N>::kSplitOff + Q], d[3], d[1]);
+  real_pair_h(cadd(A2, wb), csub(A2, wb), chalf(tw[TwLayout<N>::kSplitOff + Q]), d[3], d[1]);
   return z0.x + z0.y;
 }
 

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   constexpr int T = PL::kT, NS = PL::kSlots, NUNIT = PL::kUnits, NOUT = PL::kOut, NACC = NUNIT * NOUT;
   static_assert(NACC * T == N, "every harmonic slot has one owner");
   constexpr unsigned kRowBytes = 2 * N * sizeof(float);
+  constexpr int NSTG = PL::kStages;   // staged raw rows per slot (TMA prefetch depth)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [PL::kTwTotal] (+pad)
   cx<F>* bufs = tw + ((PL::kTwTotal + 1) & ~1);                         // [NS][N]
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   mbar_fence_init();
   __syncthreads();
   cx<F>* buf = bufs + (size_t)slot * N;
-  float* stage = stage_all + (size_t)slot * 2 * (2 * N);
+  float* stage = stage_all + (size_t)slot * NSTG * (2 * N);
 
   const int sl = blockIdx.y, s = a.s0 + sl;
   const int ch_begin = blockIdx.x * a.G;
@@ -351,13 +352,13 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   auto fetch = [&](int step) {
     if (t == 0 && row_used(step)) {
       const int ch = ch_begin + step * NS + slot;
-      unsigned long long* bar = &mbar[slot][step & 1];
+      unsigned long long* bar = &mbar[slot][step % NSTG];
       mbar_expect_tx(bar, kRowBytes);
-      bulk_g2s(stage + (size_t)(step & 1) * 2 * N, a.data + ((size_t)s * a.nchan + ch) * 2 * N, kRowBytes, bar);
+      bulk_g2s(stage + (size_t)(step % NSTG) * 2 * N, a.data + ((size_t)s * a.nchan + ch) * 2 * N, kRowBytes, bar);
     }
   };
   fetch(0);
-  fetch(1);
+  if (NSTG > 1) fetch(1);
   unsigned ph0 = 0u, ph1 = 0u;
 
   for (int step = 0; step < nsteps; ++step) {
@@ -365,10 +366,10 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     const bool inrange = ch < ch_end;
     const bool used = row_used(step);
     if (used) {
-      if (step & 1) { mbar_wait(&mbar[slot][1], ph1); ph1 ^= 1u; }
+      if (NSTG > 1 && (step & 1)) { mbar_wait(&mbar[slot][1], ph1); ph1 ^= 1u; }
       else { mbar_wait(&mbar[slot][0], ph0); ph0 ^= 1u; }
     }
-    const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
+    const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step % NSTG) * 2 * N);
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
     // FFT pass so that their latency hides behind its butterflies.  Output q of unit i
     // lives in slot PL::slot_of(t, i, q, first) (spectra_plan.cuh).
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     float2* const Xlorow = a.Xlo + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * kLo;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
-    PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + 2); latch(step - 1); }, load_mc);
+    PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + NSTG); latch(step - 1); }, load_mc);
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
@@ -419,12 +420,21 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       PL::template split<F>(buf, tw, t, i, first, d);
       float vx[NOUT], vy[NOUT];
 #pragma unroll
+      double sa0 = 0.0, sa1 = 0.0;      // two chains: the power sum is latency, not throughput, bound
+#pragma unroll
       for (int q = 0; q < NOUT; ++q) {
-        const double pw = d[q].x * d[q].x + d[q].y * d[q].y;
-        s_all += pw;
-        if (PL::top(i, q, first)) s_top += pw;      // harmonics >= kc = 3N/4
+        double& sa = (q & 1) ? sa1 : sa0;
+        if (q == 1 || q == 6 || q == 0) {           // outputs that can be in the top quarter (PL::top)
+          const double pw = fma(d[q].x, d[q].x, d[q].y * d[q].y);
+          sa += pw;
+          if (PL::top(i, q, first)) s_top += pw;    // harmonics >= kc = 3N/4
+        } else {
+          sa = fma(d[q].x, d[q].x, sa);
+          sa = fma(d[q].y, d[q].y, sa);
+        }
         vx[q] = (float)d[q].x; vy[q] = (float)d[q].y;
       }
+      s_all += sa0 + sa1;
       if (doX) {        // uniform over the row
 #pragma unroll
         for (int q = 0; q < NOUT; ++q) {

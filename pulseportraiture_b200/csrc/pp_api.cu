@@ -207,7 +207,7 @@ template <int N, typename T> static size_t fft_smem_bytes() {
 template <int N> static size_t spectra_smem_bytes() {
   using PL = SpecPlan<N>;
   return (size_t)(((PL::kTwTotal + 1) & ~1) + PL::kSlots * N) * sizeof(cx<double>) +
-         (size_t)PL::kSlots * 2 * (2 * N) * sizeof(float);
+         (size_t)PL::kSlots * PL::kStages * (2 * N) * sizeof(float);
 }
 // row slots per k_spectra CTA for this nbin
 static int spectra_slots(int N) {

@@ -22,6 +22,9 @@
 #ifndef PP_SPECTRA16_MINB
 #define PP_SPECTRA16_MINB 6
 #endif
+#ifndef PP_SPECTRA16_STAGES
+#define PP_SPECTRA16_STAGES 2
+#endif
 
 namespace ppb {
 
@@ -31,6 +34,7 @@ template <int N> struct SpecPlan8 {
   static constexpr int kUnits = S8::kQuads, kOut = 4;
   static constexpr int kTwTotal = TwLayout<N>::kTotal;
   static constexpr int kMinBlocks = (N >= 2048 ? 1 : PP_SPECTRA_MINB);
+  static constexpr int kStages = 2;
   __device__ static __forceinline__ void sync(int slot) { slot_sync<N>(slot); }
   template <typename F, typename Fn, typename Fn2>
   __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int slot, const float2* g, bool used,
@@ -61,6 +65,7 @@ struct SpecPlan16 {
   static constexpr int kSplitOff = 16;                    // tw[0..15] = e^{-2 pi i k/256}; then e^{-2 pi i p/2048}, p <= 128
   static constexpr int kTwTotal = kSplitOff + 129;
   static constexpr int kMinBlocks = PP_SPECTRA16_MINB;
+  static constexpr int kStages = PP_SPECTRA16_STAGES;
   __device__ static __forceinline__ void sync(int) { __syncthreads(); }
   template <typename F, typename Fn, typename Fn2>
   __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int, const float2* g, bool used,
