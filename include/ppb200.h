@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PPB200_ABI_VERSION 1
+#define PPB200_ABI_VERSION 2
 
 typedef struct pp_plan pp_plan_t;
 
@@ -127,6 +127,12 @@ typedef struct {
   double* phi_guess;    /* [nsub] initial phase handed to the solver           */
   double* chan_sums;    /* [nsub,nchan,9] per-channel C,Cth,Cthth,Ct,Ctt,Ctht,
                            S,St,Stt at the solution (for host epilogues)       */
+  double* align_sum;    /* [nchan,nbin] ppalign (ppalign.py:197-213), fused: the
+                           sum over the batch of w_sn * rotate(data_sn, phi_s,
+                           DM_s about nu_out_s) with the FITTED phi_s, DM_s and
+                           w_sn = scales_sn / sigma_sn^2 (0 for unused channels
+                           and failed subints); not normalised                 */
+  double* align_wsum;   /* [nchan] sum_s w_sn (required with align_sum)        */
 } pp_fit_out_t;          /* any member may be NULL                              */
 
 int pp_fit_batch(pp_plan_t* plan, const pp_fit_args_t* args,

@@ -91,7 +91,7 @@ class FitOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "params", "param_errs", "nu_out", "cov", "chi2", "red_chi2", "snr",
         "nfeval", "return_code", "scales", "scale_errs", "channel_snrs",
-        "noise", "lag_index", "phi_guess", "chan_sums")]
+        "noise", "lag_index", "phi_guess", "chan_sums", "align_sum", "align_wsum")]
 
 
 class PShiftOut(C.Structure):

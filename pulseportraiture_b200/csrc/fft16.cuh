@@ -111,8 +111,9 @@ __device__ __forceinline__ void split_oct16(const cx<F>* __restrict__ buf, const
 
 // The special unit: butterflies p = 0 and p = 128.  d[0] = Nyquist (real, slot 0),
 // d[2], d[4], d[6] = harmonics 256, 512, 768; d[1], d[3], d[5], d[7] = 896, 640, 384, 128.
+// Returns the DC term.
 template <typename F>
-__device__ __forceinline__ void split_oct0(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ w2s, cx<F> (&d)[8]) {
+__device__ __forceinline__ F split_oct0(const cx<F>* __restrict__ buf, const cx<F>* __restrict__ w2s, cx<F> (&d)[8]) {
   const F h = F(0.70710678118654752440);
   cx<F> a0 = buf[phys16(0)], a1 = buf[phys16(256)], a2 = buf[phys16(512)], a3 = buf[phys16(768)];
   cx<F> b0 = buf[phys16(128)], b1 = buf[phys16(384)], b2 = buf[phys16(640)], b3 = buf[phys16(896)];
@@ -129,6 +130,7 @@ __device__ __forceinline__ void split_oct0(const cx<F>* __restrict__ buf, const 
   const cx<F> w = w2s[128];                                              // e^{-2 pi i 128/2048}
   real_pair_h(b0, b3, chalf(w), d[7], d[1]);
   real_pair_h(b1, b2, mk<F>(hh * (w.x + w.y), hh * (w.y - w.x)), d[5], d[3]);
+  return a0.x + a0.y;                                                    // DC of the real series
 }
 
 }  // namespace ppb

@@ -286,6 +286,8 @@ struct SpectraArgs {
   float2* X;                 // [chunk,nchan,N]  (null: do not store)
   float2* Xlo;               // [chunk,nchan,LoK<N>] float32 residuals of the first slots
   float2* partial;           // [chunk,nparts,N] (null: no guess)
+  float2* D;                 // [chunk,nchan,N] data spectra d (slot layout) or null; kept for the
+  double* Ddc;               // [chunk,nchan] ... and their DC terms: the fused ppalign accumulation
   double* sigma;             // [nsub,nchan] out
   double* Ssn;               // [nsub,nchan] out: p_n / sigma_F^2 (0 = channel unused)
   double* Sdn;               // [nsub,nchan] out
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     // per-row scalars: loaded before the transform so that their latency is hidden
     float2* const Xrow = a.X + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
     float2* const Xlorow = a.Xlo + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * kLo;
+    float2* const Drow = a.D + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
     PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + NSTG); latch(step - 1); }, load_mc);
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
 #pragma unroll
     for (int i = 0; i < NUNIT; ++i) {
       cx<F> d[NOUT];
-      PL::template split<F>(buf, tw, t, i, first, d);
+      const F dc_term = PL::template split<F>(buf, tw, t, i, first, d);   // DC of the row (special unit only)
       float vx[NOUT], vy[NOUT];
 #pragma unroll
       double sa0 = 0.0, sa1 = 0.0;      // two chains: the power sum is latency, not throughput, bound
@@ -453,6 +456,11 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
             if (kMix || sk < kLo) Xlorow[sk] = make_float2((float)(pr.x - (double)xv.x), (float)(pr.y - (double)xv.y));
           }
         }
+      }
+      if (a.D != nullptr && inrange) {     // uniform: raw spectra for k_align_spec (unused rows are skipped there)
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) Drow[slot_of(i, q)] = make_float2(vx[q], vy[q]);
+        if (i == 0 && first) a.Ddc[(size_t)sl * a.nchan + ch] = dc_term;
       }
       if (shift != 0.0) {           // rotate_data with DM_guess (pptoas.py:422); uniform, rare
 #pragma unroll
@@ -2168,6 +2176,157 @@ __global__ void __launch_bounds__(256) k_align_accum(AlignArgs a) {
       dst[2 * j + 1] = -Y[j].y * sc;
     }
     if (t_row == 0) a.wsum[ch] = wtot;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Fused ppalign accumulation (ppalign.py:197-213) from the spectra k_spectra kept:
+//   acc[n,k] += sum_s w_sn d_snk e^{2 pi i k theta_sn},  w_sn = scales_sn / sigma_sn^2,
+// theta_sn from the FITTED phi_s, DM_s about nu_out_s.  k_align_spec streams the float2
+// spectra once (as k_pass2 streams X): grid (nchan, nsplit) x N/8 threads, thread t owns
+// slots 8t..8t+7; the phasor of slot 8t comes from e^{2 pi i theta} by squaring and a
+// binary product, the next seven by recurrence.  k_align_finish packs the sums and
+// inverse transforms one channel per row slot.
+// ----------------------------------------------------------------------------
+struct AlignSpecArgs {
+  const float2* D;         // [chunk,nchan,N]
+  const double* Ddc;       // [chunk,nchan]
+  const double* params;    // [nsub,5] fitted, phi at nu_out
+  const double* nu_out;    // [nsub,3]
+  const double* P;         // [nsub]
+  const double* scales;    // [nsub,nchan]
+  const double* sigma;     // [nsub,nchan] (0 = unused channel)
+  const int* rc;           // [nsub] return codes (3 = non-finite fit: skipped)
+  const double* nu2;       // [nchan]
+  double2* acc;            // [nchan,N] slot layout (slot 0: x = Nyquist sum, y = DC sum)
+  double* wsum;            // [nchan]
+  int s0, ns, nchan;
+};
+
+template <int N>
+__global__ void __launch_bounds__(N / 8) k_align_spec(AlignSpecArgs a) {
+  constexpr int T = N / 8;
+  static_assert(T >= 4 && (T & (T - 1)) == 0, "row size");
+  constexpr int LOGT = Log2<T>::value;
+  const int n = blockIdx.x, t = threadIdx.x;
+  const int per = (a.ns + gridDim.y - 1) / gridDim.y;
+  const int sb = blockIdx.y * per, se = min(a.ns, sb + per);
+  cx<double> acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = mk<double>(0.0, 0.0);
+  double wtot = 0.0, dcsum = 0.0;
+  const double n2 = a.nu2[n];
+  auto row_ptr = [&](int sl) { return reinterpret_cast<const float4*>(a.D + ((size_t)sl * a.nchan + n) * N) + 4 * t; };
+  float4 q[4], qn[4];
+  if (sb < se) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = ld_stream(row_ptr(sb) + j);
+  }
+  for (int sl = sb; sl < se; ++sl) {
+    if (sl + 1 < se) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qn[j] = ld_stream(row_ptr(sl + 1) + j);
+    }
+    const int s = a.s0 + sl;
+    const double sg = a.sigma[(size_t)s * a.nchan + n];
+    const double sc = a.scales[(size_t)s * a.nchan + n];
+    const double w = (sg > 0.0 && a.rc[s] != 3) ? sc / (sg * sg) : 0.0;       // ppalign.py:202
+    if (w > 0.0 && w < 1e300) {                                               // uniform over the CTA
+      const double nr = a.nu_out[(size_t)s * 3];
+      double theta = a.params[(size_t)s * 5] + kDconst * a.params[(size_t)s * 5 + 1] * (n2 - 1.0 / (nr * nr)) / a.P[s];
+      theta -= rint(theta);
+      cx<double> e1, f;
+      cis2pi(theta, e1.x, e1.y);
+      f = csqr(csqr(csqr(e1)));                     // e^{2 pi i 8 theta}
+      cx<double> ph = mk<double>(1.0, 0.0);
+#pragma unroll
+      for (int b = 0; b < LOGT; ++b) {              // e^{2 pi i 8 t theta}
+        if ((t >> b) & 1) ph = cmul(ph, f);
+        f = csqr(f);
+      }
+      // f is now e^{2 pi i 8 T theta} = e^{2 pi i N theta}: the Nyquist phasor
+      const float2 d[8] = {make_float2(q[0].x, q[0].y), make_float2(q[0].z, q[0].w), make_float2(q[1].x, q[1].y),
+                           make_float2(q[1].z, q[1].w), make_float2(q[2].x, q[2].y), make_float2(q[2].z, q[2].w),
+                           make_float2(q[3].x, q[3].y), make_float2(q[3].z, q[3].w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double wx = w * (double)d[j].x, wy = w * (double)d[j].y;
+        if (j == 0 && t == 0) {
+          // slot 0 = Nyquist (real): irfft keeps Re(d_N e^{i N theta}); y carries the DC sum
+          acc[0].x = fma(wx, f.x, acc[0].x);
+        } else {
+          acc[j].x += wx * ph.x - wy * ph.y;
+          acc[j].y += wx * ph.y + wy * ph.x;
+        }
+        ph = cmul(ph, e1);
+      }
+      if (t == 0) { dcsum = fma(w, a.Ddc[(size_t)sl * a.nchan + n], dcsum); wtot += w; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = qn[j];
+  }
+  double2* o = a.acc + (size_t)n * N + 8 * t;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&o[j].x, acc[j].x);
+    atomicAdd(&o[j].y, (j == 0 && t == 0) ? dcsum : acc[j].y);
+  }
+  if (t == 0) atomicAdd(&a.wsum[n], wtot);
+}
+
+struct AlignFinishArgs {
+  const double2* acc;      // [nchan,N] from k_align_spec
+  double* aligned;         // [nchan,2N] out (not normalised by the weights)
+  const void* twN;
+  const void* tw2N;
+  int nchan;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) k_align_finish(AlignFinishArgs a) {
+  using G = RowGeom<N>;
+  using T = double;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* twN = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* tw2N = twN + N;
+  cx<T>* bufs = tw2N + (N / 2 + 2);
+  const int tid = threadIdx.x, r = tid / G::kTRow, t_row = tid % G::kTRow;
+  {
+    const cx<T>* g1 = reinterpret_cast<const cx<T>*>(a.twN);
+    const cx<T>* g2 = reinterpret_cast<const cx<T>*>(a.tw2N);
+    for (int i = tid; i < N; i += 256) twN[i] = g1[i];
+    for (int i = tid; i <= N / 2; i += 256) tw2N[i] = g2[i];
+  }
+  __syncthreads();
+  cx<T>* bufA = bufs + (size_t)r * 2 * N;
+  cx<T>* bufB = bufA + N;
+  const int ch = blockIdx.x * G::kRows + r;
+  const bool valid = ch < a.nchan;
+  const double2* src = a.acc + (size_t)(valid ? ch : 0) * N;
+#pragma unroll
+  for (int i = 0; i < G::kPairs; ++i) {
+    const int p = t_row + 1 + i * G::kTRow;
+    if (p <= N / 2) {
+      const double2 vp = src[p], vq = src[(p < N / 2) ? N - p : p];
+      cx<T> zp, zq;
+      pack_pair<T>(mk<T>(vp.x, vp.y), mk<T>(vq.x, vq.y), tw2N[p], zp, zq);
+      bufA[p] = cconj(zp);
+      if (p < N / 2) bufA[N - p] = cconj(zq);
+    }
+  }
+  if (t_row == 0) {
+    const double2 v0 = src[0];   // x = Nyquist sum, y = DC sum
+    bufA[0] = mk<T>(T(0.5) * (v0.y + v0.x), -T(0.5) * (v0.y - v0.x));
+  }
+  __syncthreads();
+  cx<T>* Y = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
+  if (valid) {
+    double* dst = a.aligned + (size_t)ch * 2 * N;
+    const T sc = T(1) / T(N);
+    for (int j = t_row; j < N; j += G::kTRow) {
+      dst[2 * j] = Y[j].x * sc;
+      dst[2 * j + 1] = -Y[j].y * sc;
+    }
   }
 }
 

@@ -42,9 +42,9 @@ template <int N> struct SpecPlan8 {
     fft8_rows<N, F>(buf, tw, t, slot, g, used, after_first_reads, in_last_pass);
   }
   template <typename F>
-  __device__ static __forceinline__ void split(const cx<F>* buf, const cx<F>* tw, int t, int i, bool first, cx<F> (&d)[kOut]) {
-    if (i > 0 || !first) split_quad8<N, F>(buf, tw, t + i * kT, d);
-    else split_quad0<N, F>(buf, tw, d);
+  __device__ static __forceinline__ F split(const cx<F>* buf, const cx<F>* tw, int t, int i, bool first, cx<F> (&d)[kOut]) {
+    if (i > 0 || !first) { split_quad8<N, F>(buf, tw, t + i * kT, d); return F(0); }
+    return split_quad0<N, F>(buf, tw, d);     // the row's DC term
   }
   // slot (index into a row of X / conj(model); slot 0 = Nyquist) of output q of unit i
   __device__ static __forceinline__ int slot_of(int t, int i, int q, bool first) {
@@ -73,9 +73,9 @@ struct SpecPlan16 {
     fft16_rows1024<F>(buf, tw, t, g, used, []() { __syncthreads(); }, after_first_reads, in_last_pass);
   }
   template <typename F>
-  __device__ static __forceinline__ void split(const cx<F>* buf, const cx<F>* tw, int t, int i, bool first, cx<F> (&d)[kOut]) {
-    if (i > 0 || !first) split_oct16<F>(buf, tw + kSplitOff, t + i * kT, d);
-    else split_oct0<F>(buf, tw + kSplitOff, d);
+  __device__ static __forceinline__ F split(const cx<F>* buf, const cx<F>* tw, int t, int i, bool first, cx<F> (&d)[kOut]) {
+    if (i > 0 || !first) { split_oct16<F>(buf, tw + kSplitOff, t + i * kT, d); return F(0); }
+    return split_oct0<F>(buf, tw + kSplitOff, d);   // the row's DC term
   }
   // q = 2j: slot p + 256 j; q = 2j + 1: slot N - p - 256 j; the special unit uses p = 0 for
   // the even and p = 128 for the odd outputs

@@ -149,7 +149,7 @@ class WidebandPlan(object):
                   nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
                   log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
                   tol=0.0, semantics="full", want_chan_sums=False, nsub=None,
-                  pinned_results=False, scat_guess=None):
+                  pinned_results=False, scat_guess=None, align=False):
         """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
         CUDA torch tensor).  Returns a dict of numpy arrays.
 
@@ -200,6 +200,9 @@ class WidebandPlan(object):
         }
         if want_chan_sums:
             spec["chan_sums"] = ((nsub, nchan, 9), np.float64)
+        if align:   # fused ppalign accumulation (ppalign.py:197-213): sum_s w rotate(data) and sum_s w
+            spec["align_sum"] = ((nchan, nbin), np.float64)
+            spec["align_wsum"] = ((nchan,), np.float64)
         if pinned_results:
             res = {k: self._pool.array(k, sh, dt) for k, (sh, dt) in spec.items()}
         else:

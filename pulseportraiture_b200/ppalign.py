@@ -108,14 +108,14 @@ def align_archives(metafile, initial_guess, fit_dm=True, tscrunch=False, pscrunc
             # FFTFIT guess with Ns = nbin (ppalign.py:179-185; the device dedisperses about the
             # mean frequency and transforms the phase to nu_fit = guess_fit_freq, which is the
             # same continuous optimum), then the fit with nu_outs = zero-covariance (190-193)
+            # ... and, in the same call, rotated by the fitted phase and DM and added with the
+            # weights scales / sigma^2 (ppalign.py:197-208): the archive crosses PCIe and is
+            # Fourier transformed once per iteration
             r = pl.fit_batch(subints, Ps, errs=errs, chan_mask=mask, weights=wts, snrs=snrs,
                              DM_guess=np.full(nsub, DM_guess), nu_fit_mode=1,
-                             fit_flags=flags, log10_tau=False, Ns=nbin, semantics="full")
-            w = np.where(mask > 0, r["scales"] / np.where(errs > 0, errs, 1.0) ** 2, 0.0)   # :202
-            acc, wsum = pl.align_accumulate(subints, r["params"][:, 0], r["params"][:, 1], Ps,
-                                            r["nu_out"][:, 0], w)
-            aligned += acc
-            total_weights += wsum
+                             fit_flags=flags, log10_tau=False, Ns=nbin, semantics="full", align=True)
+            aligned += r["align_sum"]
+            total_weights += r["align_wsum"]
         good = total_weights > 0
         aligned[good] /= total_weights[good, None]                      # :210-212
         model_port = aligned

@@ -136,3 +136,33 @@ def test_zap_scans():
     thr = np.sqrt(32) * 0.5 * (srt[2] + srt[3])
     gt2.get_channels_to_zap(SNR_threshold=thr, rchi2_threshold=1e9, iterate=False)
     assert len(gt2.zap_channels[0][0]) == 3
+
+
+@pytest.mark.parametrize("nchan,nbin,nsub,chunk", [(24, 2048, 9, 4), (40, 512, 6, 0), (5, 64, 3, 0)])
+def test_fused_fit_and_align_matches_two_steps(nchan, nbin, nsub, chunk):
+    """pp_fit_batch(align_sum) = fit, then pp_align_accumulate with the fitted phi, DM, nu_out and
+    w = scales / sigma^2 (ppalign.py:197-208); also against the oracle's rotate_data."""
+    from pulseportraiture_b200.engine import WidebandPlan
+    sigma = 1.5 if nbin >= 512 else 0.4
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 9300 + 7 * nbin + s, sigma=sigma) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    mask = np.ones((nsub, nchan), dtype=np.uint8)
+    mask[1, 2] = 0
+    mask[nsub - 1, :nchan // 2] = 0
+    with WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+        if chunk:
+            pl.set_chunk(chunk)
+        r = pl.fit_batch(data, P, chan_mask=mask, nu_fit_mode=1, Ns=nbin, align=True)
+        w = np.where(mask > 0, r["scales"] / np.where(r["noise"] > 0, r["noise"], 1.0) ** 2, 0.0)
+        acc, wsum = pl.align_accumulate(data, r["params"][:, 0], r["params"][:, 1], P, r["nu_out"][:, 0], w)
+    assert rel(r["align_wsum"], wsum) < 1e-13
+    # the fused path accumulates float32-rounded spectra: 6e-8 per term
+    scale = np.max(np.abs(acc))
+    assert np.max(np.abs(r["align_sum"] - acc)) < 3e-7 * scale
+    ref = np.zeros((nchan, nbin))
+    for s in range(nsub):
+        ref += w[s][:, None] * orc.rotate_data(data[s].astype(np.float64), r["params"][s, 0], r["params"][s, 1], P,
+                                               freqs, r["nu_out"][s, 0])
+    assert np.max(np.abs(r["align_sum"] - ref)) < 3e-7 * scale
