@@ -417,10 +417,14 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
+    float wrow = wgt;
 #pragma unroll
     for (int i = 0; i < NUNIT; ++i) {
       cx<F> d[NOUT];
       const F dc_term = PL::template split<F>(buf, tw, t, i, first, d);   // DC of the row (special unit only)
+      // a NaN / Inf sample makes every harmonic of the row non-finite: such a row must not enter
+      // the profile for the FFTFIT guess (its sigma comes out non-finite, so the fit skips it too)
+      if (i == 0 && !(isfinite(d[0].x) && isfinite(d[0].y))) wrow = 0.f;
       float vx[NOUT], vy[NOUT];
 #pragma unroll
       double sa0 = 0.0, sa1 = 0.0;      // two chains: the power sum is latency, not throughput, bound
@@ -470,10 +474,12 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
           vx[q] = r.x; vy[q] = r.y;
         }
       }
+      if (wrow != 0.f) {   // uniform: 0 when no guess is wanted, the row is unused or not finite
 #pragma unroll
-      for (int q = 0; q < NOUT; ++q) {   // wgt = 0 when no guess is wanted or the row is unused
-        acc[NOUT * i + q].x = fmaf(wgt, vx[q], acc[NOUT * i + q].x);
-        acc[NOUT * i + q].y = fmaf(wgt, vy[q], acc[NOUT * i + q].y);
+        for (int q = 0; q < NOUT; ++q) {
+          acc[NOUT * i + q].x = fmaf(wrow, vx[q], acc[NOUT * i + q].x);
+          acc[NOUT * i + q].y = fmaf(wrow, vy[q], acc[NOUT * i + q].y);
+        }
       }
     }
     // ---- power sums of the row: warp totals go to shared memory (by row parity); thread

@@ -489,6 +489,41 @@ def test_edge_cases(engine):
         engine.WidebandPlan(8, 8192)
 
 
+def test_nonfinite_and_empty_subints_do_not_poison_the_batch(engine):
+    """A subint with a NaN, an all-zero subint and a fully masked subint sit between good ones:
+    the good ones give exactly the results of a clean batch, the bad ones are flagged."""
+    nsub, nchan, nbin = 6, 16, 512
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 7700 + s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    bad = data.copy()
+    bad[1, 3, 100] = np.nan
+    bad[3] = 0.0
+    mask = np.ones((nsub, nchan), dtype=np.uint8)
+    mask[4] = 0
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), cases[0]["freqs"])
+        good = pl.fit_batch(data, cases[0]["P"])
+        r = pl.fit_batch(bad, cases[0]["P"], chan_mask=mask, align=True)
+    for s in (0, 2, 5):
+        for k in ("params", "param_errs", "chi2", "scales", "lag_index", "return_code"):
+            assert np.array_equal(r[k][s], good[k][s]), (s, k)
+    # the channel with the NaN sample is dropped (noise = scale = 0), as if it were masked
+    assert r["noise"][1, 3] == 0.0 and r["scales"][1, 3] == 0.0 and int(r["return_code"][1]) == 0
+    m1 = np.ones((nsub, nchan), dtype=np.uint8)
+    m1[1, 3] = 0
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), cases[0]["freqs"])
+        ref = pl.fit_batch(data, cases[0]["P"], chan_mask=m1)
+    assert int(r["lag_index"][1]) == int(ref["lag_index"][1])
+    assert abs(r["params"][1, 0] - ref["params"][1, 0]) < 1e-3 * ref["param_errs"][1, 0]
+    assert abs(r["chi2"][1] / ref["chi2"][1] - 1) < 1e-10
+    for s in (3, 4):      # nothing to fit: no usable channel
+        assert int(r["return_code"][s]) != 0 or np.all(r["scales"][s] == 0)
+        assert np.all(r["scales"][s] == 0)
+    # the fused ppalign sum skips them too
+    assert np.all(np.isfinite(r["align_sum"])) and np.all(np.isfinite(r["align_wsum"]))
+
+
 def _fake_archive(nsub, nchan, nbin, seed0, DM_stored=0.0, tau_s=0.0, nu0=1500., bw=800., sigma=1.5):
     """The load_data field contract (pplib.py:2803-2813) filled with synthetic subints."""
     from pulseportraiture_b200.pptoas import MJD
