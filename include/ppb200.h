@@ -195,6 +195,19 @@ int pp_gen_gaussian_portrait(pp_plan_t* plan, const char* model_code,
                              const double* params, int32_t ngauss,
                              double scattering_index, double nu_ref, float* out);
 
+/* B-spline (PCA) model portrait on the device: replaces pplib.gen_spline_portrait
+ * (pplib.py:932-956) as called by read_spline_model (pplib.py:2955-2987;
+ * pptoas.py:376-379):  out[n,:] = mean_prof + sum_c s_c(freqs[n]) * eigvec[:,c]
+ * with s_c = scipy.interpolate.splev(freqs, (knots, coefs, degree), ext=0).
+ *   mean_prof HOST [nbin]; eigvec HOST [nbin, ncomp] row-major; knots HOST
+ *   [nknots]; coefs HOST [ncomp, nknots-degree-1]; out float [nchan, nbin]
+ *   host or device.  The model must already have the plan's nbin (the
+ *   reference's optional ss.resample step is not provided). */
+int pp_gen_spline_portrait(pp_plan_t* plan, const double* mean_prof,
+                           const double* eigvec, int32_t ncomp,
+                           const double* knots, int32_t nknots,
+                           const double* coefs, int32_t degree, float* out);
+
 /* ---- per-channel noise -----------------------------------------------------
  * Replaces pplib.get_noise(data, chans=True) (pplib.py:2227-2245). */
 int pp_get_noise_batch(pp_plan_t* plan, const float* data, int32_t nsub,

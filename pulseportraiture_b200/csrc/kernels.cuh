@@ -1955,6 +1955,56 @@ __global__ void __launch_bounds__(256) k_gauss_model(GaussModelArgs a) {
 }
 
 // ----------------------------------------------------------------------------
+// k_spline_model: B-spline (PCA) model portrait, gen_spline_portrait
+// (pplib.py:932-956): port[n, :] = mean_prof + sum_c s_c(nu_n) eigvec[:, c] with
+// s_c the parametric B-spline of scipy.interpolate.splev(freqs, tck, ext=0)
+// (knots t, coefficients c, degree k <= 5; outside the knot range the end
+// polynomials extrapolate, as FITPACK's splev does).  One CTA per channel.
+// ----------------------------------------------------------------------------
+struct SplineModelArgs {
+  const double* mean_prof;  // [nbin]
+  const double* eigvec;     // [nbin, ncomp]
+  const double* knots;      // [nknots]
+  const double* coefs;      // [ncomp, nknots - degree - 1]
+  const double* freqs;      // [nchan]
+  float* out;               // [nchan, nbin]
+  int ncomp, nknots, degree, nchan, nbin;
+};
+
+constexpr int kMaxSplineComp = 32;
+
+__global__ void __launch_bounds__(256) k_spline_model(SplineModelArgs a) {
+  __shared__ double proj[kMaxSplineComp];
+  const int ch = blockIdx.x, tid = threadIdx.x;
+  const int k = a.degree, n = a.nknots - k - 1;        // n coefficients per component
+  if (tid < a.ncomp) {
+    const double x = a.freqs[ch];
+    const double* t = a.knots;
+    // knot span l with t[l] <= x < t[l+1], clamped to the first / last polynomial piece
+    int l = k;
+    while (l < n - 1 && x >= t[l + 1]) ++l;
+    // de Boor: d_j = c[l-k+j], j = 0..k
+    double d[6];
+    const double* c = a.coefs + (size_t)tid * n;
+    for (int j = 0; j <= k; ++j) d[j] = c[l - k + j];
+    for (int r = 1; r <= k; ++r)
+      for (int j = k; j >= r; --j) {
+        const double tl = t[j + l - k], tr = t[j + 1 + l - r];
+        const double al = (x - tl) / (tr - tl);
+        d[j] = (1.0 - al) * d[j - 1] + al * d[j];
+      }
+    proj[tid] = d[k];
+  }
+  __syncthreads();
+  for (int b = tid; b < a.nbin; b += 256) {
+    double v = a.mean_prof[b];
+    const double* e = a.eigvec + (size_t)b * a.ncomp;
+    for (int c = 0; c < a.ncomp; ++c) v = fma(proj[c], e[c], v);
+    a.out[(size_t)ch * a.nbin + b] = (float)v;
+  }
+}
+
+// ----------------------------------------------------------------------------
 // k_rotate: rfft -> multiply harmonic k by e^{2 pi i k theta} -> irfft
 // (pplib.py:2338-2460).  One row-slot per channel row; rows = nsub*nchan.
 // ----------------------------------------------------------------------------

@@ -1042,6 +1042,49 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
   return 0;
 }
 
+extern "C" int pp_gen_spline_portrait(pp_plan_t* pl, const double* mean_prof, const double* eigvec, int32_t ncomp,
+                                      const double* knots, int32_t nknots, const double* coefs, int32_t degree,
+                                      float* outp) {
+  if (!pl || !mean_prof || !outp) return fail(-1, "NULL argument");
+  if (ncomp < 0 || ncomp > kMaxSplineComp) return fail(-1, "ncomp must be in [0, %d]", kMaxSplineComp);
+  if (ncomp > 0) {
+    if (!eigvec || !knots || !coefs) return fail(-1, "NULL spline argument");
+    if (degree < 1 || degree > 5) return fail(-1, "spline degree must be in [1, 5]");
+    if (nknots < 2 * (degree + 1)) return fail(-1, "need at least 2 (degree + 1) knots");
+  }
+  if (!pl->freqs_set) return fail(-1, "pp_set_freqs must be called before pp_gen_spline_portrait");
+  if (is_device_ptr(mean_prof) || (ncomp > 0 && (is_device_ptr(eigvec) || is_device_ptr(knots) || is_device_ptr(coefs))))
+    return fail(-1, "the spline model arrays must be host arrays");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan, nbin = 2 * N;
+  const int ncoef = ncomp > 0 ? nknots - degree - 1 : 0;
+  const size_t n_mean = nbin, n_eig = (size_t)nbin * ncomp, n_kn = ncomp > 0 ? nknots : 0, n_co = (size_t)ncomp * ncoef;
+  const size_t total = n_mean + n_eig + n_kn + n_co;
+  CK(pl->gm_params.need(sizeof(double) * total));
+  double* base = pl->gm_params.as<double>();
+  CK(cudaMemcpyAsync(base, mean_prof, sizeof(double) * n_mean, cudaMemcpyHostToDevice, pl->stream));
+  if (ncomp > 0) {
+    CK(cudaMemcpyAsync(base + n_mean, eigvec, sizeof(double) * n_eig, cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaMemcpyAsync(base + n_mean + n_eig, knots, sizeof(double) * n_kn, cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaMemcpyAsync(base + n_mean + n_eig + n_kn, coefs, sizeof(double) * n_co, cudaMemcpyHostToDevice, pl->stream));
+  }
+  const size_t tot = (size_t)nchan * nbin;
+  float* dout = outp;
+  const bool out_dev = is_device_ptr(outp);
+  if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  SplineModelArgs g;
+  g.mean_prof = base; g.eigvec = base + n_mean; g.knots = base + n_mean + n_eig; g.coefs = base + n_mean + n_eig + n_kn;
+  g.freqs = pl->freqs.as<double>(); g.out = dout; g.ncomp = ncomp; g.nknots = nknots; g.degree = degree;
+  g.nchan = nchan; g.nbin = nbin;
+  k_spline_model<<<nchan, 256, 0, pl->stream>>>(g);
+  pl->stats.launches++;
+  CK(cudaGetLastError());
+  if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
 extern "C" int pp_get_noise_batch(pp_plan_t* pl, const float* data, int32_t nsub, double* noise_out) {
   if (!pl || !data || !noise_out) return fail(-1, "NULL argument");
   if (nsub < 1) return fail(-1, "nsub must be >= 1");

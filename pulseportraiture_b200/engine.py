@@ -274,6 +274,35 @@ class WidebandPlan(object):
             float(scattering_index), float(nu_ref), op), "pp_gen_gaussian_portrait")
         return out
 
+    def gen_spline_portrait(self, mean_prof, eigvec, tck, out=None, device_out=False):
+        """B-spline (PCA) model portrait on the device (pplib.py:932-956) for the plan's
+        frequencies.  ``tck`` = (knots, [coefficient arrays], degree) as returned by
+        scipy.interpolate.splprep; eigvec is [nbin, ncomp].  Returns float32 [nchan, nbin]."""
+        mean_prof = np.ascontiguousarray(mean_prof, dtype=np.float64)
+        eigvec = np.ascontiguousarray(eigvec, dtype=np.float64).reshape(len(mean_prof), -1)
+        if mean_prof.shape != (self.nbin,):
+            raise ValueError("the spline model has %d bins, the plan %d (resampling is not provided)"
+                             % (len(mean_prof), self.nbin))
+        ncomp = eigvec.shape[1]
+        knots = np.ascontiguousarray(tck[0], dtype=np.float64)
+        degree = int(tck[2])
+        ncoef = len(knots) - degree - 1
+        coefs = np.ascontiguousarray([np.asarray(c, dtype=np.float64)[:ncoef] for c in tck[1]],
+                                     dtype=np.float64).reshape(ncomp, ncoef) if ncomp else np.zeros((0, 0))
+        if out is None:
+            if device_out:
+                import torch
+                out = torch.empty((self.nchan, self.nbin), dtype=torch.float32,
+                                  device=torch.device("cuda", self.device))
+            else:
+                out = np.empty((self.nchan, self.nbin), dtype=np.float32)
+        op = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        _ffi.check(self._lib.pp_gen_spline_portrait(
+            self._h, mean_prof.ctypes.data, eigvec.ctypes.data if ncomp else None, int(ncomp),
+            knots.ctypes.data if ncomp else None, int(len(knots)), coefs.ctypes.data if ncomp else None,
+            degree, op), "pp_gen_spline_portrait")
+        return out
+
     def rotate_batch(self, data, phase, DM, P, nu_ref, out=None, GM=None, nu_GM=None):
         if GM is not None:
             return self._rotate_full(data, phase, DM, GM, P, nu_ref, nu_GM, out)

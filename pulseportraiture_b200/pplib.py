@@ -358,6 +358,51 @@ def gen_gaussian_portrait_device(model_code, params, scattering_index, phases, f
     return pl.gen_gaussian_portrait(model_code, params, scattering_index, nu_ref).astype(np.float64)
 
 
+def gen_spline_portrait(mean_prof, freqs, eigvec, tck, nbin=None, device=False):
+    """Model portrait from a make_spline_model(...) PCA / B-spline model
+    (pplib.py:932-956): mean_prof + splev(freqs, tck).T . eigvec.T.  ``device=True``
+    evaluates it with the CUDA kernel ``k_spline_model`` (float32 precision)."""
+    mean_prof = np.asarray(mean_prof, dtype=np.float64)
+    freqs = np.asarray(freqs, dtype=np.float64)
+    eigvec = np.asarray(eigvec, dtype=np.float64).reshape(len(mean_prof), -1)
+    if nbin is not None and nbin != len(mean_prof):
+        raise NotImplementedError("resampling a spline model to another nbin (scipy.signal.resample)")
+    if device:
+        pl = get_plan(len(freqs), len(mean_prof))
+        pl.set_freqs(freqs)
+        return pl.gen_spline_portrait(mean_prof, eigvec, tck).astype(np.float64)
+    if not eigvec.shape[1]:
+        return np.tile(mean_prof, len(freqs)).reshape(len(freqs), len(mean_prof))
+    import scipy.interpolate as si
+    proj_port = np.array(si.splev(freqs, tck, der=0, ext=0)).T
+    return np.dot(proj_port, eigvec.T) + mean_prof
+
+
+def read_spline_model(modelfile, freqs=None, nbin=None, quiet=False, device=False):
+    """Read a make_spline_model(...) pickle (pplib.py:2955-2987): without freqs returns
+    (modelname, source, datafile, mean_prof, eigvec, tck), else (modelname, model)."""
+    import pickle
+    if not quiet:
+        print("Reading model from %s..." % modelfile)
+    with open(modelfile, "rb") as fh:
+        modelname, source, datafile, mean_prof, eigvec, tck = pickle.load(fh, encoding="latin1")
+    if freqs is None:
+        return (modelname, source, datafile, mean_prof, eigvec, tck)
+    return (modelname, gen_spline_portrait(mean_prof, freqs, eigvec, tck, nbin, device=device))
+
+
+def is_spline_model(modelfile):
+    """True if ``modelfile`` is a pickled spline model rather than a text .gmodel file
+    (the reference falls back to read_spline_model when read_model fails, pptoas.py:376-379)."""
+    import pickle
+    try:
+        with open(modelfile, "rb") as fh:
+            obj = pickle.load(fh, encoding="latin1")
+        return isinstance(obj, (list, tuple)) and len(obj) == 6
+    except Exception:
+        return False
+
+
 def read_model(modelfile, phases=None, freqs=None, P=None, quiet=False, device=False):
     """Read a ``.gmodel`` file (pplib.py:2867-2953).  Without phases/freqs
     returns (name, code, nu_ref, ngauss, params, fit_flags, alpha, fit_alpha);

@@ -156,6 +156,11 @@ class GetTOAs:
         if isinstance(self.modelfile, np.ndarray):
             self.model_name, self.ngauss = "array", 0
             return self.modelfile
+        if pplib.is_spline_model(self.modelfile):           # pptoas.py:376-379
+            self.ngauss = 0
+            self.model_name, model = pplib.read_spline_model(self.modelfile, freqs_row, len(phases),
+                                                             quiet=True, device=True)
+            return model
         if not fit_scat:
             self.model_name, self.ngauss, model = read_model(self.modelfile, phases, freqs_row, P,
                                                              quiet=True, device=True)

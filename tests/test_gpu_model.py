@@ -100,3 +100,39 @@ def test_device_model_argument_errors():
         # no components: DC only
         out = pl.gen_gaussian_portrait("000", np.array([0.25, 0.0]), -4.0, 1400.0)
         assert np.all(out == np.float32(0.25))
+
+
+def _spline_model(nbin, ncomp, k, s, seed):
+    """A synthetic make_spline_model-style model: mean profile, orthonormal eigenvectors and a
+    B-spline through noisy projections (scipy.interpolate.splprep, as pplib.py:1203-1206)."""
+    import scipy.interpolate as si
+    rng = np.random.RandomState(seed)
+    x = orc.get_bin_centers(nbin)
+    mean_prof = np.exp(-0.5 * ((x - 0.3) / 0.02) ** 2) + 0.3 * np.exp(-0.5 * ((x - 0.36) / 0.05) ** 2)
+    eigvec = np.linalg.qr(rng.standard_normal((nbin, max(ncomp, 1))))[0][:, :ncomp]
+    if not ncomp:
+        return mean_prof, eigvec, (np.zeros(8), [], 3)
+    f = np.linspace(1150., 1850., 48)
+    proj = np.array([0.2 * np.sin(f / (120. + 40 * i) + i) + 0.01 * rng.standard_normal(len(f)) for i in range(ncomp)])
+    tck, _ = si.splprep(proj, u=f, k=k, s=s)
+    return mean_prof, eigvec, tck
+
+
+@pytest.mark.parametrize("nchan,nbin,ncomp,k,s", [(64, 512, 4, 3, 0.02), (33, 2048, 10, 3, 0.0), (16, 256, 2, 5, 0.05),
+                                                   (8, 128, 1, 1, 0.1), (12, 1024, 0, 3, 0.0)])
+def test_device_spline_model_vs_scipy(nchan, nbin, ncomp, k, s, tmp_path):
+    import pickle
+    from pulseportraiture_b200 import pplib
+    mean_prof, eigvec, tck = _spline_model(nbin, ncomp, k, s, 11 * nbin + ncomp)
+    freqs = orc.make_freqs(nchan, 1500., 800.)      # 1100-1900 MHz: extrapolates beyond the knots
+    ref = pplib.gen_spline_portrait(mean_prof, freqs, eigvec, tck)          # scipy splev + dot, as the reference
+    out = pplib.gen_spline_portrait(mean_prof, freqs, eigvec, tck, device=True)
+    assert out.shape == (nchan, nbin)
+    assert np.max(np.abs(out - ref)) <= 2 * F32 * np.max(np.abs(ref))
+    # through the pickle reader, as GetTOAs finds its model
+    path = str(tmp_path / "model.spl")
+    with open(path, "wb") as fh:
+        pickle.dump(["mdl", "J0000+0000", "none", mean_prof, eigvec, tck], fh, protocol=2)
+    assert pplib.is_spline_model(path) and not pplib.is_spline_model(GMODEL)
+    name, model = pplib.read_spline_model(path, freqs, nbin, quiet=True, device=True)
+    assert name == "mdl" and np.array_equal(model, out)
