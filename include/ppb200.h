@@ -140,7 +140,10 @@ int pp_fit_batch(pp_plan_t* plan, const pp_fit_args_t* args,
 
 /* ---- batched 1-D FFTFIT ---------------------------------------------------
  * Replaces pplib.fit_phase_shift (pplib.py:2054-2100) for n profiles.
- * models: [nmodel, nbin] with nmodel == n or 1.  noise: [n] time-domain
+ * models: [nmodel, nbin] with nmodel a divisor of n: profile i is fit against
+ * model i mod nmodel (1 = one template; nchan = the per-channel fits of
+ * get_narrowband_TOAs, pptoas.py:980-992, with profiles [nsub*nchan, nbin];
+ * n = one model per profile).  noise: [n] time-domain
  * sigma or NULL (-> get_noise, pplib.py:2076).  The brute-force grid is
  * np.mgrid[-0.5:0.5:Ns*1j]; lag_index is its argmin; phase is the exact
  * minimiser reached from there (the reference's Nelder-Mead polish is only

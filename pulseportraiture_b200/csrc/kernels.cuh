@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   const int il = blockIdx.x, ig = a.s0 + il;
   const int kc = (3 * (N + 1)) / 4;
   const double inv_w = a.wsum ? 1.0 / a.wsum[ig] : 1.0;
-  const float2* mc = a.mconj + (size_t)(a.nmodel > 1 ? il : 0) * N;
+  const float2* mc = a.mconj + (size_t)(a.nmodel > 1 ? il % a.nmodel : 0) * N;   // profile i uses model i mod nmodel
   double v[3] = {0.0, 0.0, 0.0};  // sum |d|^2, sum |m|^2, top-quarter power
   const double tau_g = (a.scat && a.fit_scat) ? a.scat[(size_t)ig * 2] : 0.0;
   for (int i = tid; i < N; i += 256) {

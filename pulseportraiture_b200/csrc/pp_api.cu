@@ -687,7 +687,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
             pl->mconj64.as<cx<double>>(), dmask, pl->mmean.as<float2>(), pl->mmean_sub.as<float2>(), s0, nchan, N);
         pl->stats.launches++;
         ga.mconj = pl->mmean_sub.as<float2>();
-        ga.nmodel = 2;   // > 1: one template per subint of the chunk
+        ga.nmodel = ns;  // one template per subint of the chunk
       }
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
@@ -859,7 +859,7 @@ extern "C" int pp_fit_phase_shift_batch(pp_plan_t* pl, const float* profiles, in
                                         const double* noise, int32_t Ns, const pp_pshift_out_t* out) {
   if (!pl || !profiles || !models || !out) return fail(-1, "NULL argument");
   if (n < 1) return fail(-1, "n must be >= 1");
-  if (nmodel != 1 && nmodel != n) return fail(-1, "nmodel must be 1 or n");
+  if (nmodel < 1 || n % nmodel) return fail(-1, "nmodel must divide n (profile i is fit against model i mod nmodel)");
   if (Ns <= 0) Ns = 100;
   if (Ns < 2) return fail(-1, "Ns must be >= 2");
   CK(cudaSetDevice(pl->device));

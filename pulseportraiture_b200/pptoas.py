@@ -464,6 +464,113 @@ class GetTOAs:
             print("Total time: %.2f sec, ~%.4f sec/TOA" % (
                 tot_duration, tot_duration / (np.array(list(map(len, self.ok_isubs))).sum())))
 
+    def get_narrowband_TOAs(self, datafile=None, tscrunch=False, fit_scat=False, log10_tau=True,
+                            scat_guess=None, print_phase=False, print_flux=False,
+                            print_parangle=False, add_instrumental_response=False,
+                            addtnl_toa_flags={}, method='trust-ncg', bounds=None, show_plot=False,
+                            quiet=None):
+        """Measure one TOA per (subint, channel) with the 1-D FFTFIT (pptoas.py:745-1132): every
+        usable channel profile against its model channel, ``fit_phase_shift(prof, model_prof, err,
+        Ns=100)`` -- all profiles of an archive in one ``pp_fit_phase_shift_batch`` call.  As in the
+        reference the scattering fit is not active in this method (tau = 0)."""
+        if quiet is None:
+            quiet = self.quiet
+        if tscrunch or show_plot or add_instrumental_response:
+            raise NotImplementedError("tscrunch / show_plot / add_instrumental_response "
+                                      "need PSRCHIVE or matplotlib and are outside the hot path")
+        self.fit_flags = [1, 0]
+        self.log10_tau = False
+        start = time.time()
+        datafiles = self.datafiles if datafile is None else [datafile]
+        for iarch, datafile in enumerate(datafiles):
+            try:
+                d = datafile if isinstance(datafile, dict) else load_data(datafile)
+            except (RuntimeError, IOError, OSError):
+                if not quiet:
+                    print("Cannot load_data(%s).  Skipping it." % datafile)
+                continue
+            if not len(d.ok_isubs):
+                continue
+            self.ok_idatafiles.append(iarch)
+            nsub, nchan, nbin = int(d.nsub), int(d.nchan), int(d.nbin)
+            ok_isubs = np.asarray(d.ok_isubs, dtype=int)
+            freqs = np.asarray(d.freqs, dtype=np.float64)
+            Ps = np.asarray(d.Ps, dtype=np.float64)
+            if np.any(freqs != freqs[0]):
+                raise NotImplementedError("per-subint frequency tables")
+            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]], False)
+            pl = get_plan(nchan, nbin)
+            fit_start = time.time()
+            profs = _f32(np.asarray(d.subints)[ok_isubs, 0]).reshape(len(ok_isubs) * nchan, nbin)
+            noise = np.ascontiguousarray(np.asarray(d.noise_stds)[ok_isubs, 0], dtype=np.float64)
+            okmask = np.zeros((len(ok_isubs), nchan), dtype=bool)
+            for i, isub in enumerate(ok_isubs):
+                okmask[i, np.asarray(d.ok_ichans[isub], dtype=int)] = True
+            okmask &= noise > 0
+            r = pl.fit_phase_shift_batch(profs, _f32(model), noise=np.where(okmask, noise, 1.0).ravel(),
+                                         Ns=100)
+            fit_duration = time.time() - fit_start
+            shape = (nsub, nchan)
+            phis, phi_errs = np.zeros(shape), np.zeros(shape)
+            TOAs, TOA_errs = np.zeros(shape, dtype="object"), np.zeros(shape, dtype="object")
+            taus, tau_errs = np.zeros(shape), np.zeros(shape)
+            scales, scale_errs = np.zeros(shape), np.zeros(shape)
+            channel_snrs, channel_red_chi2s = np.zeros(shape), np.zeros(shape)
+            profile_fluxes, profile_flux_errs = np.zeros(shape), np.zeros(shape)
+            MJDs = np.array([e.in_days() for e in d.epochs], dtype=np.double)
+            obs = DataBunch(telescope=d.telescope, backend=d.backend, frontend=d.frontend)
+            get = lambda k: r[k].reshape(len(ok_isubs), nchan)  # noqa: E731
+            for i, isub in enumerate(ok_isubs):
+                P = Ps[isub]
+                for ichan in np.where(okmask[i])[0]:
+                    phase, phase_err = get("phase")[i, ichan], get("phase_err")[i, ichan]
+                    toa = d.epochs[isub] + MJD(0, ((phase * P) + d.backend_delay) / (3600 * 24.))
+                    toa_err = phase_err * P * 1e6                                  # [us]
+                    phis[isub, ichan], phi_errs[isub, ichan] = phase, phase_err
+                    TOAs[isub, ichan], TOA_errs[isub, ichan] = toa, toa_err
+                    scales[isub, ichan] = get("scale")[i, ichan]
+                    scale_errs[isub, ichan] = get("scale_err")[i, ichan]
+                    channel_snrs[isub, ichan] = get("snr")[i, ichan]
+                    channel_red_chi2s[isub, ichan] = get("red_chi2")[i, ichan]
+                    if print_flux:
+                        mm = model[ichan].mean()
+                        profile_fluxes[isub, ichan] = mm * scales[isub, ichan]
+                        profile_flux_errs[isub, ichan] = abs(mm) * scale_errs[isub, ichan]
+                    toa_flags = {'be': d.backend, 'fe': d.frontend, 'f': "%s_%s" % (d.frontend, d.backend),
+                                 'nbin': nbin, 'bw': abs(d.bw) / nchan, 'subint': int(isub), 'chan': int(ichan),
+                                 'tobs': d.subtimes[isub],
+                                 'tmplt': self.modelfile if isinstance(self.modelfile, str) else "array",
+                                 'snr': channel_snrs[isub, ichan], 'gof': channel_red_chi2s[isub, ichan]}
+                    if print_phase:
+                        toa_flags['phs'], toa_flags['phs_err'] = phase, phase_err
+                    if print_flux:
+                        toa_flags['flux'] = profile_fluxes[isub, ichan]
+                        toa_flags['flux_err'] = profile_flux_errs[isub, ichan]
+                    if print_parangle:
+                        toa_flags['par_angle'] = d.parallactic_angles[isub]
+                    toa_flags.update(addtnl_toa_flags)
+                    self.TOA_list.append(TOA(d.filename, freqs[isub, ichan], toa, toa_err, d.telescope,
+                                             d.telescope_code, None, None, toa_flags))
+            for name, val in (("order", d.filename), ("obs", obs), ("doppler_fs", d.doppler_factors),
+                              ("ok_isubs", ok_isubs), ("epochs", d.epochs), ("MJDs", MJDs), ("Ps", Ps),
+                              ("phis", phis), ("phi_errs", phi_errs), ("TOAs", TOAs), ("TOA_errs", TOA_errs),
+                              ("taus", taus), ("tau_errs", tau_errs), ("scales", scales),
+                              ("scale_errs", scale_errs), ("channel_snrs", channel_snrs),
+                              ("profile_fluxes", profile_fluxes), ("profile_flux_errs", profile_flux_errs),
+                              ("channel_red_chi2s", channel_red_chi2s), ("fit_durations", fit_duration)):
+                if not hasattr(self, name):
+                    setattr(self, name, [])
+                getattr(self, name).append(val)
+            if not quiet:
+                print("--------------------------")
+                print(d.filename)
+                print("~%.6f sec/TOA" % (fit_duration / max(1, int(okmask.sum()))))
+                print("Med. TOA error is %.3f us" % (np.median(phi_errs[phi_errs > 0]) * Ps.mean() * 1e6))
+        if not quiet and len(self.ok_idatafiles):
+            tot = time.time() - start
+            print("--------------------------")
+            print("Total time: %.2f sec, ~%.6f sec/TOA" % (tot, tot / max(1, len(self.TOA_list))))
+
     def get_channels_to_zap(self, SNR_threshold=8.0, rchi2_threshold=1.3, iterate=True,
                             show=False):
         """Flag channels by per-channel reduced chi-squared and S/N (pptoas.py:1208-1285).

@@ -166,3 +166,36 @@ def test_fused_fit_and_align_matches_two_steps(nchan, nbin, nsub, chunk):
         ref += w[s][:, None] * orc.rotate_data(data[s].astype(np.float64), r["params"][s, 0], r["params"][s, 1], P,
                                                freqs, r["nu_out"][s, 0])
     assert np.max(np.abs(r["align_sum"] - ref)) < 3e-7 * scale
+
+
+def test_get_narrowband_TOAs_matches_per_channel_fftfit():
+    """GetTOAs.get_narrowband_TOAs (pptoas.py:745-1132): one 1-D FFTFIT per usable channel, all in
+    one pp_fit_phase_shift_batch call with nmodel = nchan."""
+    from pulseportraiture_b200 import pptoas
+    d, cases = _fake_archive(4, 24, 512, 9500, sigma=0.5)
+    gt = pptoas.GetTOAs([d], cases[0]["model"], quiet=True)
+    gt.get_narrowband_TOAs(print_phase=True)
+    nsub, nchan = 4, 24
+    assert gt.phis[0].shape == (nsub, nchan)
+    ntoa = sum(len(d.ok_ichans[s]) for s in range(nsub))
+    assert len(gt.TOA_list) == ntoa
+    rng = np.random.RandomState(0)
+    for s in range(nsub):
+        okc = np.asarray(d.ok_ichans[s])
+        bad = np.setdiff1d(np.arange(nchan), okc)
+        assert np.all(gt.phis[0][s, bad] == 0) and np.all(gt.scales[0][s, bad] == 0)
+        for ch in rng.choice(okc, size=5, replace=False):
+            noise = d.noise_stds[s, 0, ch]
+            o = orc.fit_phase_shift(cases[s]["data"][ch], cases[0]["model"][ch], noise=noise, Ns=100, polish="exact")
+            assert abs(gt.phis[0][s, ch] - o.phase) < SIG_TOL * o.phase_err
+            assert rel(gt.phi_errs[0][s, ch], o.phase_err) < 1e-6
+            assert rel(gt.scales[0][s, ch], o.scale) < 1e-6
+            assert rel(gt.channel_snrs[0][s, ch], o.snr) < 1e-6
+            assert rel(gt.channel_red_chi2s[0][s, ch], o.red_chi2) < 1e-7
+            P = d.Ps[s]
+            want = d.epochs[s].in_days() + (gt.phis[0][s, ch] * P + d.backend_delay) / 86400.0
+            assert abs(gt.TOAs[0][s, ch].in_days() - want) < 1e-9
+            assert rel(gt.TOA_errs[0][s, ch], gt.phi_errs[0][s, ch] * P * 1e6) < 1e-14
+    t0 = gt.TOA_list[0]
+    assert t0.flags["chan"] == int(d.ok_ichans[0][0]) and t0.flags["subint"] == 0 and "phs" in t0.flags
+    assert t0.frequency == d.freqs[0, d.ok_ichans[0][0]]
