@@ -457,3 +457,63 @@ def read_model(modelfile, phases=None, freqs=None, P=None, quiet=False, device=F
         print("Model Name: %s" % modelname)
         print("Made %d component model with %d profile bins," % (ngauss, nbin))
     return (modelname, ngauss, model)
+
+
+# ---- TOA output (host text formatting; pplib.py:3380-3503) ----------------------------------
+def filter_TOAs(TOAs, flag, cutoff, criterion=">=", pass_unflagged=False, return_culled=False):
+    """Keep the TOAs whose attribute ``flag`` satisfies ``<criterion> cutoff`` (pplib.py:3380-3407)."""
+    import operator
+    ops = {">=": operator.ge, ">": operator.gt, "<=": operator.le, "<": operator.lt,
+           "==": operator.eq, "!=": operator.ne}
+    test = ops[criterion.strip()]
+    kept, culled = [], []
+    for toa in TOAs:
+        if hasattr(toa, flag):
+            (kept if test(getattr(toa, flag), cutoff) else culled).append(toa)
+        else:
+            (kept if pass_unflagged else culled).append(toa)
+    return (kept, culled) if return_culled else kept
+
+
+def _toa_flag_text(flag, value):
+    if hasattr(value, "lower"):
+        return " -%s %s" % (flag, value)
+    if "int" in str(type(value)):
+        return " -%s %d" % (flag, value)
+    if "_cov" in flag:
+        return " -%s %.1e" % (flag, value)
+    if "phs" in flag:
+        return " -%s %.8f" % (flag, value)
+    if "flux" in flag:
+        return " -%s %.5f" % (flag, value)
+    return " -%s %.3f" % (flag, value)
+
+
+def toa_line(toa, inf_is_zero=True):
+    """One loosely IPTA-formatted TOA line (pplib.py:3465-3497)."""
+    freq = 0.0 if (toa.frequency == np.inf and inf_is_zero) else toa.frequency
+    tail = "%.15f   %.3f  %s" % (toa.MJD.fracday(), toa.TOA_error, toa.telescope_code)
+    line = "%s %.8f %d" % (toa.archive, freq, toa.MJD.intday()) + tail[1:]
+    if toa.DM is not None:
+        line += " -pp_dm %.7f" % toa.DM
+    if toa.DM_error is not None:
+        line += " -pp_dme %.7f" % toa.DM_error
+    for flag, value in toa.flags.items():
+        if value is not None:
+            line += _toa_flag_text(flag, value)
+    return line
+
+
+def write_TOAs(TOAs, inf_is_zero=True, SNR_cutoff=0.0, outfile=None, append=True):
+    """Write loosely IPTA-formatted TOAs to ``outfile`` or standard output (pplib.py:3445-3503);
+    only TOAs with an ``snr`` flag >= SNR_cutoff are written."""
+    toas = TOAs if hasattr(TOAs, "__len__") else [TOAs]
+    toas = filter_TOAs(toas, "snr", SNR_cutoff, ">=", pass_unflagged=False)
+    lines = [toa_line(t, inf_is_zero) for t in toas]
+    if outfile is None:
+        for ln in lines:
+            print(ln)
+        return
+    with open(outfile, "a" if append else "w") as fh:
+        for ln in lines:
+            fh.write(ln + "\n")

@@ -66,6 +66,10 @@ class TOA:
         for flag in flags.keys():
             setattr(self, flag, flags[flag])
 
+    def write_TOA(self, inf_is_zero=True, outfile=None):
+        """Print / append this TOA as a loosely IPTA-formatted line (pptoas.py:65-73)."""
+        pplib.write_TOAs(self, inf_is_zero=inf_is_zero, outfile=outfile, append=True)
+
 
 _DB_FIELDS = ["backend", "backend_delay", "bw", "doppler_factors", "DM", "dmc",
               "epochs", "filename", "freqs", "frontend", "integration_length",

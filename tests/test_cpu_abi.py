@@ -102,3 +102,27 @@ def test_mjd_arithmetic():
     t = MJD(55000, 0.75) + MJD(0, 0.5)
     assert t.intday() == 55001 and abs(t.fracday() - 0.25) < 1e-15
     assert abs((MJD(55000, 0.1) + 1e-9).in_days() - 55000.100000001) < 1e-9
+
+
+def test_write_TOAs_matches_reference_lines(tmp_path):
+    """pplib.write_TOAs / filter_TOAs / TOA.write_TOA against lines written by the reference's own
+    write_TOAs (tests/golden/make_golden_toas.py -> toas_v1.tim)."""
+    import json
+    import os
+    import numpy as np
+    from pulseportraiture_b200 import pplib, pptoas
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    specs = json.load(open(os.path.join(gdir, "toas_v1.json")))
+    want = open(os.path.join(gdir, "toas_v1.tim")).read()
+    toas = [pptoas.TOA(s["archive"], np.inf if s["frequency"] == "inf" else s["frequency"],
+                       pptoas.MJD(s["mjd"][0], s["mjd"][1]), s["err"], s["telescope"], s["code"], s["DM"],
+                       s["DM_error"], dict(s["flags"])) for s in specs]
+    out = str(tmp_path / "out.tim")
+    pplib.write_TOAs(toas, inf_is_zero=True, SNR_cutoff=8.0, outfile=out, append=False)
+    pplib.write_TOAs([toas[1]], inf_is_zero=False, SNR_cutoff=0.0, outfile=out, append=True)
+    assert open(out).read() == want
+    kept, culled = pplib.filter_TOAs(toas, "snr", 8.0, ">=", return_culled=True)
+    assert [t.archive for t in kept] == [specs[0]["archive"], specs[1]["archive"]] and len(culled) == 2
+    one = str(tmp_path / "one.tim")
+    toas[0].write_TOA(outfile=one)
+    assert open(one).read() == want.splitlines()[0] + "\n"
