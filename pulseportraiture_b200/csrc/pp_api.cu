@@ -651,6 +651,33 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     CK(issue_copy(0));
   }
 
+  // queue the device-to-host copies of chunk c's results on the copy stream
+  auto enqueue_results = [&](int c) -> int {
+    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    CK(cudaStreamWaitEvent(pl->copy_stream, pl->ev_chunk[c], 0));
+    cudaStream_t cs = pl->copy_stream;
+    const size_t o1 = (size_t)s0, n1 = (size_t)ns, oc = (size_t)s0 * nchan, ncn = (size_t)ns * nchan;
+    if (copy_out_at(cs, out->params, pl->o_params.as<double>(), o1 * 5, n1 * 5)) return -2;
+    if (copy_out_at(cs, out->param_errs, pl->o_perrs.as<double>(), o1 * 5, n1 * 5)) return -2;
+    if (copy_out_at(cs, out->nu_out, pl->o_nuout.as<double>(), o1 * 3, n1 * 3)) return -2;
+    if (copy_out_at(cs, out->cov, pl->o_cov.as<double>(), o1 * 25, n1 * 25)) return -2;
+    if (copy_out_at(cs, out->chi2, pl->o_chi2.as<double>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->red_chi2, pl->o_rchi2.as<double>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->snr, pl->o_snr.as<double>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->nfeval, pl->o_nfev.as<int>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->return_code, pl->o_rc.as<int>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->scales, pl->o_scales.as<double>(), oc, ncn)) return -2;
+    if (copy_out_at(cs, out->scale_errs, pl->o_serrs.as<double>(), oc, ncn)) return -2;
+    if (copy_out_at(cs, out->channel_snrs, pl->o_csnr.as<double>(), oc, ncn)) return -2;
+    if (copy_out_at(cs, out->noise, pl->sigma.as<double>(), oc, ncn)) return -2;
+    if (copy_out_at(cs, out->lag_index, pl->o_lag.as<int>(), o1, n1)) return -2;
+    if (want_guess && copy_out_at(cs, out->phi_guess, pl->o_phig.as<double>(), o1, n1)) return -2;
+    if (copy_out_at(cs, out->chan_sums, pl->csum.as<double>(), oc * kNCsum, ncn * kNCsum)) return -2;
+    return 0;
+  };
+  int pending_out = -1;        // chunk whose result copies still have to be queued
+  bool expect_third = false;   // the previous chunk still had unfinished subints after two passes
+
   for (int c = 0; c < nchunks; ++c) {
     const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
     const float* dchunk;
@@ -746,15 +773,27 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       pl->stats.pass_launches++;
       // data-dependent number of passes: poll the count of unfinished subints (an empty
       // launch of the full grid costs ~80 us, the poll ~20 us)
-      const bool poll = general ? ((it & 3) == 3) : (it >= 1);
+      // (when the previous chunk needed a third pass this one most likely does too: launch it
+      // without asking first)
+      const bool poll = general ? ((it & 3) == 3) : (it >= 2 || (it == 1 && !expect_third));
+      if (it == 1 && pending_out >= 0) {   // this chunk's first passes are queued: now the old copies
+        if (enqueue_results(pending_out)) return -2;
+        pending_out = -1;
+      }
       if (poll && it + 1 < n_launch_iter) {
         k_count_running<<<1, 256, 0, pl->stream>>>(st, s0, ns, pl->running.as<int>());
         pl->stats.launches++;
         int running = 0;
         CK(cudaMemcpyAsync(&running, pl->running.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
         CK(cudaStreamSynchronize(pl->stream));
+        if (!general && it == 1) expect_third = running > 0;
+        if (!general && it == 2 && running == 0) expect_third = true;   // needed exactly three
         if (running == 0) break;
       }
+    }
+    if (pending_out >= 0) {   // (single-pass calls never reach it == 1)
+      if (enqueue_results(pending_out)) return -2;
+      pending_out = -1;
     }
     if (want_align) {   // sum_s w_sn rotate(d_sn) with the fitted phi, DM of this chunk (ppalign.py:197-208)
       AlignSpecArgs aa;
@@ -766,35 +805,18 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       DISPATCH_N(N, k_align_spec<NN><<<dim3(nchan, nsplit), NN / 8, 0, pl->stream>>>(aa));
       pl->stats.launches++;
     }
-    // results of this chunk go back on the copy stream while the next chunk computes
-    {
-      while ((int)pl->ev_chunk.size() <= c) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        pl->ev_chunk.push_back(e);
-      }
-      CK(cudaEventRecord(pl->ev_chunk[c], pl->stream));
-      CK(cudaStreamWaitEvent(pl->copy_stream, pl->ev_chunk[c], 0));
-      cudaStream_t cs = pl->copy_stream;
-      const size_t o1 = (size_t)s0, n1 = (size_t)ns, oc = (size_t)s0 * nchan, ncn = (size_t)ns * nchan;
-      if (copy_out_at(cs, out->params, pl->o_params.as<double>(), o1 * 5, n1 * 5)) return -2;
-      if (copy_out_at(cs, out->param_errs, pl->o_perrs.as<double>(), o1 * 5, n1 * 5)) return -2;
-      if (copy_out_at(cs, out->nu_out, pl->o_nuout.as<double>(), o1 * 3, n1 * 3)) return -2;
-      if (copy_out_at(cs, out->cov, pl->o_cov.as<double>(), o1 * 25, n1 * 25)) return -2;
-      if (copy_out_at(cs, out->chi2, pl->o_chi2.as<double>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->red_chi2, pl->o_rchi2.as<double>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->snr, pl->o_snr.as<double>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->nfeval, pl->o_nfev.as<int>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->return_code, pl->o_rc.as<int>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->scales, pl->o_scales.as<double>(), oc, ncn)) return -2;
-      if (copy_out_at(cs, out->scale_errs, pl->o_serrs.as<double>(), oc, ncn)) return -2;
-      if (copy_out_at(cs, out->channel_snrs, pl->o_csnr.as<double>(), oc, ncn)) return -2;
-      if (copy_out_at(cs, out->noise, pl->sigma.as<double>(), oc, ncn)) return -2;
-      if (copy_out_at(cs, out->lag_index, pl->o_lag.as<int>(), o1, n1)) return -2;
-      if (want_guess && copy_out_at(cs, out->phi_guess, pl->o_phig.as<double>(), o1, n1)) return -2;
-      if (copy_out_at(cs, out->chan_sums, pl->csum.as<double>(), oc * kNCsum, ncn * kNCsum)) return -2;
+    // the chunk is done at this point of the stream; its results go back on the copy stream
+    // while the next chunk computes.  The (host-side) enqueue of those copies is deferred until
+    // the next chunk's first kernels are in the queue, so that the device does not idle over it.
+    while ((int)pl->ev_chunk.size() <= c) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      pl->ev_chunk.push_back(e);
     }
+    CK(cudaEventRecord(pl->ev_chunk[c], pl->stream));
+    pending_out = c;
   }
+  if (pending_out >= 0 && enqueue_results(pending_out)) return -2;
   CK(cudaGetLastError());
   cudaEvent_t ev_t1 = nullptr;
   if (pl->timing) {
