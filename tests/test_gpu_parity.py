@@ -436,6 +436,67 @@ def test_rotate_roundtrip_and_fit_shift_property(engine):
     assert np.all(np.abs(dDM) < 2e-2 * a["param_errs"][:, 1])
 
 
+def test_full_size_batch_properties(engine):
+    """BASELINE config 2 at batch scale (3000 subints of 512 x 2048 generated on the device,
+    12.6 GB > L2, several chunks): every subint converges, the recovered DM offsets are unit-normal
+    about the injected ones, the results do not depend on the chunking (bit-identical), scaling
+    the data scales the amplitudes and nothing else, and a device-side rotation by (phi0, DM0)
+    moves every fit by exactly that."""
+    import torch
+    from pulseportraiture_b200 import pplib
+    nsub, nchan, nbin, nu0, bw = 3000, 512, 2048, 1500., 800.
+    freqs, model = synth.example_model(nchan, nbin, nu0, bw)
+    P = synth.P_EXAMPLE
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)
+    mFT = torch.fft.rfft(torch.from_numpy(model).to(dev), dim=-1)
+    k = torch.arange(mFT.shape[-1], device=dev, dtype=torch.float64)
+    nu2 = torch.from_numpy(freqs ** -2.0 - nu0 ** -2.0).to(dev)
+    data = torch.empty((nsub, nchan, nbin), dtype=torch.float32, device=dev)
+    phi = torch.rand(nsub, generator=g, device=dev, dtype=torch.float64) - 0.5
+    dDM = 3e-4 + 2e-4 * torch.randn(nsub, generator=g, device=dev, dtype=torch.float64)
+    for a in range(0, nsub, 100):
+        b = min(nsub, a + 100)
+        sh = -phi[a:b, None] - (pplib.Dconst * dDM[a:b, None] / P) * nu2[None, :]
+        ph = torch.exp(2j * np.pi * (sh[:, :, None] * k[None, None, :]))
+        clean = torch.fft.irfft(mFT[None] * ph, n=nbin, dim=-1)
+        data[a:b] = clean.to(torch.float32) + 1.5 * torch.randn(clean.shape, generator=g, device=dev, dtype=torch.float32)
+    del clean, ph
+    nu_outs = np.tile([nu0, np.nan, np.nan], (nsub, 1))
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(model.astype(np.float32), freqs)
+        r = pl.fit_batch(data, P, nu_outs=nu_outs)                    # default chunk (2048)
+        pl.set_chunk(777)
+        r7 = pl.fit_batch(data, P, nu_outs=nu_outs)
+        for key in ("params", "param_errs", "chi2", "scales", "lag_index", "nfeval"):
+            assert np.array_equal(r[key], r7[key]), key
+        assert np.all(r["return_code"] == 0) and r["nfeval"].max() <= 4
+        pull = (r["params"][:, 1] - dDM.cpu().numpy()) / r["param_errs"][:, 1]
+        assert abs(pull.mean()) < 4 / np.sqrt(nsub) and abs(np.sqrt(np.mean(pull ** 2)) - 1.0) < 0.06
+        dphi = (r["params"][:, 0] - phi.cpu().numpy() + 0.5) % 1 - 0.5
+        assert np.all(np.abs(dphi) < 6 * r["param_errs"][:, 0])
+        assert abs(np.median(r["red_chi2"]) - 1.0) < 5e-3
+        # amplitude scaling: phases, DMs and chi2 do not move, amplitudes and noise scale
+        data *= 4.0
+        r4 = pl.fit_batch(data, P, nu_outs=nu_outs)
+        worst = np.max(np.abs(r4["params"][:, :2] - r7["params"][:, :2]) / r7["param_errs"][:, :2])
+        same = np.mean(np.all(r4["params"] == r7["params"], axis=1))
+        print("amplitude scaling: %.1f %% of the subints bit-identical, worst shift %.2e sigma" % (100 * same, worst))
+        assert worst < SIG_TOL and same > 0.9          # a few subints take a different (equally valid) last step
+        assert rel(r4["scales"], 4.0 * r7["scales"]) < 1e-6 and rel(r4["noise"], 4.0 * r7["noise"]) < 1e-13
+        assert rel(r4["chi2"], r7["chi2"]) < 1e-9 and rel(r4["param_errs"][:, :2], r7["param_errs"][:, :2]) < 1e-6
+        data *= 0.25
+        # rotation by a known (phi0, DM0) in place, chunk by chunk
+        phi0, DM0 = 0.0371, 4.0e-4
+        for a in range(0, nsub, 500):
+            pl.rotate_batch(data[a:a + 500], -phi0, -DM0, P, nu0, out=data[a:a + 500])
+        rr = pl.fit_batch(data, P, nu_outs=nu_outs)
+    d1 = (rr["params"][:, 0] - r["params"][:, 0] - phi0 + 0.5) % 1 - 0.5
+    d2 = rr["params"][:, 1] - r["params"][:, 1] - DM0
+    assert np.all(np.abs(d1) < 3e-2 * r["param_errs"][:, 0]) and np.all(np.abs(d2) < 3e-2 * r["param_errs"][:, 1])
+
+
 def test_determinism_and_device_inputs(engine):
     """Same inputs -> bit-identical outputs; device-resident inputs (torch CUDA
     tensors) give the same answer as host inputs."""
