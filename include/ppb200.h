@@ -16,6 +16,10 @@
  *   - A plan is bound to one device and one stream; calls are synchronous
  *     with respect to the caller (they return after results are complete)
  *     unless stated otherwise.  One plan per (device, host thread).
+ *   - DEVICE inputs are read on the plan's stream: work queued on another
+ *     stream that produces them must be complete (or pp_plan_set_stream must
+ *     name that stream) before the call.  The Python wrapper synchronises the
+ *     caller's current torch stream for CUDA tensors.
  *   - Return value 0 = success, negative = error (see pp_last_error()).
  *   - nbin must be a power of two, 64 <= nbin <= 4096.
  *   - The DC harmonic is ignored (reference F0_fact = 0, pplib.py:66) and

@@ -34,6 +34,10 @@ def _ptr(x, dtype, keep, name, shape=None):
             raise ValueError("%s must be contiguous" % name)
         if shape is not None and tuple(x.shape) != tuple(shape):
             raise ValueError("%s: expected shape %s, got %s" % (name, shape, tuple(x.shape)))
+        if x.is_cuda:
+            # the plan works on its own stream: whatever torch still has queued for this tensor
+            # on the caller's current stream must be finished before the kernels read it
+            torch.cuda.current_stream(x.device).synchronize()
         keep.append(x)
         return x.data_ptr()
     a = np.ascontiguousarray(x, dtype=dtype)
