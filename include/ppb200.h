@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PPB200_ABI_VERSION 2
+#define PPB200_ABI_VERSION 3
 
 typedef struct pp_plan pp_plan_t;
 
@@ -72,6 +72,7 @@ int pp_set_model(pp_plan_t* plan, const float* model, const double* freqs);
  * (pptoaslib.py:928-1096); with fit_flags = {1,1,0,0,0} and
  * semantics = PP_SEM_FIT_PORTRAIT it is pplib.fit_portrait
  * (pplib.py:2102-2204). */
+enum { PP_DATA_F32 = 0, PP_DATA_I16 = 1 };   /* pp_fit_args_t.data_type */
 enum {
   PP_SEM_FIT_PORTRAIT_FULL = 0, /* pptoaslib.py:928: covariance incl. amplitudes */
   PP_SEM_FIT_PORTRAIT = 1       /* pplib.py:2102: scale_errs = (p_n/sigma^2)^-1/2 */
@@ -111,6 +112,14 @@ typedef struct {
   const double* scat_guess; /* [nsub,2] with init==NULL: tau start value [rot,
                                linear] at nu_fit_tau and alpha start value
                                (pptoas.py:427-452); NULL = 0, 0                */
+  int32_t data_type;        /* PP_DATA_F32 (0): data is float32.  PP_DATA_I16:
+                               data points to int16 [nsub,nchan,nbin], the
+                               PSRFITS DATA column as stored; samples are
+                               raw*dat_scl + dat_offs evaluated in float32 as
+                               PSRCHIVE decodes them (what load_data,
+                               pplib.py:2669-2700, hands to the reference)     */
+  const float* dat_scl;     /* [nsub,nchan] PSRFITS DAT_SCL (int16 only)       */
+  const float* dat_offs;    /* [nsub,nchan] PSRFITS DAT_OFFS (int16 only)      */
 } pp_fit_args_t;
 
 typedef struct {

@@ -85,6 +85,9 @@ class FitArgs(C.Structure):
         ("max_iter", C.c_int32),
         ("tol", C.c_double),
         ("scat_guess", C.c_void_p),
+        ("data_type", C.c_int32),
+        ("dat_scl", C.c_void_p),
+        ("dat_offs", C.c_void_p),
     ]
 
 

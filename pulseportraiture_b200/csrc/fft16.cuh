@@ -51,17 +51,17 @@ template <typename F> __device__ __forceinline__ void twiddle16(cx<F> (&v)[16], 
 }
 
 // The two radix-16 passes of a 1024-point row, 64 threads (t = 0..63), in place in
-// `buf` (phys16 layout).  `g`: the staged packed real row as float2; `tw16`: 16
+// `buf` (phys16 layout).  `g`: the staged packed real row (RowSrcF32 / RowSrcI16); `tw16`: 16
 // factors e^{-2 pi i k/256}.  sync(): barrier over the 64 threads of the row.
 // Afterwards buf[p + 256 c] (c = 0..3, p < 256) is the input of the last radix-4 pass.
-template <typename F, typename Sync, typename Fn, typename Fn2>
+template <typename F, typename Src, typename Sync, typename Fn, typename Fn2>
 __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw16, int t,
-                                               const float2* __restrict__ g, bool gvalid, Sync sync,
+                                               const Src g, bool gvalid, Sync sync,
                                                Fn after_first_reads, Fn2 in_last_pass) {
   cx<F> v[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
-    const float2 x = gvalid ? g[t + 64 * r] : make_float2(0.f, 0.f);
+    const float2 x = gvalid ? g(t + 64 * r) : make_float2(0.f, 0.f);
     v[r] = mk<F>((F)x.x, (F)x.y);
   }
   sync();   // staged row consumed; the previous row's split reads of buf are done

@@ -128,11 +128,30 @@ template <typename F> __device__ __forceinline__ cx<F> csqr(cx<F> a) {
   return mk<F>(fma(a.x, a.x, -a.y * a.y), F(2) * a.x * a.y);
 }
 
+// The staged raw row of a channel as N packed complex samples (x[2j], x[2j+1]):
+// float32 as stored, or 16-bit integers with the PSRFITS scale and offset of the row
+// (value = raw * DAT_SCL + DAT_OFFS, formed in float32 with the two roundings PSRCHIVE
+// makes when it decodes the DATA column, so that both sources give identical samples).
+struct RowSrcF32 {
+  const float2* g;
+  __device__ __forceinline__ bool has() const { return g != nullptr; }
+  __device__ __forceinline__ float2 operator()(int j) const { return g[j]; }
+};
+struct RowSrcI16 {
+  const short2* g;
+  float scl, offs;
+  __device__ __forceinline__ bool has() const { return g != nullptr; }
+  __device__ __forceinline__ float2 operator()(int j) const {
+    const short2 v = g[j];
+    return make_float2(__fadd_rn(__fmul_rn((float)v.x, scl), offs), __fadd_rn(__fmul_rn((float)v.y, scl), offs));
+  }
+};
+
 // One in-place pass of radix R.  First pass: inputs come from `g` (the staged
-// packed real row viewed as float2, shared memory) and carry no twiddles.
-template <int N, int R, typename F, typename Hook>
+// packed real row, shared memory) and carry no twiddles.
+template <int N, int R, typename F, typename Hook, typename Src>
 __device__ __forceinline__ void pass8(cx<F>* __restrict__ buf, const cx<F>* __restrict__ twp, int t, int slot, int Ns,
-                                      const float2* __restrict__ g, bool gvalid, Hook hook) {
+                                      const Src g, bool gvalid, Hook hook) {
   constexpr int T = Slot8<N>::kT;
   constexpr int NB = N / R;       // butterflies per pass
   constexpr int PER = NB / T;     // butterflies per thread (R=8:1, 4:2, 2:4)
@@ -141,10 +160,10 @@ __device__ __forceinline__ void pass8(cx<F>* __restrict__ buf, const cx<F>* __re
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int j = t + i * T;
-    if (g != nullptr) {
+    if (g.has()) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float2 x = gvalid ? g[j + r * NB] : make_float2(0.f, 0.f);
+        const float2 x = gvalid ? g(j + r * NB) : make_float2(0.f, 0.f);
         v[i][r] = mk<F>((F)x.x, (F)x.y);
       }
     } else {
@@ -180,32 +199,33 @@ __device__ __forceinline__ void pass8(cx<F>* __restrict__ buf, const cx<F>* __re
 // `after_first_reads` runs right after the first pass has pulled the staged row
 // into registers (the staging buffer may then be refilled); `in_last_pass` runs
 // inside the last pass, after its reads and before its butterflies.
-template <int N, typename F, typename Fn, typename Fn2>
+template <int N, typename F, typename Src, typename Fn, typename Fn2>
 __device__ __forceinline__ void fft8_rows(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw, int t, int slot,
-                                          const float2* __restrict__ g, bool gvalid, Fn after_first_reads,
+                                          const Src g, bool gvalid, Fn after_first_reads,
                                           Fn2 in_last_pass) {
   using P = Plan8<N>;
   using L = TwLayout<N>;
   auto nop = []() {};
+  const RowSrcF32 none{nullptr};
   pass8<N, P::radix(0), F>(buf, tw, t, slot, 1, g, gvalid, nop);
   after_first_reads();
   if constexpr (P::n == 2) {
     constexpr int o = L::off(1), ns = L::ns(1);
-    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, none, false, in_last_pass);
   } else {
     constexpr int o = L::off(1), ns = L::ns(1);
-    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, nullptr, false, nop);
+    pass8<N, P::radix(1), F>(buf, tw + o, t, slot, ns, none, false, nop);
   }
   if constexpr (P::n == 3) {
     constexpr int o = L::off(2), ns = L::ns(2);
-    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, none, false, in_last_pass);
   } else if constexpr (P::n > 3) {
     constexpr int o = L::off(2), ns = L::ns(2);
-    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, nullptr, false, nop);
+    pass8<N, P::radix(2), F>(buf, tw + o, t, slot, ns, none, false, nop);
   }
   if constexpr (P::n == 4) {
     constexpr int o = L::off(3), ns = L::ns(3);
-    pass8<N, P::radix(3), F>(buf, tw + o, t, slot, ns, nullptr, false, in_last_pass);
+    pass8<N, P::radix(3), F>(buf, tw + o, t, slot, ns, none, false, in_last_pass);
   }
 }
 

@@ -272,7 +272,9 @@ __global__ void k_prep(PrepArgs a) {
 // float2 plus the float32 residual of the first LoK slots.
 // ----------------------------------------------------------------------------
 struct SpectraArgs {
-  const float* data;         // [nsub,nchan,2N], global subint index
+  const void* data;          // [nsub,nchan,2N] float32 (or int16: k_spectra<N, PL, true>), global subint index
+  const float* dat_scl;      // [nsub,nchan] int16 only: value = raw * dat_scl + dat_offs (PSRFITS DAT_SCL / DAT_OFFS)
+  const float* dat_offs;     // [nsub,nchan]
   const cx<double>* mconj64; // [nchan,N]
   const cx<float>* mconj32;  // [nchan,N]
   const double* pn;          // [nchan]
@@ -296,12 +298,12 @@ struct SpectraArgs {
   int nchan, G, nparts;
 };
 
-template <int N, class PL = SpecPlan<N>>
+template <int N, class PL = SpecPlan<N>, bool I16 = false>
 __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(SpectraArgs a) {
   using F = double;
   constexpr int T = PL::kT, NS = PL::kSlots, NUNIT = PL::kUnits, NOUT = PL::kOut, NACC = NUNIT * NOUT;
   static_assert(NACC * T == N, "every harmonic slot has one owner");
-  constexpr unsigned kRowBytes = 2 * N * sizeof(float);
+  constexpr unsigned kRowBytes = 2 * N * (I16 ? sizeof(short) : sizeof(float));   // raw row as stored
   constexpr int NSTG = PL::kStages;   // staged raw rows per slot (TMA prefetch depth)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [PL::kTwTotal] (+pad)
@@ -356,7 +358,8 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       const int ch = ch_begin + step * NS + slot;
       unsigned long long* bar = &mbar[slot][step % NSTG];
       mbar_expect_tx(bar, kRowBytes);
-      bulk_g2s(stage + (size_t)(step % NSTG) * 2 * N, a.data + ((size_t)s * a.nchan + ch) * 2 * N, kRowBytes, bar);
+      bulk_g2s(stage + (size_t)(step % NSTG) * 2 * N,
+               static_cast<const char*>(a.data) + ((size_t)s * a.nchan + ch) * kRowBytes, kRowBytes, bar);
     }
   };
   fetch(0);
@@ -371,7 +374,16 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       if (NSTG > 1 && (step & 1)) { mbar_wait(&mbar[slot][1], ph1); ph1 ^= 1u; }
       else { mbar_wait(&mbar[slot][0], ph0); ph0 ^= 1u; }
     }
-    const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step % NSTG) * 2 * N);
+    const float* graw = stage + (size_t)(step % NSTG) * 2 * N;
+    auto make_src = [&]() {
+      if constexpr (I16) {
+        const size_t o = (size_t)s * a.nchan + (inrange ? ch : 0);
+        return RowSrcI16{reinterpret_cast<const short2*>(graw), a.dat_scl[o], a.dat_offs[o]};
+      } else {
+        return RowSrcF32{reinterpret_cast<const float2*>(graw)};
+      }
+    };
+    const auto g = make_src();
     // conj(model spectrum) of this thread's harmonics: L2 loads issued inside the last
     // FFT pass so that their latency hides behind its butterflies.  Output q of unit i
     // lives in slot PL::slot_of(t, i, q, first) (spectra_plan.cuh).

@@ -84,7 +84,7 @@ struct pp_plan {
   // FFTFIT grid tables keyed by Ns
   std::vector<std::pair<int, DBuf>> grid_tables;
   // per-batch staging of small inputs and per-subint / per-channel workspace
-  DBuf running, in_scat, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
+  DBuf running, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
   DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
@@ -263,6 +263,7 @@ template <int N> static cudaError_t setup_attrs() {
   cudaError_t e;
 #define SET_(fn, bytes) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (e != cudaSuccess) return e;
   SET_((k_spectra<N>), (int)spectra_smem_bytes<N>())
+  SET_((k_spectra<N, SpecPlan<N>, true>), (int)spectra_smem_bytes<N>())
   SET_((k_model<N>), b64)
   SET_((k_rfft_rows<N, float>), b32)
   SET_((k_rfft_rows<N, double>), b64)
@@ -343,7 +344,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -503,6 +504,9 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (!pl || !args || !out) return fail(-1, "NULL argument");
   if (!pl->model_set) return fail(-1, "pp_set_model must be called before pp_fit_batch");
   if (!args->data || !args->P) return fail(-1, "data and P are required");
+  const bool i16 = args->data_type == PP_DATA_I16;
+  if (args->data_type != PP_DATA_F32 && !i16) return fail(-1, "unknown data_type %d", args->data_type);
+  if (i16 && (!args->dat_scl || !args->dat_offs)) return fail(-1, "int16 data need dat_scl and dat_offs");
   if (args->nsub < 1) return fail(-1, "nsub must be >= 1");
   const uint8_t* ff = args->fit_flags;
   if (!ff[0] && !ff[1] && !ff[2] && !ff[3] && !ff[4]) return fail(-1, "nothing to fit");
@@ -603,9 +607,15 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   const bool data_on_device = is_device_ptr(args->data);
   if (data_on_device && (reinterpret_cast<uintptr_t>(args->data) & 15))
     return fail(-1, "device data pointer must be 16-byte aligned");
-  const size_t sub_floats = (size_t)nchan * 2 * N;
+  const size_t sub_bytes = (size_t)nchan * 2 * N * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as stored
+  const char* data_bytes = reinterpret_cast<const char*>(args->data);
   if (!data_on_device)
-    for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need(sizeof(float) * (size_t)chunk * sub_floats));
+    for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need((size_t)chunk * sub_bytes));
+  const float *dscl = nullptr, *doffs = nullptr;
+  if (i16) {
+    if (stage_in(pl, pl->in_scl, args->dat_scl, (size_t)nsub * nchan, &dscl)) return -2;
+    if (stage_in(pl, pl->in_offs, args->dat_offs, (size_t)nsub * nchan, &doffs)) return -2;
+  }
 
   SolverState st;
   st.x = pl->st_x.as<double>(); st.xprev = pl->st_xprev.as<double>(); st.step = pl->st_step.as<double>();
@@ -639,7 +649,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
     cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(pl->data_stage[b].p, args->data + (size_t)s0 * sub_floats, sizeof(float) * ns * sub_floats,
+    e = cudaMemcpyAsync(pl->data_stage[b].p, data_bytes + (size_t)s0 * sub_bytes, (size_t)ns * sub_bytes,
                         cudaMemcpyHostToDevice, pl->copy_stream);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(pl->ev_copy[b], pl->copy_stream);
@@ -680,18 +690,19 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   for (int c = 0; c < nchunks; ++c) {
     const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
-    const float* dchunk;
-    if (data_on_device) dchunk = args->data;
+    const char* dchunk;
+    if (data_on_device) dchunk = data_bytes;
     else {
       if (c + 1 < nchunks) CK(issue_copy(c + 1));
       CK(cudaStreamWaitEvent(pl->stream, pl->ev_copy[c & 1], 0));
       // kernels index data with the global subint number: bias the base pointer
-      dchunk = pl->data_stage[c & 1].as<float>() - (size_t)s0 * sub_floats;
+      dchunk = pl->data_stage[c & 1].as<char>() - (size_t)s0 * sub_bytes;
     }
     {
       SpanGuard g(pl, SP_SPECTRA);
       SpectraArgs a;
-      a.data = dchunk; a.mconj64 = pl->mconj64.as<cx<double>>(); a.mconj32 = pl->mconj32.as<cx<float>>();
+      a.data = dchunk; a.dat_scl = dscl; a.dat_offs = doffs;
+      a.mconj64 = pl->mconj64.as<cx<double>>(); a.mconj32 = pl->mconj32.as<cx<float>>();
       a.pn = pl->pn.as<double>(); a.nu2 = pl->nu2.as<double>();
       a.errs = derrs; a.mask = dmask; a.weights = dw; a.P = dP; a.DMg = ddmg; a.nu_mean = pl->nu_mean.as<double>();
       a.X = pl->X.as<float2>(); a.Xlo = pl->Xlo.as<float2>(); a.partial = want_guess ? pl->partial.as<float2>() : nullptr;
@@ -699,7 +710,11 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
+      if (i16) {
+        DISPATCH_N(N, (k_spectra<NN, SpecPlan<NN>, true><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a)));
+      } else {
+        DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
+      }
       pl->stats.launches++;
     }
     if (!data_on_device) CK(cudaEventRecord(pl->ev_free[c & 1], pl->stream));

@@ -36,8 +36,8 @@ template <int N> struct SpecPlan8 {
   static constexpr int kMinBlocks = (N >= 2048 ? 1 : PP_SPECTRA_MINB);
   static constexpr int kStages = 2;
   __device__ static __forceinline__ void sync(int slot) { slot_sync<N>(slot); }
-  template <typename F, typename Fn, typename Fn2>
-  __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int slot, const float2* g, bool used,
+  template <typename F, typename Src, typename Fn, typename Fn2>
+  __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int slot, const Src g, bool used,
                                                    Fn after_first_reads, Fn2 in_last_pass) {
     fft8_rows<N, F>(buf, tw, t, slot, g, used, after_first_reads, in_last_pass);
   }
@@ -67,8 +67,8 @@ struct SpecPlan16 {
   static constexpr int kMinBlocks = PP_SPECTRA16_MINB;
   static constexpr int kStages = PP_SPECTRA16_STAGES;
   __device__ static __forceinline__ void sync(int) { __syncthreads(); }
-  template <typename F, typename Fn, typename Fn2>
-  __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int, const float2* g, bool used,
+  template <typename F, typename Src, typename Fn, typename Fn2>
+  __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int, const Src g, bool used,
                                                    Fn after_first_reads, Fn2 in_last_pass) {
     fft16_rows1024<F>(buf, tw, t, g, used, []() { __syncthreads(); }, after_first_reads, in_last_pass);
   }

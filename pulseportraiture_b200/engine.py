@@ -27,7 +27,7 @@ def _ptr(x, dtype, keep, name, shape=None):
     if _is_torch(x):
         import torch
         want = {np.float32: torch.float32, np.float64: torch.float64,
-                np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+                np.uint8: torch.uint8, np.int32: torch.int32, np.int16: torch.int16}[dtype]
         if x.dtype != want:
             raise TypeError("%s: expected torch dtype %s, got %s" % (name, want, x.dtype))
         if not x.is_contiguous():
@@ -153,7 +153,7 @@ class WidebandPlan(object):
                   nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
                   log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
                   tol=0.0, semantics="full", want_chan_sums=False, nsub=None,
-                  pinned_results=False, scat_guess=None, align=False):
+                  pinned_results=False, scat_guess=None, align=False, dat_scl=None, dat_offs=None):
         """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
         CUDA torch tensor).  Returns a dict of numpy arrays.
 
@@ -164,7 +164,18 @@ class WidebandPlan(object):
             nsub = int(data.shape[0]) if hasattr(data, "shape") and len(data.shape) == 3 else 1
         nchan, nbin = self.nchan, self.nbin
         a = _ffi.FitArgs()
-        a.data = _ptr(data, np.float32, keep, "data", (nsub, nchan, nbin))
+        is_i16 = (data.dtype == np.int16) if isinstance(data, np.ndarray) else \
+            (_is_torch(data) and str(data.dtype) == "torch.int16")
+        if is_i16:
+            # PSRFITS DATA column as stored: value = raw * DAT_SCL + DAT_OFFS per (subint, channel)
+            if dat_scl is None or dat_offs is None:
+                raise ValueError("int16 data need dat_scl and dat_offs [nsub, nchan]")
+            a.data = _ptr(data, np.int16, keep, "data", (nsub, nchan, nbin))
+            a.data_type = 1
+            a.dat_scl = _ptr(dat_scl, np.float32, keep, "dat_scl", (nsub, nchan))
+            a.dat_offs = _ptr(dat_offs, np.float32, keep, "dat_offs", (nsub, nchan))
+        else:
+            a.data = _ptr(data, np.float32, keep, "data", (nsub, nchan, nbin))
         a.nsub = nsub
         a.semantics = {"full": 0, "fit_portrait": 1}[semantics]
         Parr = np.broadcast_to(np.asarray(P, dtype=np.float64), (nsub,)) \

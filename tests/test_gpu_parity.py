@@ -497,6 +497,45 @@ def test_full_size_batch_properties(engine):
     assert np.all(np.abs(d1) < 3e-2 * r["param_errs"][:, 0]) and np.all(np.abs(d2) < 3e-2 * r["param_errs"][:, 1])
 
 
+@pytest.mark.parametrize("nsub,nchan,nbin", [(5, 24, 2048), (4, 40, 1024), (3, 6, 64)])
+def test_int16_input_matches_decoded_float32(engine, nsub, nchan, nbin):
+    """PSRFITS-style int16 samples with per-(subint, channel) DAT_SCL / DAT_OFFS (data_type =
+    PP_DATA_I16) give bit-identical results to the float32 portrait PSRCHIVE would decode from
+    them; host (chunked staging) and device inputs; with the fused ppalign sum."""
+    import torch
+    sigma = 1.5 if nbin >= 512 else 0.4
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 6600 + nbin + s, sigma=sigma) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]) + 37.5            # a baseline offset, as real data have
+    lo, hi = data.min(axis=-1), data.max(axis=-1)
+    offs = (0.5 * (hi + lo)).astype(np.float32)
+    scl = ((hi - lo) / 65000.0).astype(np.float32)
+    raw = np.clip(np.rint((data - offs[..., None]) / scl[..., None]), -32768, 32767).astype(np.int16)
+    decoded = raw.astype(np.float32) * scl[..., None] + offs[..., None]      # float32: two roundings
+    assert decoded.dtype == np.float32
+    P = cases[0]["P"]
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), cases[0]["freqs"])
+        rf = pl.fit_batch(decoded, P, align=True)
+        ri = pl.fit_batch(raw, P, dat_scl=scl, dat_offs=offs, align=True)
+        pl.set_chunk(2)
+        rc = pl.fit_batch(raw, P, dat_scl=scl, dat_offs=offs, align=True)
+        rd = pl.fit_batch(torch.from_numpy(raw).cuda(), P, dat_scl=torch.from_numpy(scl).cuda(),
+                          dat_offs=torch.from_numpy(offs).cuda(), align=True)
+        with pytest.raises(ValueError):
+            pl.fit_batch(raw, P)
+    for key in rf:
+        if key in ("align_sum", "align_wsum"):      # accumulated with floating-point atomics: order varies
+            for other in (ri, rd, rc):
+                assert np.max(np.abs(other[key] - rf[key])) < 1e-12 * np.max(np.abs(rf[key])), key
+            continue
+        for other in (ri, rd, rc):
+            assert np.array_equal(rf[key], other[key], equal_nan=True), key
+    # and the quantised portrait still fits like the original one
+    assert np.all(rf["return_code"] == 0)
+    ref = orc.get_noise(cases[0]["data"], chans=True)
+    assert rel(rf["noise"][0], ref) < 2e-3
+
+
 def test_determinism_and_device_inputs(engine):
     """Same inputs -> bit-identical outputs; device-resident inputs (torch CUDA
     tensors) give the same answer as host inputs."""
