@@ -71,6 +71,9 @@ class TOA:
         pplib.write_TOAs(self, inf_is_zero=inf_is_zero, outfile=outfile, append=True)
 
 
+# optional: the subints as the archive stores them (PSRFITS DATA column, pol 0): int16
+# [nsub, nchan, nbin] with DAT_SCL / DAT_OFFS [nsub, nchan]; get_TOAs hands them to the device as they are
+_RAW_FIELDS = ["raw_subints", "dat_scl", "dat_offs"]
 _DB_FIELDS = ["backend", "backend_delay", "bw", "doppler_factors", "DM", "dmc",
               "epochs", "filename", "freqs", "frontend", "integration_length",
               "masks", "nbin", "nchan", "noise_stds", "npol", "nsub", "nu0",
@@ -96,7 +99,22 @@ def save_databunch(path, data):
             out["ok_mask"] = m
         else:
             out[k] = np.asarray(v)
+    for k in _RAW_FIELDS:
+        if data.get(k) is not None:
+            out[k] = np.asarray(data[k])
     np.savez(path, **out)
+
+
+def quantize_subints(subints):
+    """int16 samples + DAT_SCL / DAT_OFFS per (subint, channel) for float subints [nsub, nchan, nbin],
+    and the float32 portrait a PSRFITS reader decodes from them (raw * scl + offs in float32)."""
+    x = np.asarray(subints, dtype=np.float64)
+    lo, hi = x.min(axis=-1), x.max(axis=-1)
+    offs = (0.5 * (hi + lo)).astype(np.float32)
+    scl = np.where(hi > lo, (hi - lo) / 65000.0, 1.0).astype(np.float32)
+    raw = np.clip(np.rint((x - offs[..., None]) / scl[..., None]), -32768, 32767).astype(np.int16)
+    decoded = raw.astype(np.float32) * scl[..., None] + offs[..., None]
+    return raw, scl, offs, decoded
 
 
 def load_data(filename, **kwargs):
@@ -111,7 +129,7 @@ def load_data(filename, **kwargs):
     m = d.pop("ok_mask")
     d["ok_ichans"] = [np.where(row)[0] for row in m]
     d["arch"] = None
-    for k in _DB_FIELDS:
+    for k in _DB_FIELDS + _RAW_FIELDS:
         d.setdefault(k, None)
     d["filename"] = str(filename)
     for k in ("backend", "frontend", "source", "state", "telescope", "telescope_code"):
@@ -301,8 +319,15 @@ class GetTOAs:
             fit_start = time.time()
             for flags, isubs in groups.items():
                 idx = np.asarray(isubs, dtype=int)
+                raw_kw = {}
+                if d.get("raw_subints") is not None:       # stored samples go to the device as they are
+                    batch = np.ascontiguousarray(np.asarray(d.raw_subints, dtype=np.int16)[idx])
+                    raw_kw = dict(dat_scl=np.ascontiguousarray(np.asarray(d.dat_scl, dtype=np.float32)[idx]),
+                                  dat_offs=np.ascontiguousarray(np.asarray(d.dat_offs, dtype=np.float32)[idx]))
+                else:
+                    batch = np.ascontiguousarray(subints[idx])
                 r = pl.fit_batch(
-                    np.ascontiguousarray(subints[idx]), Ps[idx], errs=errs[idx],
+                    batch, Ps[idx], errs=errs[idx], **raw_kw,
                     chan_mask=mask[idx], weights=weights[idx], DM_guess=np.full(len(idx), DM_stored),
                     snrs=snrs[idx], nu_fits=None if nu_fits_in is None else nu_fits_in[idx],
                     nu_fit_mode=mode, nu_outs=None if nu_outs_in is None else nu_outs_in[idx],

@@ -691,6 +691,31 @@ def test_gettoas_facade_matches_reference_flow(tmp_path):
         assert rel(gt.DeltaDM_errs[0], var ** 0.5) < 1e-3
 
 
+def test_gettoas_from_stored_int16_subints(tmp_path):
+    """An archive that carries its subints as stored (int16 + DAT_SCL/DAT_OFFS) gives the same TOAs
+    as the archive holding the decoded float portraits; round trip through the .npz provider."""
+    from pulseportraiture_b200 import pptoas
+    d, cases = _fake_archive(5, 32, 512, 9900)
+    raw, scl, offs, decoded = pptoas.quantize_subints(np.asarray(d.subints)[:, 0])
+    d_float = pptoas.DataBunch(**dict(d))
+    d_float["subints"] = decoded[:, None].astype(np.float64)
+    d_raw = pptoas.DataBunch(**dict(d_float))
+    d_raw["raw_subints"], d_raw["dat_scl"], d_raw["dat_offs"] = raw, scl, offs
+    path = str(tmp_path / "raw_archive.npz")
+    pptoas.save_databunch(path, d_raw)
+    back = pptoas.load_data(path)
+    assert back.raw_subints.dtype == np.int16 and np.array_equal(back.raw_subints, raw)
+    g1 = pptoas.GetTOAs([d_float], cases[0]["model"], quiet=True)
+    g1.get_TOAs()
+    g2 = pptoas.GetTOAs([path], cases[0]["model"], quiet=True)
+    g2.get_TOAs()
+    assert len(g1.TOA_list) == len(g2.TOA_list) == 5
+    for a, b in zip(g1.TOA_list, g2.TOA_list):
+        assert a.MJD.intday() == b.MJD.intday() and a.MJD.fracday() == b.MJD.fracday()
+        assert a.TOA_error == b.TOA_error and a.DM == b.DM
+    assert np.array_equal(g1.phis[0], g2.phis[0]) and np.array_equal(g1.DMs[0], g2.DMs[0])
+
+
 def test_gettoas_scattering_fit():
     """fit_scat=True through the facade: scat_guess handling (pptoas.py:427-452), unscattered model,
     log10 tau, TOA flags."""
