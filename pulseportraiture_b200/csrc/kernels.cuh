@@ -2266,8 +2266,8 @@ struct AlignSpecArgs {
   const double* sigma;     // [nsub,nchan] (0 = unused channel)
   const int* rc;           // [nsub] return codes (3 = non-finite fit: skipped)
   const double* nu2;       // [nchan]
-  double2* acc;            // [nchan,N] slot layout (slot 0: x = Nyquist sum, y = DC sum)
-  double* wsum;            // [nchan]
+  double2* acc;            // [nsplit,nchan,N] slot layout (slot 0: x = Nyquist sum, y = DC sum): one slice
+  double* wsum;            // [nsplit,nchan]     per blockIdx.y, added to by one CTA only (deterministic)
   int s0, ns, nchan;
 };
 
@@ -2333,21 +2333,23 @@ __global__ void __launch_bounds__(N / 8) k_align_spec(AlignSpecArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) q[j] = qn[j];
   }
-  double2* o = a.acc + (size_t)n * N + 8 * t;
+  double2* o = a.acc + ((size_t)blockIdx.y * a.nchan + n) * N + 8 * t;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&o[j].x, acc[j].x);
-    atomicAdd(&o[j].y, (j == 0 && t == 0) ? dcsum : acc[j].y);
+    o[j].x += acc[j].x;
+    o[j].y += (j == 0 && t == 0) ? dcsum : acc[j].y;
   }
-  if (t == 0) atomicAdd(&a.wsum[n], wtot);
+  if (t == 0) a.wsum[(size_t)blockIdx.y * a.nchan + n] += wtot;
 }
 
 struct AlignFinishArgs {
-  const double2* acc;      // [nchan,N] from k_align_spec
+  const double2* acc;      // [nsplit,nchan,N] from k_align_spec
+  const double* wsum_parts;// [nsplit,nchan]
   double* aligned;         // [nchan,2N] out (not normalised by the weights)
+  double* wsum;            // [nchan] out
   const void* twN;
   const void* tw2N;
-  int nchan;
+  int nchan, nsplit;
 };
 
 template <int N>
@@ -2370,12 +2372,23 @@ __global__ void __launch_bounds__(256) k_align_finish(AlignFinishArgs a) {
   cx<T>* bufB = bufA + N;
   const int ch = blockIdx.x * G::kRows + r;
   const bool valid = ch < a.nchan;
-  const double2* src = a.acc + (size_t)(valid ? ch : 0) * N;
+  const double2* src0 = a.acc + (size_t)(valid ? ch : 0) * N;
+  const size_t part = (size_t)a.nchan * N;
+  auto total = [&](int slot_i) {        // the slices in a fixed order
+    double2 v = make_double2(0.0, 0.0);
+    for (int q = 0; q < a.nsplit; ++q) { const double2 u = src0[q * part + slot_i]; v.x += u.x; v.y += u.y; }
+    return v;
+  };
+  if (valid && t_row == 0) {
+    double w = 0.0;
+    for (int q = 0; q < a.nsplit; ++q) w += a.wsum_parts[(size_t)q * a.nchan + ch];
+    a.wsum[ch] = w;
+  }
 #pragma unroll
   for (int i = 0; i < G::kPairs; ++i) {
     const int p = t_row + 1 + i * G::kTRow;
     if (p <= N / 2) {
-      const double2 vp = src[p], vq = src[(p < N / 2) ? N - p : p];
+      const double2 vp = total(p), vq = total((p < N / 2) ? N - p : p);
       cx<T> zp, zq;
       pack_pair<T>(mk<T>(vp.x, vp.y), mk<T>(vq.x, vq.y), tw2N[p], zp, zq);
       bufA[p] = cconj(zp);
@@ -2383,7 +2396,7 @@ __global__ void __launch_bounds__(256) k_align_finish(AlignFinishArgs a) {
     }
   }
   if (t_row == 0) {
-    const double2 v0 = src[0];   // x = Nyquist sum, y = DC sum
+    const double2 v0 = total(0);   // x = Nyquist sum, y = DC sum
     bufA[0] = mk<T>(T(0.5) * (v0.y + v0.x), -T(0.5) * (v0.y - v0.x));
   }
   __syncthreads();

@@ -91,7 +91,7 @@ struct pp_plan {
   DBuf rot_gm, rot_nugm, al_w, al_out, al_wsum, ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
       rot_phase, rot_dm, rot_P, rot_nuref;
   // chunk-sized
-  DBuf X, Xlo, partial, data_stage[2], Dspec, Ddc, al_acc;
+  DBuf X, Xlo, partial, data_stage[2], Dspec, Ddc, al_acc, al_wparts;
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev_chunk;   // "chunk finished" events for the overlapped result copies
@@ -352,7 +352,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
                  &pl->Ssn, &pl->Sdn, &pl->csum, &pl->st_x, &pl->st_xprev, &pl->st_step, &pl->st_fprev, &pl->st_lam,
                  &pl->st_iter, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
                  &pl->o_snr, &pl->o_nfev, &pl->o_rc, &pl->o_scales, &pl->o_serrs, &pl->o_csnr, &pl->o_lag, &pl->o_phig,
-                 &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->Dspec, &pl->Ddc, &pl->al_acc, &pl->X, &pl->Xlo,
+                 &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->Dspec, &pl->Ddc, &pl->al_acc, &pl->al_wparts, &pl->X, &pl->Xlo,
                  &pl->partial, &pl->data_stage[0], &pl->data_stage[1]};
   for (DBuf* b : all) b->release();
   for (auto& gt : pl->grid_tables) gt.second.release();
@@ -592,15 +592,20 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->X.need(sizeof(float2) * (size_t)chunk * nchan * N));
   // fused ppalign accumulation (ppalign.py:197-213): keep the data spectra of the chunk
   const bool want_align = out->align_sum != nullptr;
+  int align_nsplit = 1;
   if (want_align) {
     if (!out->align_wsum) return fail(-1, "align_sum needs align_wsum");
     CK(pl->Dspec.need(sizeof(float2) * (size_t)chunk * nchan * N));
     CK(pl->Ddc.need(sizeof(double) * (size_t)chunk * nchan));
-    CK(pl->al_acc.need(sizeof(double2) * (size_t)nchan * N));
+    // partial sums per k_align_spec grid slice (each slice is owned by one CTA: no atomics, so the
+    // result is reproducible); the slice count depends on nchan only
+    align_nsplit = std::max(1, (8 * 148 * 8) / std::max(1, nchan));   // ~8 CTAs per SM
+    CK(pl->al_acc.need(sizeof(double2) * (size_t)align_nsplit * nchan * N));
+    CK(pl->al_wparts.need(sizeof(double) * (size_t)align_nsplit * nchan));
     CK(pl->al_wsum.need(sizeof(double) * nchan));
     CK(pl->al_out.need(sizeof(double) * (size_t)nchan * 2 * N));
-    CK(cudaMemsetAsync(pl->al_acc.p, 0, sizeof(double2) * (size_t)nchan * N, pl->stream));
-    CK(cudaMemsetAsync(pl->al_wsum.p, 0, sizeof(double) * nchan, pl->stream));
+    CK(cudaMemsetAsync(pl->al_acc.p, 0, sizeof(double2) * (size_t)align_nsplit * nchan * N, pl->stream));
+    CK(cudaMemsetAsync(pl->al_wparts.p, 0, sizeof(double) * (size_t)align_nsplit * nchan, pl->stream));
   }
   CK(pl->Xlo.need(sizeof(float2) * (size_t)chunk * nchan * std::min(N, 64)));
   if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
@@ -815,9 +820,8 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       aa.D = pl->Dspec.as<float2>(); aa.Ddc = pl->Ddc.as<double>(); aa.params = pl->o_params.as<double>();
       aa.nu_out = pl->o_nuout.as<double>(); aa.P = dP; aa.scales = pl->o_scales.as<double>(); aa.sigma = pl->sigma.as<double>();
       aa.rc = pl->o_rc.as<int>(); aa.nu2 = pl->nu2.as<double>(); aa.acc = pl->al_acc.as<double2>();
-      aa.wsum = pl->al_wsum.as<double>(); aa.s0 = s0; aa.ns = ns; aa.nchan = nchan;
-      const int nsplit = std::max(1, std::min(ns, (8 * 148 * 8) / std::max(1, nchan)));   // ~8 CTAs per SM
-      DISPATCH_N(N, k_align_spec<NN><<<dim3(nchan, nsplit), NN / 8, 0, pl->stream>>>(aa));
+      aa.wsum = pl->al_wparts.as<double>(); aa.s0 = s0; aa.ns = ns; aa.nchan = nchan;
+      DISPATCH_N(N, k_align_spec<NN><<<dim3(nchan, align_nsplit), NN / 8, 0, pl->stream>>>(aa));
       pl->stats.launches++;
     }
     // the chunk is done at this point of the stream; its results go back on the copy stream
@@ -842,8 +846,9 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   if (want_align) {
     AlignFinishArgs fa;
-    fa.acc = pl->al_acc.as<double2>(); fa.aligned = pl->al_out.as<double>(); fa.twN = pl->twN64.p; fa.tw2N = pl->tw2N64.p;
-    fa.nchan = nchan;
+    fa.acc = pl->al_acc.as<double2>(); fa.wsum_parts = pl->al_wparts.as<double>(); fa.aligned = pl->al_out.as<double>();
+    fa.wsum = pl->al_wsum.as<double>(); fa.twN = pl->twN64.p; fa.tw2N = pl->tw2N64.p;
+    fa.nchan = nchan; fa.nsplit = align_nsplit;
     DISPATCH_N(N, {
       const int rows = RowGeom<NN>::kRows;
       k_align_finish<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(fa);
