@@ -252,6 +252,35 @@ def test_config3_like_scattering_sigma15(engine):
             assert int(r["return_code"][s]) == 0
 
 
+def test_config3_full_shape_4096x1024(engine):
+    """BASELINE config 3 at its real shape (4096 chan x 1024 bin, CHIME-like, tau = 50 us, alpha = -4,
+    flags [1,1,0,1,1], log10 tau) for one subint: the oracle needs ~30 s for it (the verbatim
+    reference cannot run this size at all: its amplitude Hessian is [4101, 4101, 4096])."""
+    nchan, nbin, nu0, bw, tau_s = 4096, 1024, 600., 400., 50e-6
+    c = synth.make_case(nchan, nbin, nu0, bw, 7300, tau_data_s=tau_s)
+    P, freqs = c["P"], c["freqs"]
+    errs = orc.get_noise(c["data"], chans=True)
+    flags = [1, 1, 0, 1, 1]
+    g = orc.fit_phase_shift(c["data"].mean(0), c["model"].mean(0), Ns=100, polish="exact")
+    init = np.array([[g.phase, 0.0, 0.0, np.log10(0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0), -4.0]])
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(c["model"].astype(np.float32), freqs)
+        r = pl.fit_batch(c["data"].astype(np.float32)[None], P, errs=errs[None], init=init, fit_flags=flags,
+                         log10_tau=True)
+    ref = orc.fit_portrait_full(c["data"], c["model"], list(init[0]), P, freqs, errs=errs, fit_flags=flags,
+                                log10_tau=True)
+    for i, nm in enumerate(["phi", "DM", "GM", "tau", "alpha"]):
+        if flags[i]:
+            assert abs(r["params"][0, i] - ref[nm]) / ref[nm + "_err"] < SIG_TOL, nm
+            assert rel(r["param_errs"][0, i], ref[nm + "_err"]) < 1e-4
+    assert abs(r["chi2"][0] / ref.chi2 - 1) < CHI2_TOL
+    assert rel(r["nu_out"][0], [ref.nu_DM, ref.nu_GM, ref.nu_tau]) < 1e-4
+    assert rel(r["scales"][0], ref.scales) < 1e-4 and rel(r["scale_errs"][0], ref.scale_errs) < 1e-4
+    assert int(r["return_code"][0]) == 0
+    tau_600 = 10 ** r["params"][0, 3] * (nu0 / r["nu_out"][0, 2]) ** r["params"][0, 4] * P
+    assert abs(tau_600 - tau_s) < 5 * tau_s * r["param_errs"][0, 3] * np.log(10) + 1e-7
+
+
 def test_batch_64x512_vs_oracle(engine):
     """64 subints of config-1 shape in one batch, several chunk sizes."""
     nsub, nchan, nbin = 64, 64, 512
