@@ -605,25 +605,38 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   const double d_tot = v[0] / err2, p_tot = v[1] / err2;
 
   // ---- brute-force grid (scipy.optimize.brute over np.mgrid[-0.5:0.5:Ns j]) ----
+  // phi_j = -1/2 + j/M, M = Ns - 1:  C_j = -Re sum_k Y_k e^{-i pi k} rho_j^k / err2 with rho_j = e^{2 pi i j/M}.
+  // One grid point per lane; the phasors of the odd and of the even harmonics advance by rho_j^2
+  // (two independent FP64 recurrences, no table look-up or index arithmetic in the loop); Y_k is a
+  // shared-memory broadcast.  Harmonic N sits in slot 0.
   const int M = a.Ns - 1;
   double bv = CUDART_INF;
   int bi = 0x7fffffff;
-  for (int j = w; j < a.Ns; j += 8) {
-    // e^{2 pi i k phi_j} = e^{-i pi k} e^{2 pi i (k j mod M)/M}; a lane's harmonics k = lane + 32 m all
-    // have the parity of the lane (the Nyquist term k = N in slot 0 is even, like lane 0)
-    double acc = 0.0;
-    const int stepi = (32 * j) % M;
-    int idx = (lane == 0) ? (int)(((long long)N * j) % M) : (lane * j) % M;
-    for (int i = lane; i < N; i += 32) {
-      const double2 t = a.table[idx];
-      acc += Y[i].x * t.x - Y[i].y * t.y;
-      idx = (i == 0) ? stepi : idx + stepi;      // slot 0 held k = N; next is k = 32
-      if (idx >= M) idx -= M;
+  for (int j0 = w * 32; j0 < a.Ns; j0 += 256) {
+    const int j = j0 + lane;
+    if (j < a.Ns) {
+      const double2 r1 = a.table[j % M];
+      const cx<double> rho = mk<double>(r1.x, r1.y), rho2 = csqr(rho);
+      cx<double> po = rho, pe = rho2;                 // harmonics 1 and 2
+      double acc_o = 0.0, acc_e = 0.0;
+#pragma unroll 4
+      for (int m = 0; m < N / 2; ++m) {
+        const double2 yo = Y[2 * m + 1];
+        const double2 ye = Y[(2 * m + 2 == N) ? 0 : 2 * m + 2];
+        acc_o = fma(yo.x, po.x, fma(-yo.y, po.y, acc_o));
+        acc_e = fma(ye.x, pe.x, fma(-ye.y, pe.y, acc_e));
+        po = cmul(po, rho2);
+        pe = cmul(pe, rho2);
+      }
+      const double cj = -(acc_e - acc_o) / err2;       // e^{-i pi k}: odd harmonics change sign
+      if (cj < bv) { bv = cj; bi = j; }                // j ascending within a lane: first index wins ties
     }
-    if (lane & 1) acc = -acc;
-    acc = warp_sum(acc);
-    const double cj = -acc / err2;
-    if (cj < bv) { bv = cj; bi = j; }  // j ascending: first index wins ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {                   // warp argmin, lowest index on ties
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
   if (lane == 0) { bestv[w] = bv; besti[w] = bi; }
   __syncthreads();
