@@ -477,8 +477,17 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
 // ----------------------------------------------------------------------------
 // fit
 // ----------------------------------------------------------------------------
-static int pick_chunk(pp_plan* pl, int nsub) {
+static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host) {
   if (pl->chunk_req > 0) return std::min(pl->chunk_req, nsub);
+  if (data_on_host) {
+    // Host data arrive over PCIe (~50 GB/s), ten times slower than the kernels consume them: small
+    // chunks so that the copy of chunk c+1 runs under the kernels of chunk c from early on (the
+    // kernels' per-chunk overheads stay hidden behind the copies).  ~16 chunks, 64..512 subints.
+    const double per_in = 4.0 * pl->nbin * (double)pl->nchan;
+    long c = std::max(64L, std::min(512L, (long)nsub / 16));
+    c = std::min(c, std::max(1L, (long)floor(2.0 * 1073741824.0 / per_in)));   // staging <= 2 GiB each
+    return (int)std::min<long>(c, nsub);
+  }
   // Streaming mode: chunks large enough that every launch fills the GPU many
   // times over (launch latency and the serial FFTFIT-guess tail amortised);
   // the cross-spectrum scratch (8 N nchan bytes per subint) is capped at 8 GiB.
@@ -583,7 +592,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->o_phig.need(sizeof(double) * nsub));
   CK(pl->running.need(sizeof(int)));
 
-  const int chunk = pick_chunk(pl, nsub);
+  const int chunk = pick_chunk(pl, nsub, !is_device_ptr(args->data));
   const int G = rows_per_cta(pl, chunk);
   const int rows_conc = spectra_slots(N);
   const int gx = (nchan + G - 1) / G;
