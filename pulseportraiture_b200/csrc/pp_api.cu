@@ -657,10 +657,19 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (want_guess && grid_table(pl, Ns, &table)) return -2;
 
   // when the data live on the host: the first chunk's copy starts right away
-  const int nchunks = (nsub + chunk - 1) / chunk;
+  // chunk boundaries; with several chunks the last one is kept short (<= 256 subints) because its
+  // result copy is the only one that cannot hide under a following chunk's kernels
+  std::vector<int> cstart;
+  for (int s0 = 0; s0 < nsub; s0 += chunk) cstart.push_back(s0);
+  if (cstart.size() >= 2) {
+    const int tail = 256, last0 = cstart.back();
+    if (nsub - last0 > tail) cstart.push_back(nsub - tail);
+  }
+  cstart.push_back(nsub);
+  const int nchunks = (int)cstart.size() - 1;
   auto issue_copy = [&](int c) -> cudaError_t {
     const int b = c & 1;
-    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    const int s0 = cstart[c], ns = cstart[c + 1] - s0;
     cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(pl->data_stage[b].p, data_bytes + (size_t)s0 * sub_bytes, (size_t)ns * sub_bytes,
@@ -677,7 +686,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   // queue the device-to-host copies of chunk c's results on the copy stream
   auto enqueue_results = [&](int c) -> int {
-    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    const int s0 = cstart[c], ns = cstart[c + 1] - s0;
     CK(cudaStreamWaitEvent(pl->copy_stream, pl->ev_chunk[c], 0));
     cudaStream_t cs = pl->copy_stream;
     const size_t o1 = (size_t)s0, n1 = (size_t)ns, oc = (size_t)s0 * nchan, ncn = (size_t)ns * nchan;
@@ -703,7 +712,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   bool expect_third = false;   // the previous chunk still had unfinished subints after two passes
 
   for (int c = 0; c < nchunks; ++c) {
-    const int s0 = c * chunk, ns = std::min(chunk, nsub - s0);
+    const int s0 = cstart[c], ns = cstart[c + 1] - s0;
     const char* dchunk;
     if (data_on_device) dchunk = data_bytes;
     else {
