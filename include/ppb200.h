@@ -190,7 +190,7 @@ int pp_rotate_full_batch(pp_plan_t* plan, const float* in, float* out, int32_t n
  * Replaces the per-subint accumulation of ppalign.align_archives
  * (ppalign.py:202-208): aligned[n] = sum_s weights[s,n] * rotate_data(data[s,n],
  * phase_s, DM_s, P_s, freqs, nu_ref_s), accumulated in the Fourier domain in
- * double; rows with weight <= 0 are skipped.  aligned: [nchan,nbin] float64
+ * double; rows with weight 0 are skipped (negative weights count, as in the reference).  aligned: [nchan,nbin] float64
  * (not normalised), wsum: [nchan] float64. */
 int pp_align_accumulate(pp_plan_t* plan, const float* data, int32_t nsub,
                         const double* phase, const double* DM, const double* P,

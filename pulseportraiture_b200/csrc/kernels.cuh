@@ -2163,7 +2163,7 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
 // ----------------------------------------------------------------------------
 struct AlignArgs {
   RotateArgs r;            // in = data [nsub,nchan,2N]; out unused
-  const double* weights;   // [nsub,nchan] (scales / sigma^2, ppalign.py:202); <= 0 skips the row
+  const double* weights;   // [nsub,nchan] (scales / sigma^2, ppalign.py:202); 0 skips the row
   double* aligned;         // [nchan,2N] sum (not normalised)
   double* wsum;            // [nchan] sum of the weights used
 };
@@ -2194,7 +2194,7 @@ __global__ void __launch_bounds__(256) k_align_accum(AlignArgs a) {
   T acc0 = 0, accN = 0, wtot = 0;
   for (int s = 0; s < a.r.nsub; ++s) {
     const double w = valid ? a.weights[(size_t)s * a.r.nchan + chc] : 0.0;
-    const bool use = w > 0.0;
+    const bool use = w != 0.0 && fabs(w) < 1e300;   // negative weights (negative fitted amplitudes) count, ppalign.py:202-209
     const float4* src = reinterpret_cast<const float4*>(a.r.in + ((size_t)s * a.r.nchan + chc) * 2 * N);
     __syncthreads();   // previous iteration's reads of the buffers are done
 #pragma unroll
@@ -2312,7 +2312,7 @@ __global__ void __launch_bounds__(N / 8) k_align_spec(AlignSpecArgs a) {
     const double sg = a.sigma[(size_t)s * a.nchan + n];
     const double sc = a.scales[(size_t)s * a.nchan + n];
     const double w = (sg > 0.0 && a.rc[s] != 3) ? sc / (sg * sg) : 0.0;       // ppalign.py:202
-    if (w > 0.0 && w < 1e300) {                                               // uniform over the CTA
+    if (w != 0.0 && fabs(w) < 1e300) {    // uniform over the CTA; negative amplitudes weigh in as in the reference
       const double nr = a.nu_out[(size_t)s * 3];
       double theta = a.params[(size_t)s * 5] + kDconst * a.params[(size_t)s * 5 + 1] * (n2 - 1.0 / (nr * nr)) / a.P[s];
       theta -= rint(theta);

@@ -48,6 +48,7 @@ def test_align_accumulate_vs_oracle():
     w = rng.uniform(0.5, 2.0, (nsub, nchan))
     w[2, 5] = 0.0
     w[4, :] = 0.0
+    w[1, 7] = -0.3          # a negative fitted amplitude weighs in with its sign (ppalign.py:202-209)
     with WidebandPlan(nchan, nbin) as pl:
         pl.set_freqs(freqs)
         acc, wsum = pl.align_accumulate(data, phi, DM, P, nu_ref, w)
