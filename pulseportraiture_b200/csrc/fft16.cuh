@@ -59,10 +59,15 @@ __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx
                                                const Src g, bool gvalid, Sync sync,
                                                Fn after_first_reads, Fn2 in_last_pass) {
   cx<F> v[16];
+  if (gvalid) {      // uniform over the row
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const float2 x = gvalid ? g(t + 64 * r) : make_float2(0.f, 0.f);
-    v[r] = mk<F>((F)x.x, (F)x.y);
+    for (int r = 0; r < 16; ++r) {
+      const float2 x = g(t + 64 * r);
+      v[r] = mk<F>((F)x.x, (F)x.y);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = mk<F>(F(0), F(0));
   }
   sync();   // staged row consumed; the previous row's split reads of buf are done
   after_first_reads();

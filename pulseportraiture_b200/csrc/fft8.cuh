@@ -161,10 +161,15 @@ __device__ __forceinline__ void pass8(cx<F>* __restrict__ buf, const cx<F>* __re
   for (int i = 0; i < PER; ++i) {
     const int j = t + i * T;
     if (g.has()) {
+      if (gvalid) {      // uniform over the row
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float2 x = gvalid ? g(j + r * NB) : make_float2(0.f, 0.f);
-        v[i][r] = mk<F>((F)x.x, (F)x.y);
+        for (int r = 0; r < R; ++r) {
+          const float2 x = g(j + r * NB);
+          v[i][r] = mk<F>((F)x.x, (F)x.y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[i][r] = mk<F>(F(0), F(0));
       }
     } else {
       const int k = j & (Ns - 1);
