@@ -126,3 +126,20 @@ def test_write_TOAs_matches_reference_lines(tmp_path):
     one = str(tmp_path / "one.tim")
     toas[0].write_TOA(outfile=one)
     assert open(one).read() == want.splitlines()[0] + "\n"
+
+
+def test_plain_c_client_compiles_and_links(tmp_path):
+    """tests/c/abi_fit.c (C99, -Wall -Werror) builds against include/ppb200.h and links with the library:
+    the header is usable from C and every symbol the client needs is exported (run: test_gpu_c_client)."""
+    import os
+    import subprocess
+    from pulseportraiture_b200 import _ffi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _ffi.lib()                                   # builds the library if needed
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    exe = str(tmp_path / "abi_fit")
+    r = subprocess.run(["gcc", "-O1", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "abi_fit.c"), "-o", exe, "-L", libdir, "-lppb200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.isfile(exe)
