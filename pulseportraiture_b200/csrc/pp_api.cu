@@ -236,7 +236,13 @@ template <class PL> struct TwBuilder;
 template <> struct TwBuilder<SpecPlan16> {
   static void build(std::vector<double2>& out) {
     out.assign(SpecPlan16::kTwTotal, make_double2(0.0, 0.0));
-    for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
+    if (PP_SPECTRA16_TWTAB) {
+      const int pw[6] = {1, 2, 3, 4, 8, 12};
+      for (int c = 0; c < 6; ++c)
+        for (int k = 0; k < 16; ++k) out[c * 16 + k] = unit_root((long)k * pw[c], 256);
+    } else {
+      for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
+    }
     for (int p2 = 0; p2 <= 128; ++p2) out[SpecPlan16::kSplitOff + p2] = unit_root(p2, 2048);
   }
 };
@@ -503,7 +509,10 @@ static int rows_per_cta(pp_plan* pl, int chunk) {
   // are bit-identical for any chunking): a function of nchan only, ~16 CTAs per subint.
   (void)chunk;
   const int rows_conc = spectra_slots(pl->N);
-  int g = std::max(rows_conc, std::min(32, pl->nchan / 16));
+#ifndef PP_SPECTRA_GMAX
+#define PP_SPECTRA_GMAX 32
+#endif
+  int g = std::max(rows_conc, std::min(PP_SPECTRA_GMAX, pl->nchan / (512 / PP_SPECTRA_GMAX)));
   g = ((g + rows_conc - 1) / rows_conc) * rows_conc;
   // k_spectra finalises one row per thread of a row slot: rows per slot <= N/8 (32 <= 128 here)
   return g;
