@@ -50,24 +50,9 @@ template <typename F> __device__ __forceinline__ void twiddle16(cx<F> (&v)[16], 
   v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
 }
 
-// v[r] *= w^r with the six base powers w, w^2, w^3, w^4, w^8, w^12 given (table fed)
-template <typename F> __device__ __forceinline__ void twiddle16_tab(cx<F> (&v)[16], const cx<F>* __restrict__ tb, int k) {
-  const cx<F> w1 = tb[k], w2 = tb[16 + k], w3 = tb[32 + k], w4 = tb[48 + k], w8 = tb[64 + k], w12 = tb[80 + k];
-  v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
-  v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
-  v[8] = cmul(v[8], w8);
-  v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
-  v[12] = cmul(v[12], w12);
-  v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
-}
-
-#ifndef PP_SPECTRA16_TWTAB
-#define PP_SPECTRA16_TWTAB 0
-#endif
-
 // The two radix-16 passes of a 1024-point row, 64 threads (t = 0..63), in place in
 // `buf` (phys16 layout).  `g`: the staged packed real row (RowSrcF32 / RowSrcI16); `tw16`: 16
-// factors e^{-2 pi i k/256} (PP_SPECTRA16_TWTAB: their powers 1, 2, 3, 4, 8, 12 as [6][16]).  sync(): barrier over the 64 threads of the row.
+// factors e^{-2 pi i k/256}.  sync(): barrier over the 64 threads of the row.
 // Afterwards buf[p + 256 c] (c = 0..3, p < 256) is the input of the last radix-4 pass.
 template <typename F, typename Src, typename Sync, typename Fn, typename Fn2>
 __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw16, int t,
@@ -91,18 +76,12 @@ __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx
   for (int k = 0; k < 16; ++k) buf[phys16(16 * t + k)] = v[dft16_at(k)];
   sync();
   const int k = t & 15;
-#if !PP_SPECTRA16_TWTAB
   const cx<F> w1 = tw16[k];
-#endif
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = buf[phys16(t + 64 * r)];
   sync();
   in_last_pass();
-#if PP_SPECTRA16_TWTAB
-  twiddle16_tab(v, tw16, k);
-#else
   twiddle16(v, w1);
-#endif
   dft16(v);
   const int j0 = (t - k) * 16 + k;
 #pragma unroll

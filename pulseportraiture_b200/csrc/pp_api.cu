@@ -236,13 +236,7 @@ template <class PL> struct TwBuilder;
 template <> struct TwBuilder<SpecPlan16> {
   static void build(std::vector<double2>& out) {
     out.assign(SpecPlan16::kTwTotal, make_double2(0.0, 0.0));
-    if (PP_SPECTRA16_TWTAB) {
-      const int pw[6] = {1, 2, 3, 4, 8, 12};
-      for (int c = 0; c < 6; ++c)
-        for (int k = 0; k < 16; ++k) out[c * 16 + k] = unit_root((long)k * pw[c], 256);
-    } else {
-      for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
-    }
+    for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
     for (int p2 = 0; p2 <= 128; ++p2) out[SpecPlan16::kSplitOff + p2] = unit_root(p2, 2048);
   }
 };

@@ -62,8 +62,7 @@ struct SpecPlan16 {
   static constexpr int N = 1024;
   static constexpr int kT = 64, kSlots = 1, kThreads = 64;
   static constexpr int kUnits = 2, kOut = 8;
-  static constexpr int kSplitOff = PP_SPECTRA16_TWTAB ? 96 : 16;   // pass-2 factors e^{-2 pi i k/256} (k < 16; or their
-                                                                   // powers [6][16]); then e^{-2 pi i p/2048}, p <= 128
+  static constexpr int kSplitOff = 16;                    // tw[0..15] = e^{-2 pi i k/256}; then e^{-2 pi i p/2048}, p <= 128
   static constexpr int kTwTotal = kSplitOff + 129;
   static constexpr int kMinBlocks = PP_SPECTRA16_MINB;
   static constexpr int kStages = PP_SPECTRA16_STAGES;
