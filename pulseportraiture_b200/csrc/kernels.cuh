@@ -1463,11 +1463,12 @@ __device__ __forceinline__ double chan_H(double C, double S, double d2C, double 
                  C * (dCa * dSb + dSa * dCb) * iS * iS);
 }
 
-__global__ void __launch_bounds__(128) k_update5(Update5Args a) {
+template <int NT>
+__global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   const int s = a.s0 + blockIdx.x;
   const int state = a.st.done[s];
   if (state == 1) return;
-  __shared__ double sh[24 * 4];
+  __shared__ double sh[24 * (NT / 32)];
   __shared__ double bc[48];
   const int tid = threadIdx.x, nchan = a.nchan;
   const double* cs = a.csum + (size_t)s * nchan * kNCsum;
@@ -1490,7 +1491,7 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
     double v[23];
     for (int i = 0; i < 23; ++i) v[i] = 0.0;   // f, g[5], H upper [15], Sd, spare
     double gmax1 = 0.0, gmax2 = 0.0;
-    for (int n = tid; n < nchan; n += 128) {
+    for (int n = tid; n < nchan; n += NT) {
       double c[9];
       for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
       const double S = c[6];
@@ -1510,14 +1511,15 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
       gmax1 = fmax(gmax1, fabs(j.Jth[1]));
       gmax2 = fmax(gmax2, fabs(j.Jth[2]));
     }
-    block_sum<23, 128>(v, sh);
+    block_sum<23, NT>(v, sh);
     double gm[2] = {gmax1, gmax2};
     for (int o = 16; o > 0; o >>= 1) { gm[0] = fmax(gm[0], __shfl_xor_sync(0xffffffffu, gm[0], o)); gm[1] = fmax(gm[1], __shfl_xor_sync(0xffffffffu, gm[1], o)); }
     __syncthreads();
-    if ((tid & 31) == 0) { sh[tid >> 5] = gm[0]; sh[8 + (tid >> 5)] = gm[1]; }
+    if ((tid & 31) == 0) { sh[tid >> 5] = gm[0]; sh[NT / 32 + (tid >> 5)] = gm[1]; }
     __syncthreads();
-    gmax1 = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3]));
-    gmax2 = fmax(fmax(sh[8], sh[9]), fmax(sh[10], sh[11]));
+    gmax1 = gmax2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < NT / 32; ++q) { gmax1 = fmax(gmax1, sh[q]); gmax2 = fmax(gmax2, sh[NT / 32 + q]); }
     if (tid == 0) {
       const int it = a.st.iter[s] + 1;
       a.st.iter[s] = it;
@@ -1604,7 +1606,7 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
   for (int i = 0; i < 24; ++i) u[i] = 0.0;
   // u[0..14]: for j=0..4: sum h_th(j), sum nu^-2 h_th(j), sum nu^-4 h_th(j)
   // u[15..20]: for j in {0,1,3}: sum h_ln(j), sum ln(nu) h_ln(j) ; u[21]: f ; u[22]: Sd ; u[23]: snr^2
-  for (int n = tid; n < nchan; n += 128) {
+  for (int n = tid; n < nchan; n += NT) {
     double c[9];
     for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
     const double S = c[6];
@@ -1638,12 +1640,12 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
     u[22] += a.Sdn[(size_t)s * nchan + n];
     u[23] += C * C / S;
   }
-  block_sum<24, 128>(u, sh);
+  block_sum<24, NT>(u, sh);
   // full Hessian at the fit frequencies (needed by some nu_zero formulas)
   double hv[15];
   for (int i = 0; i < 15; ++i) hv[i] = 0.0;
   double fmean = 0.0;
-  for (int n = tid; n < nchan; n += 128) {
+  for (int n = tid; n < nchan; n += NT) {
     double c[9];
     for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
     const double S = c[6];
@@ -1658,9 +1660,9 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
         hv[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * zfl[i] * zfl[k];
     fmean += a.freqs[n];
   }
-  block_sum<15, 128>(hv, sh);
+  block_sum<15, NT>(hv, sh);
   double fm[1] = {fmean};
-  block_sum<1, 128>(fm, sh);
+  block_sum<1, NT>(fm, sh);
   if (tid == 0) {
     double Hz[25];
     int q = 0;
@@ -1745,7 +1747,7 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
   // ---- Hessian at the output frequencies, covariance incl. amplitudes (645-731) -------------
   double ho[15];
   for (int i = 0; i < 15; ++i) ho[i] = 0.0;
-  for (int n = tid; n < nchan; n += 128) {
+  for (int n = tid; n < nchan; n += NT) {
     double c[9];
     for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
     const double S = c[6];
@@ -1759,7 +1761,7 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
       for (int k = i; k < 5; ++k, ++q)
         ho[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * fl[i] * fl[k];
   }
-  block_sum<15, 128>(ho, sh);
+  block_sum<15, NT>(ho, sh);
   if (tid == 0) {
     double Hf[25], H[25], L[25], Inv[25];
     int q = 0;
@@ -1773,7 +1775,7 @@ __global__ void __launch_bounds__(128) k_update5(Update5Args a) {
   __syncthreads();
   double Xinv[25];
   for (int i = 0; i < 25; ++i) Xinv[i] = bc[8 + i];
-  for (int n = tid; n < nchan; n += 128) {
+  for (int n = tid; n < nchan; n += NT) {
     double c[9];
     for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
     const double S = c[6];

@@ -807,7 +807,10 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       }
       {
         SpanGuard g(pl, SP_UPDATE);
-        if (general) k_update5<<<ns, 128, 0, pl->stream>>>(u5);
+        if (general) {   // many channels: more threads per subint for the per-channel chain rule
+          if (nchan >= 1024) k_update5<256><<<ns, 256, 0, pl->stream>>>(u5);
+          else k_update5<128><<<ns, 128, 0, pl->stream>>>(u5);
+        }
         else k_update2<<<ns, 128, 0, pl->stream>>>(ua);
       }
       pl->stats.launches += 2;
