@@ -1175,8 +1175,11 @@ struct Pass5Args {
   int s0, nchan, log10_tau;
 };
 
+#ifndef PP_PASS5_MINB
+#define PP_PASS5_MINB 2
+#endif
 template <int N>
-__global__ void __launch_bounds__(256, 2) k_pass5(Pass5Args a) {
+__global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
   const int sl = blockIdx.y, s = a.s0 + sl;
   if (a.st.done[s] == 1) return;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
