@@ -477,8 +477,9 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
 // ----------------------------------------------------------------------------
 // fit
 // ----------------------------------------------------------------------------
+static const int kMaxChunk = 32768;   // the chunk index is gridDim.y of the row kernels (<= 65535)
 static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host) {
-  if (pl->chunk_req > 0) return std::min(pl->chunk_req, nsub);
+  if (pl->chunk_req > 0) return std::min(std::min(pl->chunk_req, kMaxChunk), nsub);
   if (data_on_host) {
     // Host data arrive over PCIe (~50 GB/s), ten times slower than the kernels consume them: small
     // chunks so that the copy of chunk c+1 runs under the kernels of chunk c from early on (the
@@ -493,7 +494,7 @@ static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host) {
   // the cross-spectrum scratch (8 N nchan bytes per subint) is capped at 8 GiB.
   const double per = 8.0 * pl->N * (double)pl->nchan;
   long c = (long)floor(8.0 * 1073741824.0 / per);
-  c = std::max(c, 64L);
+  c = std::min<long>(std::max(c, 64L), kMaxChunk);
   return (int)std::min<long>(c, nsub);
 }
 

@@ -565,6 +565,21 @@ def test_int16_input_matches_decoded_float32(engine, nsub, nchan, nbin):
     assert rel(rf["noise"][0], ref) < 2e-3
 
 
+def test_many_small_portraits_in_one_batch(engine):
+    """100 000 small portraits (4 chan x 64 bin) in one call: more subints than a grid dimension
+    holds, so the batch must be cut into chunks; every copy of the same portrait gives the same fit."""
+    nsub, nchan, nbin = 100000, 4, 64
+    c = synth.make_case(nchan, nbin, 1500., 800., 8700, sigma=0.3)
+    one = c["data"].astype(np.float32)
+    data = np.ascontiguousarray(np.broadcast_to(one, (nsub, nchan, nbin)))
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(c["model"].astype(np.float32), c["freqs"])
+        r = pl.fit_batch(data, c["P"])
+        r1 = pl.fit_batch(one[None], c["P"])
+    assert np.all(r["return_code"] == 0)
+    assert np.all(r["params"] == r1["params"][0]) and np.all(r["chi2"] == r1["chi2"][0])
+
+
 def test_determinism_and_device_inputs(engine):
     """Same inputs -> bit-identical outputs; device-resident inputs (torch CUDA
     tensors) give the same answer as host inputs."""
