@@ -575,9 +575,12 @@ def test_many_small_portraits_in_one_batch(engine):
     with engine.WidebandPlan(nchan, nbin) as pl:
         pl.set_model(c["model"].astype(np.float32), c["freqs"])
         r = pl.fit_batch(data, c["P"])
+        import torch
+        rd = pl.fit_batch(torch.from_numpy(data).cuda(), c["P"])      # device input: chunks of 32768
         r1 = pl.fit_batch(one[None], c["P"])
     assert np.all(r["return_code"] == 0)
-    assert np.all(r["params"] == r1["params"][0]) and np.all(r["chi2"] == r1["chi2"][0])
+    for res in (r, rd):
+        assert np.all(res["params"] == r1["params"][0]) and np.all(res["chi2"] == r1["chi2"][0])
 
 
 def test_determinism_and_device_inputs(engine):
