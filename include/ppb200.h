@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PPB200_ABI_VERSION 3
+#define PPB200_ABI_VERSION 4
 
 typedef struct pp_plan pp_plan_t;
 
@@ -120,6 +120,15 @@ typedef struct {
                                pplib.py:2669-2700, hands to the reference)     */
   const float* dat_scl;     /* [nsub,nchan] PSRFITS DAT_SCL (int16 only)       */
   const float* dat_offs;    /* [nsub,nchan] PSRFITS DAT_OFFS (int16 only)      */
+  const double* bounds;     /* HOST [5,2] (lower, upper) for phi, DM, GM, tau
+                               (log10 tau with log10_tau) and alpha, applied to
+                               the parameters at the FIT reference frequencies
+                               as scipy's TNC applies them (pplib.py:2146-2148,
+                               pptoaslib.py:1008-1014; defaults of
+                               pptoas.py:461-469).  NaN or +-inf = unbounded;
+                               NULL = no bounds.  Parameters at a bound still
+                               get their Hessian-based errors, as in the
+                               reference                                       */
 } pp_fit_args_t;
 
 typedef struct {

@@ -88,6 +88,7 @@ class FitArgs(C.Structure):
         ("data_type", C.c_int32),
         ("dat_scl", C.c_void_p),
         ("dat_offs", C.c_void_p),
+        ("bounds", C.c_void_p),
     ]
 
 

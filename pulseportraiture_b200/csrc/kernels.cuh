@@ -725,6 +725,24 @@ struct SolverState {
   int* done;        // [nsub] 0 running, 1 finished
 };
 
+// Box constraints on the parameters at the fit reference frequencies (scipy TNC bounds:
+// pplib.py:2146-2148, pptoaslib.py:1008-1014).  Handled by the Newton solvers as an active set:
+// a parameter that sits on a bound with the gradient pushing outwards is held for that step,
+// steps are clipped to the box.
+struct Box {
+  double lo[5], hi[5];
+  int on;
+};
+__device__ __forceinline__ bool box_holds(const Box& b, int p, double x, double g) {
+  return b.on && ((x <= b.lo[p] && g > 0.0) || (x >= b.hi[p] && g < 0.0));
+}
+__device__ __forceinline__ double box_clip(const Box& b, int p, double xn, bool& clipped) {
+  if (!b.on) return xn;
+  if (xn < b.lo[p]) { clipped = true; return b.lo[p]; }
+  if (xn > b.hi[p]) { clipped = true; return b.hi[p]; }
+  return xn;
+}
+
 // ----------------------------------------------------------------------------
 // k_pass2: K3 for (phi, DM).  8 lanes per channel row, 4 rows per warp,
 // 8 warps per CTA: grid = (ceil(nchan/32), subints in chunk).
@@ -919,6 +937,7 @@ struct UpdateArgs {
   double* snr; int* nfeval; int* rc; double* scales; double* scale_errs; double* channel_snrs;
   int s0, nchan, nbin, max_iter, semantics, fit_phi, fit_dm, is_toa;
   double tol;
+  Box box;
 };
 
 __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
@@ -979,8 +998,10 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
       else { x[0] = xp[0] + lam * stp[0]; x[1] = xp[1] + lam * stp[1]; }
     } else {
       double h00 = v[3], h01 = v[4], h11 = v[5], g0 = v[1], g1 = v[2];
-      if (!a.fit_dm) { h01 = 0.0; h11 = 1.0; g1 = 0.0; }
-      if (!a.fit_phi) { h01 = 0.0; h00 = 1.0; g0 = 0.0; }
+      const bool free0 = a.fit_phi && !box_holds(a.box, 0, x[0], g0);
+      const bool free1 = a.fit_dm && !box_holds(a.box, 1, x[1], g1);
+      if (!free1) { h01 = 0.0; h11 = 1.0; g1 = 0.0; }
+      if (!free0) { h01 = 0.0; h00 = 1.0; g0 = 0.0; }
       double det = h00 * h11 - h01 * h01;
       bool pd = h00 > 0.0 && h11 > 0.0 && det > 1e-14 * h00 * h11;
       if (pd) {
@@ -993,11 +1014,14 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
       // keep every channel's rotation change below 0.1 turn
       const double big = fmax(fabs(d0), fabs(d1) * gmax);
       if (big > 0.1) { d0 *= 0.1 / big; d1 *= 0.1 / big; }
+      bool clipped = false;
+      const double xn0 = box_clip(a.box, 0, x[0] + d0, clipped), xn1 = box_clip(a.box, 1, x[1] + d1, clipped);
+      if (clipped) { d0 = xn0 - x[0]; d1 = xn1 - x[1]; }
       bool conv = false;
-      if (pd) {
+      if (pd && !clipped) {
         // 1-sigma from cov = inv(H/2) (pplib.py:2187-2190)
         const double s0 = sqrt(2.0 * h11 / det), s1 = sqrt(2.0 * h00 / det);
-        conv = (fabs(d0) <= a.tol * s0 || !a.fit_phi) && (fabs(d1) <= a.tol * s1 || !a.fit_dm);
+        conv = (fabs(d0) <= a.tol * s0 || !free0) && (fabs(d1) <= a.tol * s1 || !free1);
       }
       xp[0] = x[0]; xp[1] = x[1];
       stp[0] = d0; stp[1] = d1;
@@ -1005,7 +1029,7 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
       a.st.lam[s] = 1.0;
       if (conv) { finish = 1; rc = 0; }
       else if (it >= a.max_iter) { finish = 1; rc = 1; }
-      else { x[0] += d0; x[1] += d1; }
+      else { x[0] = xn0; x[1] = xn1; }
     }
     bc[0] = (double)finish; bc[1] = d0; bc[2] = d1; bc[3] = (double)rc; bc[4] = (double)it;
   }
@@ -1148,6 +1172,18 @@ __global__ void k_reset_state(SolverState st, int s0, int n) {
   const int s = s0 + i;
   for (int q = 0; q < 5; ++q) { st.xprev[(size_t)s * 5 + q] = st.x[(size_t)s * 5 + q]; st.step[(size_t)s * 5 + q] = 0.0; }
   st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+}
+
+// start values are moved into the box, as scipy's TNC does with x0
+__global__ void k_clamp_state(SolverState st, Box box, int s0, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = s0 + i;
+  for (int q = 0; q < 5; ++q) {
+    bool c = false;
+    const double v = box_clip(box, q, st.x[(size_t)s * 5 + q], c);
+    if (c) { st.x[(size_t)s * 5 + q] = v; st.xprev[(size_t)s * 5 + q] = v; }
+  }
 }
 
 // ----------------------------------------------------------------------------
@@ -1413,6 +1449,7 @@ struct Update5Args {
   int s0, nchan, nbin, max_iter, log10_tau, option, is_toa;
   int flags[5];
   double tol;
+  Box box;
 };
 
 struct ChanJ {   // per-channel Jacobians of (theta_n, tau_n) w.r.t. the five parameters
@@ -1541,6 +1578,12 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         int q = 6;
         double Hf[25];
         for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) { Hf[i * 5 + k] = v[q]; Hf[k * 5 + i] = v[q]; }
+        if (a.box.on) {   // active set: parameters held on a bound leave this step's system (idx, nfit are
+                          // not used again in this invocation: the epilogue below runs on action 3 only)
+          int nfree = 0;
+          for (int i = 0; i < nfit; ++i) if (!box_holds(a.box, idx[i], x[idx[i]], v[1 + idx[i]])) idx[nfree++] = idx[i];
+          nfit = nfree;
+        }
         for (int i = 0; i < nfit; ++i) { g[i] = v[1 + idx[i]]; for (int k = 0; k < nfit; ++k) H[i * 5 + k] = Hf[idx[i] * 5 + idx[k]]; }
         bool pd = chol5(H, nfit, L);
         double Inv[25];
@@ -1574,7 +1617,11 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         else if (fl[3] && x[3] > 0.0 && fabs(d[3]) > 0.5 * x[3]) sc = fmin(sc, 0.5 * x[3] / fabs(d[3]));
         if (fabs(d[4]) > 1.0) sc = fmin(sc, 1.0 / fabs(d[4]));
         for (int i = 0; i < 5; ++i) d[i] *= sc;
-        bool conv = pd && sc == 1.0;
+        bool clipped = false;
+        double xn[5];
+        for (int i = 0; i < 5; ++i) xn[i] = box_clip(a.box, i, x[i] + d[i], clipped);
+        if (clipped) for (int i = 0; i < 5; ++i) d[i] = xn[i] - x[i];
+        bool conv = pd && sc == 1.0 && !clipped;
         if (conv) for (int i = 0; i < nfit; ++i) {
           const double sg = sqrt(2.0 * Inv[i * 5 + i]);     // 1-sigma from inv(H/2)
           if (!(fabs(dr[i]) <= a.tol * sg)) conv = false;
@@ -1582,7 +1629,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         for (int i = 0; i < 5; ++i) { xp[i] = x[i]; stp[i] = d[i]; }
         a.st.fprev[s] = f;
         a.st.lam[s] = 1.0;
-        for (int i = 0; i < 5; ++i) x[i] += d[i];
+        for (int i = 0; i < 5; ++i) x[i] = xn[i];
         if (conv) { action = 1; rc = 0; }
         else if (it >= a.max_iter) { action = 1; rc = 1; }
       }

@@ -563,6 +563,18 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (stage_in(pl, pl->in_nuouts, args->nu_outs, (size_t)nsub * 3, &dnuouts)) return -2;
   if (stage_in(pl, pl->in_scat, args->scat_guess, (size_t)nsub * 2, &dscat)) return -2;
   const bool want_guess = (args->init == nullptr);
+  Box box;
+  box.on = 0;
+  for (int i = 0; i < 5; ++i) { box.lo[i] = -INFINITY; box.hi[i] = INFINITY; }
+  if (args->bounds) {
+    if (is_device_ptr(args->bounds)) return fail(-1, "bounds must be a host pointer");
+    for (int i = 0; i < 5; ++i) {
+      const double lo = args->bounds[2 * i], hi = args->bounds[2 * i + 1];
+      if (lo == lo && lo > -INFINITY) { box.lo[i] = lo; box.on = 1; }
+      if (hi == hi && hi < INFINITY) { box.hi[i] = hi; box.on = 1; }
+      if (box.lo[i] > box.hi[i]) return fail(-1, "bounds[%d]: lower %g > upper %g", i, lo, hi);
+    }
+  }
 
   // ---- workspace -------------------------------------------------------------------
   CK(pl->nu_fit.need(sizeof(double) * nsub * 3));
@@ -654,6 +666,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   }
   if (!want_guess) {
     k_init_state<<<(nsub + 127) / 128, 128, 0, pl->stream>>>(st, dinit, 0, nsub);
+    if (box.on) k_clamp_state<<<(nsub + 127) / 128, 128, 0, pl->stream>>>(st, box, 0, nsub);
     pl->stats.launches++;
     CK(cudaMemsetAsync(pl->o_lag.p, 0xff, sizeof(int) * nsub, pl->stream));
   }
@@ -766,6 +779,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       k_guess<<<ns, 256, sizeof(double2) * N, pl->stream>>>(ga);
       k_reset_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
       pl->stats.launches += 2;
+      if (box.on) { k_clamp_state<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, box, s0, ns); pl->stats.launches++; }
     }
     PassArgs pa;
     pa.X = pl->X.as<float2>(); pa.Xlo = pl->Xlo.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
@@ -781,7 +795,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     ua.snr = pl->o_snr.as<double>(); ua.nfeval = pl->o_nfev.as<int>(); ua.rc = pl->o_rc.as<int>();
     ua.scales = pl->o_scales.as<double>(); ua.scale_errs = pl->o_serrs.as<double>(); ua.channel_snrs = pl->o_csnr.as<double>();
     ua.s0 = s0; ua.nchan = nchan; ua.nbin = 2 * N; ua.max_iter = max_iter; ua.semantics = args->semantics;
-    ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol;
+    ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol; ua.box = box;
     Pass5Args p5;
     Update5Args u5;
     if (general) {
@@ -797,7 +811,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       u5.red_chi2 = ua.red_chi2; u5.snr = ua.snr; u5.nfeval = ua.nfeval; u5.rc = ua.rc; u5.scales = ua.scales;
       u5.scale_errs = ua.scale_errs; u5.channel_snrs = ua.channel_snrs;
       u5.s0 = s0; u5.nchan = nchan; u5.nbin = 2 * N; u5.max_iter = max_iter; u5.log10_tau = args->log10_tau;
-      u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol;
+      u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol; u5.box = box;
       for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
     }
     for (int it = 0; it < n_launch_iter; ++it) {

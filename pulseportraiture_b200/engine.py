@@ -75,6 +75,21 @@ class PinnedPool(object):
         self._bufs = {}
 
 
+def bounds_array(bounds):
+    """scipy-style bounds [(lo, hi), ...] (None = open) for the leading parameters -> float64
+    [5, 2] with NaN for open ends, or None when nothing is bounded."""
+    if bounds is None:
+        return None
+    out = np.full((5, 2), np.nan)
+    for i, b in enumerate(bounds):
+        if b is None:
+            continue
+        lo, hi = b
+        out[i, 0] = np.nan if lo is None else float(lo)
+        out[i, 1] = np.nan if hi is None else float(hi)
+    return None if np.all(np.isnan(out)) else out
+
+
 class WidebandPlan(object):
     """Device plan for portraits of shape [nchan, nbin] (C ABI pp_plan_*)."""
 
@@ -153,9 +168,13 @@ class WidebandPlan(object):
                   nu_fit_mode=0, nu_outs=None, fit_flags=(1, 1, 0, 0, 0),
                   log10_tau=False, option=0, is_toa=True, Ns=100, max_iter=0,
                   tol=0.0, semantics="full", want_chan_sums=False, nsub=None,
-                  pinned_results=False, scat_guess=None, align=False, dat_scl=None, dat_offs=None):
+                  pinned_results=False, scat_guess=None, align=False, dat_scl=None, dat_offs=None,
+                  bounds=None):
         """Fit every subint of data[nsub, nchan, nbin] (float32, host numpy or
         CUDA torch tensor).  Returns a dict of numpy arrays.
+
+        bounds: up to five (lower, upper) pairs for phi, DM, GM, tau (log10 tau with
+        log10_tau) and alpha as scipy's TNC takes them (None = unbounded).
 
         pinned_results=True returns views of plan-owned page-locked buffers
         (full-speed D2H); they are overwritten by the next call on this plan."""
@@ -202,6 +221,7 @@ class WidebandPlan(object):
         a.max_iter = int(max_iter)
         a.tol = float(tol)
         a.scat_guess = _ptr(scat_guess, np.float64, keep, "scat_guess", (nsub, 2))
+        a.bounds = _ptr(bounds_array(bounds), np.float64, keep, "bounds", (5, 2))
 
         spec = {
             "params": ((nsub, 5), np.float64), "param_errs": ((nsub, 5), np.float64),

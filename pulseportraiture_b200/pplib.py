@@ -69,14 +69,15 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def _check_bounds(bounds):
-    for b in bounds or []:
-        if b is None:
-            continue
-        if any(v is not None for v in b):
-            raise NotImplementedError(
-                "parameter bounds are a scipy-TNC feature of the reference; "
-                "the device solver is an unconstrained Newton method")
+def _check_bounds(bounds, nparam):
+    """scipy-style bounds -> what WidebandPlan.fit_batch takes (None when nothing is bounded)."""
+    bounds = list(bounds or [])
+    if len(bounds) > nparam:
+        raise ValueError("bounds has %d entries for %d parameters" % (len(bounds), nparam))
+    for b in bounds:
+        if b is not None and len(b) != 2:
+            raise ValueError("each bound is a (lower, upper) pair")
+    return bounds if any(b is not None and any(v is not None for v in b) for b in bounds) else None
 
 
 # ---- A3: 1-D FFTFIT -------------------------------------------------------------
@@ -113,8 +114,9 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
     """Fit a phase offset and DM between data and model portraits
     (pplib.py:2102-2204).  Same arguments and DataBunch fields as the
     reference; the TNC minimiser is replaced by the on-device Newton solver
-    (``return_code`` 0 = converged, 1 = max passes, 3 = non-finite)."""
-    _check_bounds(bounds)
+    (``return_code`` 0 = converged, 1 = max passes, 3 = non-finite), which
+    honours ``bounds`` as an active set."""
+    bounds = _check_bounds(bounds, 2)
     data = np.asarray(data)
     nchan, nbin = data.shape
     freqs = np.asarray(freqs, dtype=np.float64)
@@ -128,7 +130,7 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
     r = pl.fit_batch(_f32(data)[None], P,
                      errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],
                      init=init, nu_fits=nu_fits, nu_outs=nu_outs,
-                     fit_flags=(1, 1, 0, 0, 0), semantics="fit_portrait")
+                     fit_flags=(1, 1, 0, 0, 0), semantics="fit_portrait", bounds=bounds)
     duration = time.time() - start
     rc = int(r["return_code"][0])
     if not quiet and rc not in (0, 1):
@@ -205,11 +207,22 @@ def rotate_data(data, phase=0.0, DM=0.0, Ps=None, freqs=None, nu_ref=np.inf):
         nsub, npol, nchan, _ = shape
         cube = data.reshape(nsub * npol, nchan, nbin)
         f = np.asarray(freqs, dtype=np.float64)
-        if f.ndim == 2:
-            if np.any(f != f[0]):
-                raise NotImplementedError("per-subint frequency arrays")
-            f = f[0]
         Pv = np.repeat(np.ones(nsub) * (1.0 if Ps is None else Ps), npol)
+        if f.ndim == 2 and np.any(f != f[0]):
+            # per-subint frequency arrays (pplib.py:2398-2411): one batch per distinct table
+            if DM != 0.0 and Ps is None:
+                raise ValueError("Ps and freqs are needed when DM != 0")
+            tables, table_of = np.unique(f, axis=0, return_inverse=True)
+            table_of = np.repeat(np.asarray(table_of).reshape(-1), npol)
+            pl = get_plan(nchan, nbin)
+            out = np.empty(cube.shape, dtype=np.float32)
+            for t in range(len(tables)):
+                sel = np.where(table_of == t)[0]
+                pl.set_freqs(tables[t])
+                out[sel] = pl.rotate_batch(_f32(cube[sel]), phase, DM if DM else 0.0, Pv[sel], nu)
+            return out.astype(np.float64).reshape(shape)
+        if f.ndim == 2:
+            f = f[0]
     else:
         raise ValueError("Wrong number of dimensions.")
     if DM != 0.0 and (Ps is None or freqs is None):
@@ -365,17 +378,28 @@ def gen_spline_portrait(mean_prof, freqs, eigvec, tck, nbin=None, device=False):
     mean_prof = np.asarray(mean_prof, dtype=np.float64)
     freqs = np.asarray(freqs, dtype=np.float64)
     eigvec = np.asarray(eigvec, dtype=np.float64).reshape(len(mean_prof), -1)
+    shift = 0.0
     if nbin is not None and nbin != len(mean_prof):
-        raise NotImplementedError("resampling a spline model to another nbin (scipy.signal.resample)")
+        # pplib.py:951-955: Fourier resampling, then the half-bin-difference rotation that undoes
+        # the shift ss.resample introduces.  Resampling is linear along the bin axis, so it is
+        # applied to the basis (mean profile, eigenvectors) once instead of to every channel.
+        import scipy.signal as ss
+        shift = 0.5 * (nbin ** -1 - len(mean_prof) ** -1)
+        mean_prof = ss.resample(mean_prof, nbin)
+        eigvec = ss.resample(eigvec, nbin, axis=0)
     if device:
         pl = get_plan(len(freqs), len(mean_prof))
         pl.set_freqs(freqs)
-        return pl.gen_spline_portrait(mean_prof, eigvec, tck).astype(np.float64)
-    if not eigvec.shape[1]:
-        return np.tile(mean_prof, len(freqs)).reshape(len(freqs), len(mean_prof))
-    import scipy.interpolate as si
-    proj_port = np.array(si.splev(freqs, tck, der=0, ext=0)).T
-    return np.dot(proj_port, eigvec.T) + mean_prof
+        port = pl.gen_spline_portrait(mean_prof, eigvec, tck).astype(np.float64)
+    elif not eigvec.shape[1]:
+        port = np.tile(mean_prof, len(freqs)).reshape(len(freqs), len(mean_prof))
+    else:
+        import scipy.interpolate as si
+        proj_port = np.array(si.splev(freqs, tck, der=0, ext=0)).T
+        port = np.dot(proj_port, eigvec.T) + mean_prof
+    if shift:
+        port = rotate_portrait(port, shift)
+    return port
 
 
 def read_spline_model(modelfile, freqs=None, nbin=None, quiet=False, device=False):

@@ -137,6 +137,13 @@ def load_data(filename, **kwargs):
     return DataBunch(**d)
 
 
+def _freq_tables(freqs):
+    """Distinct rows of a [nsub, nchan] frequency array and the row each subint uses."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    tables, table_of = np.unique(freqs, axis=0, return_inverse=True)
+    return tables, np.asarray(table_of).reshape(-1)
+
+
 def weighted_mean(data, errs=1.0):
     """pplib.py:686-705."""
     data = np.asarray(data, dtype=np.float64)
@@ -248,9 +255,13 @@ class GetTOAs:
             DM_stored = float(d.DM)
             DM0_arch = DM_stored if self.DM0 is None else self.DM0
             MJDs = np.array([e.in_days() for e in d.epochs], dtype=np.double)
-            if np.any(freqs != freqs[0]):
-                raise NotImplementedError("per-subint frequency tables")
-            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]], fit_scat)
+            # Per-subint frequency tables (freqs = data.freqs[isub], pptoas.py:346): the reference
+            # rebuilds the model for every subint (pptoas.py:356-379); here subints that share a
+            # table share one model and one batch.
+            tables, table_of = _freq_tables(freqs)
+            models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]], fit_scat)
+                      for t in np.unique(table_of[ok_isubs])}
+            model = models[table_of[ok_isubs[0]]]
 
             mask = np.zeros((nsub, nchan), dtype=np.uint8)
             for isub in ok_isubs:
@@ -266,7 +277,8 @@ class GetTOAs:
                 for isub in ok_isubs:
                     okc = np.asarray(d.ok_ichans[isub], dtype=int)
                     nu_fits_in[isub, :] = pplib.guess_fit_freq(freqs[isub, okc], snrs[isub, okc])
-                nu_fits_in[nu_fits_in[:, 0] == 0] = freqs[0].mean()
+                empty = nu_fits_in[:, 0] == 0
+                nu_fits_in[empty] = freqs[empty].mean(axis=1)[:, None]
                 mode = 0
             elif nu_fit_tuple is None:
                 nu_fits_in, mode = None, 1                 # guess_fit_freq, pptoas.py:402
@@ -299,10 +311,19 @@ class GetTOAs:
                         else:
                             tau_guess = 0.0
                     scat_in[isub] = [tau_guess, alpha_guess]
+            if method == 'TNC':                             # bounds act with TNC only (pptoaslib.py:1008)
+                if bounds is None:                          # pptoas.py:461-469
+                    tau_bounds = (np.log10((10 * nbin) ** -1), None) if self.log10_tau else (0.0, None)
+                    bounds = [(None, None), (None, None), (None, None), tau_bounds, (-10.0, 10.0)]
+                fit_bounds = pplib._check_bounds(bounds, 5)
+            else:
+                fit_bounds = None
             pl = get_plan(nchan, nbin)
-            pl.set_model(_f32(model), freqs[0])
             self._models = getattr(self, "_models", {})
             self._models[iarch] = np.asarray(model, dtype=np.float64)
+            self._model_tables = getattr(self, "_model_tables", {})
+            self._model_tables[iarch] = (table_of, {t: np.asarray(m, dtype=np.float64)
+                                                    for t, m in models.items()})
 
             # subints with a single usable channel are fit for phase only
             # (pptoas.py:475-478); two channels drop GM (479-483)
@@ -314,10 +335,14 @@ class GetTOAs:
                     flags = tuple(self.fit_flags[:2] + [0] + self.fit_flags[3:])
                 else:
                     flags = tuple(self.fit_flags)
-                groups.setdefault(flags, []).append(isub)
+                groups.setdefault((int(table_of[isub]), flags), []).append(isub)
             res = {}
             fit_start = time.time()
-            for flags, isubs in groups.items():
+            table_set = None
+            for (t, flags), isubs in sorted(groups.items()):
+                if t != table_set:
+                    pl.set_model(_f32(models[t]), tables[t])
+                    table_set = t
                 idx = np.asarray(isubs, dtype=int)
                 raw_kw = {}
                 if d.get("raw_subints") is not None:       # stored samples go to the device as they are
@@ -332,7 +357,7 @@ class GetTOAs:
                     snrs=snrs[idx], nu_fits=None if nu_fits_in is None else nu_fits_in[idx],
                     nu_fit_mode=mode, nu_outs=None if nu_outs_in is None else nu_outs_in[idx],
                     fit_flags=flags, log10_tau=self.log10_tau, option=0, is_toa=True,
-                    Ns=100, semantics="full",
+                    Ns=100, semantics="full", bounds=fit_bounds,
                     scat_guess=None if scat_in is None else scat_in[idx])
                 for j, isub in enumerate(idx):
                     res[isub] = (flags, {k: v[j] for k, v in r.items()})
@@ -373,7 +398,7 @@ class GetTOAs:
                 else:
                     df = 1.0
                 if print_flux:                              # pptoas.py:554-577
-                    means = np.asarray(model)[okc].mean(axis=1)
+                    means = np.asarray(models[table_of[isub]])[okc].mean(axis=1)
                     profile_fluxes[isub, okc] = means * r["scales"][okc]
                     profile_flux_errs[isub, okc] = abs(means) * r["scale_errs"][okc]
                     fluxes[isub], flux_errs[isub] = weighted_mean(profile_fluxes[isub, okc],
@@ -525,9 +550,10 @@ class GetTOAs:
             ok_isubs = np.asarray(d.ok_isubs, dtype=int)
             freqs = np.asarray(d.freqs, dtype=np.float64)
             Ps = np.asarray(d.Ps, dtype=np.float64)
-            if np.any(freqs != freqs[0]):
-                raise NotImplementedError("per-subint frequency tables")
-            model = self._model_for(d.phases, freqs[0], Ps[ok_isubs[0]], False)
+            tables, table_of = _freq_tables(freqs)          # freqs = data.freqs[isub], pptoas.py:927
+            models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]], False)
+                      for t in np.unique(table_of[ok_isubs])}
+            model_of = [models[t] for t in table_of]
             pl = get_plan(nchan, nbin)
             fit_start = time.time()
             profs = _f32(np.asarray(d.subints)[ok_isubs, 0]).reshape(len(ok_isubs) * nchan, nbin)
@@ -536,7 +562,11 @@ class GetTOAs:
             for i, isub in enumerate(ok_isubs):
                 okmask[i, np.asarray(d.ok_ichans[isub], dtype=int)] = True
             okmask &= noise > 0
-            r = pl.fit_phase_shift_batch(profs, _f32(model), noise=np.where(okmask, noise, 1.0).ravel(),
+            if len(models) == 1:
+                mstack = _f32(model_of[ok_isubs[0]])
+            else:                                           # one model row per profile
+                mstack = _f32(np.concatenate([model_of[isub] for isub in ok_isubs]))
+            r = pl.fit_phase_shift_batch(profs, mstack, noise=np.where(okmask, noise, 1.0).ravel(),
                                          Ns=100)
             fit_duration = time.time() - fit_start
             shape = (nsub, nchan)
@@ -562,7 +592,7 @@ class GetTOAs:
                     channel_snrs[isub, ichan] = get("snr")[i, ichan]
                     channel_red_chi2s[isub, ichan] = get("red_chi2")[i, ichan]
                     if print_flux:
-                        mm = model[ichan].mean()
+                        mm = model_of[isub][ichan].mean()
                         profile_fluxes[isub, ichan] = mm * scales[isub, ichan]
                         profile_flux_errs[isub, ichan] = abs(mm) * scale_errs[isub, ichan]
                     toa_flags = {'be': d.backend, 'fe': d.frontend, 'f': "%s_%s" % (d.frontend, d.backend),
@@ -610,11 +640,11 @@ class GetTOAs:
             raise NotImplementedError("plots need matplotlib")
         from .pplib import scattering_portrait_FT, scattering_times
         for k, iarch in enumerate(self.ok_idatafiles):
-            d, model0 = self._archives[iarch], self._models[iarch]
+            d = self._archives[iarch]
+            table_of, models = self._model_tables[iarch]
             nchan, nbin = int(d.nchan), int(d.nbin)
             pl = get_plan(nchan, nbin)
             freqs = np.asarray(d.freqs, dtype=np.float64)
-            pl.set_freqs(freqs[0])
             ok_isubs = np.asarray(self.ok_isubs[k], dtype=int)
             phi, DM, GM = self.phis[k][ok_isubs], self.DMs[k][ok_isubs].copy(), self.GMs[k][ok_isubs].copy()
             if self.bary:                                   # back to the fitted values (1353-1355)
@@ -622,11 +652,17 @@ class GetTOAs:
                 DM /= df
                 GM /= df ** 3
             nus = np.array([self.nu_refs[k][i] for i in ok_isubs], dtype=np.float64)
-            rot = pl.rotate_batch(_f32(np.asarray(d.subints)[ok_isubs, 0]), phi, DM,
-                                  np.asarray(d.Ps)[ok_isubs], nus[:, 0], GM=GM, nu_GM=nus[:, 1])
+            rot = np.empty((len(ok_isubs), nchan, nbin), dtype=np.float32)
+            for t in np.unique(table_of[ok_isubs]):         # one rotation batch per frequency table
+                sel = np.where(table_of[ok_isubs] == t)[0]
+                pl.set_freqs(freqs[ok_isubs[sel[0]]])
+                rot[sel] = pl.rotate_batch(_f32(np.asarray(d.subints)[ok_isubs[sel], 0]), phi[sel], DM[sel],
+                                           np.asarray(d.Ps)[ok_isubs[sel]], nus[sel, 0], GM=GM[sel],
+                                           nu_GM=nus[sel, 1])
             channel_red_chi2s, zap_channels = [], []
             for j, isub in enumerate(ok_isubs):
                 ok_ichans = np.asarray(d.ok_ichans[isub], dtype=int)
+                model0 = models[table_of[isub]]
                 model = model0
                 if self.taus[k][isub] != 0.0:               # 1388-1394
                     tau = 10 ** self.taus[k][isub] if self.log10_tau else self.taus[k][isub]

@@ -24,11 +24,12 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
     (pptoaslib.py:928-1096).  ``method`` is accepted for compatibility; the
     scipy minimisers are replaced by the on-device safeguarded Newton solver,
     which converges to the same optimum (``return_code`` 0 = converged,
-    1 = max passes, 3 = non-finite objective).  ``bounds`` (TNC only in the
-    reference) must be unset.
+    1 = max passes, 3 = non-finite objective).  ``bounds`` are used with
+    method='TNC' only, as in the reference (pptoaslib.py:1008-1014); the
+    solver treats them as an active set.
     """
     if method == 'TNC':
-        _check_bounds(bounds)
+        bounds = _check_bounds(bounds, 5)
     elif method not in ('trust-ncg', 'Newton-CG'):
         print("Method '%s' is not implemented." % method)
         sys.exit()
@@ -51,7 +52,8 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
                      init=init, nu_fits=three(nu_fits), nu_outs=three(nu_outs),
                      fit_flags=[1 if f else 0 for f in fit_flags],
                      log10_tau=bool(log10_tau), option=int(option),
-                     is_toa=bool(is_toa), semantics="full")
+                     is_toa=bool(is_toa), semantics="full",
+                     bounds=bounds if method == 'TNC' else None)
     duration = time.time() - start
     rc = int(r["return_code"][0])
     if rc not in (0, 1):

@@ -136,3 +136,25 @@ def test_device_spline_model_vs_scipy(nchan, nbin, ncomp, k, s, tmp_path):
     assert pplib.is_spline_model(path) and not pplib.is_spline_model(GMODEL)
     name, model = pplib.read_spline_model(path, freqs, nbin, quiet=True, device=True)
     assert name == "mdl" and np.array_equal(model, out)
+
+
+@pytest.mark.parametrize("nbin_model,nbin,ncomp", [(512, 1024, 3), (1024, 256, 4), (256, 2048, 0)])
+def test_spline_model_resampled_to_another_nbin(nbin_model, nbin, ncomp):
+    """gen_spline_portrait(..., nbin != len(mean_prof)) (pplib.py:951-955): ss.resample along the bin
+    axis, then the rotation by half the bin-width difference.  Restated here per channel, as the
+    reference does it; the product resamples the basis instead (linear), on host or device."""
+    import scipy.interpolate as si
+    import scipy.signal as ss
+    from pulseportraiture_b200 import pplib
+    mean_prof, eigvec, tck = _spline_model(nbin_model, ncomp, 3, 0.02, 5 * nbin + ncomp)
+    freqs = orc.make_freqs(24, 1500., 700.)
+    if ncomp:
+        port = np.dot(np.array(si.splev(freqs, tck, der=0, ext=0)).T, eigvec.T) + mean_prof
+    else:
+        port = np.tile(mean_prof, (len(freqs), 1))
+    shift = 0.5 * (nbin ** -1.0 - nbin_model ** -1.0)
+    ref = orc.rotate_data(ss.resample(port, nbin, axis=1), shift)
+    for device in (False, True):
+        out = pplib.gen_spline_portrait(mean_prof, freqs, eigvec, tck, nbin=nbin, device=device)
+        assert out.shape == (len(freqs), nbin)
+        assert np.max(np.abs(out - ref)) <= 4 * F32 * np.max(np.abs(ref))

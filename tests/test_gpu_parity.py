@@ -788,3 +788,69 @@ def test_gettoas_scattering_fit():
         # the injected scattering time is recovered (50 us at 600 MHz)
         tau_600 = 10 ** ref.tau * (600. / ref.nu_tau) ** ref.alpha * c["P"]
         assert abs(tau_600 - tau_s) < 6 * ref.tau_err * np.log(10) * tau_s + 0.3 * tau_s
+
+
+def test_gettoas_per_subint_frequency_tables():
+    """freqs = data.freqs[isub] (pptoas.py:346): an archive whose subints sit on two different
+    frequency tables (as after a Doppler correction or a receiver retune).  Each subint is fit
+    against the model built for its own table; wideband and narrowband TOAs and the zap scan."""
+    from pulseportraiture_b200 import pptoas
+    nsub, nchan, nbin = 5, 32, 512
+    dA, cA = _fake_archive(nsub, nchan, nbin, 8300)
+    dB, cB = _fake_archive(nsub, nchan, nbin, 8300, nu0=1500.7)
+    data, cases = dA, list(cA)
+    for s in (1, 3):
+        data.freqs[s] = dB.freqs[s]
+        data.subints[s] = dB.subints[s]
+        data.noise_stds[s] = dB.noise_stds[s]
+        cases[s] = cB[s]
+    assert np.any(data.freqs[1] != data.freqs[0])
+    gt = pptoas.GetTOAs([data], synth.GMODEL, quiet=True)
+    gt.get_TOAs(print_flux=True)
+    assert len(gt.TOA_list) == nsub
+    for s, c in enumerate(cases):
+        ok = data.ok_ichans[s]
+        ref, _, _ = orc.toa_core(c["data"][ok], c["model"][ok], c["P"], c["freqs"][ok],
+                                 data.noise_stds[s, 0, ok], weights=data.weights[s, ok],
+                                 SNRs=data.SNRs[s, 0, ok], polish="exact")
+        df = data.doppler_factors[s]
+        assert abs(gt.phis[0][s] - ref.phi) / ref.phi_err < SIG_TOL
+        assert abs(gt.DMs[0][s] - ref.DM * df) / ref.DM_err < SIG_TOL
+        assert rel(gt.red_chi2s[0][s], ref.red_chi2) < CHI2_TOL
+        assert rel(gt.nu_refs[0][s][0], ref.nu_DM) < 1e-4
+        assert rel(gt.scales[0][s][ok], ref.scales) < 1e-4
+    # the single-table archive gives the same numbers for the subints that kept table A
+    g0 = pptoas.GetTOAs([dA2 := _fake_archive(nsub, nchan, nbin, 8300)[0]], synth.GMODEL, quiet=True)
+    g0.get_TOAs()
+    for s in (0, 2, 4):
+        assert g0.phis[0][s] == gt.phis[0][s] and g0.DMs[0][s] == gt.DMs[0][s]
+    # zap scan and narrowband TOAs run on mixed tables as well
+    gt.get_channels_to_zap()
+    assert len(gt.channel_red_chi2s[0]) == nsub
+    for s in range(nsub):
+        red = np.asarray(gt.channel_red_chi2s[0][s])
+        assert np.all(np.isfinite(red)) and 0.7 < np.median(red) < 1.4
+    gn = pptoas.GetTOAs([data], synth.GMODEL, quiet=True)
+    gn.get_narrowband_TOAs()
+    for s in (1, 3):
+        c = cases[s]
+        for ichan in data.ok_ichans[s][:4]:
+            ref = orc.fit_phase_shift(c["data"][ichan], c["model"][ichan], data.noise_stds[s, 0, ichan],
+                                      polish="exact")
+            assert abs(gn.phis[0][s, ichan] - ref.phase) / ref.phase_err < SIG_TOL
+
+
+def test_rotate_data_per_subint_frequency_tables():
+    """rotate_data on a 4-D cube with a [nsub, nchan] frequency array (pplib.py:2398-2411)."""
+    from pulseportraiture_b200 import pplib
+    rng = np.random.RandomState(5)
+    nsub, npol, nchan, nbin = 4, 2, 16, 256
+    cube = rng.standard_normal((nsub, npol, nchan, nbin)).astype(np.float32).astype(np.float64)
+    fA, fB = orc.make_freqs(nchan, 1500., 800.), orc.make_freqs(nchan, 1400., 600.)
+    freqs = np.stack([fA, fB, fA, fB])
+    Ps = np.array([0.003, 0.0031, 0.0032, 0.0033])
+    out = pplib.rotate_data(cube, 0.123, 2e-3, Ps, freqs, 1450.)
+    for s in range(nsub):
+        for p in range(npol):
+            ref = orc.rotate_data(cube[s, p], 0.123, 2e-3, Ps[s], freqs[s], 1450.)
+            assert np.max(np.abs(out[s, p] - ref)) < 2e-6 * np.max(np.abs(ref))
