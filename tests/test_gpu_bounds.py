@@ -26,7 +26,7 @@ def test_fit_portrait_dm_bound_active_and_inactive():
     hi = free.DM - 2 * free.DM_err
     for bounds, init in (([(None, None), (None, hi)], [0.12, 0.0]),          # reached from inside
                          ([(None, None), (None, hi)], [0.12, hi + 1e-3]),    # start outside the box
-                         ([(0.1231, 0.2), (None, None)], [0.15, 0.0]),       # phase bound active
+                         ([(0.1231, 0.2), (None, None)], [0.1235, 0.0]),     # phase bound active
                          ([(-0.5, 0.5), (free.DM - 5 * free.DM_err, free.DM + 5 * free.DM_err)], [0.12, 0.0])):
         ref = orc.fit_portrait(c["data"], c["model"], init, c["P"], c["freqs"], bounds=bounds)
         r = pplib.fit_portrait(c["data"], c["model"], init, c["P"], c["freqs"], bounds=bounds)
