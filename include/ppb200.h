@@ -58,6 +58,13 @@ int pp_plan_set_chunk(pp_plan_t* plan, int32_t subints_per_chunk);
  * is measured from a small portrait, float otherwise), 32, 64. */
 int pp_plan_set_fft_precision(pp_plan_t* plan, int32_t bits);
 
+/* (phi, DM) solver: Newton steps taken per pass on the local model built from
+ * the per-channel theta-derivatives up to the fourth order (0 = default 8).
+ * 1 = one Newton step per pass over the cross-spectrum, i.e. every step is
+ * evaluated on the data (more passes, same optimum; used by the tests to
+ * check the model-based steps). */
+int pp_plan_set_model_steps(pp_plan_t* plan, int32_t steps);
+
 /* Channel frequencies [nchan] MHz only (enough for pp_rotate_batch). */
 int pp_set_freqs(pp_plan_t* plan, const double* freqs);
 
@@ -148,7 +155,9 @@ typedef struct {
   int32_t* lag_index;   /* [nsub] FFTFIT integer grid argmin (-1 if init given)*/
   double* phi_guess;    /* [nsub] initial phase handed to the solver           */
   double* chan_sums;    /* [nsub,nchan,9] per-channel C,Cth,Cthth,Ct,Ctt,Ctht,
-                           S,St,Stt at the solution (for host epilogues)       */
+                           S,St,Stt at the last evaluated point (for host
+                           epilogues); for the (phi, DM) solver slots 3, 4 hold
+                           the third and fourth theta-derivatives of C instead */
   double* align_sum;    /* [nchan,nbin] ppalign (ppalign.py:197-213), fused: the
                            sum over the batch of w_sn * rotate(data_sn, phi_s,
                            DM_s about nu_out_s) with the FITTED phi_s, DM_s and

@@ -786,7 +786,9 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
   const double Ssn = a.Ssn[(size_t)s * a.nchan + chc];
   const bool used = inrange && Ssn > 0.0;
 
-  double C = 0.0, C1 = 0.0, C2 = 0.0;
+  // C3, C4: sums for the third and fourth theta-derivatives; they let k_update2 follow the objective
+  // along the Newton path without another pass over X
+  double C = 0.0, C1 = 0.0, C2 = 0.0, C3 = 0.0, C4 = 0.0;
   if (used) {
     const double phi = a.st.x[(size_t)s * 5 + 0], DM = a.st.x[(size_t)s * 5 + 1];
     const double nf = a.nu_fit[(size_t)s * 3 + 0];
@@ -833,9 +835,14 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     auto accum = [&](double xr0, double xi0, double xr1, double xi1) {
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
       const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
+      const double kk0 = k0 * k0, kk1 = k1 * k1;
+      const double ki0 = k0 * im0, ki1 = k1 * im1;     // k Im z
+      const double kr0 = kk0 * re0, kr1 = kk1 * re1;   // k^2 Re z
       C += re0 + re1;
-      C1 = fma(k0, im0, C1); C1 = fma(k1, im1, C1);
-      C2 = fma(k0 * k0, re0, C2); C2 = fma(k1 * k1, re1, C2);
+      C1 += ki0 + ki1;
+      C2 += kr0 + kr1;
+      C3 = fma(kk0, ki0, C3); C3 = fma(kk1, ki1, C3);
+      C4 = fma(kk0, kr0, C4); C4 = fma(kk1, kr1, C4);
       // advance both phasors by 16 harmonics
       const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
       const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
@@ -895,7 +902,8 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
       const double cn = en.x, sn = en.y;
       const double re = xnx * cn - xny * sn;
       const double im = xnx * sn + xny * cn;
-      C += re; C1 = fma((double)N, im, C1); C2 = fma((double)N * (double)N, re, C2);
+      const double n1 = (double)N, n2 = n1 * n1;
+      C += re; C1 = fma(n1, im, C1); C2 = fma(n2, re, C2); C3 = fma(n2 * n1, im, C3); C4 = fma(n2 * n2, re, C4);
     }
   }
 #pragma unroll
@@ -903,6 +911,8 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     C += __shfl_xor_sync(0xffffffffu, C, o);
     C1 += __shfl_xor_sync(0xffffffffu, C1, o);
     C2 += __shfl_xor_sync(0xffffffffu, C2, o);
+    C3 += __shfl_xor_sync(0xffffffffu, C3, o);
+    C4 += __shfl_xor_sync(0xffffffffu, C4, o);
   }
   if (inrange && l8 == 0) {
     double* o = a.csum + ((size_t)s * a.nchan + ch) * kNCsum;
@@ -912,8 +922,10 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
       o[0] = C * isF2;                         // C_n      (pplib.py:1322)
       o[1] = -kTwoPi * C1 * isF2;              // dC/dtheta  (1344)
       o[2] = -kTwoPi * kTwoPi * C2 * isF2;     // d2C/dtheta2 (1380)
+      o[3] = kTwoPi * kTwoPi * kTwoPi * C3 * isF2;             // d3C/dtheta3 = Re sum (2 pi i k)^3 X e^{..}
+      o[4] = kTwoPi * kTwoPi * kTwoPi * kTwoPi * C4 * isF2;    // d4C/dtheta4
     } else {
-      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0;
+      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0;
     }
   }
 }
@@ -936,9 +948,22 @@ struct UpdateArgs {
   double* params; double* param_errs; double* nu_out; double* cov; double* chi2; double* red_chi2;
   double* snr; int* nfeval; int* rc; double* scales; double* scale_errs; double* channel_snrs;
   int s0, nchan, nbin, max_iter, semantics, fit_phi, fit_dm, is_toa;
-  double tol;
+  int model_steps;         // Newton steps taken on the local fourth-order model per pass (<= 1: one step per pass)
+  double tol;              // one step per pass: convergence when the step is below tol sigma
+  double tol_model;        // model steps: step and estimated truncation shift below tol_model sigma
   Box box;
 };
+
+// C_n, dC_n/dtheta, d2C_n/dtheta2 at theta + t from the derivatives c[0..4] at theta
+struct Tay4 { double C, C1, C2; };
+__device__ __forceinline__ Tay4 taylor4(const double* c, double t) {
+  const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
+  Tay4 y;
+  y.C = c0 + t * (c1 + t * (0.5 * c2 + t * (c3 * (1.0 / 6.0) + t * c4 * (1.0 / 24.0))));
+  y.C1 = c1 + t * (c2 + t * (0.5 * c3 + t * c4 * (1.0 / 6.0)));
+  y.C2 = c2 + t * (c3 + t * 0.5 * c4);
+  return y;
+}
 
 __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
   const int s = a.s0 + blockIdx.x;
@@ -981,82 +1006,142 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
   double* x = a.st.x + (size_t)s * 5;
   double* xp = a.st.xprev + (size_t)s * 5;
   double* stp = a.st.step + (size_t)s * 5;
-  // ---- thread 0: safeguarded Newton ----------------------------------------------
-  if (tid == 0) {
-    const int it = a.st.iter[s] + 1;
-    a.st.iter[s] = it;
-    const double f = v[0];
-    int finish = 0, rc = 0;
-    double d0 = 0.0, d1 = 0.0;   // step to apply on top of the evaluated point
-    if (!(f == f) || fabs(f) > 1e300) { finish = 1; rc = 3; }
-    else if (a.max_iter < 0) { finish = 2; rc = 0; }   // evaluate-only (get_scales)
-    else if (it > 1 && f > a.st.fprev[s] + 1e-12 * fabs(a.st.fprev[s])) {
-      // uphill: shrink the previous step and re-evaluate
-      const double lam = a.st.lam[s] * 0.25;
+  // ---- safeguarded Newton.  Every thread holds the same sums and takes the same decisions;
+  // thread 0 writes the state.  The per-channel derivatives up to the fourth order (k_pass2) give a
+  // local model C_n(theta_n + t) of the objective; the Newton iteration runs on that model
+  // (a few reductions over nchan numbers) instead of costing one pass over X per step, and the
+  // fit finishes without another pass when the model's truncation error at the point reached is
+  // far below the tolerance.  Otherwise the point reached is evaluated by the next pass.
+  const int it = a.st.iter[s] + 1;
+  const double f = v[0];
+  const double fprev = a.st.fprev[s], lam_prev = a.st.lam[s];
+  const double x0 = x[0], x1 = x[1], xp0 = xp[0], xp1 = xp[1], stp0 = stp[0], stp1 = stp[1];
+  __syncthreads();                       // all reads of the state precede thread 0's writes
+  int finish = 0, rc = 0;
+  double d0 = 0.0, d1 = 0.0;             // displacement applied on top of the evaluated point
+  if (!(f == f) || fabs(f) > 1e300) { finish = 1; rc = 3; }
+  else if (a.max_iter < 0) { finish = 2; rc = 0; }   // evaluate-only (get_scales)
+  else if (it > 1 && f > fprev + 1e-12 * fabs(fprev)) {
+    // uphill: shrink the previous step and re-evaluate
+    const double lam = lam_prev * 0.25;
+    if (it >= a.max_iter || lam < 1e-6) { finish = 2; rc = 1; }  // give up: report this point
+    if (tid == 0) {
       a.st.lam[s] = lam;
-      if (it >= a.max_iter || lam < 1e-6) { finish = 2; rc = 1; }  // give up: report this point
-      else { x[0] = xp[0] + lam * stp[0]; x[1] = xp[1] + lam * stp[1]; }
-    } else {
-      double h00 = v[3], h01 = v[4], h11 = v[5], g0 = v[1], g1 = v[2];
-      const bool free0 = a.fit_phi && !box_holds(a.box, 0, x[0], g0);
-      const bool free1 = a.fit_dm && !box_holds(a.box, 1, x[1], g1);
+      if (!finish) { x[0] = xp0 + lam * stp0; x[1] = xp1 + lam * stp1; }
+    }
+  } else {
+    double m[6] = {v[0], v[1], v[2], v[3], v[4], v[5]};   // f, g0, g1, h00, h01, h11 at x + (d0, d1)
+    bool conv = false, clipped = false, pd = true, free0 = true, free1 = true;
+    double sg0 = 0.0, sg1 = 0.0, cv01 = 0.0;
+    const int n_inner = a.model_steps > 0 ? a.model_steps : 1;
+    for (int inner = 0; inner < n_inner; ++inner) {
+      if (inner > 0) {
+        for (int i = 0; i < 6; ++i) m[i] = 0.0;
+        for (int n = tid; n < nchan; n += 128) {
+          const double S = Sv[n];
+          if (!(S > 0.0)) continue;
+          const double g = KP * (a.nu2[n] - nf2);
+          const Tay4 y = taylor4(cs + n * kNCsum, d0 + d1 * g);
+          const double t = -2.0 * y.C * y.C1 / S;
+          const double W = (y.C1 * y.C1 + y.C * y.C2) / S;
+          m[0] -= y.C * y.C / S;
+          m[1] += t; m[2] += t * g;
+          m[3] -= 2.0 * W; m[4] -= 2.0 * W * g; m[5] -= 2.0 * W * g * g;
+        }
+        block_sum<6, 128>(m, sh);
+        __syncthreads();
+      }
+      double h00 = m[3], h01 = m[4], h11 = m[5], g0 = m[1], g1 = m[2];
+      free0 = a.fit_phi && !box_holds(a.box, 0, x0 + d0, g0);
+      free1 = a.fit_dm && !box_holds(a.box, 1, x1 + d1, g1);
       if (!free1) { h01 = 0.0; h11 = 1.0; g1 = 0.0; }
       if (!free0) { h01 = 0.0; h00 = 1.0; g0 = 0.0; }
-      double det = h00 * h11 - h01 * h01;
-      bool pd = h00 > 0.0 && h11 > 0.0 && det > 1e-14 * h00 * h11;
+      const double det = h00 * h11 - h01 * h01;
+      pd = h00 > 0.0 && h11 > 0.0 && det > 1e-14 * h00 * h11;
+      double e0, e1;
       if (pd) {
-        d0 = -(h11 * g0 - h01 * g1) / det;
-        d1 = -(-h01 * g0 + h00 * g1) / det;
-      } else {  // not convex here: scaled steepest descent
-        d0 = -g0 / (fabs(h00) + 1e-300);
-        d1 = -g1 / (fabs(h11) + 1e-300);
+        e0 = -(h11 * g0 - h01 * g1) / det;
+        e1 = -(-h01 * g0 + h00 * g1) / det;
+      } else if (inner == 0) {  // not convex here: scaled steepest descent
+        e0 = -g0 / (fabs(h00) + 1e-300);
+        e1 = -g1 / (fabs(h11) + 1e-300);
+      } else break;             // the model left the convex region: evaluate where we are
+      // keep every channel's rotation change below 0.1 turn per pass
+      const double big = fmax(fabs(d0 + e0), fabs(d1 + e1) * gmax);
+      bool limited = false;
+      if (big > 0.1) {
+        const double bstep = fmax(fabs(e0), fabs(e1) * gmax);
+        if (inner == 0) { e0 *= 0.1 / bstep; e1 *= 0.1 / bstep; }
+        else { e0 = 0.0; e1 = 0.0; }
+        limited = true;
       }
-      // keep every channel's rotation change below 0.1 turn
-      const double big = fmax(fabs(d0), fabs(d1) * gmax);
-      if (big > 0.1) { d0 *= 0.1 / big; d1 *= 0.1 / big; }
-      bool clipped = false;
-      const double xn0 = box_clip(a.box, 0, x[0] + d0, clipped), xn1 = box_clip(a.box, 1, x[1] + d1, clipped);
-      if (clipped) { d0 = xn0 - x[0]; d1 = xn1 - x[1]; }
-      bool conv = false;
-      if (pd && !clipped) {
-        // 1-sigma from cov = inv(H/2) (pplib.py:2187-2190)
-        const double s0 = sqrt(2.0 * h11 / det), s1 = sqrt(2.0 * h00 / det);
-        conv = (fabs(d0) <= a.tol * s0 || !free0) && (fabs(d1) <= a.tol * s1 || !free1);
+      clipped = false;
+      const double xn0 = box_clip(a.box, 0, x0 + d0 + e0, clipped), xn1 = box_clip(a.box, 1, x1 + d1 + e1, clipped);
+      if (clipped) { e0 = xn0 - (x0 + d0); e1 = xn1 - (x1 + d1); }
+      d0 += e0; d1 += e1;
+      if (!pd || limited) break;
+      // 1-sigma from cov = inv(H/2) (pplib.py:2187-2190)
+      sg0 = sqrt(2.0 * h11 / det); sg1 = sqrt(2.0 * h00 / det); cv01 = -2.0 * h01 / det;
+      const double tol_step = n_inner > 1 ? a.tol_model : a.tol;
+      if (!clipped && (fabs(e0) <= tol_step * sg0 || !free0) && (fabs(e1) <= tol_step * sg1 || !free1)) { conv = true; break; }
+    }
+    if (conv && n_inner > 1) {
+      // ---- is the model good enough at (d0, d1)?  The first neglected term of the gradient series
+      // is estimated from the last one kept, c4 t^3/6, times r t/4 with r^2 = sum|c4| / sum|c2|
+      // (~ (2 pi k_eff)^2); likewise for the objective.  Required: parameter shifts below
+      // tol_model sigma, an objective error below 1e-9 |f| and a curvature error below 1e-5.
+      double q[6] = {0, 0, 0, 0, 0, 0};   // sum|c2|, sum|c4|, gradient terms (phi, DM), objective term, Hessian term
+      for (int n = tid; n < nchan; n += 128) {
+        const double S = Sv[n];
+        if (!(S > 0.0)) continue;
+        const double* c = cs + n * kNCsum;
+        const double g = KP * (a.nu2[n] - nf2);
+        const double t = fabs(d0 + d1 * g);
+        const double e = 2.0 * fabs(c[0]) * fabs(c[4]) * t * t * t / (6.0 * S);
+        q[0] += fabs(c[2]); q[1] += fabs(c[4]); q[2] += e; q[3] += e * fabs(g); q[4] += e * t * 0.25;
+        q[5] += fabs(c[0]) * fabs(c[4]) * t * t / S;
       }
-      xp[0] = x[0]; xp[1] = x[1];
+      block_sum<6, 128>(q, sh);
+      __syncthreads();
+      const double r = sqrt(q[1] / fmax(q[0], 1e-300));
+      const double rt = r * (fabs(d0) + fabs(d1) * gmax);
+      const double eg0 = free0 ? q[2] * rt * 0.25 : 0.0, eg1 = free1 ? q[3] * rt * 0.25 : 0.0;
+      const double err0 = 0.5 * (sg0 * sg0 * eg0 + fabs(cv01) * eg1), err1 = 0.5 * (fabs(cv01) * eg0 + sg1 * sg1 * eg1);
+      const bool good = rt < 0.5 && (err0 <= a.tol_model * sg0 || !free0) && (err1 <= a.tol_model * sg1 || !free1) &&
+                        q[4] * rt * 0.2 <= 1e-9 * fabs(m[0]) &&
+                        q[5] * rt * (1.0 / 3.0) <= 1e-5 * fabs(m[3]);   // curvature (error bars) to 1e-5
+      if (!good) conv = false;
+    }
+    if (conv) { finish = 1; rc = 0; }
+    else if (it >= a.max_iter) { finish = 1; rc = 1; }
+    if (tid == 0) {
+      xp[0] = x0; xp[1] = x1;
       stp[0] = d0; stp[1] = d1;
       a.st.fprev[s] = f;
       a.st.lam[s] = 1.0;
-      if (conv) { finish = 1; rc = 0; }
-      else if (it >= a.max_iter) { finish = 1; rc = 1; }
-      else { x[0] = xn0; x[1] = xn1; }
+      if (!finish) { x[0] = x0 + d0; x[1] = x1 + d1; }
     }
-    bc[0] = (double)finish; bc[1] = d0; bc[2] = d1; bc[3] = (double)rc; bc[4] = (double)it;
   }
-  __syncthreads();
-  const int finish = (int)bc[0];
+  if (tid == 0) a.st.iter[s] = it;
   if (!finish) return;
-  // ---- epilogue: sums are at x (= xprev), the final point is x + (d0, d1) --------
+  // ---- epilogue: sums are at x, the final point is x + (d0, d1) --------------------
   // finish == 2: back-tracking gave up, report the evaluated point without a step.
-  const double d0 = (finish == 1 && bc[3] != 3.0) ? bc[1] : 0.0;
-  const double d1 = (finish == 1 && bc[3] != 3.0) ? bc[2] : 0.0;
-  const double phi_fit = x[0] + d0, DM_fit = x[1] + d1;
-  // second-order Taylor of the per-channel sums to the final point
+  if (finish != 1 || rc == 3) { d0 = 0.0; d1 = 0.0; }
+  const double phi_fit = x0 + d0, DM_fit = x1 + d1;
+  // the per-channel sums at the final point from their Taylor series
   double u[4] = {0, 0, 0, 0};  // f, sumW, sumW nu^-2, snr^2
   for (int n = tid; n < nchan; n += 128) {
     const double S = Sv[n];
     if (!(S > 0.0)) continue;
     const double g = KP * (a.nu2[n] - nf2);
-    const double dth = d0 + d1 * g;
-    const double C2 = cs[n * kNCsum + 2];
-    const double C1 = cs[n * kNCsum + 1] + C2 * dth;
-    const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
-    const double W = (C1 * C1 + C * C2) / S;
-    u[0] -= C * C / S;
+    const Tay4 y = taylor4(cs + n * kNCsum, d0 + d1 * g);
+    const double W = (y.C1 * y.C1 + y.C * y.C2) / S;
+    u[0] -= y.C * y.C / S;
     u[1] += W; u[2] += W * a.nu2[n];
-    u[3] += C * C / S;
+    u[3] += y.C * y.C / S;
   }
   block_sum<4, 128>(u, sh);
+  __syncthreads();
   const double fmin = u[0];
   // zero-covariance frequency (pplib.py:1390; pptoaslib.py:746-752)
   double nu_zero = nf;
@@ -1069,11 +1154,8 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
     const double S = Sv[n];
     if (!(S > 0.0)) continue;
     const double g = KP * (a.nu2[n] - nf2);
-    const double dth = d0 + d1 * g;
-    const double C2 = cs[n * kNCsum + 2];
-    const double C1 = cs[n * kNCsum + 1] + C2 * dth;
-    const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
-    const double W = (C1 * C1 + C * C2) / S;
+    const Tay4 y = taylor4(cs + n * kNCsum, d0 + d1 * g);
+    const double W = (y.C1 * y.C1 + y.C * y.C2) / S;
     const double go = KP * (a.nu2[n] - no2);
     hh[0] -= 2.0 * W; hh[1] -= 2.0 * W * go; hh[2] -= 2.0 * W * go * go;
   }
@@ -1097,10 +1179,8 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
     double sc = 0.0, se = 0.0, csn = 0.0;
     if (S > 0.0) {
       const double g = KP * (a.nu2[n] - nf2);
-      const double dth = d0 + d1 * g;
-      const double C2 = cs[n * kNCsum + 2];
-      const double C1 = cs[n * kNCsum + 1] + C2 * dth;
-      const double C = cs[n * kNCsum] + cs[n * kNCsum + 1] * dth + 0.5 * C2 * dth * dth;
+      const Tay4 y = taylor4(cs + n * kNCsum, d0 + d1 * g);
+      const double C = y.C, C1 = y.C1;
       sc = C / S;                                         // pptoaslib.py:688
       csn = sc * sqrt(S);                                 // pptoaslib.py:1081
       if (a.semantics == 1) se = 1.0 / sqrt(S);           // pplib.py:2197
@@ -1135,8 +1215,8 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
     a.chi2[s] = chi2;
     a.red_chi2[s] = chi2 / dof;
     a.snr[s] = sqrt(u[3]);
-    a.nfeval[s] = (int)bc[4];
-    a.rc[s] = (int)bc[3];
+    a.nfeval[s] = it;
+    a.rc[s] = rc;
     x[0] = phi_fit; x[1] = DM_fit;
     a.st.done[s] = 1;
   }

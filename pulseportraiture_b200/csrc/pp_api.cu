@@ -80,6 +80,7 @@ struct pp_plan {
   // tables + model
   DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, mmean_sub, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
+  int model_steps = 8;     // (phi, DM) solver: Newton steps on the local fourth-order model per pass
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
   std::vector<std::pair<int, DBuf>> grid_tables;
@@ -436,6 +437,13 @@ extern "C" int pp_set_freqs(pp_plan_t* pl, const double* freqs) {
   if (!pl || !freqs) return fail(-1, "NULL argument");
   CK(cudaSetDevice(pl->device));
   return set_freqs_impl(pl, freqs);
+}
+
+extern "C" int pp_plan_set_model_steps(pp_plan_t* pl, int32_t steps) {
+  if (!pl) return fail(-1, "NULL plan");
+  if (steps < 0 || steps > 64) return fail(-1, "model steps must be 0 (default) .. 64");
+  pl->model_steps = steps == 0 ? 8 : steps;
+  return 0;
 }
 
 extern "C" int pp_plan_set_fft_precision(pp_plan_t* pl, int32_t bits) {
@@ -796,6 +804,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     ua.scales = pl->o_scales.as<double>(); ua.scale_errs = pl->o_serrs.as<double>(); ua.channel_snrs = pl->o_csnr.as<double>();
     ua.s0 = s0; ua.nchan = nchan; ua.nbin = 2 * N; ua.max_iter = max_iter; ua.semantics = args->semantics;
     ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol; ua.box = box;
+    ua.model_steps = pl->model_steps; ua.tol_model = (args->tol > 0 && args->tol < 1e-4) ? args->tol : 1e-4;
     Pass5Args p5;
     Update5Args u5;
     if (general) {

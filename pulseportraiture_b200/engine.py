@@ -138,6 +138,11 @@ class WidebandPlan(object):
         _ffi.check(self._lib.pp_plan_set_fft_precision(self._h, int(bits)),
                    "pp_plan_set_fft_precision")
 
+    def set_model_steps(self, steps):
+        """(phi, DM) solver: Newton steps per pass on the local fourth-order model (0 = default,
+        1 = every step evaluated on the data)."""
+        _ffi.check(self._lib.pp_plan_set_model_steps(self._h, int(steps)), "pp_plan_set_model_steps")
+
     def set_freqs(self, freqs):
         keep = []
         fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",

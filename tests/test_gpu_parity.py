@@ -854,3 +854,32 @@ def test_rotate_data_per_subint_frequency_tables():
         for p in range(npol):
             ref = orc.rotate_data(cube[s, p], 0.123, 2e-3, Ps[s], freqs[s], 1450.)
             assert np.max(np.abs(out[s, p] - ref)) < 2e-6 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("nsub,nchan,nbin,sigma", [(48, 64, 512, 1.5), (12, 512, 2048, 1.5), (24, 128, 1024, 0.2),
+                                                    (24, 32, 256, 6.0)])
+def test_model_steps_match_one_step_per_pass(engine, nsub, nchan, nbin, sigma):
+    """The (phi, DM) solver takes its Newton steps on the local fourth-order model of the per-channel
+    sums and finishes without another pass when the model's estimated truncation error is negligible
+    (pp_plan_set_model_steps).  With one step per pass (every step evaluated on the data) the same
+    optimum must come out; the model-based run needs fewer passes."""
+    cases = [synth.make_case(nchan, nbin, 1500., 800., 31000 + s, sigma=sigma) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+        rm = pl.fit_batch(data, P)
+        pl.set_model_steps(1)
+        r1 = pl.fit_batch(data, P, tol=1e-5)
+    assert np.all(rm["return_code"] == 0) and np.all(r1["return_code"] == 0)
+    assert np.array_equal(rm["lag_index"], r1["lag_index"])
+    dphi = np.abs(rm["params"][:, 0] - r1["params"][:, 0]) / r1["param_errs"][:, 0]
+    dDM = np.abs(rm["params"][:, 1] - r1["params"][:, 1]) / r1["param_errs"][:, 1]
+    assert dphi.max() < 2e-4 and dDM.max() < 2e-4
+    assert rel(rm["chi2"], r1["chi2"]) < 1e-9
+    assert rel(rm["param_errs"][:, :2], r1["param_errs"][:, :2]) < 2e-5
+    assert rel(rm["nu_out"][:, 0], r1["nu_out"][:, 0]) < 2e-5
+    assert rel(rm["scales"], r1["scales"]) < 1e-6
+    assert rm["nfeval"].mean() < r1["nfeval"].mean()
+    if sigma <= 1.5:            # at low S/N the steps are long and the model is (rightly) not trusted
+        assert rm["nfeval"].mean() <= 1.5
