@@ -54,8 +54,10 @@ int pp_plan_set_stream(pp_plan_t* plan, void* cuda_stream);
  * chunk's cross-spectra stay L2-resident). */
 int pp_plan_set_chunk(pp_plan_t* plan, int32_t subints_per_chunk);
 
-/* FFT arithmetic of the data rows: 0 = automatic (double when the noise level
- * is measured from a small portrait, float otherwise), 32, 64. */
+/* FFT arithmetic of the auxiliary row transforms (pp_fit_phase_shift_batch
+ * profiles, pp_get_noise_batch; pp_rotate_batch uses double only with 64):
+ * 0 = automatic (double), 32, 64.  pp_fit_batch always transforms the data
+ * rows in double (chi^2 to 1e-8 needs it). */
 int pp_plan_set_fft_precision(pp_plan_t* plan, int32_t bits);
 
 /* (phi, DM) solver: Newton steps taken per pass on the local model built from
