@@ -391,7 +391,7 @@ def run_ours(args):
                            "tol_sigma": args.tol or 1e-2, "mean_passes": mean_pass,
                            "solver": "Newton steps on the 4th-order local model of the per-channel sums; finishes "
                                      "without another pass when the estimated truncation shift is < 1e-4 sigma",
-                           "fft_arith": {0: "auto", 32: "f32", 64: "f64"}[args.fft],
+                           "fft_arith": "f64",
                            "converged": "%d/%d" % (ok, nsub),
                            "dDM_pull_rms": float(np.sqrt(np.mean(pull ** 2)))},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
