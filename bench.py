@@ -203,7 +203,7 @@ def run_reference(args):
                                    "bounded sample of %d subints per step" % nsamp},
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": "TOAs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -397,10 +397,22 @@ def run_ours(args):
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof, "cpu_baseline": cpu, "e2e_i16": e2e_i16,
                 "host_wall_ms_per_step": 1e3 * wall / args.steps}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(text.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, text)
 
 
 def main():
@@ -418,6 +430,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 (e.g. NCCL's version
+    # banner under NCCL_DEBUG=VERSION) is sent to stderr, the line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
