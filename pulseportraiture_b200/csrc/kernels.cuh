@@ -969,7 +969,6 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
   const int s = a.s0 + blockIdx.x;
   if (a.st.done[s]) return;
   __shared__ double sh[8 * 4];
-  __shared__ double bc[16];
   const int tid = threadIdx.x;
   const int nchan = a.nchan;
   const double* cs = a.csum + (size_t)s * nchan * kNCsum;
