@@ -1527,9 +1527,21 @@ struct Update5Args {
   double* snr; int* nfeval; int* rc; double* scales; double* scale_errs; double* channel_snrs;
   int s0, nchan, nbin, max_iter, log10_tau, option, is_toa;
   int flags[5];
+  int taylor_finish;   // finish a converged fit from the sums at the last evaluated point (no final pass)
   double tol;
   Box box;
 };
+
+// the per-channel sums c[0..8] = C, C_th, C_thth, C_t, C_tt, C_tht, S, S_t, S_tt carried from (theta_n, tau_n) to
+// (theta_n + dth, tau_n + dta): values to second order, first derivatives to first order
+__device__ __forceinline__ void chan_shift(double* c, double dth, double dta) {
+  const double C = c[0] + c[1] * dth + c[3] * dta + 0.5 * (c[2] * dth * dth + 2.0 * c[5] * dth * dta + c[4] * dta * dta);
+  const double Cth = c[1] + c[2] * dth + c[5] * dta;
+  const double Ct = c[3] + c[5] * dth + c[4] * dta;
+  const double S = c[6] + c[7] * dta + 0.5 * c[8] * dta * dta;
+  const double St = c[7] + c[8] * dta;
+  c[0] = C; c[1] = Cth; c[3] = Ct; c[6] = S; c[7] = St;
+}
 
 struct ChanJ {   // per-channel Jacobians of (theta_n, tau_n) w.r.t. the five parameters
   double Jth[3], Jt[2], Ktt, Kta, Kaa, lnf, taun;
@@ -1598,6 +1610,13 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   double* stp = a.st.step + (size_t)s * 5;
   const double tau_lin = a.log10_tau ? pow(10.0, x[3]) : x[3];
   const double alpha = x[4];
+  // The epilogue reports the point x + dx: dx = 0 when the sums in csum were evaluated at the
+  // reported point (final pass), or the last (converged, <= tol sigma) Newton step, in which case
+  // the per-channel sums are carried there by their second-order Taylor series (chan_shift) and the
+  // final evaluation pass is saved.
+  bool shifted = false;
+  double dx[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double tau_e = tau_lin, alpha_e = alpha;
   // mirror of the reference: with all tau_n == 0 the scattering derivatives are zero
   // (pptoaslib.py:325-330, 341-356)
   const bool scat_on = tau_lin != 0.0;
@@ -1657,8 +1676,10 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         int q = 6;
         double Hf[25];
         for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) { Hf[i * 5 + k] = v[q]; Hf[k * 5 + i] = v[q]; }
-        if (a.box.on) {   // active set: parameters held on a bound leave this step's system (idx, nfit are
-                          // not used again in this invocation: the epilogue below runs on action 3 only)
+        const int nfit_all = nfit;
+        int idx_all[5];
+        for (int i = 0; i < 5; ++i) idx_all[i] = idx[i];
+        if (a.box.on) {   // active set: parameters held on a bound leave this step's system
           int nfree = 0;
           for (int i = 0; i < nfit; ++i) if (!box_holds(a.box, idx[i], x[idx[i]], v[1 + idx[i]])) idx[nfree++] = idx[i];
           nfit = nfree;
@@ -1701,20 +1722,28 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         for (int i = 0; i < 5; ++i) xn[i] = box_clip(a.box, i, x[i] + d[i], clipped);
         if (clipped) for (int i = 0; i < 5; ++i) d[i] = xn[i] - x[i];
         bool conv = pd && sc == 1.0 && !clipped;
+        bool tiny = conv;   // last step <= 0.1 tol sigma: the sums can be carried to the final point (chan_shift)
         if (conv) for (int i = 0; i < nfit; ++i) {
           const double sg = sqrt(2.0 * Inv[i * 5 + i]);     // 1-sigma from inv(H/2)
           if (!(fabs(dr[i]) <= a.tol * sg)) conv = false;
+          if (!(fabs(dr[i]) <= 0.1 * a.tol * sg)) tiny = false;
         }
         for (int i = 0; i < 5; ++i) { xp[i] = x[i]; stp[i] = d[i]; }
         a.st.fprev[s] = f;
         a.st.lam[s] = 1.0;
         for (int i = 0; i < 5; ++i) x[i] = xn[i];
-        if (conv) { action = 1; rc = 0; }
+        nfit = nfit_all;
+        for (int i = 0; i < 5; ++i) idx[i] = idx_all[i];
+        if (conv && tiny && a.taylor_finish) {   // report x + d from the sums at x (no final pass)
+          action = 4; rc = 0;
+          for (int i = 0; i < 5; ++i) { bc[33 + i] = d[i]; bc[38 + i] = xn[i]; }
+        }
+        else if (conv) { action = 1; rc = 0; }
         else if (it >= a.max_iter) { action = 1; rc = 1; }
       }
       if (action == 1) a.st.done[s] = 2;   // one more pass at the final point, then the epilogue
       bc[0] = (double)action; bc[1] = (double)rc;
-      if (action == 1 || action == 2 || action == 3) a.rc[s] = rc;
+      if (action >= 1) a.rc[s] = rc;
       if (action == 2) {                    // non-finite objective: report what we have
         double* po = a.params + (size_t)s * 5;
         for (int i = 0; i < 5; ++i) po[i] = x[i];
@@ -1722,8 +1751,33 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
       }
     }
     __syncthreads();
-    if ((int)bc[0] != 3) return;   // 3: run the epilogue right now with the sums at x
+    const int act = (int)bc[0];
+    if (act != 3 && act != 4) return;   // 3: run the epilogue right now with the sums at x; 4: at x + d
+    if (act == 4) {
+      shifted = true;
+      for (int i = 0; i < 5; ++i) dx[i] = bc[33 + i];
+      tau_e = a.log10_tau ? pow(10.0, bc[38 + 3]) : bc[38 + 3];
+      alpha_e = bc[38 + 4];
+    }
   }
+  // per-channel sums at the reported point
+  auto load_c = [&](int n, double* c) {
+    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    if (!(c[6] > 0.0)) return;
+    if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
+    if (shifted) {
+      const double n2 = a.nu2[n];
+      const double dth = dx[0] + dx[1] * (kDconst * (n2 - 1.0 / (nD * nD)) / P) +
+                         dx[2] * (kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P);
+      double dta = 0.0;
+      if (scat_on) {
+        const double lnf = log(a.freqs[n] / nT);
+        const double dl = (a.log10_tau ? 2.302585092994045684 * dx[3] : log1p(dx[3] / tau_lin)) + dx[4] * lnf;
+        dta = tau_lin * pow(a.freqs[n] / nT, alpha) * expm1(dl);
+      }
+      chan_shift(c, dth, dta);
+    }
+  };
 
   // ======================= epilogue: sums in csum are at the final x =======================
   const double K1 = kDconst / P, K2 = kDconst * kDconst / P;
@@ -1737,11 +1791,11 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   // u[15..20]: for j in {0,1,3}: sum h_ln(j), sum ln(nu) h_ln(j) ; u[21]: f ; u[22]: Sd ; u[23]: snr^2
   for (int n = tid; n < nchan; n += NT) {
     double c[9];
-    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    load_c(n, c);
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_e, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
     const double C = c[0], n2 = a.nu2[n], lnnu = log(a.freqs[n]);
@@ -1754,7 +1808,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
     {
       // Hessian row w.r.t. alpha divided by ln(nu_n/nu_tau): d/dalpha = lnf * tau_n d/dtau_n
       const double Cta = c[3] * j.taun, Sta = c[7] * j.taun;
-      const double k10 = a.log10_tau ? 2.302585092994045684 * j.taun : (tau_lin != 0.0 ? j.taun / tau_lin : 0.0);
+      const double k10 = a.log10_tau ? 2.302585092994045684 * j.taun : (tau_e != 0.0 ? j.taun / tau_e : 0.0);
       const int ps[3] = {0, 1, 3};
       for (int q = 0; q < 3; ++q) {
         const int p = ps[q];
@@ -1776,11 +1830,11 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   double fmean = 0.0;
   for (int n = tid; n < nchan; n += NT) {
     double c[9];
-    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    load_c(n, c);
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_e, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
     int q = 0;
@@ -1872,17 +1926,17 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   __syncthreads();
   const double noD = bc[2], noG = bc[3], noT = bc[4];
   // ---- re-reference phi and tau (pptoaslib.py:1052-1065) -----------------------------------
-  const double tau_out_lin = tau_lin * pow(noT / nT, alpha);
+  const double tau_out_lin = tau_e * pow(noT / nT, alpha_e);
   // ---- Hessian at the output frequencies, covariance incl. amplitudes (645-731) -------------
   double ho[15];
   for (int i = 0; i < 15; ++i) ho[i] = 0.0;
   for (int n = tid; n < nchan; n += NT) {
     double c[9];
-    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    load_c(n, c);
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha, a.log10_tau);
+    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
     int q = 0;
@@ -1906,13 +1960,13 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   for (int i = 0; i < 25; ++i) Xinv[i] = bc[8 + i];
   for (int n = tid; n < nchan; n += NT) {
     double c[9];
-    for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
+    load_c(n, c);
     const double S = c[6];
     const size_t o = (size_t)s * nchan + n;
     double sc = 0.0, se = 0.0, csn = 0.0;
     if (S > 0.0) {
       if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha, a.log10_tau);
+      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha_e, a.log10_tau);
       double dC[5], dS[5];
       chan_first(c, j, dC, dS);
       sc = c[0] / S;                                               // :688

@@ -821,6 +821,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       u5.scale_errs = ua.scale_errs; u5.channel_snrs = ua.channel_snrs;
       u5.s0 = s0; u5.nchan = nchan; u5.nbin = 2 * N; u5.max_iter = max_iter; u5.log10_tau = args->log10_tau;
       u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol; u5.box = box;
+      u5.taylor_finish = pl->model_steps != 1;
       for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
     }
     for (int it = 0; it < n_launch_iter; ++it) {
@@ -843,7 +844,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       // launch of the full grid costs ~80 us, the poll ~20 us)
       // (when the previous chunk needed a third pass this one most likely does too: launch it
       // without asking first)
-      const bool poll = general ? ((it & 3) == 3) : (it >= 2 || (it == 1 && !expect_third));
+      const bool poll = general ? (it >= 3) : (it >= 2 || (it == 1 && !expect_third));
       if (it == 1 && pending_out >= 0) {   // this chunk's first passes are queued: now the old copies
         if (enqueue_results(pending_out)) return -2;
         pending_out = -1;

@@ -883,3 +883,39 @@ def test_model_steps_match_one_step_per_pass(engine, nsub, nchan, nbin, sigma):
     assert rm["nfeval"].mean() < r1["nfeval"].mean()
     if sigma <= 1.5:            # at low S/N the steps are long and the model is (rightly) not trusted
         assert rm["nfeval"].mean() <= 1.5
+
+
+@pytest.mark.parametrize("flags,log10_tau", [((1, 1, 0, 1, 1), True), ((1, 1, 1, 1, 1), True), ((1, 1, 0, 1, 0), False),
+                                             ((1, 1, 1, 0, 0), False)])
+def test_general_solver_finish_without_final_pass(engine, flags, log10_tau):
+    """The general solver reports a converged fit (last step <= 1e-3 sigma) from the sums of the last
+    evaluated point, carried to the final point by their second-order Taylor series, instead of
+    spending a final evaluation pass.  pp_plan_set_model_steps(plan, 1) restores the final pass: same
+    results, one pass more."""
+    nsub, nchan, nbin, nu0, bw = 6, 64, 512, 600., 400.
+    tau_s = 50e-6
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 7300 + s, tau_data_s=tau_s, sigma=0.5) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    errs = np.stack([orc.get_noise(c["data"], chans=True) for c in cases])
+    tau_g = 0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0
+    scat = np.tile([tau_g, -4.0], (nsub, 1))
+    kw = dict(errs=errs, fit_flags=flags, log10_tau=log10_tau, scat_guess=scat)
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+        ra = pl.fit_batch(data, P, **kw)
+        pl.set_model_steps(1)
+        rb = pl.fit_batch(data, P, **kw)
+    assert np.all(ra["return_code"] == 0) and np.all(rb["return_code"] == 0)
+    # fits whose last step was <= 1e-4 sigma skip the final pass
+    assert np.all((ra["nfeval"] == rb["nfeval"]) | (ra["nfeval"] + 1 == rb["nfeval"]))
+    assert np.sum(ra["nfeval"] + 1 == rb["nfeval"]) >= 1
+    fit = [i for i in range(5) if flags[i]]
+    for i in fit:
+        assert np.max(np.abs(ra["params"][:, i] - rb["params"][:, i]) / rb["param_errs"][:, i]) < 1e-4, i
+    assert rel(ra["param_errs"][:, fit], rb["param_errs"][:, fit]) < 1e-5
+    assert rel(ra["chi2"], rb["chi2"]) < 1e-10
+    assert rel(ra["nu_out"], rb["nu_out"]) < 1e-5
+    assert rel(ra["scales"], rb["scales"]) < 1e-7
+    assert rel(ra["scale_errs"], rb["scale_errs"]) < 1e-6
+    assert rel(ra["snr"], rb["snr"]) < 1e-9
