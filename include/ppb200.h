@@ -191,6 +191,15 @@ int pp_fit_phase_shift_batch(pp_plan_t* plan, const float* profiles, int32_t n,
                              const double* noise, int32_t Ns,
                              const pp_pshift_out_t* out);
 
+/* Same with the `bounds` argument of pplib.fit_phase_shift (pplib.py:2054,
+ * 2085): the brute-force grid is np.mgrid[phi_lo:phi_hi:Ns*1j].  As in the
+ * reference the polish is not confined to the bounds. */
+int pp_fit_phase_shift_batch_bounds(pp_plan_t* plan, const float* profiles,
+                                    int32_t n, const float* models,
+                                    int32_t nmodel, const double* noise,
+                                    int32_t Ns, double phi_lo, double phi_hi,
+                                    const pp_pshift_out_t* out);
+
 /* ---- batched Fourier-domain rotation -------------------------------------
  * Replaces pplib.rotate_data / rotate_portrait (pplib.py:2338-2460) for
  * [nsub,nchan,nbin] float32: harmonic k of channel n is multiplied by

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
            "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_set_freqs",
            "pp_set_model", "pp_fit_batch",
-           "pp_fit_phase_shift_batch", "pp_rotate_batch", "pp_rotate_full_batch",
+           "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch",
            "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
            "pp_get_noise_batch",
            "pp_plan_enable_timing", "pp_get_stats", "pp_host_alloc",
@@ -149,6 +149,9 @@ def lib():
     L.pp_fit_phase_shift_batch.argtypes = [vp, vp, i32, vp, i32, vp, i32,
                                            C.POINTER(PShiftOut)]
     L.pp_fit_phase_shift_batch.restype = C.c_int
+    L.pp_fit_phase_shift_batch_bounds.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_double, C.c_double,
+                                                  C.POINTER(PShiftOut)]
+    L.pp_fit_phase_shift_batch_bounds.restype = C.c_int
     L.pp_rotate_batch.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     L.pp_rotate_batch.restype = C.c_int
     L.pp_rotate_full_batch.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]

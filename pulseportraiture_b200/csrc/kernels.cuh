@@ -548,7 +548,9 @@ struct GuessArgs {
   double polish_tol;       // stop the exact polish when |dx| < polish_tol [rot]
   const double* wsum;      // [n] divisor of the partial sum, or null (=1)
   const double* noise;     // [n] time-domain sigma or null (measure from spectrum)
-  const double2* table;    // [Ns-1] e^{2 pi i m/(Ns-1)}
+  const double2* table;    // [Ns-1] e^{2 pi i m/(Ns-1)}; general grid: [Ns] e^{2 pi i phi_j}
+  int grid_general;        // 0: np.mgrid[-0.5:0.5:Ns j]; 1: phi_j = phi_lo + j phi_step (other bounds)
+  double phi_lo, phi_step;
   int s0;                  // global index offset for per-subint arrays below
   // outputs of the 1-D fit (global index), any may be null
   double* phase; double* phase_err; double* scale; double* scale_err; double* snr; double* red_chi2;
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   for (int j0 = w * 32; j0 < a.Ns; j0 += 256) {
     const int j = j0 + lane;
     if (j < a.Ns) {
-      const double2 r1 = a.table[j % M];
+      const double2 r1 = a.grid_general ? a.table[j] : a.table[j % M];
       const cx<double> rho = mk<double>(r1.x, r1.y), rho2 = csqr(rho);
       cx<double> po = rho, pe = rho2;                 // harmonics 1 and 2
       double acc_o = 0.0, acc_e = 0.0;
@@ -628,7 +630,8 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
         po = cmul(po, rho2);
         pe = cmul(pe, rho2);
       }
-      const double cj = -(acc_e - acc_o) / err2;       // e^{-i pi k}: odd harmonics change sign
+      // default grid: e^{-i pi k} of phi = -1/2 + j/M, i.e. the odd harmonics change sign
+      const double cj = a.grid_general ? -(acc_e + acc_o) / err2 : -(acc_e - acc_o) / err2;
       if (cj < bv) { bv = cj; bi = j; }                // j ascending within a lane: first index wins ties
     }
   }
@@ -648,8 +651,8 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   }
   __syncthreads();
   const int lagi = besti[0];
-  const double h = 1.0 / (double)M;
-  double x = -0.5 + (double)lagi * h;
+  const double h = a.grid_general ? a.phi_step : 1.0 / (double)M;
+  double x = (a.grid_general ? a.phi_lo : -0.5) + (double)lagi * h;
   double lo = x - h, hi = x + h;
   double C0 = 0, C1 = 0, C2 = 0;
   // ---- exact polish: safeguarded Newton on C'(phi) = 0 inside the bracket ------

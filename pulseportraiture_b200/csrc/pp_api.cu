@@ -84,6 +84,7 @@ struct pp_plan {
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
   std::vector<std::pair<int, DBuf>> grid_tables;
+  DBuf grid_general;   // table of the last grid with bounds other than [-0.5, 0.5]
   // per-batch staging of small inputs and per-subint / per-channel workspace
   DBuf running, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
@@ -406,6 +407,22 @@ static int grid_table(pp_plan* pl, int Ns, const double2** out) {
   CK(cudaMemcpyAsync(b.p, t.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));  // t goes out of scope
   *out = b.as<double2>();
+  return 0;
+}
+
+// general grid np.mgrid[lo:hi:Ns j] = lo + arange(Ns) * (hi - lo)/(Ns - 1): e^{2 pi i phi_j}, j < Ns
+static int grid_table_general(pp_plan* pl, int Ns, double lo, double hi, const double2** out) {
+  const double step = (hi - lo) / (double)(Ns - 1);
+  std::vector<double2> t(Ns);
+  for (int j = 0; j < Ns; ++j) {
+    double phi = lo + (double)j * step;
+    phi -= nearbyint(phi);
+    t[j] = make_double2(cos(2.0 * M_PI * phi), sin(2.0 * M_PI * phi));
+  }
+  CK(pl->grid_general.need(sizeof(double2) * Ns));
+  CK(cudaMemcpyAsync(pl->grid_general.p, t.data(), sizeof(double2) * Ns, cudaMemcpyHostToDevice, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));  // t goes out of scope
+  *out = pl->grid_general.as<double2>();
   return 0;
 }
 
@@ -946,8 +963,26 @@ static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spe
   return 0;
 }
 
+static int pshift_impl(pp_plan_t* pl, const float* profiles, int32_t n, const float* models, int32_t nmodel,
+                       const double* noise, int32_t Ns, bool general, double phi_lo, double phi_hi,
+                       const pp_pshift_out_t* out);
+
 extern "C" int pp_fit_phase_shift_batch(pp_plan_t* pl, const float* profiles, int32_t n, const float* models, int32_t nmodel,
                                         const double* noise, int32_t Ns, const pp_pshift_out_t* out) {
+  return pshift_impl(pl, profiles, n, models, nmodel, noise, Ns, false, -0.5, 0.5, out);
+}
+
+extern "C" int pp_fit_phase_shift_batch_bounds(pp_plan_t* pl, const float* profiles, int32_t n, const float* models,
+                                               int32_t nmodel, const double* noise, int32_t Ns, double phi_lo,
+                                               double phi_hi, const pp_pshift_out_t* out) {
+  if (!(phi_hi > phi_lo)) return fail(-1, "bounds: need phi_lo < phi_hi");
+  const bool dflt = phi_lo == -0.5 && phi_hi == 0.5;
+  return pshift_impl(pl, profiles, n, models, nmodel, noise, Ns, !dflt, phi_lo, phi_hi, out);
+}
+
+static int pshift_impl(pp_plan_t* pl, const float* profiles, int32_t n, const float* models, int32_t nmodel,
+                       const double* noise, int32_t Ns, bool general, double phi_lo, double phi_hi,
+                       const pp_pshift_out_t* out) {
   if (!pl || !profiles || !models || !out) return fail(-1, "NULL argument");
   if (n < 1) return fail(-1, "n must be >= 1");
   if (nmodel < 1 || n % nmodel) return fail(-1, "nmodel must divide n (profile i is fit against model i mod nmodel)");
@@ -971,9 +1006,11 @@ extern "C" int pp_fit_phase_shift_batch(pp_plan_t* pl, const float* profiles, in
   if (launch_rfft_rows(pl, dprof, n, pl->ps_spec.as<float2>(), 0, nullptr, bits)) return -2;
   if (launch_rfft_rows(pl, dmod, nmodel, pl->ps_mspec.as<float2>(), 1, nullptr, 64)) return -2;
   const double2* table = nullptr;
-  if (grid_table(pl, Ns, &table)) return -2;
+  if (general) { if (grid_table_general(pl, Ns, phi_lo, phi_hi, &table)) return -2; }
+  else if (grid_table(pl, Ns, &table)) return -2;
   GuessArgs ga;
   memset(&ga, 0, sizeof ga);
+  ga.grid_general = general ? 1 : 0; ga.phi_lo = phi_lo; ga.phi_step = (phi_hi - phi_lo) / (double)(Ns - 1);
   ga.partial = pl->ps_spec.as<float2>(); ga.mconj = pl->ps_mspec.as<float2>(); ga.nparts = 1; ga.nmodel = nmodel;
   ga.N = N; ga.Ns = Ns; ga.wsum = nullptr; ga.noise = dnoise; ga.table = table; ga.s0 = 0; ga.polish_tol = 1e-14;
   ga.phase = pl->ps_phase.as<double>(); ga.phase_err = pl->ps_perr.as<double>(); ga.scale = pl->ps_scale.as<double>();

@@ -256,7 +256,8 @@ class WidebandPlan(object):
         return res
 
     # ---- batched 1-D FFTFIT --------------------------------------------------------
-    def fit_phase_shift_batch(self, profiles, models, noise=None, Ns=100):
+    def fit_phase_shift_batch(self, profiles, models, noise=None, Ns=100, bounds=(-0.5, 0.5)):
+        """Batched pplib.fit_phase_shift; ``bounds`` = ends of the brute-force grid (pplib.py:2085)."""
         keep = []
         n = int(profiles.shape[0])
         nmodel = int(models.shape[0]) if len(models.shape) == 2 else 1
@@ -269,9 +270,9 @@ class WidebandPlan(object):
         o = _ffi.PShiftOut()
         for k, v in res.items():
             setattr(o, k, v.ctypes.data)
-        _ffi.check(self._lib.pp_fit_phase_shift_batch(self._h, pp, n, mp, nmodel,
-                                                      nz, int(Ns), C.byref(o)),
-                   "pp_fit_phase_shift_batch")
+        _ffi.check(self._lib.pp_fit_phase_shift_batch_bounds(self._h, pp, n, mp, nmodel, nz, int(Ns),
+                                                             float(bounds[0]), float(bounds[1]), C.byref(o)),
+                   "pp_fit_phase_shift_batch_bounds")
         return res
 
     # ---- batched rotation -------------------------------------------------------------

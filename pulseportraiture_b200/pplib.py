@@ -85,21 +85,21 @@ def fit_phase_shift(data, model, noise=None, bounds=[-0.5, 0.5], Ns=100):
     """Fit a phase shift between data and model (pplib.py:2054-2100).
 
     Returns DataBunch(phase, phase_err, scale, scale_err, snr, red_chi2,
-    duration).  The brute-force grid (Ns points on [-0.5, 0.5], both ends) is
+    duration).  The brute-force grid (Ns points on ``bounds``, both ends) is
     evaluated on the device; ``phase`` is the exact minimiser reached from the
     grid argmin (the reference's Nelder-Mead polish is accurate to ~1e-4 rot).
     The integer argmin is returned as the extra field ``lag_index``.
     """
     data = np.asarray(data)
-    if list(bounds) != [-0.5, 0.5]:
-        raise NotImplementedError("only bounds=[-0.5, 0.5] is supported")
+    if len(bounds) != 2 or not bounds[1] > bounds[0]:
+        raise ValueError("bounds = [lower, upper]")
     nbin = data.shape[-1]
     pl = get_plan(1, nbin)
     start = time.time()
     r = pl.fit_phase_shift_batch(_f32(data).reshape(1, nbin),
                                  _f32(model).reshape(1, nbin),
                                  None if noise is None else np.array([noise], dtype=np.float64),
-                                 Ns=Ns)
+                                 Ns=Ns, bounds=bounds)
     duration = time.time() - start
     return DataBunch(phase=r["phase"][0], phase_err=r["phase_err"][0],
                      scale=r["scale"][0], scale_err=r["scale_err"][0],

@@ -919,3 +919,21 @@ def test_general_solver_finish_without_final_pass(engine, flags, log10_tau):
     assert rel(ra["scales"], rb["scales"]) < 1e-7
     assert rel(ra["scale_errs"], rb["scale_errs"]) < 1e-6
     assert rel(ra["snr"], rb["snr"]) < 1e-9
+
+
+@pytest.mark.parametrize("bounds,Ns", [((-0.25, 0.25), 100), ((0.0, 1.0), 64), ((-0.1, 0.3), 37), ((-0.5, 0.5), 100)])
+def test_fit_phase_shift_other_bounds(bounds, Ns):
+    """pplib.fit_phase_shift(bounds=...): the brute-force grid is np.mgrid[lo:hi:Ns j] (pplib.py:2085);
+    integer argmin bit-exact against the oracle, phase against its exact polish."""
+    from pulseportraiture_b200 import pplib
+    nbin = 512
+    _, model = synth.example_model(1, nbin, 1500., 800.)
+    model = model[0].astype(np.float32).astype(np.float64)
+    rng = np.random.RandomState(77)
+    for phi in (0.07, -0.06, 0.21):
+        data = (orc.rotate_data(model, -phi) + 0.05 * rng.standard_normal(nbin)).astype(np.float32).astype(np.float64)
+        ref = orc.fit_phase_shift(data, model, 0.05, bounds=bounds, Ns=Ns, polish="exact")
+        r = pplib.fit_phase_shift(data, model, 0.05, bounds=list(bounds), Ns=Ns)
+        assert r.lag_index == ref.lag_index
+        assert abs(r.phase - ref.phase) / ref.phase_err < SIG_TOL
+        assert rel(r.scale, ref.scale) < 1e-6 and rel(r.snr, ref.snr) < 1e-6 and rel(r.red_chi2, ref.red_chi2) < 1e-6
