@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__(128) k_update2(UpdateArgs a) {
       if (!good) conv = false;
     }
     if (conv) { finish = 1; rc = 0; }
-    else if (it >= a.max_iter) { finish = 1; rc = 1; }
+    else if (it >= a.max_iter) { finish = 2; rc = 1; }   // out of passes: report the evaluated point as it is
     if (tid == 0) {
       xp[0] = x0; xp[1] = x1;
       stp[0] = d0; stp[1] = d1;

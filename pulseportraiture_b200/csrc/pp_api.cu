@@ -564,7 +564,10 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   const int nsub = args->nsub, nchan = pl->nchan, N = pl->N;
   const int Ns = args->Ns > 0 ? args->Ns : 100;
   if (Ns < 2) return fail(-1, "Ns must be >= 2");
-  const int dflt_iter = general ? 40 : 8;
+  // passes are launched only while some subint is still running (polled), so a generous limit costs
+  // nothing for batches started from the FFTFIT guess (1-2 passes) and lets caller-supplied start
+  // values far from the optimum converge (10-14 passes from 0.05-0.08 turn away, tools/far_start_probe.py)
+  const int dflt_iter = 40;
   const int max_iter = args->max_iter > 0 ? args->max_iter : (args->max_iter < 0 ? -1 : dflt_iter);
   const int n_launch_iter = max_iter < 0 ? 1 : (general ? max_iter + 1 : max_iter);
 

@@ -937,3 +937,17 @@ def test_fit_phase_shift_other_bounds(bounds, Ns):
         assert r.lag_index == ref.lag_index
         assert abs(r.phase - ref.phase) / ref.phase_err < SIG_TOL
         assert rel(r.scale, ref.scale) < 1e-6 and rel(r.snr, ref.snr) < 1e-6 and rel(r.red_chi2, ref.red_chi2) < 1e-6
+
+
+@pytest.mark.parametrize("phi0", [0.15, 0.2, 0.05])
+def test_fit_portrait_from_far_start_values(phi0):
+    """fit_portrait with caller-supplied init_params 0.03-0.08 turn from the optimum (no FFTFIT guess):
+    the safeguarded Newton solver reaches the optimum the reference's TNC reaches (10-14 passes)."""
+    from pulseportraiture_b200 import pplib
+    c = synth.make_case(64, 512, 1500., 800., 4242, phi=0.123, dDM=3e-4)
+    ref = orc.fit_portrait(c["data"], c["model"], [phi0, 0.0], c["P"], c["freqs"])
+    r = pplib.fit_portrait(c["data"], c["model"], [phi0, 0.0], c["P"], c["freqs"])
+    assert r.return_code == 0 and r.nfeval <= 20
+    assert abs(r.phase - ref.phase) / ref.phase_err < SIG_TOL
+    assert abs(r.DM - ref.DM) / ref.DM_err < SIG_TOL
+    assert abs(r.chi2 / ref.chi2 - 1) < CHI2_TOL
