@@ -388,7 +388,7 @@ def run_ours(args):
                                        "(config 2), FFTFIT guess + Newton solve, noise measured"
                                        % nsub,
                            "l2": "inputs (%.1f GB) larger than L2" % (data.numel() * 4 / 1e9),
-                           "tol_sigma": args.tol or 1e-2, "mean_passes": mean_pass,
+                           "tol_sigma": min(args.tol, 1e-4) if args.tol else 1e-4, "mean_passes": mean_pass,
                            "solver": "Newton steps on the 4th-order local model of the per-channel sums; finishes "
                                      "without another pass when the estimated truncation shift is < 1e-4 sigma",
                            "fft_arith": "f64",

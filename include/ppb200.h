@@ -116,8 +116,12 @@ typedef struct {
   int32_t option;           /* get_nu_zeros option (pptoaslib.py:734)          */
   int32_t is_toa;           /* pptoaslib.py:1048-1050                          */
   int32_t Ns;               /* FFTFIT grid size (pplib.py:2054), default 100   */
-  int32_t max_iter;         /* Newton passes per subint (0 = default)          */
-  double tol;               /* convergence: |step| < tol * 1-sigma (0=default) */
+  int32_t max_iter;         /* Newton passes per subint (0 = default 40; passes run
+                               only while some subint has not converged)       */
+  double tol;               /* convergence: |step| < tol * 1-sigma (0 = default:
+                               1e-3; the (phi, DM) solver's model-based steps
+                               stop at min(tol, 1e-4), see
+                               pp_plan_set_model_steps)                        */
   const double* scat_guess; /* [nsub,2] with init==NULL: tau start value [rot,
                                linear] at nu_fit_tau and alpha start value
                                (pptoas.py:427-452); NULL = 0, 0                */
