@@ -79,10 +79,7 @@ def align_archives(metafile, initial_guess, fit_dm=True, tscrunch=False, pscrunc
             continue
         if d.prof_SNR is not None and d.prof_SNR < SNR_cutoff:
             continue
-        if model_freqs is not None and np.any(np.asarray(d.freqs[0]) != model_freqs):
-            raise NotImplementedError("archives on a different frequency grid than the template")
         archives.append(d)
-    pl = get_plan(nchan, nbin)
     count = 1
     total_weights = np.zeros(nchan)
     while niter:
@@ -92,10 +89,23 @@ def align_archives(metafile, initial_guess, fit_dm=True, tscrunch=False, pscrunc
         total_weights = np.zeros(nchan)
         for d in archives:
             freqs = np.asarray(d.freqs[0], dtype=np.float64)
-            pl.set_model(_f32(model_port), freqs)
+            model_ichans = None
+            if model_freqs is not None and (len(freqs) != nchan or np.any(freqs != model_freqs)):
+                # a different frequency grid than the template: every data channel is fit against
+                # (and added to) the template channel closest in frequency (ppalign.py:166-176)
+                model_ichans = np.array([np.argmin(abs(model_freqs - f)) for f in freqs])
+                if len(np.unique(model_ichans)) != len(model_ichans):
+                    # the reference's `aligned_port[ipol, model_ichans] += ...` keeps only the last of
+                    # several data channels that share a template channel (numpy fancy-index +=)
+                    raise NotImplementedError("several data channels map onto one template channel")
+            elif len(freqs) != nchan:
+                raise ValueError("%s has %d channels, the template %d" % (d.filename, len(freqs), nchan))
+            nchan_d = len(freqs)
+            pl = get_plan(nchan_d, nbin)
+            pl.set_model(_f32(model_port if model_ichans is None else model_port[model_ichans]), freqs)
             ok_isubs = np.asarray(d.ok_isubs, dtype=int)
             nsub = len(ok_isubs)
-            mask = np.zeros((nsub, nchan), dtype=np.uint8)
+            mask = np.zeros((nsub, nchan_d), dtype=np.uint8)
             for i, isub in enumerate(ok_isubs):
                 mask[i, np.asarray(d.ok_ichans[isub], dtype=int)] = 1
             subints = _f32(np.asarray(d.subints)[ok_isubs, 0])
@@ -114,8 +124,12 @@ def align_archives(metafile, initial_guess, fit_dm=True, tscrunch=False, pscrunc
             r = pl.fit_batch(subints, Ps, errs=errs, chan_mask=mask, weights=wts, snrs=snrs,
                              DM_guess=np.full(nsub, DM_guess), nu_fit_mode=1,
                              fit_flags=flags, log10_tau=False, Ns=nbin, semantics="full", align=True)
-            aligned += r["align_sum"]
-            total_weights += r["align_wsum"]
+            if model_ichans is None:
+                aligned += r["align_sum"]
+                total_weights += r["align_wsum"]
+            else:
+                aligned[model_ichans] += r["align_sum"]
+                total_weights[model_ichans] += r["align_wsum"]
         good = total_weights > 0
         aligned[good] /= total_weights[good, None]                      # :210-212
         model_port = aligned

@@ -200,3 +200,36 @@ def test_get_narrowband_TOAs_matches_per_channel_fftfit():
     t0 = gt.TOA_list[0]
     assert t0.flags["chan"] == int(d.ok_ichans[0][0]) and t0.flags["subint"] == 0 and "phs" in t0.flags
     assert t0.frequency == d.freqs[0, d.ok_ichans[0][0]]
+
+
+def test_align_archives_on_a_different_frequency_grid():
+    """An archive whose channels are a shifted sub-band of the template archive's grid: every data
+    channel is fit against, and added to, the nearest template channel (ppalign.py:166-176)."""
+    from pulseportraiture_b200 import ppalign
+    from pulseportraiture_b200.pplib import DataBunch
+    full, cases = _fake_archive(5, 32, 256, 9700)
+    sel = np.arange(8, 24)
+    sub = DataBunch(**dict(full))
+    sub["nchan"] = len(sel)
+    sub["freqs"] = full.freqs[:, sel] + 0.3                     # 0.3 MHz off the template's centres
+    sub["subints"] = full.subints[:, :, sel]
+    sub["noise_stds"] = full.noise_stds[:, :, sel]
+    sub["SNRs"] = full.SNRs[:, :, sel]
+    sub["weights"] = full.weights[:, sel]
+    sub["ok_ichans"] = [np.arange(len(sel)) for _ in range(5)]
+    tmpl = DataBunch(**dict(full))                              # template archive: first subint, full grid
+    tmpl["subints"] = np.asarray(orc.rotate_data(cases[0]["model"], 0.013))[None, None]
+    tmpl["nsub"] = 1
+    out = ppalign.align_archives([sub], tmpl, fit_dm=True, niter=2, quiet=True)
+    assert out.port.shape == (32, 256)
+    outside = np.setdiff1d(np.arange(32), sel)
+    assert np.all(out.weights[outside] == 0) and np.all(out.weights[sel] > 0)
+    # the same archive aligned against the matching template rows given as a plain array
+    ref = ppalign.align_archives([sub], np.asarray(tmpl.subints[0, 0])[sel], fit_dm=True, niter=1, quiet=True)
+    one = ppalign.align_archives([sub], tmpl, fit_dm=True, niter=1, quiet=True)
+    assert np.array_equal(one.port[sel], ref.port) and np.array_equal(one.weights[sel], ref.weights)
+    # several data channels per template channel: the reference keeps only the last one (numpy +=)
+    dup = DataBunch(**dict(sub))
+    dup["freqs"] = np.tile(np.linspace(1400., 1410., len(sel)), (5, 1))
+    with pytest.raises(NotImplementedError):
+        ppalign.align_archives([dup], tmpl, niter=1, quiet=True)
