@@ -143,3 +143,29 @@ def test_plain_c_client_compiles_and_links(tmp_path):
                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert os.path.isfile(exe)
+
+
+def test_bounds_and_frequency_table_helpers():
+    """Host-side argument handling added with the bounds / per-subint frequency tables (no GPU)."""
+    from pulseportraiture_b200 import pplib, pptoas
+    from pulseportraiture_b200.engine import bounds_array
+    # scipy-style bounds -> [5, 2] with NaN for open ends; nothing bounded -> None (NULL in the ABI)
+    assert bounds_array(None) is None
+    assert bounds_array([(None, None)] * 5) is None
+    b = bounds_array([(None, None), (None, 1e-3), None, (-2.5, None), (-10.0, 10.0)])
+    assert b.shape == (5, 2) and b.dtype == np.float64
+    assert np.isnan(b[0]).all() and np.isnan(b[1, 0]) and b[1, 1] == 1e-3 and np.isnan(b[2]).all()
+    assert b[3, 0] == -2.5 and np.isnan(b[3, 1]) and list(b[4]) == [-10.0, 10.0]
+    assert pplib._check_bounds([(None, None), (None, None)], 2) is None
+    assert pplib._check_bounds([(0.0, None), (None, None)], 2) == [(0.0, None), (None, None)]
+    with pytest.raises(ValueError):
+        pplib._check_bounds([(None, None)] * 3, 2)
+    with pytest.raises(ValueError):
+        pplib._check_bounds([(0.0, 1.0, 2.0)], 2)
+    # distinct frequency tables of an archive and the table each subint uses
+    fA, fB = np.linspace(1100., 1900., 8), np.linspace(1100.5, 1900.5, 8)
+    tables, table_of = pptoas._freq_tables(np.stack([fA, fB, fA, fA, fB]))
+    assert tables.shape == (2, 8) and list(table_of) == [0, 1, 0, 0, 1]
+    assert np.array_equal(tables[0], fA) and np.array_equal(tables[1], fB)
+    tables, table_of = pptoas._freq_tables(np.tile(fA, (4, 1)))
+    assert tables.shape == (1, 8) and list(table_of) == [0, 0, 0, 0]
