@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PPB200_ABI_VERSION 4
+#define PPB200_ABI_VERSION 5
 
 typedef struct pp_plan pp_plan_t;
 
@@ -218,6 +218,14 @@ int pp_rotate_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
 int pp_rotate_full_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
                          const double* phase, const double* DM, const double* GM,
                          const double* P, const double* nu_DM, const double* nu_GM);
+
+/* Per-channel, per-harmonic real response applied in the Fourier domain:
+ * out[s,n] = irfft(resp[n,:] * rfft(in[s,n])), resp float64 [nchan, nbin/2+1] (host or device).
+ * Replaces the model multiply of pptoas.py:388-394, modelx = irfft(instrumental_response_port_FT(...)
+ * * rfft(modelx)) (the response table itself, pptoaslib.py:112-179, is a few kB of host arithmetic:
+ * pptoaslib.instrumental_response_port_FT).  in/out may alias. */
+int pp_apply_response_batch(pp_plan_t* plan, const float* in, float* out, int32_t nsub,
+                            const double* resp);
 
 /* ---- align-and-accumulate (ppalign inner loop) ---------------------------------
  * Replaces the per-subint accumulation of ppalign.align_archives

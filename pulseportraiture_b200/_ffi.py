@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
            "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_set_freqs",
            "pp_set_model", "pp_fit_batch",
-           "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch",
+           "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch", "pp_apply_response_batch",
            "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
            "pp_get_noise_batch",
            "pp_plan_enable_timing", "pp_get_stats", "pp_host_alloc",
@@ -33,7 +33,7 @@ SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
 
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
-                  if f.endswith((".cu", ".cuh"))) + \
+                  if f.endswith((".cu", ".cuh", ".h"))) + \
         [os.path.join(INCLUDE, "ppb200.h")]
 
 
@@ -156,6 +156,8 @@ def lib():
     L.pp_rotate_batch.restype = C.c_int
     L.pp_rotate_full_batch.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.pp_rotate_full_batch.restype = C.c_int
+    L.pp_apply_response_batch.argtypes = [vp, vp, vp, i32, vp]
+    L.pp_apply_response_batch.restype = C.c_int
     L.pp_align_accumulate.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pp_align_accumulate.restype = C.c_int
     L.pp_gen_gaussian_portrait.argtypes = [vp, C.c_char_p, vp, i32, C.c_double, C.c_double, vp]

@@ -12,6 +12,28 @@ namespace ppb {
 // stride-16 within 256 (pass 2); XOR the column with bits 4..6 of the position.
 __device__ __forceinline__ int phys16(int i) { return i ^ ((i >> 4) & 7); }
 
+// float -> double by integer operations (ALU pipe; F2F runs on the XU pipe): exact for normal floats
+// and zero, subnormals flush towards zero, Inf/NaN come out as huge finite values (callers that must
+// keep them non-finite test the biased exponent themselves).
+__device__ __forceinline__ double f2d_bits(float f) {
+  const unsigned b = __float_as_uint(f);
+  const unsigned a = b & 0x7fffffffu;
+  unsigned hi = (a >> 3) + (a >= 0x00800000u ? 0x38000000u : 0u);
+  hi |= b & 0x80000000u;
+  return __hiloint2double((int)hi, (int)(b << 29));
+}
+// double -> float, round to nearest even, by integer operations: |d| below the float normal range
+// gives zero; |d| >= 2^128 (and Inf/NaN) is not handled (the caller's values are bounded).
+__device__ __forceinline__ float d2f_bits(double d) {
+  const unsigned hi = (unsigned)__double2hiint(d), lo = (unsigned)__double2loint(d);
+  const unsigned a = hi & 0x7fffffffu;
+  unsigned f = __funnelshift_l(lo, a - 0x38000000u, 3);
+  const unsigned t = (lo & 0x1fffffffu) + 0x0fffffffu + (f & 1u);   // bit 29: round up (ties to even)
+  f += t >> 29;
+  if (a < 0x38100000u) f = 0u;
+  return __uint_as_float(f | (hi & 0x80000000u));
+}
+
 template <typename F> __device__ __forceinline__ cx<F> mul_c(cx<F> a, F c, F s) {   // a * (c - i s)
   return mk<F>(fma(a.x, c, a.y * s), fma(a.y, c, -a.x * s));
 }
@@ -50,20 +72,39 @@ template <typename F> __device__ __forceinline__ void twiddle16(cx<F> (&v)[16], 
   v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
 }
 
+// v[r] *= tab[16 r + k], r = 1..15: the powers come from a table (r-major, so that the 16 values of k a
+// warp holds are consecutive 16-byte words: two wavefronts per load)
+template <typename F> __device__ __forceinline__ void twiddle16_tab(cx<F> (&v)[16], const cx<F>* __restrict__ tabk) {
+#pragma unroll
+  for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], tabk[16 * r]);
+}
+
 // The two radix-16 passes of a 1024-point row, 64 threads (t = 0..63), in place in
 // `buf` (phys16 layout).  `g`: the staged packed real row (RowSrcF32 / RowSrcI16); `tw16`: 16
 // factors e^{-2 pi i k/256}.  sync(): barrier over the 64 threads of the row.
 // Afterwards buf[p + 256 c] (c = 0..3, p < 256) is the input of the last radix-4 pass.
-template <typename F, typename Src, typename Sync, typename Fn, typename Fn2>
-__device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw16, int t,
+template <typename F, bool TWTAB = false, bool ICVT = false, typename Src, typename Sync, typename Fn, typename Fn2>
+__device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx<F>* __restrict__ tw16,
+                                               const cx<F>* __restrict__ tab, int t,
                                                const Src g, bool gvalid, Sync sync,
                                                Fn after_first_reads, Fn2 in_last_pass) {
   cx<F> v[16];
   if (gvalid) {      // uniform over the row
+    if constexpr (ICVT) {
+      unsigned amax = 0u;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float2 x = g(t + 64 * r);
-      v[r] = mk<F>((F)x.x, (F)x.y);
+      for (int r = 0; r < 16; ++r) {
+        const float2 x = g(t + 64 * r);
+        amax = max(amax, max(__float_as_uint(x.x) & 0x7fffffffu, __float_as_uint(x.y) & 0x7fffffffu));
+        v[r] = mk<F>((F)f2d_bits(x.x), (F)f2d_bits(x.y));
+      }
+      if (amax >= 0x7f800000u) v[0].x = F(__longlong_as_double(0x7ff8000000000000LL));   // Inf/NaN sample: poison the row
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 x = g(t + 64 * r);
+        v[r] = mk<F>((F)x.x, (F)x.y);
+      }
     }
   } else {
 #pragma unroll
@@ -76,12 +117,12 @@ __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx
   for (int k = 0; k < 16; ++k) buf[phys16(16 * t + k)] = v[dft16_at(k)];
   sync();
   const int k = t & 15;
-  const cx<F> w1 = tw16[k];
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = buf[phys16(t + 64 * r)];
   sync();
   in_last_pass();
-  twiddle16(v, w1);
+  if constexpr (TWTAB) twiddle16_tab(v, tab + k);
+  else twiddle16(v, tw16[k]);
   dft16(v);
   const int j0 = (t - k) * 16 + k;
 #pragma unroll

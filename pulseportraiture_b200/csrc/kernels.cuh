@@ -84,6 +84,11 @@ __device__ __noinline__ float2 rot2pi(float vx, float vy, double x) {
   return make_float2(vx * cf - vy * sf, vx * sf + vy * cf);
 }
 
+// fire-and-forget float2 add in L2 (sm_90+: red.global.add.v2.f32); no destination registers
+__device__ __forceinline__ void red_add_f32x2(float2* p, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
+
 __device__ __forceinline__ double wrap_phase(double phi) {
   // pplib.py:2611-2613 / pptoaslib.py:1056-1057: onto [-0.5, 0.5)
   if (fabs(phi) >= 0.5) phi = phi - floor(phi);
@@ -308,7 +313,11 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<F>* tw = reinterpret_cast<cx<F>*>(smem_raw);                       // [PL::kTwTotal] (+pad)
   cx<F>* bufs = tw + ((PL::kTwTotal + 1) & ~1);                         // [NS][N]
-  float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * N);   // [NS][2][2N]
+  float* stage_all = reinterpret_cast<float*>(bufs + (size_t)NS * N);   // [NS][NSTG][2N]
+  constexpr int kAcc = PL::kAcc;                  // where the guess profile accumulates (spectra_plan.cuh)
+  constexpr bool kMcLate = PL::kMcLate;
+  static_assert(kAcc == 0 || NS == 1, "shared / global guess accumulators: one row slot per CTA");
+  float2* acc_sh = reinterpret_cast<float2*>(stage_all + (size_t)NS * PL::kStages * 2 * N);   // [N] (kAcc == 2)
   __shared__ double red[2][NS][(T >= 32 ? T / 32 : 1)][2];   // per-warp power sums, by row parity
   __shared__ __align__(8) unsigned long long mbar[NS][2];
   const int tid = threadIdx.x, slot = tid / T, t = tid % T;
@@ -331,9 +340,22 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   const double numean = a.nu_mean[s];
   const double numean2 = 1.0 / (numean * numean);
 
-  float2 acc[NACC];
+  float2 acc[kAcc == 0 ? NACC : 1];
+  float2* const part_row = want_guess ? a.partial + ((size_t)sl * a.nparts + blockIdx.x * NS + slot) * N : nullptr;
+  if constexpr (kAcc == 0) {
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < NACC; ++i) acc[i] = make_float2(0.f, 0.f);
+  } else if (want_guess) {   // every slot of the CTA's partial row has one owner thread: zero it, then add row by row
+#pragma unroll
+    for (int i = 0; i < NUNIT; ++i) {
+#pragma unroll
+      for (int q = 0; q < NOUT; ++q) {
+        const int sk = PL::slot_of(t, i, q, t == 0);
+        if constexpr (kAcc == 1) part_row[sk] = make_float2(0.f, 0.f);
+        else acc_sh[sk] = make_float2(0.f, 0.f);
+      }
+    }
+  }
   double keep_all = 0.0, keep_top = 0.0;
   // thread r of a slot collects the power sums of row r (T > 32: from the per-warp totals)
   auto latch = [&](int r) {
@@ -397,25 +419,39 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     const bool doX = a.X != nullptr && inrange;
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
     const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
+    static_assert(!kMcLate || kMix, "late conj(model) loads: mixed-precision plans only");
     cx<F> mc64[kMix ? 1 : NACC];
-    cx<float> mc32[kMix ? NACC : 1];
-    auto load_mc = [&]() {
+    cx<float> mc32[kMix ? (kMcLate ? NOUT : NACC) : 1];
+    auto load_mc_unit = [&](int i) {   // kMcLate: the loads of unit i, issued right before its split
       if (doX && used) {
-        if constexpr (kMix) mc64[0] = mc[t];
+        if (i == 0) mc64[0] = mc[t];
 #pragma unroll
-        for (int i = 0; i < NUNIT; ++i) {
+        for (int q = 0; q < NOUT; ++q) mc32[q] = mcf[slot_of(i, q)];
+      } else {
+        if (i == 0) mc64[0] = mk<F>(0.0, 0.0);
 #pragma unroll
-          for (int q = 0; q < NOUT; ++q) {
-            if constexpr (kMix) mc32[NOUT * i + q] = mcf[slot_of(i, q)];
-            else mc64[NOUT * i + q] = mc[slot_of(i, q)];
+        for (int q = 0; q < NOUT; ++q) mc32[q] = mk<float>(0.f, 0.f);
+      }
+    };
+    auto load_mc = [&]() {
+      if constexpr (!kMcLate) {
+        if (doX && used) {
+          if constexpr (kMix) mc64[0] = mc[t];
+#pragma unroll
+          for (int i = 0; i < NUNIT; ++i) {
+#pragma unroll
+            for (int q = 0; q < NOUT; ++q) {
+              if constexpr (kMix) mc32[NOUT * i + q] = mcf[slot_of(i, q)];
+              else mc64[NOUT * i + q] = mc[slot_of(i, q)];
+            }
           }
-        }
-      } else {   // unused rows store zeros
-        if constexpr (kMix) mc64[0] = mk<F>(0.0, 0.0);
+        } else {   // unused rows store zeros
+          if constexpr (kMix) mc64[0] = mk<F>(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) {
-          if constexpr (kMix) mc32[i] = mk<float>(0.f, 0.f);
-          else mc64[i] = mk<F>(0.0, 0.0);
+          for (int i = 0; i < NACC; ++i) {
+            if constexpr (kMix) mc32[i] = mk<float>(0.f, 0.f);
+            else mc64[i] = mk<F>(0.0, 0.0);
+          }
         }
       }
     };
@@ -433,6 +469,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
 #pragma unroll
     for (int i = 0; i < NUNIT; ++i) {
       cx<F> d[NOUT];
+      if constexpr (kMcLate) load_mc_unit(i);
       const F dc_term = PL::template split<F>(buf, tw, t, i, first, d);   // DC of the row (special unit only)
       // a NaN / Inf sample makes every harmonic of the row non-finite: such a row must not enter
       // the profile for the FFTFIT guess (its sigma comes out non-finite, so the fit skips it too)
@@ -451,7 +488,8 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
           sa = fma(d[q].x, d[q].x, sa);
           sa = fma(d[q].y, d[q].y, sa);
         }
-        vx[q] = (float)d[q].x; vy[q] = (float)d[q].y;
+        if constexpr ((PL::kCvt & 2) != 0) { vx[q] = d2f_bits(d[q].x); vy[q] = d2f_bits(d[q].y); }
+        else { vx[q] = (float)d[q].x; vy[q] = (float)d[q].y; }
       }
       s_all += sa0 + sa1;
       if (doX) {        // uniform over the row
@@ -463,7 +501,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
           if constexpr (kMix) lo = (i == 0 && q == 0) && (t < kLo);
           else lo = true;
           if (!lo) {
-            const cx<float> m = mc32[kMix ? idx : 0];
+            const cx<float> m = mc32[kMix ? (kMcLate ? q : idx) : 0];
             Xrow[sk] = make_float2(fmaf(vx[q], m.x, -vy[q] * m.y), fmaf(vx[q], m.y, vy[q] * m.x));
           } else {
             const cx<F> pr = cmul(d[q], mc64[kMix ? 0 : idx]);
@@ -489,8 +527,16 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       if (wrow != 0.f) {   // uniform: 0 when no guess is wanted, the row is unused or not finite
 #pragma unroll
         for (int q = 0; q < NOUT; ++q) {
-          acc[NOUT * i + q].x = fmaf(wrow, vx[q], acc[NOUT * i + q].x);
-          acc[NOUT * i + q].y = fmaf(wrow, vy[q], acc[NOUT * i + q].y);
+          if constexpr (kAcc == 0) {
+            acc[NOUT * i + q].x = fmaf(wrow, vx[q], acc[NOUT * i + q].x);
+            acc[NOUT * i + q].y = fmaf(wrow, vy[q], acc[NOUT * i + q].y);
+          } else if constexpr (kAcc == 1) {
+            red_add_f32x2(part_row + slot_of(i, q), wrow * vx[q], wrow * vy[q]);
+          } else {
+            float2* const p = acc_sh + slot_of(i, q);
+            const float2 o = *p;
+            *p = make_float2(fmaf(wrow, vx[q], o.x), fmaf(wrow, vy[q], o.y));
+          }
         }
       }
     }
@@ -526,17 +572,23 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       a.Sdn[o] = ok ? keep_all / sF2 : 0.0;
     }
   }
-  if (want_guess) {
-    const int part = blockIdx.x * NS + slot;
-    float2* pr = a.partial + ((size_t)sl * a.nparts + part) * N;
+  if (want_guess && kAcc != 1) {
     const bool first = (t == 0);
 #pragma unroll
     for (int i = 0; i < NUNIT; ++i) {
 #pragma unroll
-      for (int q = 0; q < NOUT; ++q) pr[PL::slot_of(t, i, q, first)] = acc[NOUT * i + q];
+      for (int q = 0; q < NOUT; ++q) {
+        const int sk = PL::slot_of(t, i, q, first);
+        if constexpr (kAcc == 0) part_row[sk] = acc[NOUT * i + q];
+        else part_row[sk] = acc_sh[sk];
+      }
     }
   }
 }
+
+}  // namespace ppb
+#include "spectra16.cuh"
+namespace ppb {
 
 // ----------------------------------------------------------------------------
 // k_guess: K4, one CTA (256 threads) per profile / subint.
@@ -2233,6 +2285,8 @@ struct RotateArgs {
   const double* nu2;    // [nchan]
   const double* taus;   // [nchan] scattering times [rot] or null: multiply harmonic k by 1/(1 + 2 pi i k tau_n)
                         // (scattering_portrait_FT, pplib.py:4080-4095)
+  const double* resp;   // [nchan,N+1] real per-harmonic response or null: multiply harmonic k of channel n by resp[n][k]
+                        // (instrumental_response_port_FT, pptoaslib.py:147-179; pptoas.py:388-394)
   const void* twN;
   const void* tw2N;
   int nsub, nchan;
@@ -2298,6 +2352,7 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
   cx<T>* other = (Z == bufA) ? bufB : bufA;
   const double theta = rot_theta(a, s, ch);
   const double wtau = a.taus ? kTwoPi * a.taus[ch] : 0.0;
+  const double* const resp = a.resp ? a.resp + (size_t)ch * (N + 1) : nullptr;
 #pragma unroll
   for (int i = 0; i < G::kPairs; ++i) {
     const int p = t_row + 1 + i * G::kTRow;
@@ -2307,10 +2362,12 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
       double c, sn;
       cis2pi((double)p * theta, c, sn);
       if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)p);
+      if (resp) { const double g = resp[p]; c *= g; sn *= g; }
       dp = cmul(dp, mk<T>((T)c, (T)sn));
       if (p < N / 2) {
         cis2pi((double)(N - p) * theta, c, sn);
         if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)(N - p));
+        if (resp) { const double g = resp[N - p]; c *= g; sn *= g; }
         dq = cmul(dq, mk<T>((T)c, (T)sn));
       } else {
         dq = dp;
@@ -2322,10 +2379,11 @@ __global__ void __launch_bounds__(256) k_rotate(RotateArgs a) {
     }
   }
   if (t_row == 0) {
-    const T d0 = Z[0].x + Z[0].y;
+    T d0 = Z[0].x + Z[0].y;
     double c, sn;
     cis2pi((double)N * theta, c, sn);
     if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)N);
+    if (resp) { d0 *= (T)resp[0]; c *= resp[N]; }
     const T dN = (Z[0].x - Z[0].y) * (T)c;   // irfft keeps the real part of the Nyquist term
     Z[0] = mk<T>(T(0.5) * (d0 + dN), -T(0.5) * (d0 - dN));
   }

@@ -8,11 +8,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
 #include "../../include/ppb200.h"
 #include "kernels.cuh"
+#include "tw_host.h"
 
 using namespace ppb;
 
@@ -90,7 +92,7 @@ struct pp_plan {
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
   DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
-  DBuf rot_gm, rot_nugm, al_w, al_out, al_wsum, ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
+  DBuf resp, rot_gm, rot_nugm, al_w, al_out, al_wsum, ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
       rot_phase, rot_dm, rot_P, rot_nuref;
   // chunk-sized
   DBuf X, Xlo, partial, data_stage[2], Dspec, Ddc, al_acc, al_wparts;
@@ -206,11 +208,7 @@ template <int N, typename T> static size_t fft_smem_bytes() {
     default: return fail(-1, "unsupported nbin %d", 2 * (Nval)); \
   }
 
-template <int N> static size_t spectra_smem_bytes() {
-  using PL = SpecPlan<N>;
-  return (size_t)(((PL::kTwTotal + 1) & ~1) + PL::kSlots * N) * sizeof(cx<double>) +
-         (size_t)PL::kSlots * PL::kStages * (2 * N) * sizeof(float);
-}
+template <int N> static size_t spectra_smem_bytes() { return spectra_smem_bytes_of<N>(); }
 // row slots per k_spectra CTA for this nbin
 static int spectra_slots(int N) {
   switch (N) {
@@ -224,40 +222,32 @@ static int spectra_slots(int N) {
   }
 }
 
-static double2 unit_root(long num, long den) {   // e^{-2 pi i num/den} with exact quadrant values
-  num %= den;
-  if (num == 0) return make_double2(1.0, 0.0);
-  if (4 * num == den) return make_double2(0.0, -1.0);
-  if (2 * num == den) return make_double2(-1.0, 0.0);
-  if (4 * num == 3 * den) return make_double2(0.0, 1.0);
-  const double a = -2.0 * M_PI * (double)num / (double)den;
-  return make_double2(cos(a), sin(a));
-}
-// twiddle tables of the row-transform plan (spectra_plan.cuh)
-template <class PL> struct TwBuilder;
-template <> struct TwBuilder<SpecPlan16> {
-  static void build(std::vector<double2>& out) {
-    out.assign(SpecPlan16::kTwTotal, make_double2(0.0, 0.0));
-    for (int k = 0; k < 16; ++k) out[k] = unit_root(k, 256);
-    for (int p2 = 0; p2 <= 128; ++p2) out[SpecPlan16::kSplitOff + p2] = unit_root(p2, 2048);
-  }
-};
-template <int N> static void build_tw8_impl(std::vector<double2>& out);
-template <int N> struct TwBuilder<SpecPlan8<N>> {
-  static void build(std::vector<double2>& out) { build_tw8_impl<N>(out); }
-};
 template <int N> static void build_tw8(std::vector<double2>& out) { TwBuilder<SpecPlan<N>>::build(out); }
-// per-pass twiddle tables in the layout of TwLayout<N> (fft8.cuh)
-template <int N> static void build_tw8_impl(std::vector<double2>& out) {
-  using P = Plan8<N>;
-  using L = TwLayout<N>;
-  out.assign(L::kTotal, make_double2(0.0, 0.0));
-  auto root = unit_root;
-  for (int i = 1; i < P::n; ++i) {
-    const int Ns = L::ns(i), R = P::radix(i);
-    for (int k = 0; k < Ns; ++k) out[L::off(i) + k] = root((long)k, (long)Ns * R);
+
+// k_spectra16 (nbin = 2048): one instantiation per (16-bit samples, FFTFIT guess, kept data spectra)
+template <bool I16, bool GUESS, bool KEEPD> static cudaError_t spectra16_attr() {
+  return cudaFuncSetAttribute(k_spectra16<I16, GUESS, KEEPD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)spectra_smem_bytes_of<1024, SpecPlan16>());
+}
+static cudaError_t spectra16_attrs() {
+  cudaError_t e;
+#define S16_(a, b, c) e = spectra16_attr<a, b, c>(); if (e != cudaSuccess) return e;
+  S16_(false, false, false) S16_(false, false, true) S16_(false, true, false) S16_(false, true, true)
+  S16_(true, false, false) S16_(true, false, true) S16_(true, true, false) S16_(true, true, true)
+#undef S16_
+  return cudaSuccess;
+}
+static void launch_spectra16(bool i16, bool guess, bool keepd, dim3 grid, cudaStream_t st, const SpectraArgs& a) {
+  const size_t sm = spectra_smem_bytes_of<1024, SpecPlan16>();
+#define L16_(A, B, C) k_spectra16<A, B, C><<<grid, 64, sm, st>>>(a)
+  if (!i16) {
+    if (!guess) { if (!keepd) L16_(false, false, false); else L16_(false, false, true); }
+    else { if (!keepd) L16_(false, true, false); else L16_(false, true, true); }
+  } else {
+    if (!guess) { if (!keepd) L16_(true, false, false); else L16_(true, false, true); }
+    else { if (!keepd) L16_(true, true, false); else L16_(true, true, true); }
   }
-  for (int p2 = 0; p2 <= N / 2; ++p2) out[L::kSplitOff + p2] = root(p2, 2L * N);
+#undef L16_
 }
 
 template <int N> static cudaError_t setup_attrs() {
@@ -333,6 +323,7 @@ extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_pl
     cudaError_t e = cudaSuccess;
     DISPATCH_N(N, e = setup_attrs<NN>());
     CK(e);
+    if (N == 1024) CK(spectra16_attrs());
     std::vector<double2> t8;
     DISPATCH_N(N, build_tw8<NN>(t8));
     CK(pl->tw8.need(t8.size() * sizeof(double2)));
@@ -346,7 +337,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -778,7 +769,9 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      if (i16) {
+      if (N == 1024 && G <= kSpec16MaxRows && std::is_same<SpecPlan<1024>, SpecPlan16>::value) {
+        launch_spectra16(i16, want_guess, want_align, dim3(gx, ns), pl->stream, a);
+      } else if (i16) {
         DISPATCH_N(N, (k_spectra<NN, SpecPlan<NN>, true><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a)));
       } else {
         DISPATCH_N(N, k_spectra<NN><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a));
@@ -1058,7 +1051,7 @@ extern "C" int pp_rotate_full_batch(pp_plan_t* pl, const float* in, float* outp,
   if (stage_in(pl, pl->rot_nugm, nu_GM, (size_t)nsub, &dng)) return -2;
   RotateArgs a;
   a.in = din; a.out = dout; a.phase = dph; a.DM = ddm; a.P = dP; a.nu_ref = dnr; a.GM = dgm; a.nu_GM = dng;
-  a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.nsub = nsub; a.nchan = nchan;
+  a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.resp = nullptr; a.nsub = nsub; a.nchan = nchan;
   const long nrows = (long)nsub * nchan;
   if (pl->fft_precision == 64) {
     a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
@@ -1085,6 +1078,55 @@ extern "C" int pp_rotate_batch(pp_plan_t* pl, const float* in, float* outp, int3
   return pp_rotate_full_batch(pl, in, outp, nsub, phase, DM, nullptr, P, nu_ref, nullptr);
 }
 
+extern "C" int pp_apply_response_batch(pp_plan_t* pl, const float* in, float* outp, int32_t nsub, const double* resp) {
+  if (!pl || !in || !outp || !resp) return fail(-1, "NULL argument");
+  if (nsub < 1) return fail(-1, "nsub must be >= 1");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan;
+  const size_t tot = (size_t)nsub * nchan * 2 * N;
+  const float* din;
+  if (stage_in(pl, pl->rot_in, in, tot, &din)) return -2;
+  float* dout = outp;
+  const bool out_dev = is_device_ptr(outp);
+  if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  const double* dresp;
+  if (stage_in(pl, pl->resp, resp, (size_t)nchan * (N + 1), &dresp)) return -2;
+  if (!pl->gm_zero.p) {
+    const double z = 0.0, o = 1.0;
+    CK(pl->gm_zero.need(sizeof(double)));
+    CK(pl->gm_one.need(sizeof(double)));
+    CK(cudaMemcpyAsync(pl->gm_zero.p, &z, sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaMemcpyAsync(pl->gm_one.p, &o, sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaStreamSynchronize(pl->stream));
+  }
+  // zero rotation for every subint: phase, DM from a zero-filled array
+  CK(pl->rot_phase.need(sizeof(double) * nsub));
+  CK(pl->rot_P.need(sizeof(double) * nsub));
+  CK(cudaMemsetAsync(pl->rot_phase.p, 0, sizeof(double) * nsub, pl->stream));
+  {
+    std::vector<double> ones((size_t)nsub, 1.0);
+    CK(cudaMemcpyAsync(pl->rot_P.p, ones.data(), sizeof(double) * nsub, cudaMemcpyHostToDevice, pl->stream));
+    CK(cudaStreamSynchronize(pl->stream));
+  }
+  RotateArgs a;
+  a.in = din; a.out = dout; a.phase = pl->rot_phase.as<double>(); a.DM = pl->rot_phase.as<double>();
+  a.P = pl->rot_P.as<double>(); a.nu_ref = pl->rot_P.as<double>(); a.GM = nullptr; a.nu_GM = nullptr;
+  a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.resp = dresp; a.nsub = nsub; a.nchan = nchan;
+  a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
+  if (!pl->nu2.p) { CK(pl->nu2.need(sizeof(double) * nchan)); CK(cudaMemsetAsync(pl->nu2.p, 0, sizeof(double) * nchan, pl->stream)); a.nu2 = pl->nu2.as<double>(); }
+  const long nrows = (long)nsub * nchan;
+  DISPATCH_N(N, {
+    const int rows = RowGeom<NN>::kRows;
+    k_rotate<NN, double><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+  });
+  pl->stats.launches++;
+  CK(cudaGetLastError());
+  if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
 extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsub, const double* phase, const double* DM,
                                    const double* P, const double* nu_ref, const double* weights, double* aligned,
                                    double* wsum) {
@@ -1106,7 +1148,7 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   CK(pl->al_wsum.need(sizeof(double) * nchan));
   AlignArgs a;
   a.r.in = din; a.r.out = nullptr; a.r.phase = dph; a.r.DM = ddm; a.r.P = dP; a.r.nu_ref = dnr; a.r.GM = nullptr;
-  a.r.nu_GM = nullptr; a.r.taus = nullptr; a.r.nu2 = pl->nu2.as<double>(); a.r.twN = pl->twN64.p; a.r.tw2N = pl->tw2N64.p;
+  a.r.nu_GM = nullptr; a.r.taus = nullptr; a.r.resp = nullptr; a.r.nu2 = pl->nu2.as<double>(); a.r.twN = pl->twN64.p; a.r.tw2N = pl->tw2N64.p;
   a.r.nsub = nsub; a.r.nchan = nchan;
   a.weights = dw; a.aligned = pl->al_out.as<double>(); a.wsum = pl->al_wsum.as<double>();
   DISPATCH_N(N, {
@@ -1159,7 +1201,7 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
     RotateArgs a;
     a.in = dout; a.out = dout; a.phase = pl->gm_zero.as<double>(); a.DM = pl->gm_zero.as<double>();
     a.P = pl->gm_one.as<double>(); a.nu_ref = pl->gm_one.as<double>(); a.GM = nullptr; a.nu_GM = nullptr;
-    a.nu2 = pl->nu2.as<double>(); a.taus = pl->gm_taus.as<double>(); a.nsub = 1; a.nchan = nchan;
+    a.nu2 = pl->nu2.as<double>(); a.taus = pl->gm_taus.as<double>(); a.resp = nullptr; a.nsub = 1; a.nchan = nchan;
     a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
     DISPATCH_N(N, {
       const int rows = RowGeom<NN>::kRows;

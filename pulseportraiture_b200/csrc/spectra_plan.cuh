@@ -35,6 +35,10 @@ template <int N> struct SpecPlan8 {
   static constexpr int kTwTotal = TwLayout<N>::kTotal;
   static constexpr int kMinBlocks = (N >= 2048 ? 1 : PP_SPECTRA_MINB);
   static constexpr int kStages = 2;
+  static constexpr int kAcc = 0;
+  static constexpr bool kMcLate = false;
+  static constexpr int kCvt = 0;
+  static constexpr int kAccSmemBytes = 0;
   __device__ static __forceinline__ void sync(int slot) { slot_sync<N>(slot); }
   template <typename F, typename Src, typename Fn, typename Fn2>
   __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int slot, const Src g, bool used,
@@ -58,19 +62,36 @@ template <int N> struct SpecPlan8 {
   __device__ static __forceinline__ bool top(int i, int q, bool first) { return q == 1 || (q == 0 && i == 0 && first); }
 };
 
-struct SpecPlan16 {
+// Knobs of the radix-16 plan (template parameters so that variants can be timed side by side,
+// tools/micro/spectra_probe.cu):
+//   STAGES  staged raw rows per CTA (TMA prefetch depth)
+//   MINB    CTAs per SM asked of the compiler (register budget 65536 / (64 MINB))
+//   ACC     where the partial profile spectra of the FFTFIT guess accumulate over the CTA's rows:
+//           0 registers (32 per thread), 1 red.global.add.v2.f32 on the CTA's own partial row
+//           (one thread per address, program order: still deterministic), 2 shared memory
+//   MCLATE  conj(model) loads issued per split unit instead of inside the last transform pass
+//   TWTAB   pass-2 twiddle powers w^2..w^15 from a shared-memory table instead of registers
+//   CVT     bit 0: float -> double of the samples by integer operations (ALU pipe) instead of F2F (XU pipe);
+//           bit 1: double -> float of the spectra likewise (round to nearest even)
+template <int STAGES, int MINB, int ACC, bool MCLATE, bool TWTAB, int CVT = 0>
+struct SpecPlan16T {
   static constexpr int N = 1024;
   static constexpr int kT = 64, kSlots = 1, kThreads = 64;
   static constexpr int kUnits = 2, kOut = 8;
   static constexpr int kSplitOff = 16;                    // tw[0..15] = e^{-2 pi i k/256}; then e^{-2 pi i p/2048}, p <= 128
-  static constexpr int kTwTotal = kSplitOff + 129;
-  static constexpr int kMinBlocks = PP_SPECTRA16_MINB;
-  static constexpr int kStages = PP_SPECTRA16_STAGES;
+  static constexpr int kTabOff = kSplitOff + 130;         // TWTAB: tw[kTabOff + 16 r + k] = e^{-2 pi i k r/256}
+  static constexpr int kTwTotal = TWTAB ? kTabOff + 256 : kSplitOff + 129;
+  static constexpr int kMinBlocks = MINB;
+  static constexpr int kStages = STAGES;
+  static constexpr int kAcc = ACC;
+  static constexpr bool kMcLate = MCLATE;
+  static constexpr int kCvt = CVT;
+  static constexpr int kAccSmemBytes = ACC == 2 ? N * 8 : 0;
   __device__ static __forceinline__ void sync(int) { __syncthreads(); }
   template <typename F, typename Src, typename Fn, typename Fn2>
   __device__ static __forceinline__ void transform(cx<F>* buf, const cx<F>* tw, int t, int, const Src g, bool used,
                                                    Fn after_first_reads, Fn2 in_last_pass) {
-    fft16_rows1024<F>(buf, tw, t, g, used, []() { __syncthreads(); }, after_first_reads, in_last_pass);
+    fft16_rows1024<F, TWTAB, (CVT & 1) != 0>(buf, tw, tw + kTabOff, t, g, used, []() { __syncthreads(); }, after_first_reads, in_last_pass);
   }
   template <typename F>
   __device__ static __forceinline__ F split(const cx<F>* buf, const cx<F>* tw, int t, int i, bool first, cx<F> (&d)[kOut]) {
@@ -86,6 +107,16 @@ struct SpecPlan16 {
   }
   __device__ static __forceinline__ bool top(int i, int q, bool first) { return q == 1 || q == 6 || (q == 0 && i == 0 && first); }
 };
+#ifndef PP_SPECTRA16_ACC
+#define PP_SPECTRA16_ACC 0
+#endif
+#ifndef PP_SPECTRA16_MCLATE
+#define PP_SPECTRA16_MCLATE 0
+#endif
+#ifndef PP_SPECTRA16_TWTAB
+#define PP_SPECTRA16_TWTAB 0
+#endif
+using SpecPlan16 = SpecPlan16T<PP_SPECTRA16_STAGES, PP_SPECTRA16_MINB, PP_SPECTRA16_ACC, PP_SPECTRA16_MCLATE != 0, PP_SPECTRA16_TWTAB != 0>;
 
 template <int N> struct SpecPlanSel { using type = SpecPlan8<N>; };
 #if PP_SPECTRA_R16

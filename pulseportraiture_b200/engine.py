@@ -366,6 +366,25 @@ class WidebandPlan(object):
             _ptr(bc(nu_ref), np.float64, keep, "nu_ref")), "pp_rotate_batch")
         return out
 
+    def apply_response_batch(self, data, resp, out=None):
+        """out[s, n] = irfft(resp[n] * rfft(data[s, n])): a real per-channel, per-harmonic response
+        [nchan, nbin/2 + 1] applied in the Fourier domain (pp_apply_response_batch; the model
+        multiply of pptoas.py:388-394)."""
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        if out is None:
+            if _is_torch(data):
+                import torch
+                out = torch.empty_like(data)
+            else:
+                out = np.empty((nsub, self.nchan, self.nbin), dtype=np.float32)
+        op = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        _ffi.check(self._lib.pp_apply_response_batch(
+            self._h, ip, op, nsub,
+            _ptr(resp, np.float64, keep, "resp", (self.nchan, self.nbin // 2 + 1))), "pp_apply_response_batch")
+        return out
+
     def _rotate_full(self, data, phase, DM, GM, P, nu_DM, nu_GM, out=None):
         keep = []
         nsub = int(data.shape[0])

@@ -37,10 +37,7 @@ def gather_results(local, group=None, dst=0):
     dist.gather_object(local, bucket, dst=dst, group=group)
     if rank != dst:
         return None
-    out = {}
-    for k in bucket[0]:
-        out[k] = np.concatenate([np.asarray(b[k]) for b in bucket], axis=0)
-    return out
+    return merge_results([b for b in bucket if b is not None and len(b)])
 
 
 class MultiGPUFitter(object):
@@ -60,6 +57,12 @@ class MultiGPUFitter(object):
         for p in self.plans:
             p.close()
 
+    # keyword arguments of WidebandPlan.fit_batch that carry one row per subint
+    PER_SUBINT = ("errs", "chan_mask", "weights", "init", "DM_guess", "snrs", "nu_fits", "nu_outs",
+                  "scat_guess", "dat_scl", "dat_offs")
+    # results that are sums over the subints of a shard (the fused ppalign accumulation)
+    SUMMED = ("align_sum", "align_wsum")
+
     def fit_batch(self, data, P, **kw):
         nsub = int(data.shape[0])
         world = len(self.plans)
@@ -70,8 +73,7 @@ class MultiGPUFitter(object):
         def slice_kw(a, b):
             out = {}
             for k, v in kw.items():
-                if hasattr(v, "shape") and len(getattr(v, "shape", ())) >= 1 \
-                        and v.shape[0] == nsub:
+                if k in self.PER_SUBINT and v is not None and np.ndim(v) >= 1 and np.shape(v)[0] == nsub:
                     out[k] = v[a:b]
                 else:
                     out[k] = v
@@ -95,4 +97,16 @@ class MultiGPUFitter(object):
             if e is not None:
                 raise e
         parts = [r for r in results if r is not None]
-        return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+        return merge_results(parts, self.SUMMED)
+
+
+def merge_results(parts, summed=("align_sum", "align_wsum")):
+    """Merge per-shard result dicts: per-subint arrays are concatenated in shard order, the fused
+    ppalign sums (one array per shard) are added."""
+    out = {}
+    for k in parts[0]:
+        if k in summed:
+            out[k] = np.sum([np.asarray(p[k]) for p in parts], axis=0)
+        else:
+            out[k] = np.concatenate([np.asarray(p[k]) for p in parts], axis=0)
+    return out

@@ -30,10 +30,38 @@ wid_max = 0.25
 default_model = "000"
 binshift = 1.0
 
-# return codes of the device solver, in the spirit of RCSTRINGS (pplib.py:111)
-RCSTRINGS = {"0": "CONVERGED: Newton step below tolerance.",
-             "1": "MAXITER: Maximum number of objective passes reached.",
-             "3": "NONFINITE: Objective is not finite."}
+# Return codes.  The device solver reports 0 converged / 1 pass limit / 3 non-finite objective
+# (DEVICE_RCSTRINGS).  The facades hand callers the scipy status the reference's minimiser would
+# have returned for the same outcome (pplib.py:2159-2171, pptoaslib.py:1018-1033: callers treat
+# TNC's {1, 2, 4} and trust-ncg's 2 as the normal exits), with the messages of pplib.py:111-119;
+# the device's own code stays available as the extra DataBunch field ``device_return_code``.
+DEVICE_RCSTRINGS = {"0": "CONVERGED: Newton step below tolerance.",
+                    "1": "MAXITER: Maximum number of objective passes reached.",
+                    "3": "NONFINITE: Objective is not finite."}
+RCSTRINGS = {'-1': 'INFEASIBLE: Infeasible (low > up).',
+             '0': 'LOCALMINIMUM: Local minima reach (|pg| ~= 0).',
+             '1': 'FCONVERGED: Converged (|f_n-f_(n-1)| ~= 0.)',
+             '2': 'XCONVERGED: Converged (|x_n-x_(n-1)| ~= 0.)',
+             '3': 'MAXFUN: Max. number of function evaluations reach.',
+             '4': 'LSFAIL: Linear search failed.',
+             '5': 'CONSTANT: All lower bounds are equal to the upper bounds.',
+             '6': 'NOPROGRESS: Unable to progress.',
+             '7': 'USERABORT: User requested end of minimization.'}
+# device code -> scipy status, per minimiser
+_RC_MAP = {'TNC': {0: 1, 1: 3, 3: 6},            # FCONVERGED / MAXFUN / NOPROGRESS
+           'trust-ncg': {0: 2, 1: 1, 3: 3},      # "failure to predict improvement" is the normal exit
+           'Newton-CG': {0: 0, 1: 1, 3: 3}}      # success / maxiter / NaN result encountered
+_RC_BENIGN = {'TNC': (0, 1, 2, 4), 'trust-ncg': (0, 1, 2, 4), 'Newton-CG': (0, 1, 2, 4)}
+
+
+def scipy_return_code(device_rc, method='TNC'):
+    """The status scipy's ``method`` reports for the outcome the device solver reports as ``device_rc``
+    (scalar or array)."""
+    m = _RC_MAP[method]
+    if np.ndim(device_rc) == 0:
+        return m.get(int(device_rc), int(device_rc))
+    return np.array([m.get(int(v), int(v)) for v in np.asarray(device_rc).ravel()],
+                    dtype=int).reshape(np.shape(device_rc))
 
 
 class DataBunch(dict):
@@ -132,8 +160,9 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
                      init=init, nu_fits=nu_fits, nu_outs=nu_outs,
                      fit_flags=(1, 1, 0, 0, 0), semantics="fit_portrait", bounds=bounds)
     duration = time.time() - start
-    rc = int(r["return_code"][0])
-    if not quiet and rc not in (0, 1):
+    drc = int(r["return_code"][0])
+    rc = scipy_return_code(drc, 'TNC')
+    if not quiet and rc not in _RC_BENIGN['TNC']:
         if id is not None:
             ii = id[::-1].index("_")
             isub, filename = id[-ii:], id[:-ii - 1]
@@ -147,7 +176,7 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
                      nu_ref=r["nu_out"][0, 0], covariance=r["cov"][0, 0, 1],
                      chi2=r["chi2"][0], red_chi2=r["red_chi2"][0],
                      snr=r["snr"][0], duration=duration,
-                     nfeval=int(r["nfeval"][0]), return_code=rc)
+                     nfeval=int(r["nfeval"][0]), return_code=rc, device_return_code=drc)
 
 
 def get_scales(data, model, phase, DM, P, freqs, nu_ref=np.inf):

@@ -79,7 +79,9 @@ _DB_FIELDS = ["backend", "backend_delay", "bw", "doppler_factors", "DM", "dmc",
               "masks", "nbin", "nchan", "noise_stds", "npol", "nsub", "nu0",
               "ok_ichans", "ok_isubs", "parallactic_angles", "phases", "Ps",
               "SNRs", "source", "state", "subints", "subtimes", "telescope",
-              "telescope_code", "weights"]
+              "telescope_code", "weights",
+              # optional products of load_data(flux_prof=True / return_arch) that callers test for
+              "flux_prof", "prof", "prof_noise", "prof_SNR"]
 
 
 def save_databunch(path, data):
@@ -153,6 +155,56 @@ def weighted_mean(data, errs=1.0):
     return mean, sum_weights ** -0.5
 
 
+def restore_dispersion(d):
+    """What ``load_data(..., dededisperse=True)`` returns for an archive stored dedispersed
+    (dmc = 1; pptoas.py:256-265): the dispersive delays of the stored DM are put back, about the
+    centre frequency as ``arch.dededisperse()`` does, on the device (pplib.rotate_data)."""
+    out = DataBunch(**d)
+    out.subints = pplib.rotate_data(np.asarray(d.subints, dtype=np.float64), 0.0, -float(d.DM),
+                                    np.asarray(d.Ps, dtype=np.float64), np.asarray(d.freqs, dtype=np.float64),
+                                    float(d.nu0))
+    for k in _RAW_FIELDS:                        # the stored samples no longer describe the subints
+        out[k] = None
+    out.dmc = 0
+    return out
+
+
+def tscrunch_databunch(d):
+    """PSRCHIVE-free stand-in for ``load_data(..., tscrunch=True)`` (pplib.py:2690): the good
+    subints are averaged per channel with their weights (what ``arch.tscrunch()`` does for subints
+    folded with one ephemeris), the epoch and period are the duration-weighted means, the channel
+    noise levels are re-measured from the averaged profiles (get_noise on the device) and the
+    per-channel S/N add in quadrature."""
+    ok = np.asarray(d.ok_isubs, dtype=int)
+    if not len(ok):
+        return d
+    sub = np.asarray(d.subints, dtype=np.float64)[ok]            # [nok, npol, nchan, nbin]
+    w = np.asarray(d.weights, dtype=np.float64)[ok]              # [nok, nchan]
+    wsum = w.sum(axis=0)
+    avg = (sub * w[:, None, :, None]).sum(axis=0) / np.where(wsum > 0, wsum, 1.0)[None, :, None]
+    npol, nchan, nbin = avg.shape
+    tw = np.asarray(d.subtimes, dtype=np.float64)[ok]
+    tw = tw / tw.sum() if tw.sum() > 0 else np.full(len(ok), 1.0 / len(ok))
+    days = np.array([d.epochs[i].intday() for i in ok], dtype=np.float64)
+    fracs = np.array([d.epochs[i].fracday() for i in ok], dtype=np.float64)
+    day0 = int(days.min())
+    epoch = MJD(day0, float(np.sum(tw * ((days - day0) + fracs))))
+    noise = pplib.get_plan(nchan, nbin).get_noise_batch(pplib._f32(avg))     # [npol, nchan]
+    snrs = np.sqrt((np.asarray(d.SNRs, dtype=np.float64)[ok] ** 2).sum(axis=0))
+    okc = np.where(wsum > 0)[0]
+    out = DataBunch(**d)
+    out.update(subints=avg[None], weights=wsum[None], noise_stds=noise[None], SNRs=snrs[None],
+               masks=None, nsub=1, ok_isubs=np.array([0]), ok_ichans=[okc], epochs=[epoch],
+               Ps=np.array([float(np.sum(tw * np.asarray(d.Ps, dtype=np.float64)[ok]))]),
+               freqs=np.asarray(d.freqs, dtype=np.float64)[ok][:1],
+               doppler_factors=np.array([float(np.sum(tw * np.asarray(d.doppler_factors)[ok]))]),
+               parallactic_angles=np.array([float(np.sum(tw * np.asarray(d.parallactic_angles)[ok]))]),
+               subtimes=np.array([float(np.asarray(d.subtimes, dtype=np.float64)[ok].sum())]))
+    for k in _RAW_FIELDS:
+        out[k] = None
+    return out
+
+
 class GetTOAs:
     """Measure TOAs and DMs from wideband data (pptoas.py:75-743)."""
 
@@ -181,7 +233,25 @@ class GetTOAs:
         self.instrumental_response_dict = self.ird = {'DM': 0.0, 'wids': [], 'irf_types': []}
         self.quiet = quiet
 
-    def _model_for(self, phases, freqs_row, P, fit_scat=False):
+    def _model_depends_on_P(self, fit_scat, add_instrumental_response):
+        """True when the model portrait differs from subint to subint through the period: a .gmodel
+        with TAU != 0 (seconds -> rotations, pplib.py:2944-2945) or a DM-smearing instrumental
+        response (pptoaslib.py:175).  The reference rebuilds the model per subint (pptoas.py:356-394)."""
+        if add_instrumental_response and self.ird['DM']:
+            return True
+        if isinstance(self.modelfile, np.ndarray) or pplib.is_spline_model(self.modelfile) or fit_scat:
+            return False
+        return read_model(self.modelfile, quiet=True)[4][1] != 0.0
+
+    def _model_for(self, phases, freqs_row, P, fit_scat=False, add_instrumental_response=False, chan_bw=None):
+        model = self._bare_model_for(phases, freqs_row, P, fit_scat)
+        if add_instrumental_response and (self.ird['DM'] or len(self.ird['wids'])):   # pptoas.py:388-394
+            from .pptoaslib import add_instrumental_response as _air
+            model = _air(model, freqs_row, self.ird['DM'], P, self.ird['wids'], self.ird['irf_types'],
+                         chan_bw=chan_bw)
+        return model
+
+    def _bare_model_for(self, phases, freqs_row, P, fit_scat=False):
         if isinstance(self.modelfile, np.ndarray):
             self.model_name, self.ngauss = "array", 0
             return self.modelfile
@@ -213,9 +283,13 @@ class GetTOAs:
         as the reference; results fill the attribute lists of the instance."""
         if quiet is None:
             quiet = self.quiet
-        if tscrunch or show_plot or add_instrumental_response:
-            raise NotImplementedError("tscrunch / show_plot / add_instrumental_response "
-                                      "need PSRCHIVE or matplotlib and are outside the hot path")
+        if show_plot:
+            raise NotImplementedError("show_plot needs matplotlib and is outside the hot path")
+        if method not in pplib._RC_MAP:                     # pptoaslib.py:1003-1005
+            print("Method '%s' is not implemented." % method)
+            sys.exit()
+        self.tscrunch = tscrunch
+        self.add_instrumental_response = add_instrumental_response
         self.nfit = 1 + int(bool(fit_DM)) + int(bool(fit_GM)) + 2 * int(bool(fit_scat)) - \
             int(bool(fix_alpha))
         self.fit_phi, self.fit_DM, self.fit_GM = True, fit_DM, fit_GM
@@ -238,6 +312,12 @@ class GetTOAs:
                 if not quiet:
                     print("Cannot load_data(%s).  Skipping it." % datafile)
                 continue
+            if data.get("dmc"):                             # pptoas.py:256-265
+                if not quiet:
+                    print("%s is dedispersed (dmc = 1).  Restoring the dispersion." % data.filename)
+                data = restore_dispersion(data)
+            if tscrunch:                                    # load_data(..., tscrunch=True), pptoas.py:253
+                data = tscrunch_databunch(data)
             if not len(data.ok_isubs):
                 if not quiet:
                     print("No subints to fit for %s.  Skipping it." % data.filename)
@@ -259,8 +339,27 @@ class GetTOAs:
             # rebuilds the model for every subint (pptoas.py:356-379); here subints that share a
             # table share one model and one batch.
             tables, table_of = _freq_tables(freqs)
-            models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]], fit_scat)
-                      for t in np.unique(table_of[ok_isubs])}
+            if self._model_depends_on_P(fit_scat, add_instrumental_response):
+                # one model per (frequency table, period): subints with their own period get their own
+                # model and batch, as in the reference's per-subint loop
+                # (the smearing width uses the spacing of the subint's first two usable channels: the
+                # reference evaluates instrumental_response_port_FT on freqsx, pptoas.py:390-392)
+                def cbw(i):
+                    okc_ = np.asarray(d.ok_ichans[i], dtype=int)
+                    if not (add_instrumental_response and self.ird['DM']) or len(okc_) < 2:
+                        return 0.0
+                    return float(abs(freqs[i, okc_[1]] - freqs[i, okc_[0]]))
+                keys = [(int(table_of[i]), float(Ps[i]), cbw(i) if i in set(ok_isubs) else 0.0) for i in range(nsub)]
+                uniq = sorted(set(keys[i] for i in ok_isubs))
+                table_of = np.array([uniq.index(k) if k in uniq else -1 for k in keys])
+                tables = np.array([tables[k[0]] for k in uniq])
+                models = {t: self._model_for(d.phases, tables[t], uniq[t][1], fit_scat, add_instrumental_response,
+                                             chan_bw=uniq[t][2] or None)
+                          for t in range(len(uniq))}
+            else:
+                models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]],
+                                             fit_scat, add_instrumental_response)
+                          for t in np.unique(table_of[ok_isubs])}
             model = models[table_of[ok_isubs[0]]]
 
             mask = np.zeros((nsub, nchan), dtype=np.uint8)
@@ -405,13 +504,18 @@ class GetTOAs:
                                                                  profile_flux_errs[isub, okc])
                     flux_freqs[isub], _ = weighted_mean(freqsx, profile_flux_errs[isub, okc])
                 nu_refs_arr[isub] = list(r["nu_out"])
+                if nu_fits_in is not None:                  # pptoas.py:400-407
+                    nu_fits_arr[isub] = list(nu_fits_in[isub])
+                else:
+                    nu_fits_arr[isub] = [pplib.guess_fit_freq(freqsx, snrs[isub, okc])] * 3
                 phis[isub], phi_errs[isub] = phi, phi_err
                 TOAs[isub], TOA_errs[isub] = TOA_mjd, TOA_err
                 DMs[isub], DM_errs[isub] = DM, DM_err
                 GMs[isub], GM_errs[isub] = GM, GM_err
                 taus[isub], tau_errs[isub] = r["params"][3], r["param_errs"][3]
                 alphas[isub], alpha_errs[isub] = r["params"][4], r["param_errs"][4]
-                nfevals[isub], rcs[isub] = r["nfeval"], r["return_code"]
+                nfevals[isub] = r["nfeval"]
+                rcs[isub] = pplib.scipy_return_code(r["return_code"], method)   # pptoaslib.py:1017
                 scales[isub, okc] = r["scales"][okc]
                 scale_errs[isub, okc] = r["scale_errs"][okc]
                 snrs_out[isub] = r["snr"]
@@ -529,9 +633,8 @@ class GetTOAs:
         reference the scattering fit is not active in this method (tau = 0)."""
         if quiet is None:
             quiet = self.quiet
-        if tscrunch or show_plot or add_instrumental_response:
-            raise NotImplementedError("tscrunch / show_plot / add_instrumental_response "
-                                      "need PSRCHIVE or matplotlib and are outside the hot path")
+        if show_plot:
+            raise NotImplementedError("show_plot needs matplotlib and is outside the hot path")
         self.fit_flags = [1, 0]
         self.log10_tau = False
         start = time.time()
@@ -543,6 +646,10 @@ class GetTOAs:
                 if not quiet:
                     print("Cannot load_data(%s).  Skipping it." % datafile)
                 continue
+            if d.get("dmc"):                                # pptoas.py:817-826
+                d = restore_dispersion(d)
+            if tscrunch:
+                d = tscrunch_databunch(d)
             if not len(d.ok_isubs):
                 continue
             self.ok_idatafiles.append(iarch)
@@ -551,7 +658,8 @@ class GetTOAs:
             freqs = np.asarray(d.freqs, dtype=np.float64)
             Ps = np.asarray(d.Ps, dtype=np.float64)
             tables, table_of = _freq_tables(freqs)          # freqs = data.freqs[isub], pptoas.py:927
-            models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]], False)
+            models = {t: self._model_for(d.phases, tables[t], Ps[ok_isubs[table_of[ok_isubs] == t][0]], False,
+                                         add_instrumental_response)
                       for t in np.unique(table_of[ok_isubs])}
             model_of = [models[t] for t in table_of]
             pl = get_plan(nchan, nbin)

@@ -8,7 +8,83 @@ import time
 import numpy as np
 
 from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32,  # noqa: F401
-                    get_plan, scattering_times, scattering_portrait_FT)
+                    get_plan, scattering_times, scattering_portrait_FT, scipy_return_code, _RC_BENIGN)
+
+
+def gaussian_profile_FT(nbin, loc, wid, amp):
+    """Analytic Fourier transform of a Gaussian profile of FWHM ``wid`` [rot] at phase ``loc``,
+    windowed (Gaussian convolved with a sinc), sampled at the nbin/2 + 1 harmonics
+    (pptoaslib.py:14-50).  Host arithmetic: a few kB per call."""
+    from scipy.special import erf
+    nharm = nbin // 2 + 1
+    if wid <= 0.0:
+        return np.zeros(nharm, 'd')
+    sigma = wid / (2 * np.sqrt(2 * np.log(2)))
+    amp = amp * (2 * np.pi * sigma ** 2) ** 0.5
+    sigma = 1.0 / (sigma * 2 * np.pi)
+    harmind = np.arange(nharm)
+    a = sigma / ((1.0 / np.pi) * 2 ** 0.5)
+    b = harmind / (sigma * 2 ** 0.5)
+    retvals = np.exp(-b ** 2) * (erf(a - b * 1j) + erf(a + b * 1j)) / 2
+    retvals = retvals * (amp * nbin)
+    if loc != 0.0:
+        retvals = retvals * np.exp(-harmind * 2.0j * np.pi * loc)
+    return np.nan_to_num(retvals)
+
+
+def instrumental_response_FT(nbin, wid=0.0, irf_type='rect'):
+    """Fourier transform of an instrumental response of width ``wid`` [rot]: a rectangle ('rect')
+    or a Gaussian of that FWHM ('gauss') (pptoaslib.py:112-145)."""
+    nharm = nbin // 2 + 1
+    if wid == 0.0:
+        return np.ones(nharm)
+    if irf_type == 'rect':
+        return np.sinc(np.arange(nharm) * wid)
+    if irf_type == 'gauss':
+        gp_FT = gaussian_profile_FT(nbin, 0.0, wid, 1.0)
+        return gp_FT / gp_FT[0]
+    print("Unrecognized instrumental response function type '%s'." % irf_type)
+    return 0
+
+
+def instrumental_response_port_FT(nbin, freqs, DM=0.0, P=1.0, wids=[], irf_types=[], chan_bw=None):
+    """Combined instrumental responses per channel and harmonic, [nchan, nbin/2 + 1]
+    (pptoaslib.py:147-179): the product of the constant responses ``wids`` / ``irf_types`` and,
+    when DM is non-zero, of a rectangle of the per-channel smearing width
+    8.3e-6 chan_bw / (nu/GHz)^3 / P (the expression of pptoaslib.py:175, which carries no DM factor).
+    ``chan_bw`` (extra argument) overrides abs(freqs[1] - freqs[0]): get_TOAs passes the spacing of the
+    first two *usable* channels, which is what the reference computes from ``freqsx``."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    nharm = nbin // 2 + 1
+    nchan = len(freqs)
+    if DM == 0.0 and len(wids) == 0:
+        return np.ones([nchan, nharm])
+    resp = np.ones([nchan, nharm], dtype=complex)
+    for wid, irf_type in zip(wids, irf_types):
+        resp = resp * instrumental_response_FT(nbin, wid, irf_type)[None, :]
+    if DM:
+        if chan_bw is None:
+            chan_bw = abs(freqs[1] - freqs[0])
+        for ichan, freq in enumerate(freqs):
+            wid = 8.3e-6 * chan_bw / (freq / 1e3) ** 3 / P
+            resp[ichan] = resp[ichan] * instrumental_response_FT(nbin, wid, 'rect')
+    return resp
+
+
+def add_instrumental_response(model_port, freqs, DM=0.0, P=1.0, wids=[], irf_types=[], chan_bw=None):
+    """model -> irfft(instrumental_response_port_FT(...) * rfft(model)) (pptoas.py:388-394); the
+    per-harmonic multiply runs on the device (pp_apply_response_batch).  The responses of
+    pptoaslib.py:112-145 with loc = 0 are real."""
+    model_port = np.asarray(model_port)
+    nchan, nbin = model_port.shape
+    resp = instrumental_response_port_FT(nbin, freqs, DM, P, wids, irf_types, chan_bw=chan_bw)
+    if np.iscomplexobj(resp):
+        if np.abs(resp.imag).max() > 1e-14 * np.abs(resp.real).max():
+            raise ValueError("complex instrumental response")
+        resp = resp.real
+    pl = get_plan(nchan, nbin)
+    return pl.apply_response_batch(_f32(model_port)[None], np.ascontiguousarray(resp, dtype=np.float64))[0] \
+        .astype(np.float64)
 
 
 def fit_portrait_full(data_port, model_port, init_params, P, freqs,
@@ -23,8 +99,9 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
     Same arguments, units and DataBunch fields as pptoaslib.fit_portrait_full
     (pptoaslib.py:928-1096).  ``method`` is accepted for compatibility; the
     scipy minimisers are replaced by the on-device safeguarded Newton solver,
-    which converges to the same optimum (``return_code`` 0 = converged,
-    1 = max passes, 3 = non-finite objective).  ``bounds`` are used with
+    which converges to the same optimum; ``return_code`` is the scipy status ``method`` reports
+    for the same outcome (trust-ncg: 2 normal exit, 1 pass limit, 3 non-finite; pplib._RC_MAP), the
+    device's own code is the extra field ``device_return_code``.  ``bounds`` are used with
     method='TNC' only, as in the reference (pptoaslib.py:1008-1014); the
     solver treats them as an active set.
     """
@@ -55,8 +132,9 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
                      is_toa=bool(is_toa), semantics="full",
                      bounds=bounds if method == 'TNC' else None)
     duration = time.time() - start
-    rc = int(r["return_code"][0])
-    if rc not in (0, 1):
+    drc = int(r["return_code"][0])
+    rc = scipy_return_code(drc, method)
+    if rc not in _RC_BENIGN[method]:
         if sub_id is not None:
             ii = sub_id[::-1].index("_")
             isub, filename = sub_id[-ii:], sub_id[:-ii - 1]
@@ -78,7 +156,7 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
                      chi2=r["chi2"][0], red_chi2=r["red_chi2"][0],
                      snr=r["snr"][0], channel_snrs=r["channel_snrs"][0],
                      duration=duration, nfeval=int(r["nfeval"][0]),
-                     return_code=rc)
+                     return_code=rc, device_return_code=drc)
 
 
 def rotate_portrait_full(port, phi, DM, GM, freqs, nu_DM=np.inf, nu_GM=np.inf, P=None):

@@ -26,22 +26,40 @@ def get_zap_channels(data, nstd=3):
 
 
 def print_paz_cmds(datafiles, zap_channels, all_subs=False, modify=True, outfile=None, quiet=False):
-    """paz command lines for the proposed channels (ppzap.py:50-96)."""
+    """paz command lines for the proposed channels (ppzap.py:50-96).
+
+    modify=True edits the archive in place (``paz -m ... <datafile>``); otherwise one
+    ``paz -e zap <datafile>`` writes <datafile stem>.zap and every following command modifies that
+    copy.  all_subs=True zaps a channel flagged in any subint in all of them.  The lines go to
+    standard output, or are appended to ``outfile``; they are also returned."""
+    if not len(datafiles) or not len(zap_channels):
+        if not quiet:
+            print("Nothing to zap.")
+        return None
     lines = []
-    for datafile, per_sub in zip(datafiles, zap_channels):
-        if all_subs:
-            chans = sorted(set(c for sub in per_sub for c in sub))
-            if chans:
-                lines.append("paz %s -z '%s' %s" % ("-m" if modify else "-e zap",
-                                                     " ".join(map(str, chans)), datafile))
-        else:
-            for isub, chans in enumerate(per_sub):
-                for c in chans:
-                    lines.append("paz %s -I -z %d -w %d %s" % ("-m" if modify else "-e zap", c,
-                                                               isub, datafile))
+    for iarch, datafile in enumerate(datafiles):
+        count = sum(len(sub) for sub in zap_channels[iarch])
+        paz_outfile = datafile
+        if count and not modify:
+            ii = datafile[::-1].find(".")
+            paz_outfile = datafile + ".zap" if ii < 0 else datafile[:-ii] + "zap"
+            lines.append("paz -e zap %s" % datafile)
+        last_line = ""
+        for isub, bad_ichans in enumerate(zap_channels[iarch]):
+            for bad_ichan in bad_ichans:
+                if not all_subs:
+                    lines.append("paz -m -I -z %d -w %d %s" % (bad_ichan, isub, paz_outfile))
+                else:
+                    line = "paz -m -z %d %s" % (bad_ichan, paz_outfile)
+                    if line != last_line:
+                        lines.append(line)
+                    last_line = line
     text = "\n".join(lines)
     if outfile is not None:
-        open(outfile, "a").write(text + ("\n" if text else ""))
-    elif not quiet:
+        with open(outfile, "a") as fh:
+            fh.write(text + ("\n" if text else ""))
+        if not quiet:
+            print("Wrote %s." % outfile)
+    else:
         print(text)
     return lines

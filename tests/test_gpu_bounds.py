@@ -30,7 +30,7 @@ def test_fit_portrait_dm_bound_active_and_inactive():
                          ([(-0.5, 0.5), (free.DM - 5 * free.DM_err, free.DM + 5 * free.DM_err)], [0.12, 0.0])):
         ref = orc.fit_portrait(c["data"], c["model"], init, c["P"], c["freqs"], bounds=bounds)
         r = pplib.fit_portrait(c["data"], c["model"], init, c["P"], c["freqs"], bounds=bounds)
-        assert r.return_code == 0
+        assert r.device_return_code == 0 and r.return_code in (1, 2)     # a converged TNC status, pplib.py:2159
         assert abs(r.phase - ref.phase) / ref.phase_err < SIG_TOL
         assert abs(r.DM - ref.DM) / ref.DM_err < SIG_TOL
         assert abs(r.chi2 / ref.chi2 - 1) < CHI2_TOL
@@ -65,7 +65,7 @@ def test_fit_portrait_full_tnc_bounds():
     for ib, bounds in enumerate(boxes):
         ref = orc.fit_portrait_full(c["data"], c["model"], init, P, c["freqs"], bounds=bounds, **kw)
         r = pptoaslib.fit_portrait_full(c["data"], c["model"], init, P, c["freqs"], bounds=bounds, **kw)
-        assert r.return_code == 0, ib
+        assert r.device_return_code == 0 and r.return_code in (0, 1, 2), ib   # scipy's converged statuses
         for i, nm in ((0, "phi"), (1, "DM"), (3, "tau"), (4, "alpha")):
             assert abs(r[nm] - ref[nm]) / ref[nm + "_err"] < SIG_TOL, (ib, nm)
             assert rel(r[nm + "_err"], ref[nm + "_err"]) < 1e-4, (ib, nm)

@@ -947,7 +947,7 @@ def test_fit_portrait_from_far_start_values(phi0):
     c = synth.make_case(64, 512, 1500., 800., 4242, phi=0.123, dDM=3e-4)
     ref = orc.fit_portrait(c["data"], c["model"], [phi0, 0.0], c["P"], c["freqs"])
     r = pplib.fit_portrait(c["data"], c["model"], [phi0, 0.0], c["P"], c["freqs"])
-    assert r.return_code == 0 and r.nfeval <= 20
+    assert r.device_return_code == 0 and r.return_code == 1 and r.nfeval <= 20   # TNC's FCONVERGED
     assert abs(r.phase - ref.phase) / ref.phase_err < SIG_TOL
     assert abs(r.DM - ref.DM) / ref.DM_err < SIG_TOL
     assert abs(r.chi2 / ref.chi2 - 1) < CHI2_TOL

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(T, MINB) probe(const float* data, const cx<dou
     const float2* g = reinterpret_cast<const float2*>(stage + (size_t)(step & 1) * 2 * N);
     auto nop = []() {};
     if constexpr (R16) {
-      fft16_rows1024<double>(buf, tw, t, RowSrcF32{g}, true, []() { __syncthreads(); }, [&]() { fetch(step + 2); }, nop);
+      fft16_rows1024<double>(buf, tw, tw, t, RowSrcF32{g}, true, []() { __syncthreads(); }, [&]() { fetch(step + 2); }, nop);
 #pragma unroll
       for (int i = 0; i < 16; ++i) { const cx<double> z = buf[phys16(t + 64 * i)]; accx += z.x; accy += z.y; }
     } else {
