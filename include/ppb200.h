@@ -81,7 +81,7 @@ int pp_set_model(pp_plan_t* plan, const float* model, const double* freqs);
  * (pptoaslib.py:928-1096); with fit_flags = {1,1,0,0,0} and
  * semantics = PP_SEM_FIT_PORTRAIT it is pplib.fit_portrait
  * (pplib.py:2102-2204). */
-enum { PP_DATA_F32 = 0, PP_DATA_I16 = 1 };   /* pp_fit_args_t.data_type */
+enum { PP_DATA_F32 = 0, PP_DATA_I16 = 1, PP_DATA_F64 = 2 };   /* pp_fit_args_t.data_type */
 enum {
   PP_SEM_FIT_PORTRAIT_FULL = 0, /* pptoaslib.py:928: covariance incl. amplitudes */
   PP_SEM_FIT_PORTRAIT = 1       /* pplib.py:2102: scale_errs = (p_n/sigma^2)^-1/2 */
@@ -130,7 +130,11 @@ typedef struct {
                                PSRFITS DATA column as stored; samples are
                                raw*dat_scl + dat_offs evaluated in float32 as
                                PSRCHIVE decodes them (what load_data,
-                               pplib.py:2669-2700, hands to the reference)     */
+                               pplib.py:2669-2700, hands to the reference).
+                               PP_DATA_F64: data is float64 (the reference's own
+                               array type, pplib.py:2803); rounded to float32
+                               on the device, chunk by chunk, so that a caller
+                               holding float64 portraits needs no host pass    */
   const float* dat_scl;     /* [nsub,nchan] PSRFITS DAT_SCL (int16 only)       */
   const float* dat_offs;    /* [nsub,nchan] PSRFITS DAT_OFFS (int16 only)      */
   const double* bounds;     /* HOST [5,2] (lower, upper) for phi, DM, GM, tau
@@ -265,10 +269,19 @@ int pp_gen_spline_portrait(pp_plan_t* plan, const double* mean_prof,
                            const double* knots, int32_t nknots,
                            const double* coefs, int32_t degree, float* out);
 
+/* Measured FP64 yardstick for the roofline record: DFMA thread-instructions per second of a kernel
+ * of independent DFMA chains on the plan's device (no reference counterpart: measurement support). */
+int pp_measure_fp64(pp_plan_t* plan, double* dfma_per_second);
+
 /* ---- per-channel noise -----------------------------------------------------
  * Replaces pplib.get_noise(data, chans=True) (pplib.py:2227-2245). */
 int pp_get_noise_batch(pp_plan_t* plan, const float* data, int32_t nsub,
                        double* noise_out);
+
+/* The same estimate from the harmonics k >= kc of each row (kc < 0: the default int(0.75 nharm));
+ * get_noise_PS(data, frac) of pplib.py:2227-2253 is kc = int((1 - 1/frac) * (nbin/2 + 1)). */
+int pp_get_noise_cut_batch(pp_plan_t* plan, const float* data, int32_t nsub, int32_t kc,
+                           double* noise_out);
 
 /* ---- diagnostics ------------------------------------------------------------ */
 typedef struct {

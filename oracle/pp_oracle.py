@@ -184,6 +184,90 @@ def get_noise_PS(data, frac=4, chans=False):
 get_noise = get_noise_PS
 
 
+def find_kc(pows):
+    """Critical harmonic where the noise floor of a power spectrum begins: scipy.optimize.brute fit
+    (Ns = 20 per axis, no polish) of b exp(-a k) + dc to log10(pows); the first k with exp(-a k) < 0.005
+    (pplib.py:1448-1495, fn = 'exp_dc')."""
+    data = np.log10(np.asarray(pows, dtype=np.float64))
+    k = np.arange(len(data))
+
+    def chi2(params):
+        a, b, dc = params
+        return np.sum((data - (b * np.exp(-a * k) + dc)) ** 2.0)
+    ranges = [(len(data) ** -1.0, 1.0), (0, data.max() - data.min()), (data.min(), data.max())]
+    a, b, dc = opt.brute(chi2, ranges, Ns=20, full_output=False, finish=None)
+    hit = np.where(np.exp(-a * k) < 0.005)[0]
+    return hit.min() if len(hit) else len(data) - 1
+
+
+def get_noise_fit(data, fact=1.1, chans=False):
+    """Noise from the harmonics above fact * find_kc(power spectrum) (pplib.py:2255-2284)."""
+    data = np.asarray(data, dtype=np.float64)
+
+    def one(x):
+        FT = np.fft.rfft(x)
+        pows = (FT.real ** 2 + FT.imag ** 2) / len(x)
+        k_crit = fact * find_kc(pows)
+        if k_crit >= len(pows):
+            k_crit = min(int(0.99 * len(pows)), k_crit)
+        return np.sqrt(np.mean(pows[int(k_crit):]))
+    if chans:
+        return np.array([one(row) for row in data])
+    return one(data.ravel())
+
+
+def gaussian_profile_FT(nbin, loc, wid, amp):
+    """Windowed analytic Fourier transform of a Gaussian profile (pptoaslib.py:14-50)."""
+    from scipy.special import erf
+    nharm = nbin // 2 + 1
+    if wid <= 0.0:
+        return np.zeros(nharm, 'd')
+    sigma = wid / (2 * np.sqrt(2 * np.log(2)))
+    amp = amp * (2 * np.pi * sigma ** 2) ** 0.5
+    sigma = 1.0 / (sigma * 2 * np.pi)
+    harmind = np.arange(nharm)
+    a = sigma / ((1.0 / np.pi) * 2 ** 0.5)
+    b = harmind / (sigma * 2 ** 0.5)
+    retvals = np.exp(-b ** 2) * (erf(a - b * 1j) + erf(a + b * 1j)) / 2 * (amp * nbin)
+    if loc != 0.0:
+        retvals = retvals * np.exp(-harmind * 2.0j * np.pi * loc)
+    return np.nan_to_num(retvals)
+
+
+def instrumental_response_FT(nbin, wid=0.0, irf_type='rect'):
+    """pptoaslib.py:112-145."""
+    nharm = nbin // 2 + 1
+    if wid == 0.0:
+        return np.ones(nharm)
+    if irf_type == 'rect':
+        return np.sinc(np.arange(nharm) * wid)
+    gp = gaussian_profile_FT(nbin, 0.0, wid, 1.0)
+    return gp / gp[0]
+
+
+def instrumental_response_port_FT(nbin, freqs, DM=0.0, P=1.0, wids=(), irf_types=()):
+    """pptoaslib.py:147-179 (the smearing width has no DM factor there: kept)."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    nharm = nbin // 2 + 1
+    if DM == 0.0 and len(wids) == 0:
+        return np.ones([len(freqs), nharm])
+    resp = np.ones([len(freqs), nharm], dtype=complex)
+    for wid, typ in zip(wids, irf_types):
+        resp *= instrumental_response_FT(nbin, wid, typ)[None, :]
+    if DM:
+        chan_bw = abs(freqs[1] - freqs[0])
+        for i, f in enumerate(freqs):
+            resp[i] *= instrumental_response_FT(nbin, 8.3e-6 * chan_bw / (f / 1e3) ** 3 / P, 'rect')
+    return resp
+
+
+def add_instrumental_response(model, freqs, DM=0.0, P=1.0, wids=(), irf_types=()):
+    """pptoas.py:388-394: modelx = irfft(inst_resp_port_FT * rfft(modelx))."""
+    nbin = model.shape[-1]
+    resp = instrumental_response_port_FT(nbin, freqs, DM, P, wids, irf_types)
+    return np.fft.irfft(resp * np.fft.rfft(model, axis=-1), axis=-1)
+
+
 def rotate_data(data, phase=0.0, DM=0.0, P=None, freqs=None, nu_ref=np.inf):
     """Fourier-domain rotation / dedispersion of a profile or portrait
     (pplib.py:2338-2426 for 1-D/2-D input; 2428-2460; 2548-2559).

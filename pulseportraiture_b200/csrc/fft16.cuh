@@ -40,7 +40,49 @@ template <typename F> __device__ __forceinline__ cx<F> mul_c(cx<F> a, F c, F s) 
 
 // In-register forward DFT of 16 points.  Input natural order; output X[k] is left
 // in v[(k >> 2) + 4 (k & 3)] (read it through dft16_at()).
+// 4 x 4 decomposition.  The inner twiddles W16^(r q) are not applied as separate complex multiplications:
+// W16^2 and W16^6 are h (1 -/+ i)-type factors, W16^1, W16^3, W16^9 are c1 (1 - i t), c1 (t - i), -c1 (1 - i t)
+// with t = tan(pi/8); the unscaled rotations cost two operations each and the common factors h, c1 ride on the
+// FMAs of the second stage's butterflies (constant multiplier: two register operands, full FP64 rate).
+// 144 operations instead of 160.
+template <typename F> __device__ __forceinline__ void dft16_group13(cx<F>& x0, cx<F>& v1, cx<F>& v2, cx<F>& v3, bool third) {
+  const F h = F(0.70710678118654752440), c1 = F(0.92387953251128675613), t = F(0.41421356237309504880);
+  cx<F> p2, q1, q3;
+  if (!third) {   // W16^1, W16^2, W16^3
+    p2 = mk<F>(v2.x + v2.y, v2.y - v2.x);
+    q1 = mk<F>(fma(t, v1.y, v1.x), fma(-t, v1.x, v1.y));
+    q3 = mk<F>(fma(t, v3.x, v3.y), fma(t, v3.y, -v3.x));
+  } else {        // W16^3, W16^6, W16^9
+    p2 = mk<F>(v2.y - v2.x, -(v2.x + v2.y));
+    q1 = mk<F>(fma(t, v1.x, v1.y), fma(t, v1.y, -v1.x));
+    q3 = mk<F>(-fma(t, v3.y, v3.x), fma(t, v3.x, -v3.y));
+  }
+  const cx<F> a0 = mk<F>(fma(h, p2.x, x0.x), fma(h, p2.y, x0.y)), a1 = mk<F>(fma(-h, p2.x, x0.x), fma(-h, p2.y, x0.y));
+  const cx<F> b2 = cadd(q1, q3), b3 = csub(q1, q3);
+  x0 = mk<F>(fma(c1, b2.x, a0.x), fma(c1, b2.y, a0.y));
+  v2 = mk<F>(fma(-c1, b2.x, a0.x), fma(-c1, b2.y, a0.y));
+  v1 = mk<F>(fma(c1, b3.y, a1.x), fma(-c1, b3.x, a1.y));
+  v3 = mk<F>(fma(-c1, b3.y, a1.x), fma(c1, b3.x, a1.y));
+}
 template <typename F> __device__ __forceinline__ void dft16(cx<F> (&v)[16]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) dft4(v[r], v[r + 4], v[r + 8], v[r + 12]);   // A_r[q] -> v[r + 4q]
+  const F h = F(0.70710678118654752440);
+  dft4(v[0], v[1], v[2], v[3]);                                            // q = 0: X[4s] -> v[s]
+  dft16_group13(v[4], v[5], v[6], v[7], false);                            // q = 1: X[1 + 4s] -> v[4 + s]
+  {                                                                        // q = 2: W16^2, W16^4 = -i, W16^6
+    const cx<F> p1 = mk<F>(v[9].x + v[9].y, v[9].y - v[9].x), p3 = mk<F>(v[11].y - v[11].x, -(v[11].x + v[11].y));
+    const cx<F> x2 = mk<F>(v[10].y, -v[10].x);
+    const cx<F> a0 = cadd(v[8], x2), a1 = csub(v[8], x2), b2 = cadd(p1, p3), b3 = csub(p1, p3);
+    v[8] = mk<F>(fma(h, b2.x, a0.x), fma(h, b2.y, a0.y));
+    v[10] = mk<F>(fma(-h, b2.x, a0.x), fma(-h, b2.y, a0.y));
+    v[9] = mk<F>(fma(h, b3.y, a1.x), fma(-h, b3.x, a1.y));
+    v[11] = mk<F>(fma(-h, b3.y, a1.x), fma(h, b3.x, a1.y));
+  }
+  dft16_group13(v[12], v[13], v[14], v[15], true);                         // q = 3: X[3 + 4s] -> v[12 + s]
+}
+// the textbook form (twiddle multiplications, then the second stage): kept for the probes
+template <typename F> __device__ __forceinline__ void dft16_plain(cx<F> (&v)[16]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) dft4(v[r], v[r + 4], v[r + 8], v[r + 12]);   // A_r[q] -> v[r + 4q]
   const F h = F(0.70710678118654752440), c1 = F(0.92387953251128675613), s1 = F(0.38268343236508977173);
@@ -112,7 +154,7 @@ __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx
   }
   sync();   // staged row consumed; the previous row's split reads of buf are done
   after_first_reads();
-  dft16(v);
+  dft16_plain(v);
 #pragma unroll
   for (int k = 0; k < 16; ++k) buf[phys16(16 * t + k)] = v[dft16_at(k)];
   sync();
@@ -123,7 +165,7 @@ __device__ __forceinline__ void fft16_rows1024(cx<F>* __restrict__ buf, const cx
   in_last_pass();
   if constexpr (TWTAB) twiddle16_tab(v, tab + k);
   else twiddle16(v, tw16[k]);
-  dft16(v);
+  dft16_plain(v);
   const int j0 = (t - k) * 16 + k;
 #pragma unroll
   for (int r = 0; r < 16; ++r) buf[phys16(j0 + 16 * r)] = v[dft16_at(r)];

@@ -208,6 +208,31 @@ __global__ void k_model_mean_masked(const cx<double>* __restrict__ mconj, const 
   out[(size_t)sl * N + i] = (cnt == nchan || cnt == 0) ? mmean_all[i] : make_float2((float)(sx / cnt), (float)(sy / cnt));
 }
 
+// FP64 pipe yardstick for the roofline record: independent DFMA chains, 8 per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fma(v[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+
+// float64 portraits (the reference's array type) -> the float32 the row kernels stage
+__global__ void __launch_bounds__(256) k_cvt_f64_f32(const double2* __restrict__ in, float2* __restrict__ out, size_t n2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = in[i];
+    out[i] = make_float2((float)v.x, (float)v.y);
+  }
+}
+
 // ----------------------------------------------------------------------------
 // k_prep: one warp per subint.
 // ----------------------------------------------------------------------------
@@ -2076,6 +2101,7 @@ struct RowsArgs {
   const void* twN;
   const void* tw2N;
   int nrows, conj;
+  int kc;               // first harmonic of the noise estimate (get_noise_PS: int((1 - 1/frac) nharm), pplib.py:2244)
 };
 
 template <int N, typename T>
@@ -2107,8 +2133,8 @@ __global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
   }
   __syncthreads();
   cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
-  constexpr int kc = (3 * (N + 1)) / 4;
-  constexpr int ntop = N + 1 - kc;
+  const int kc = a.kc;
+  const int ntop = N + 1 - kc;
   double top = 0.0;
   float2* out = (a.spec && valid) ? a.spec + (size_t)row * N : nullptr;
   const float sgn = a.conj ? -1.f : 1.f;
@@ -2126,7 +2152,10 @@ __global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
       if (p < N / 2) put(N - p, dq);
     }
   }
-  if (t_row == 0) put(N, mk<T>(Z[0].x - Z[0].y, 0));
+  if (t_row == 0) {
+    put(N, mk<T>(Z[0].x - Z[0].y, 0));
+    if (kc == 0) { const double d0 = (double)(Z[0].x + Z[0].y); top += d0 * d0; }   // frac = 1: the DC term counts
+  }
   if (a.noise) {
 #pragma unroll
     for (int o = (G::kTRow < 32 ? G::kTRow : 32) / 2; o > 0; o >>= 1) top += __shfl_xor_sync(0xffffffffu, top, o);

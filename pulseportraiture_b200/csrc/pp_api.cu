@@ -5,9 +5,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <type_traits>
 #include <string>
 #include <vector>
@@ -95,7 +97,7 @@ struct pp_plan {
   DBuf resp, rot_gm, rot_nugm, al_w, al_out, al_wsum, ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
       rot_phase, rot_dm, rot_P, rot_nuref;
   // chunk-sized
-  DBuf X, Xlo, partial, data_stage[2], Dspec, Ddc, al_acc, al_wparts;
+  DBuf X, Xlo, partial, data_stage[2], data_stage64[2], Dspec, Ddc, al_acc, al_wparts;
   // timing
   bool timing = false;
   std::vector<cudaEvent_t> ev_chunk;   // "chunk finished" events for the overlapped result copies
@@ -346,7 +348,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
                  &pl->st_iter, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
                  &pl->o_snr, &pl->o_nfev, &pl->o_rc, &pl->o_scales, &pl->o_serrs, &pl->o_csnr, &pl->o_lag, &pl->o_phig,
                  &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->Dspec, &pl->Ddc, &pl->al_acc, &pl->al_wparts, &pl->X, &pl->Xlo,
-                 &pl->partial, &pl->data_stage[0], &pl->data_stage[1]};
+                 &pl->partial, &pl->data_stage[0], &pl->data_stage[1], &pl->data_stage64[0], &pl->data_stage64[1]};
   for (DBuf* b : all) b->release();
   for (auto& gt : pl->grid_tables) gt.second.release();
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
@@ -494,13 +496,13 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
 // fit
 // ----------------------------------------------------------------------------
 static const int kMaxChunk = 32768;   // the chunk index is gridDim.y of the row kernels (<= 65535)
-static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host) {
+static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host, double bytes_per_sample = 4.0) {
   if (pl->chunk_req > 0) return std::min(std::min(pl->chunk_req, kMaxChunk), nsub);
   if (data_on_host) {
     // Host data arrive over PCIe (~50 GB/s), ten times slower than the kernels consume them: small
     // chunks so that the copy of chunk c+1 runs under the kernels of chunk c from early on (the
     // kernels' per-chunk overheads stay hidden behind the copies).  ~16 chunks, 64..512 subints.
-    const double per_in = 4.0 * pl->nbin * (double)pl->nchan;
+    const double per_in = bytes_per_sample * pl->nbin * (double)pl->nchan;
     long c = std::max(64L, std::min(512L, (long)nsub / 16));
     c = std::min(c, std::max(1L, (long)floor(2.0 * 1073741824.0 / per_in)));   // staging <= 2 GiB each
     return (int)std::min<long>(c, nsub);
@@ -533,8 +535,8 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   if (!pl || !args || !out) return fail(-1, "NULL argument");
   if (!pl->model_set) return fail(-1, "pp_set_model must be called before pp_fit_batch");
   if (!args->data || !args->P) return fail(-1, "data and P are required");
-  const bool i16 = args->data_type == PP_DATA_I16;
-  if (args->data_type != PP_DATA_F32 && !i16) return fail(-1, "unknown data_type %d", args->data_type);
+  const bool i16 = args->data_type == PP_DATA_I16, f64 = args->data_type == PP_DATA_F64;
+  if (args->data_type != PP_DATA_F32 && !i16 && !f64) return fail(-1, "unknown data_type %d", args->data_type);
   if (i16 && (!args->dat_scl || !args->dat_offs)) return fail(-1, "int16 data need dat_scl and dat_offs");
   if (args->nsub < 1) return fail(-1, "nsub must be >= 1");
   const uint8_t* ff = args->fit_flags;
@@ -552,6 +554,13 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     return fail(-1, "PP_SEM_FIT_PORTRAIT is defined for the (phi, DM) fit only");
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
+  // PP_TRACE=1: host-side wall-clock marks of the call on stderr (where a step's time goes outside the kernels)
+  static const bool trace = getenv("PP_TRACE") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (trace) fprintf(stderr, "[pp_fit_batch] %-22s %8.3f ms\n", what,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+  };
   const int nsub = args->nsub, nchan = pl->nchan, N = pl->N;
   const int Ns = args->Ns > 0 ? args->Ns : 100;
   if (Ns < 2) return fail(-1, "Ns must be >= 2");
@@ -627,7 +636,8 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->o_phig.need(sizeof(double) * nsub));
   CK(pl->running.need(sizeof(int)));
 
-  const int chunk = pick_chunk(pl, nsub, !is_device_ptr(args->data));
+  mark("inputs staged");
+  const int chunk = pick_chunk(pl, nsub, !is_device_ptr(args->data), f64 ? 8.0 : 4.0);
   const int G = rows_per_cta(pl, chunk);
   const int rows_conc = spectra_slots(N);
   const int gx = (nchan + G - 1) / G;
@@ -656,10 +666,19 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   const bool data_on_device = is_device_ptr(args->data);
   if (data_on_device && (reinterpret_cast<uintptr_t>(args->data) & 15))
     return fail(-1, "device data pointer must be 16-byte aligned");
-  const size_t sub_bytes = (size_t)nchan * 2 * N * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as stored
+  const size_t sub_bytes = (size_t)nchan * 2 * N * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as the kernels read it
+  const size_t src_bytes = f64 ? (size_t)nchan * 2 * N * sizeof(double) : sub_bytes;           // ... and as the caller stores it
   const char* data_bytes = reinterpret_cast<const char*>(args->data);
-  if (!data_on_device)
+  if (!data_on_device || f64)
     for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need((size_t)chunk * sub_bytes));
+  if (f64 && !data_on_device)
+    for (int i = 0; i < 2; ++i) CK(pl->data_stage64[i].need((size_t)chunk * src_bytes));
+  auto convert_f64 = [&](const void* src, void* dst, int ns, cudaStream_t st) {   // float64 rows -> float32 rows
+    const size_t n2 = (size_t)ns * nchan * N;
+    k_cvt_f64_f32<<<(unsigned)std::min<size_t>((n2 + 255) / 256, 148 * 32), 256, 0, st>>>(
+        static_cast<const double2*>(src), static_cast<float2*>(dst), n2);
+    pl->stats.launches++;
+  };
   const float *dscl = nullptr, *doffs = nullptr;
   if (i16) {
     if (stage_in(pl, pl->in_scl, args->dat_scl, (size_t)nsub * nchan, &dscl)) return -2;
@@ -708,9 +727,11 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     const int s0 = cstart[c], ns = cstart[c + 1] - s0;
     cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(pl->data_stage[b].p, data_bytes + (size_t)s0 * sub_bytes, (size_t)ns * sub_bytes,
+    void* dst = f64 ? pl->data_stage64[b].p : pl->data_stage[b].p;
+    e = cudaMemcpyAsync(dst, data_bytes + (size_t)s0 * src_bytes, (size_t)ns * src_bytes,
                         cudaMemcpyHostToDevice, pl->copy_stream);
     if (e != cudaSuccess) return e;
+    if (f64) convert_f64(dst, pl->data_stage[b].p, ns, pl->copy_stream);
     return cudaEventRecord(pl->ev_copy[b], pl->copy_stream);
   };
   if (!data_on_device) {
@@ -747,10 +768,15 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   int pending_out = -1;        // chunk whose result copies still have to be queued
   bool expect_third = false;   // the previous chunk still had unfinished subints after two passes
 
+  mark("before chunk loop");
   for (int c = 0; c < nchunks; ++c) {
     const int s0 = cstart[c], ns = cstart[c + 1] - s0;
+    if (trace) { char b[64]; snprintf(b, sizeof b, "chunk %d (%d subints)", c, ns); mark(b); }
     const char* dchunk;
-    if (data_on_device) dchunk = data_bytes;
+    if (data_on_device && f64) {   // round the chunk to float32 next to the kernels that read it
+      convert_f64(data_bytes + (size_t)s0 * src_bytes, pl->data_stage[c & 1].p, ns, pl->stream);
+      dchunk = pl->data_stage[c & 1].as<char>() - (size_t)s0 * sub_bytes;
+    } else if (data_on_device) dchunk = data_bytes;
     else {
       if (c + 1 < nchunks) CK(issue_copy(c + 1));
       CK(cudaStreamWaitEvent(pl->stream, pl->ev_copy[c & 1], 0));
@@ -898,6 +924,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     pending_out = c;
   }
   if (pending_out >= 0 && enqueue_results(pending_out)) return -2;
+  mark("all chunks queued");
   CK(cudaGetLastError());
   cudaEvent_t ev_t1 = nullptr;
   if (pl->timing) {
@@ -926,7 +953,9 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
                          is_device_ptr(out->phi_guess) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, pl->stream));
   }
   CK(cudaStreamSynchronize(pl->copy_stream));
+  mark("copy stream drained");
   CK(cudaStreamSynchronize(pl->stream));
+  mark("done");
   CK(cudaGetLastError());
   stats_end(pl);
   return 0;
@@ -938,10 +967,12 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 template <typename T> static const void* tw1(pp_plan* pl) { return sizeof(T) == 8 ? pl->twN64.p : pl->twN32.p; }
 template <typename T> static const void* tw2(pp_plan* pl) { return sizeof(T) == 8 ? pl->tw2N64.p : pl->tw2N32.p; }
 
-static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spec, int conj, double* noise, int bits) {
+static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spec, int conj, double* noise, int bits,
+                            int kc = -1) {
   const int N = pl->N;
   RowsArgs a;
   a.in = in; a.spec = spec; a.noise = noise; a.nrows = nrows; a.conj = conj;
+  a.kc = kc >= 0 ? kc : (3 * (N + 1)) / 4;
   if (bits == 64) {
     a.twN = tw1<double>(pl); a.tw2N = tw2<double>(pl);
     DISPATCH_N(N, {
@@ -1258,9 +1289,39 @@ extern "C" int pp_gen_spline_portrait(pp_plan_t* pl, const double* mean_prof, co
   return 0;
 }
 
+extern "C" int pp_measure_fp64(pp_plan_t* pl, double* dfma_per_second) {
+  if (!pl || !dfma_per_second) return fail(-1, "NULL argument");
+  CK(cudaSetDevice(pl->device));
+  const int ctas = pl->sm_count * 4, iters = 2048;
+  CK(pl->ps_noise.need(sizeof(double) * (size_t)ctas * 256));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, pl->stream));
+    k_fp64_peak<<<ctas, 256, 0, pl->stream>>>(pl->ps_noise.as<double>(), iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(e1, pl->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *dfma_per_second = (double)ctas * 256.0 * (double)iters * 64.0 / ((double)best * 1e-3);
+  return 0;
+}
+
 extern "C" int pp_get_noise_batch(pp_plan_t* pl, const float* data, int32_t nsub, double* noise_out) {
+  return pp_get_noise_cut_batch(pl, data, nsub, -1, noise_out);
+}
+
+extern "C" int pp_get_noise_cut_batch(pp_plan_t* pl, const float* data, int32_t nsub, int32_t kc, double* noise_out) {
   if (!pl || !data || !noise_out) return fail(-1, "NULL argument");
   if (nsub < 1) return fail(-1, "nsub must be >= 1");
+  if (kc > pl->N) return fail(-1, "kc must be <= nbin/2 (got %d)", kc);
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
@@ -1269,7 +1330,7 @@ extern "C" int pp_get_noise_batch(pp_plan_t* pl, const float* data, int32_t nsub
   if (stage_in(pl, pl->rot_in, data, (size_t)nrows * 2 * N, &din)) return -2;
   CK(pl->ps_noise.need(sizeof(double) * nrows));
   const int bits = pl->fft_precision ? pl->fft_precision : 64;
-  if (launch_rfft_rows(pl, din, (int)nrows, nullptr, 0, pl->ps_noise.as<double>(), bits)) return -2;
+  if (launch_rfft_rows(pl, din, (int)nrows, nullptr, 0, pl->ps_noise.as<double>(), bits, kc)) return -2;
   CK(cudaGetLastError());
   if (copy_out(pl, noise_out, pl->ps_noise.as<double>(), (size_t)nrows)) return -2;
   CK(cudaStreamSynchronize(pl->stream));

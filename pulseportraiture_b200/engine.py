@@ -150,6 +150,12 @@ class WidebandPlan(object):
         _ffi.check(self._lib.pp_set_freqs(self._h, fp), "pp_set_freqs")
         self.freqs = np.array(freqs, dtype=np.float64)
 
+    def measure_fp64(self):
+        """DFMA thread-instructions per second of an FP64-only kernel on this device (roofline yardstick)."""
+        v = C.c_double(0.0)
+        _ffi.check(self._lib.pp_measure_fp64(self._h, C.byref(v)), "pp_measure_fp64")
+        return float(v.value)
+
     def enable_timing(self, on=True):
         _ffi.check(self._lib.pp_plan_enable_timing(self._h, 1 if on else 0),
                    "pp_plan_enable_timing")
@@ -198,6 +204,11 @@ class WidebandPlan(object):
             a.data_type = 1
             a.dat_scl = _ptr(dat_scl, np.float32, keep, "dat_scl", (nsub, nchan))
             a.dat_offs = _ptr(dat_offs, np.float32, keep, "dat_offs", (nsub, nchan))
+        elif (isinstance(data, np.ndarray) and data.dtype == np.float64) or \
+                (_is_torch(data) and str(data.dtype) == "torch.float64"):
+            # the reference's array type: rounded to float32 on the device (PP_DATA_F64), no host pass
+            a.data = _ptr(data, np.float64, keep, "data", (nsub, nchan, nbin))
+            a.data_type = 2
         else:
             a.data = _ptr(data, np.float32, keep, "data", (nsub, nchan, nbin))
         a.nsub = nsub
@@ -404,11 +415,12 @@ class WidebandPlan(object):
             _ptr(bc(nu_GM), np.float64, keep, "nu_GM")), "pp_rotate_full_batch")
         return out
 
-    def get_noise_batch(self, data):
+    def get_noise_batch(self, data, kc=-1):
+        """Per-row noise level from the harmonics k >= kc (default int(0.75 nharm), pplib.py:2244)."""
         keep = []
         nsub = int(data.shape[0])
         ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
         out = np.empty((nsub, self.nchan))
-        _ffi.check(self._lib.pp_get_noise_batch(self._h, ip, nsub, out.ctypes.data),
-                   "pp_get_noise_batch")
+        _ffi.check(self._lib.pp_get_noise_cut_batch(self._h, ip, nsub, int(kc), out.ctypes.data),
+                   "pp_get_noise_cut_batch")
         return out

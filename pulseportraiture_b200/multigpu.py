@@ -16,6 +16,45 @@ import threading
 import numpy as np
 
 
+def gpu_local_cpus(device):
+    """CPUs that share a NUMA node / PCIe root with CUDA device ``device`` (sysfs ``local_cpulist`` of
+    its PCI function), or None when that cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return sorted(cpus) or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_numa(device):
+    """Pin the calling thread to the CPUs local to ``device`` so that page-locked buffers allocated
+    afterwards (first touch) and the copies out of them stay on the GPU's own NUMA node and PCIe root.
+    Returns {"cpus": n, "bound": bool}."""
+    import os
+    cpus = gpu_local_cpus(device)
+    if not cpus:
+        return {"cpus": 0, "bound": False}
+    try:
+        allowed = set(os.sched_getaffinity(0))
+        use = sorted(allowed.intersection(cpus))
+        if not use:
+            return {"cpus": 0, "bound": False}
+        os.sched_setaffinity(0, use)
+        return {"cpus": len(use), "bound": True}
+    except (AttributeError, OSError):
+        return {"cpus": 0, "bound": False}
+
+
 def shard_range(n, rank, world):
     """Contiguous [start, stop) of n items for ``rank`` of ``world`` (sizes
     differ by at most one; earlier ranks take the remainder)."""
@@ -83,6 +122,7 @@ class MultiGPUFitter(object):
             a, b = shard_range(nsub, i, world)
             if b <= a:
                 return
+            bind_to_gpu_numa(self.devices[i])      # this thread's staging and copies stay on the GPU's node
             try:
                 results[i] = self.plans[i].fit_batch(data[a:b], P[a:b], **slice_kw(a, b))
             except Exception as exc:  # noqa: BLE001

@@ -97,6 +97,15 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _dev(a):
+    """Portrait data as the device takes them without a host pass: float32 and float64 arrays go as
+    they are (float64 is rounded to float32 on the device, PP_DATA_F64), anything else via float64."""
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a)
+
+
 def _check_bounds(bounds, nparam):
     """scipy-style bounds -> what WidebandPlan.fit_batch takes (None when nothing is bounded)."""
     bounds = list(bounds or [])
@@ -155,7 +164,7 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
     nu_fits = None if nu_fit is None else np.full((1, 3), float(nu_fit))
     nu_outs = None if nu_out is None else np.full((1, 3), float(nu_out))
     start = time.time()
-    r = pl.fit_batch(_f32(data)[None], P,
+    r = pl.fit_batch(_dev(data)[None], P,
                      errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],
                      init=init, nu_fits=nu_fits, nu_outs=nu_outs,
                      fit_flags=(1, 1, 0, 0, 0), semantics="fit_portrait", bounds=bounds)
@@ -203,16 +212,16 @@ def get_noise(data, method=default_noise_method, **kwargs):
 
 
 def get_noise_PS(data, frac=4, chans=False):
-    """Mean of the top quarter of the power spectrum (pplib.py:2227-2253)."""
-    if frac != 4:
-        raise NotImplementedError("frac != 4")
+    """Mean of the highest 1/frac of the power spectrum (pplib.py:2227-2253)."""
     data = np.asarray(data)
     if chans:
         nchan, nbin = data.shape
-        return get_plan(nchan, nbin).get_noise_batch(_f32(data)[None])[0]
+        kc = int((1 - frac ** -1) * (nbin // 2 + 1))         # pplib.py:2244
+        return get_plan(nchan, nbin).get_noise_batch(_f32(data)[None], kc=kc)[0]
     rav = data.ravel()
     n = rav.size
-    return get_plan(1, n).get_noise_batch(_f32(rav).reshape(1, 1, n))[0, 0]
+    kc = int((1 - frac ** -1) * (n // 2 + 1))
+    return get_plan(1, n).get_noise_batch(_f32(rav).reshape(1, 1, n), kc=kc)[0, 0]
 
 
 # ---- A10: rotation ----------------------------------------------------------------------

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import pplib
 from .pplib import DataBunch, read_model, gen_gaussian_portrait, scattering_alpha  # noqa: F401
-from .pplib import get_plan, _f32
+from .pplib import get_plan, _f32, _dev
 
 max_nfile = 999                                  # pptoas.py:18-23
 rm_baseline = bool(pplib.F0_fact)                # pptoas.py:25-29
@@ -366,7 +366,7 @@ class GetTOAs:
             for isub in ok_isubs:
                 mask[isub, np.asarray(d.ok_ichans[isub], dtype=int)] = 1
             nok = mask.sum(axis=1)
-            subints = _f32(np.asarray(d.subints)[:, 0])
+            subints = _dev(np.asarray(d.subints)[:, 0])      # float64 goes to the device as it is
             errs = np.ascontiguousarray(np.asarray(d.noise_stds)[:, 0], dtype=np.float64)
             snrs = np.ascontiguousarray(np.asarray(d.SNRs)[:, 0], dtype=np.float64)
             weights = np.ascontiguousarray(d.weights, dtype=np.float64)
@@ -443,6 +443,9 @@ class GetTOAs:
                     pl.set_model(_f32(models[t]), tables[t])
                     table_set = t
                 idx = np.asarray(isubs, dtype=int)
+                if len(idx) > 1 and np.all(np.diff(idx) == 1):
+                    idx = slice(int(idx[0]), int(idx[-1]) + 1)      # a contiguous range: views, no gather copy
+                nidx = len(isubs)
                 raw_kw = {}
                 if d.get("raw_subints") is not None:       # stored samples go to the device as they are
                     batch = np.ascontiguousarray(np.asarray(d.raw_subints, dtype=np.int16)[idx])
@@ -452,13 +455,13 @@ class GetTOAs:
                     batch = np.ascontiguousarray(subints[idx])
                 r = pl.fit_batch(
                     batch, Ps[idx], errs=errs[idx], **raw_kw,
-                    chan_mask=mask[idx], weights=weights[idx], DM_guess=np.full(len(idx), DM_stored),
+                    chan_mask=mask[idx], weights=weights[idx], DM_guess=np.full(nidx, DM_stored),
                     snrs=snrs[idx], nu_fits=None if nu_fits_in is None else nu_fits_in[idx],
                     nu_fit_mode=mode, nu_outs=None if nu_outs_in is None else nu_outs_in[idx],
                     fit_flags=flags, log10_tau=self.log10_tau, option=0, is_toa=True,
                     Ns=100, semantics="full", bounds=fit_bounds,
                     scat_guess=None if scat_in is None else scat_in[idx])
-                for j, isub in enumerate(idx):
+                for j, isub in enumerate(isubs):
                     res[isub] = (flags, {k: v[j] for k, v in r.items()})
             fit_duration = time.time() - fit_start
 

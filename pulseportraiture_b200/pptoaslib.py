@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32,  # noqa: F401
+from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32, _dev,  # noqa: F401
                     get_plan, scattering_times, scattering_portrait_FT, scipy_return_code, _RC_BENIGN)
 
 
@@ -124,7 +124,7 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
         return np.array([[np.nan if v is None else float(v) for v in vals]])
 
     start = time.time()
-    r = pl.fit_batch(_f32(data_port)[None], P,
+    r = pl.fit_batch(_dev(data_port)[None], P,
                      errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],
                      init=init, nu_fits=three(nu_fits), nu_outs=three(nu_outs),
                      fit_flags=[1 if f else 0 for f in fit_flags],

@@ -334,19 +334,32 @@ def test_every_supported_nbin(engine, nbin):
         assert rel(r["scales"][s], ref.scales) < 1e-5
 
 
+def _oracle_config2(seed):
+    c = synth.make_case(512, 2048, 1500., 800., seed)
+    noise = orc.get_noise(c["data"], chans=True)
+    ref, _, _ = orc.toa_core(c["data"], c["model"], c["P"], c["freqs"], noise, polish="exact")
+    keep = ("phi", "phi_err", "DM", "DM_err", "chi2", "red_chi2", "nu_DM", "snr", "scales", "scale_errs",
+            "channel_snrs", "lag_index")
+    return c["data"].astype(np.float32), {k: ref[k] for k in keep}
+
+
 def test_config2_subset_512x2048(engine):
-    """BASELINE config 2 shape (512 chan x 2048 bin): parity subset vs oracle."""
-    nsub, nchan, nbin = 12, 512, 2048
-    cases = [synth.make_case(nchan, nbin, 1500., 800., 2000 + s) for s in range(nsub)]
-    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    """BASELINE config 2 shape (512 chan x 2048 bin): the 64-subint parity subset of SURVEY 8d against
+    the oracle (host processes in parallel), default float64 transform and the explicit setting."""
+    import multiprocessing as mp
+    nsub, nchan, nbin = 64, 512, 2048
+    freqs, model = synth.example_model(nchan, nbin, 1500., 800.)      # warms the cache the workers inherit
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        out = pool.map(_oracle_config2, [2000 + s for s in range(nsub)], chunksize=1)
+    data = np.stack([o[0] for o in out])
+    from oracle.pp_oracle import DataBunch
     with engine.WidebandPlan(nchan, nbin) as pl:
-        pl.set_model(cases[0]["model"].astype(np.float32), cases[0]["freqs"])
-        r = pl.fit_batch(data, cases[0]["P"])
+        pl.set_model(model.astype(np.float32), freqs)
+        r = pl.fit_batch(data, synth.P_EXAMPLE)
         pl.set_fft_precision(64)
-        r64 = pl.fit_batch(data, cases[0]["P"])
-    for s, c in enumerate(cases):
-        noise = orc.get_noise(c["data"], chans=True)
-        ref, _, _ = orc.toa_core(c["data"], c["model"], c["P"], c["freqs"], noise, polish="exact")
+        r64 = pl.fit_batch(data, synth.P_EXAMPLE)
+    for s in range(nsub):
+        ref = DataBunch(**out[s][1])
         assert int(r["lag_index"][s]) == ref.lag_index
         check_against(r, s, ref)
         check_against(r64, s, ref)

@@ -75,7 +75,15 @@ int main(int argc, char** argv) {
     CKC(cudaGetLastError());
     Outs o; fetch(o);
     if (ref.X.empty()) ref = o;
-    size_t nx = 0, nlo = 0, ns = 0; double perr = 0, pmax = 0;
+    size_t nx = 0, nlo = 0, ns = 0; double perr = 0, pmax = 0, xrel = 0, srel = 0;
+    for (size_t i = 0; i < o.X.size(); ++i) {
+      const double m = std::max(fabs((double)ref.X[i].x), fabs((double)ref.X[i].y));
+      if (m > 0) xrel = std::max(xrel, std::max(fabs((double)o.X[i].x - ref.X[i].x), fabs((double)o.X[i].y - ref.X[i].y)) / m);
+    }
+    for (size_t i = 0; i < o.sigma.size(); ++i) {
+      if (ref.sigma[i] > 0) srel = std::max(srel, fabs(o.sigma[i] / ref.sigma[i] - 1.0));
+      if (ref.Sdn[i] > 0) srel = std::max(srel, fabs(o.Sdn[i] / ref.Sdn[i] - 1.0));
+    }
     for (size_t i = 0; i < o.X.size(); ++i) nx += (o.X[i].x != ref.X[i].x) || (o.X[i].y != ref.X[i].y);
     for (size_t i = 0; i < o.Xlo.size(); ++i) nlo += (o.Xlo[i].x != ref.Xlo[i].x) || (o.Xlo[i].y != ref.Xlo[i].y);
     for (size_t i = 0; i < o.sigma.size(); ++i) ns += (o.sigma[i] != ref.sigma[i]) || (o.Ssn[i] != ref.Ssn[i]) || (o.Sdn[i] != ref.Sdn[i]);
@@ -83,8 +91,8 @@ int main(int argc, char** argv) {
       perr = std::max(perr, (double)std::max(fabsf(o.part[i].x - ref.part[i].x), fabsf(o.part[i].y - ref.part[i].y)));
       pmax = std::max(pmax, (double)std::max(fabsf(ref.part[i].x), fabsf(ref.part[i].y)));
     }
-    printf("%-34s regs %3d smem %6zu CTAs/SM %d | %.3f ms per %d subints = %.0f GB/s (2B) | diff X %zu Xlo %zu sig %zu partial %.2e (max %.2e)\n",
-           name, fa.numRegs, smem, nb, best, nsub, 2.0 * nfl * 4 / best / 1e6, nx, nlo, ns, perr, pmax);
+    printf("%-34s regs %3d smem %6zu CTAs/SM %d | %.3f ms per %d subints = %.0f GB/s (2B) | diff X %zu (rel %.1e) Xlo %zu sig %zu (rel %.1e) partial %.2e (max %.2e)\n",
+           name, fa.numRegs, smem, nb, best, nsub, 2.0 * nfl * 4 / best / 1e6, nx, xrel, nlo, ns, srel, perr, pmax);
     fflush(stdout);
     cudaFree(dtw);
   };
@@ -96,14 +104,7 @@ int main(int argc, char** argv) {
   run("base  st2 mb6 acc0", SpecPlan16T<2, 6, 0, false, false>{});
   run_k("k_spectra16<f32, guess>", SpecPlan16{}, k_spectra16<false, true, false>, spectra_smem_bytes_of<N, SpecPlan16>());
   const size_t sm16 = spectra_smem_bytes_of<N, SpecPlan16>();
-  run_k("k16 EXP1 no model loads", SpecPlan16{}, k_spectra16<false, true, false, 1>, sm16);
-  run_k("k16 EXP2 no X stores", SpecPlan16{}, k_spectra16<false, true, false, 2>, sm16);
-  run_k("k16 EXP4 no X product", SpecPlan16{}, k_spectra16<false, true, false, 4>, sm16);
-  run_k("k16 EXP8 no F2F out", SpecPlan16{}, k_spectra16<false, true, false, 8>, sm16);
-  run_k("k16 EXP3 no loads, no stores", SpecPlan16{}, k_spectra16<false, true, false, 3>, sm16);
-  run_k("k16 EXP7 no loads/stores/product", SpecPlan16{}, k_spectra16<false, true, false, 7>, sm16);
+  run_k("k16 noguess", SpecPlan16{}, k_spectra16<false, false, false>, sm16, 2);
   run_k("k16 EXP15 none of them", SpecPlan16{}, k_spectra16<false, true, false, 15>, sm16);
-  run_k("k16 noguess EXP15", SpecPlan16{}, k_spectra16<false, false, false, 15>, sm16, 2);
-  run_k("k16 guess no X", SpecPlan16{}, k_spectra16<false, true, false>, sm16, 1);
   return 0;
 }
