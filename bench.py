@@ -559,7 +559,9 @@ def facade_timing(data, freqs, model, nsub):
     out = {"nsub": nsub, "unit": "TOAs/s"}
     for name, extra in (("get_TOAs_f64", dict(subints=sub32[:, None].astype(np.float64))),
                         ("get_TOAs_i16", dict(subints=dec[:, None], raw_subints=raw, dat_scl=scl, dat_offs=offs))):
-        d = DataBunch(**dict(common, raw_subints=None, dat_scl=None, dat_offs=None, **extra))
+        fields = dict(common, raw_subints=None, dat_scl=None, dat_offs=None)
+        fields.update(extra)
+        d = DataBunch(**fields)
         best = None
         for _ in range(3):
             gt = pptoas.GetTOAs([d], GMODEL, quiet=True)

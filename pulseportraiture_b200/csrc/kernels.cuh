@@ -1547,6 +1547,39 @@ __device__ inline void chol5_inverse(const double* L, int n, double* Inv) {
 
 // Real positive roots of sum_i c[i] x^(deg-i) (np.roots convention), Aberth iteration in
 // complex double; returns the count written to out[].
+// Eigen-decomposition of a symmetric n x n matrix (n <= 5, row stride 5) by cyclic Jacobi rotations:
+// A = V diag(w) V^T (V column k = eigenvector k).  Used where the Hessian is not positive definite.
+__device__ inline void sym_eig5(const double* A_in, int n, double* V, double* w) {
+  double A[25];
+  for (int i = 0; i < n; ++i) for (int k = 0; k < n; ++k) { A[i * 5 + k] = A_in[i * 5 + k]; V[i * 5 + k] = (i == k) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < n; ++i) { dg += A[i * 5 + i] * A[i * 5 + i]; for (int k = i + 1; k < n; ++k) off += A[i * 5 + k] * A[i * 5 + k]; }
+    if (off <= 1e-30 * dg) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * 5 + q];
+        if (apq == 0.0) continue;
+        const double th = (A[q * 5 + q] - A[p * 5 + p]) / (2.0 * apq);
+        const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {   // columns p, q
+          const double akp = A[k * 5 + p], akq = A[k * 5 + q];
+          A[k * 5 + p] = c * akp - sn * akq; A[k * 5 + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {   // rows p, q
+          const double apk = A[p * 5 + k], aqk = A[q * 5 + k];
+          A[p * 5 + k] = c * apk - sn * aqk; A[q * 5 + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = V[k * 5 + p], vkq = V[k * 5 + q];
+          V[k * 5 + p] = c * vkp - sn * vkq; V[k * 5 + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) w[i] = A[i * 5 + i];
+}
+
 __device__ inline int real_pos_roots(const double* c_in, int deg_in, double* out) {
   double c[8];
   int deg = deg_in, off = 0;
@@ -1773,19 +1806,26 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
           chol5_solve(L, nfit, mg, dr);
           chol5_inverse(L, nfit, Inv);
         } else {
-          // Levenberg damping until positive definite
-          double lamd = 0.0;
-          for (int i = 0; i < nfit; ++i) lamd = fmax(lamd, fabs(H[i * 5 + i]));
-          lamd *= 1e-3;
-          bool ok = false;
-          for (int tr = 0; tr < 40 && !ok; ++tr) {
-            double Hd[25];
-            for (int i = 0; i < nfit; ++i) for (int k = 0; k < nfit; ++k) Hd[i * 5 + k] = H[i * 5 + k] + (i == k ? lamd : 0.0);
-            ok = chol5(Hd, nfit, L);
-            lamd *= 4.0;
+          // Not convex here (a saddle or a flat valley of the tau / alpha / GM surface): Newton step on the
+          // Hessian with its eigenvalues replaced by their moduli, in the coordinates scaled by the
+          // diagonal (the parameters' natural scales differ by orders of magnitude, so an unscaled
+          // Levenberg shift freezes the weakly constrained ones: 35 passes of crawling on a sigma = 1.5,
+          // 32-channel, all-five-parameter golden).  Negative-curvature directions are descended at the
+          // rate of their |curvature|; the objective-decrease test above backs a bad step off.
+          double Dh[5], Hs[25], V[25], w[5], gs[5], y[5];
+          for (int i = 0; i < nfit; ++i) { const double hd = fabs(H[i * 5 + i]); Dh[i] = hd > 0.0 ? 1.0 / sqrt(hd) : 1.0; }
+          for (int i = 0; i < nfit; ++i) { gs[i] = g[i] * Dh[i]; for (int k = 0; k < nfit; ++k) Hs[i * 5 + k] = H[i * 5 + k] * Dh[i] * Dh[k]; }
+          sym_eig5(Hs, nfit, V, w);
+          for (int k = 0; k < nfit; ++k) {
+            double pk = 0.0;
+            for (int i = 0; i < nfit; ++i) pk += V[i * 5 + k] * gs[i];
+            y[k] = -pk / fmax(fabs(w[k]), 1e-8);
           }
-          if (ok) { double mg[5]; for (int i = 0; i < nfit; ++i) mg[i] = -g[i]; chol5_solve(L, nfit, mg, dr); }
-          else for (int i = 0; i < nfit; ++i) dr[i] = -g[i] / (fabs(H[i * 5 + i]) + 1e-300);
+          for (int i = 0; i < nfit; ++i) {
+            double di = 0.0;
+            for (int k = 0; k < nfit; ++k) di += V[i * 5 + k] * y[k];
+            dr[i] = di * Dh[i];
+          }
         }
         for (int i = 0; i < nfit; ++i) d[idx[i]] = dr[i];
         // step limits: rotation of any channel <= 0.1 turn, log10(tau) <= 0.5, alpha <= 1,

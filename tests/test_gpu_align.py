@@ -231,5 +231,5 @@ def test_align_archives_on_a_different_frequency_grid():
     # several data channels per template channel: the reference keeps only the last one (numpy +=)
     dup = DataBunch(**dict(sub))
     dup["freqs"] = np.tile(np.linspace(1400., 1410., len(sel)), (5, 1))
-    with pytest.raises(NotImplementedError):
-        ppalign.align_archives([dup], tmpl, niter=1, quiet=True)
+    many = ppalign.align_archives([dup], tmpl, niter=1, quiet=True)      # tests/test_gpu_round2.py checks the values
+    assert many.port.shape == (32, 256) and 1 <= np.count_nonzero(many.weights) < len(sel)

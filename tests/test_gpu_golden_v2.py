@@ -65,6 +65,25 @@ def test_config2_shape_against_reference(case):
     assert r.return_code == int(g("return_code")) == 2          # trust-ncg's normal exit (pptoaslib.py:1001)
 
 
+def polished_reference(case, c, flags, log10):
+    """The reference's trust-ncg stops when it can no longer predict an improvement of an objective of
+    size ~1e7, which leaves some of these weakly constrained fits up to ~2e-3 sigma short of the minimum
+    of the reference's own objective (b3_601: 1.8e-3 sigma in alpha).  Exact Newton steps on the oracle's
+    restatement of that objective (pinned to the reference's f, gradient and Hessian at 1e-9) from the
+    reference's solution, at the reference's output frequencies: the point the reference converges to."""
+    from oracle import pp_oracle as orc
+    g = lambda f: G2[case + "/full." + f]  # noqa: E731
+    nbin = c["data"].shape[1]
+    dFT, mFT = orc._spectra(c["data"], c["model"])
+    prob = orc._FullProblem(dFT, mFT, G2[case + "/errs"] * np.sqrt(nbin / 2.0), c["P"], c["freqs"], float(g("nu_DM")),
+                            float(g("nu_GM")), float(g("nu_tau")), flags, log10)
+    x = np.array(g("params"), dtype=np.float64)
+    ifit = np.where(flags)[0]
+    for _ in range(4):
+        x[ifit] -= np.linalg.solve(prob.hess(x)[np.ix_(ifit, ifit)], prob.grad(x)[ifit])
+    return x
+
+
 def run_full(case):
     from pulseportraiture_b200.engine import WidebandPlan
     cfg = G2[case + "/cfg"]
@@ -79,9 +98,20 @@ def run_full(case):
                          log10_tau=log10, option=option)
     g = lambda f: G2[case + "/full." + f]  # noqa: E731
     assert int(r["return_code"][0]) == 0
+    xp = polished_reference(case, c, flags, log10)
+    # "at the same output reference frequencies" (SURVEY 8c): both sides report tau at their own
+    # zero-covariance frequency nu_tau; with alpha ~ -4 a 1e-6 relative difference between the two
+    # frequencies moves log10(tau) by 2e-3 sigma, so the device's tau is carried to the reference's nu_tau
+    got = r["params"][0].copy()
+    if flags[3]:
+        ratio = float(g("nu_tau")) / r["nu_out"][0, 2]
+        got[3] = got[3] + got[4] * np.log10(ratio) if log10 else got[3] * ratio ** got[4]
     for i, nm in enumerate(["phi", "DM", "GM", "tau", "alpha"]):
         if flags[i]:
-            assert abs(r["params"][0, i] - g(nm)) / g(nm + "_err") < SIG_TOL, nm
+            slop = abs(xp[i] - g(nm)) / g(nm + "_err")        # how far the reference stopped from its own minimum
+            assert slop < 5e-3, (nm, slop)
+            assert abs(got[i] - xp[i]) / g(nm + "_err") < SIG_TOL, nm
+            assert abs(got[i] - g(nm)) / g(nm + "_err") < SIG_TOL + slop, nm
             assert rel(r["param_errs"][0, i], g(nm + "_err")) < 1e-4, nm
         else:
             assert abs(r["params"][0, i] - g(nm)) <= 1e-9 * max(1.0, abs(g(nm))), nm

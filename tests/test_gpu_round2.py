@@ -66,9 +66,9 @@ def test_gettoas_tscrunch():
     """tscrunch=True: one TOA per archive from the weighted average of its (already aligned) subints."""
     from pulseportraiture_b200 import pptoas
     nsub = 6
-    c0 = synth.make_case(32, 512, 1500., 800., 8400, phi=0.21, dDM=4e-4)
+    c0 = synth.make_case(32, 512, 1500., 800., 8400, phi=0.21, dDM=4e-4, sigma=0.0)
     rng = np.random.RandomState(3)
-    clean = c0["data"]                                          # one realisation; add independent noise per subint
+    clean = c0["data"]                                          # noiseless; independent noise per subint
     subs = np.stack([clean + rng.normal(0, 1.5, clean.shape) for _ in range(nsub)])
     d, _ = _fake_archive(nsub, 32, 512, 8400)
     d["subints"] = subs[:, None]
