@@ -79,6 +79,69 @@ def gather_results(local, group=None, dst=0):
     return merge_results([b for b in bucket if b is not None and len(b)])
 
 
+class SharedGather(object):
+    """Host-side gather for the one-process-per-GPU launch on ONE node: every rank copies its packed
+    per-subint results (float64 [n_local, width]) into its slot of a POSIX shared-memory segment and
+    rank ``dst`` reads the slots in rank order.  No network stack and no NCCL: a few MB of memcpy per
+    rank and one (gloo) barrier.  ``group`` is a torch.distributed group used for the barriers only."""
+
+    def __init__(self, max_rows, width, group=None, dst=0, tag="g"):
+        import os
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.dist, self.group, self.dst = dist, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.max_rows, self.width = int(max_rows), int(width)
+        self.slot = self.max_rows * self.width
+        name = "ppb200_%s_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.getppid(), tag)
+        nbytes = 8 * (self.world * (self.slot + 1))
+        if self.rank == dst:
+            try:                                   # a stale segment of a killed run
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            dist.barrier(group=group)
+        else:
+            dist.barrier(group=group)
+            self.shm = shared_memory.SharedMemory(name=name)
+        buf = np.ndarray((self.world, self.slot + 1), dtype=np.float64, buffer=self.shm.buf)
+        self.buf = buf
+
+    def gather(self, local):
+        """local: float64 [n, width] (n <= max_rows).  Returns the rows of all ranks in rank order on
+        ``dst``, None elsewhere."""
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        n = local.shape[0]
+        if n > self.max_rows or (n and local.shape[1] != self.width):
+            raise ValueError("gather: got %r, slots are [%d, %d]" % (local.shape, self.max_rows, self.width))
+        row = self.buf[self.rank]
+        row[0] = n
+        row[1:1 + n * self.width] = local.ravel()
+        self.dist.barrier(group=self.group)        # every slot is written
+        out = None
+        if self.rank == self.dst:
+            parts = []
+            for r in range(self.world):
+                m = int(self.buf[r, 0])
+                parts.append(self.buf[r, 1:1 + m * self.width].reshape(m, self.width).copy())
+            out = np.concatenate(parts, axis=0)
+        self.dist.barrier(group=self.group)        # the slots may be overwritten
+        return out
+
+    def close(self):
+        self.buf = None
+        try:
+            self.shm.close()
+            self.dist.barrier(group=self.group)
+            if self.rank == self.dst:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class MultiGPUFitter(object):
     """Fit one batch on several GPUs from one process: one plan, one stream and
     one host thread per device; results are concatenated on the host."""
