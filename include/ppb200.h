@@ -21,7 +21,9 @@
  *     name that stream) before the call.  The Python wrapper synchronises the
  *     caller's current torch stream for CUDA tensors.
  *   - Return value 0 = success, negative = error (see pp_last_error()).
- *   - nbin must be a power of two, 64 <= nbin <= 4096.
+ *   - nbin: any even number, 64 <= nbin <= 4096 (the reference's np.fft.rfft takes any length,
+ *     pplib.py:2127).  Powers of two run the tuned row kernels; other lengths run the same DFT as a
+ *     chirp-z (Bluestein) transform on top of them (csrc/bluestein.cuh): same results, not tuned.
  *   - The DC harmonic is ignored (reference F0_fact = 0, pplib.py:66) and
  *     Dconst = 1/0.000241 (pplib.py:48-51).
  */

@@ -23,6 +23,7 @@
 
 #include "fft.cuh"
 #include "spectra_plan.cuh"
+#include "bluestein.cuh"
 
 namespace ppb {
 
@@ -326,9 +327,14 @@ struct SpectraArgs {
   const cx<double>* tw8;     // [TwLayout<N>::kTotal] per-pass twiddle tables
   int s0;                    // first global subint of the chunk
   int nchan, G, nparts;
+  // arbitrary nbin (bluestein.cuh; k_spectra<N, PL, false, true>): the rows' FP64 spectra, already
+  // transformed, in rows of N = Npad slots; the normalisations take the true nbin = 2 nhalf
+  const cx<double>* dspec;   // [chunk,nchan,N] or null
+  const double* ddc;         // [chunk,nchan] harmonic 0 of those rows
+  int nhalf, kc_true;        // true nbin/2; first harmonic of the noise estimate, int(0.75 (nhalf + 1))
 };
 
-template <int N, class PL = SpecPlan<N>, bool I16 = false>
+template <int N, class PL = SpecPlan<N>, bool I16 = false, bool FROMSPEC = false>
 __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(SpectraArgs a) {
   using F = double;
   constexpr int T = PL::kT, NS = PL::kSlots, NUNIT = PL::kUnits, NOUT = PL::kOut, NACC = NUNIT * NOUT;
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   __shared__ double red[2][NS][(T >= 32 ? T / 32 : 1)][2];   // per-warp power sums, by row parity
   __shared__ __align__(8) unsigned long long mbar[NS][2];
   const int tid = threadIdx.x, slot = tid / T, t = tid % T;
-  for (int i = tid; i < PL::kTwTotal; i += PL::kThreads) tw[i] = a.tw8[i];
+  if constexpr (!FROMSPEC) { for (int i = tid; i < PL::kTwTotal; i += PL::kThreads) tw[i] = a.tw8[i]; }
   if (t == 0) { mbar_init(&mbar[slot][0], 1); mbar_init(&mbar[slot][1], 1); }
   mbar_fence_init();
   __syncthreads();
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
   };
   // TMA producer (one thread per slot): bulk-copy the raw row into the staging buffer
   auto fetch = [&](int step) {
+    if constexpr (FROMSPEC) return;
     if (t == 0 && row_used(step)) {
       const int ch = ch_begin + step * NS + slot;
       unsigned long long* bar = &mbar[slot][step % NSTG];
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     const int ch = ch_begin + step * NS + slot;
     const bool inrange = ch < ch_end;
     const bool used = row_used(step);
-    if (used) {
+    if (used && !FROMSPEC) {
       if (NSTG > 1 && (step & 1)) { mbar_wait(&mbar[slot][1], ph1); ph1 ^= 1u; }
       else { mbar_wait(&mbar[slot][0], ph0); ph0 ^= 1u; }
     }
@@ -486,7 +493,15 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     float2* const Drow = a.D + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N;
     const float wgt = (used && want_guess) ? (float)(a.weights ? a.weights[(size_t)s * a.nchan + ch] : 1.0) : 0.f;
     const double shift = (Dfac != 0.0 && inrange) ? Dfac * (a.nu2[ch] - numean2) : 0.0;
-    PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + NSTG); latch(step - 1); }, load_mc);
+    if constexpr (FROMSPEC) {     // the rows arrive transformed: only the barrier discipline of the power-sum hand-off
+      PL::sync(slot);
+      latch(step - 1);
+      load_mc();
+      (void)g;
+    } else {
+      PL::template transform<F>(buf, tw, t, slot, g, used, [&]() { fetch(step + NSTG); latch(step - 1); }, load_mc);
+    }
+    const cx<F>* const dsrow = FROMSPEC ? a.dspec + ((size_t)sl * a.nchan + (inrange ? ch : 0)) * N : nullptr;
 
     // ---- split + power sums; X and the guess accumulators need no sigma ------------
     double s_all = 0.0, s_top = 0.0;
@@ -495,7 +510,14 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     for (int i = 0; i < NUNIT; ++i) {
       cx<F> d[NOUT];
       if constexpr (kMcLate) load_mc_unit(i);
-      const F dc_term = PL::template split<F>(buf, tw, t, i, first, d);   // DC of the row (special unit only)
+      F dc_term = F(0);
+      if constexpr (FROMSPEC) {
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) d[q] = used ? dsrow[slot_of(i, q)] : mk<F>(F(0), F(0));
+        if (i == 0 && first && used) dc_term = a.ddc[(size_t)sl * a.nchan + ch];
+      } else {
+        dc_term = PL::template split<F>(buf, tw, t, i, first, d);   // DC of the row (special unit only)
+      }
       // a NaN / Inf sample makes every harmonic of the row non-finite: such a row must not enter
       // the profile for the FFTFIT guess (its sigma comes out non-finite, so the fit skips it too)
       if (i == 0 && !(isfinite(d[0].x) && isfinite(d[0].y))) wrow = 0.f;
@@ -505,7 +527,11 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
 #pragma unroll
       for (int q = 0; q < NOUT; ++q) {
         double& sa = (q & 1) ? sa1 : sa0;
-        if (q == 1 || q == 6 || q == 0) {           // outputs that can be in the top quarter (PL::top)
+        if (FROMSPEC) {                             // any nbin: the cut is a run-time harmonic (slot = harmonic)
+          const double pw = fma(d[q].x, d[q].x, d[q].y * d[q].y);
+          sa += pw;
+          if (slot_of(i, q) >= a.kc_true) s_top += pw;
+        } else if (q == 1 || q == 6 || q == 0) {    // outputs that can be in the top quarter (PL::top)
           const double pw = fma(d[q].x, d[q].x, d[q].y * d[q].y);
           sa += pw;
           if (PL::top(i, q, first)) s_top += pw;    // harmonics >= kc = 3N/4
@@ -587,9 +613,11 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     if (t < nsteps && fch < ch_end) {
       const bool fused = row_used(t);
       double sig;
+      const double nh = FROMSPEC ? (double)a.nhalf : (double)N;             // true nbin / 2
+      const double nt = FROMSPEC ? (double)(a.nhalf + 1 - a.kc_true) : (double)ntop;
       if (a.errs) sig = fused ? a.errs[(size_t)s * a.nchan + fch] : 0.0;
-      else sig = sqrt(keep_top / ((double)(2 * N) * (double)ntop));      // pplib.py:2243-2245
-      const double sF2 = sig * sig * (double)N;                           // sigma^2 * nbin/2
+      else sig = sqrt(keep_top / (2.0 * nh * nt));                         // pplib.py:2243-2245
+      const double sF2 = sig * sig * nh;                                  // sigma^2 * nbin/2
       const bool ok = fused && (sF2 > 0.0) && (sF2 < 1e300);
       const size_t o = (size_t)s * a.nchan + fch;
       a.sigma[o] = ok ? sig : 0.0;
@@ -622,6 +650,7 @@ struct GuessArgs {
   const float2* partial;   // [n, nparts, N] spectra to be summed (slot layout)
   const float2* mconj;     // [nmodel, N] conj(model spectrum)
   int nparts, nmodel, N, Ns;
+  int nhalf;               // true nbin/2 when the spectra sit in N = Npad > nbin/2 slots (arbitrary nbin), else 0
   double polish_tol;       // stop the exact polish when |dx| < polish_tol [rot]
   const double* wsum;      // [n] divisor of the partial sum, or null (=1)
   const double* noise;     // [n] time-domain sigma or null (measure from spectrum)
@@ -652,7 +681,8 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   __shared__ double bc[4];
   const int N = a.N, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int il = blockIdx.x, ig = a.s0 + il;
-  const int kc = (3 * (N + 1)) / 4;
+  const int NH = a.nhalf > 0 ? a.nhalf : N;          // true nbin/2: noise cut, normalisations, degrees of freedom
+  const int kc = (3 * (NH + 1)) / 4;
   const double inv_w = a.wsum ? 1.0 / a.wsum[ig] : 1.0;
   const float2* mc = a.mconj + (size_t)(a.nmodel > 1 ? il % a.nmodel : 0) * N;   // profile i uses model i mod nmodel
   double v[3] = {0.0, 0.0, 0.0};  // sum |d|^2, sum |m|^2, top-quarter power
@@ -664,7 +694,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       sx += t.x; sy += t.y;
     }
     const double dx = (double)sx * inv_w, dy = (double)sy * inv_w;
-    const int k = (i == 0) ? N : i;
+    const int k = (i == 0) ? N : i;   // (arbitrary nbin: slot 0 and the slots above nbin/2 are zero)
     double mx = mc[i].x, my = mc[i].y;
     if (tau_g != 0.0) {   // scattered mean model (pptoas.py:444-447): conj(m B) = conj(m) conj(B)
       const double b = kTwoPi * (double)k * tau_g, q = 1.0 / (1.0 + b * b);
@@ -679,8 +709,8 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   }
   block_sum<3, 256>(v, sh);
   double err2;  // Fourier-domain variance (pplib.py:2076-2079)
-  if (a.noise) { const double nz = a.noise[ig]; err2 = nz * nz * (double)N; }
-  else err2 = v[2] / ((double)(2 * N) * (double)(N + 1 - kc)) * (double)N;
+  if (a.noise) { const double nz = a.noise[ig]; err2 = nz * nz * (double)NH; }
+  else err2 = v[2] / ((double)(2 * NH) * (double)(NH + 1 - kc)) * (double)NH;
   const double d_tot = v[0] / err2, p_tot = v[1] / err2;
 
   // ---- brute-force grid (scipy.optimize.brute over np.mgrid[-0.5:0.5:Ns j]) ----
@@ -770,7 +800,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
     if (a.phase_err) a.phase_err[ig] = 1.0 / sqrt(scale * C2);       // pplib.py:2092-2093
     if (a.scale) a.scale[ig] = scale;
     if (a.scale_err) a.scale_err[ig] = 1.0 / sqrt(p_tot);
-    if (a.red_chi2) a.red_chi2[ig] = (d_tot - fmin * fmin / p_tot) / (double)(2 * N - 2);
+    if (a.red_chi2) a.red_chi2[ig] = (d_tot - fmin * fmin / p_tot) / (double)(2 * NH - 2);
     if (a.snr) a.snr[ig] = sqrt(scale * scale * p_tot);
     if (a.x) {
       const double dmg = a.DMg ? a.DMg[ig] : 0.0;
@@ -785,7 +815,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       xs[4] = a.init ? a.init[(size_t)ig * 5 + 4] : 0.0;
       if (a.scat) {                                  // pptoas.py:427-452
         double tg = a.scat[(size_t)ig * 2];
-        if (a.log10_tau) { if (tg == 0.0) tg = 1.0 / (double)(2 * N); tg = log10(tg); }
+        if (a.log10_tau) { if (tg == 0.0) tg = 1.0 / (double)(2 * NH); tg = log10(tg); }
         xs[3] = tg; xs[4] = a.scat[(size_t)ig * 2 + 1];
       }
     }
@@ -838,6 +868,7 @@ struct PassArgs {
   double* csum;            // [nsub,nchan,kNCsum]
   SolverState st;
   int s0, nchan, N;
+  int nhalf;               // true nbin/2 of the noise normalisation (0: N; arbitrary nbin runs on N = Npad slots)
 };
 
 // streaming 16-byte load: read-only path, do not keep in L1
@@ -998,7 +1029,7 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     double* o = a.csum + ((size_t)s * a.nchan + ch) * kNCsum;
     if (used) {
       const double sg = a.sigma[(size_t)s * a.nchan + ch];
-      const double isF2 = 1.0 / (sg * sg * (double)N);
+      const double isF2 = 1.0 / (sg * sg * (double)(a.nhalf > 0 ? a.nhalf : N));
       o[0] = C * isF2;                         // C_n      (pplib.py:1322)
       o[1] = -kTwoPi * C1 * isF2;              // dC/dtheta  (1344)
       o[2] = -kTwoPi * kTwoPi * C2 * isF2;     // d2C/dtheta2 (1380)
@@ -1368,6 +1399,7 @@ struct Pass5Args {
   double* csum;            // [nsub,nchan,kNCsum]
   SolverState st;
   int s0, nchan, log10_tau;
+  int nhalf;               // true nbin/2 (0: N)
 };
 
 #ifndef PP_PASS5_MINB
@@ -1490,7 +1522,7 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
     double* o = a.csum + ((size_t)s * a.nchan + ch) * kNCsum;
     if (used) {
       const double sg = a.sigma[(size_t)s * a.nchan + ch];
-      const double isF2 = 1.0 / (sg * sg * (double)N);
+      const double isF2 = 1.0 / (sg * sg * (double)(a.nhalf > 0 ? a.nhalf : N));
       const double p2 = kTwoPi * kTwoPi;
       o[0] = acc[0] * isF2;                        // C
       o[1] = -kTwoPi * acc[1] * isF2;              // C_th   = -sum w Im(A1)
@@ -2736,6 +2768,101 @@ __global__ void __launch_bounds__(256) k_align_finish(AlignFinishArgs a) {
       dst[2 * j] = Y[j].x * sc;
       dst[2 * j + 1] = -Y[j].y * sc;
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Arbitrary nbin (bluestein.cuh): element-wise kernels on the FP64 spectrum scratch the Bluestein row
+// transforms write / read.  Rows have Npad slots, slot k = harmonic k for 1 <= k <= L = nbin/2.
+// ----------------------------------------------------------------------------
+// conj(m), |m|^2, p_n of the model from its spectra (k_model for any nbin): one CTA per channel
+__global__ void __launch_bounds__(256) k_model_from_spec(const cx<double>* __restrict__ spec, cx<float>* mconj32,
+                                                          cx<double>* mconj64, double* mpow, double* pn, int Npad) {
+  __shared__ double sh[8];
+  const int ch = blockIdx.x, tid = threadIdx.x;
+  double v[1] = {0.0};
+  for (int k = tid; k < Npad; k += 256) {
+    const cx<double> d = spec[(size_t)ch * Npad + k];
+    const double pw = d.x * d.x + d.y * d.y;
+    v[0] += pw;
+    mconj64[(size_t)ch * Npad + k] = cconj(d);
+    mconj32[(size_t)ch * Npad + k] = mk<float>((float)d.x, (float)(-d.y));
+    mpow[(size_t)ch * Npad + k] = pw;
+  }
+  block_sum<1, 256>(v, sh);
+  if (tid == 0) pn[ch] = v[0];
+}
+
+// float spectra (optionally conjugated) and the noise level of transformed rows (k_rfft_rows for any nbin)
+__global__ void __launch_bounds__(256) k_rows_from_spec(const cx<double>* __restrict__ spec, const double* __restrict__ dc,
+                                                         float2* out, double* noise, int Npad, int L, int kc, int conj) {
+  __shared__ double sh[8];
+  const long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  double v[1] = {0.0};
+  const float sgn = conj ? -1.f : 1.f;
+  for (int k = tid; k < Npad; k += 256) {
+    const cx<double> d = spec[(size_t)row * Npad + k];
+    if (k >= kc && k >= 1) v[0] += d.x * d.x + d.y * d.y;
+    if (out) out[(size_t)row * Npad + k] = make_float2((float)d.x, sgn * (float)d.y);
+  }
+  if (tid == 0 && kc == 0) v[0] += dc[row] * dc[row];     // frac = 1: the DC term counts
+  block_sum<1, 256>(v, sh);
+  if (tid == 0 && noise) noise[row] = sqrt(v[0] / ((double)(2 * L) * (double)(L + 1 - kc)));
+}
+
+// harmonic k of row (s, ch) times e^{2 pi i k theta} [/(1 + 2 pi i k tau_n)] [resp_n(k)] (k_rotate's multiply)
+__global__ void __launch_bounds__(256) k_rot_mul(RotateArgs a, cx<double>* spec, double* dc, int Npad, int L) {
+  const long row = blockIdx.x;
+  const int s = (int)(row / a.nchan), ch = (int)(row % a.nchan);
+  const double theta = rot_theta(a, s, ch);
+  const double wtau = a.taus ? kTwoPi * a.taus[ch] : 0.0;
+  const double* const resp = a.resp ? a.resp + (size_t)ch * (L + 1) : nullptr;
+  for (int k = threadIdx.x + 1; k <= L; k += 256) {
+    double c, sn;
+    cis2pi((double)k * theta, c, sn);
+    if (wtau != 0.0) scatter_factor(c, sn, wtau * (double)k);
+    if (resp) { c *= resp[k]; sn *= resp[k]; }
+    cx<double>& d = spec[(size_t)row * Npad + k];
+    d = (k < L) ? cmul(d, mk<double>(c, sn)) : mk<double>(d.x * c, 0.0);   // irfft keeps the real part of the Nyquist term
+  }
+  if (threadIdx.x == 0 && resp) dc[row] *= resp[0];
+}
+
+// aligned[n] += sum_s w[s,n] rot[s,n,:] in double (the accumulation of ppalign.py:202-208 on rotated rows)
+__global__ void __launch_bounds__(256) k_wsum_rows(const float* __restrict__ rot, const double* __restrict__ w, double* aligned,
+                                                    double* wsum, int nsub, int nchan, int nbin, int first_call) {
+  const int ch = blockIdx.x;
+  for (int j = threadIdx.x; j < nbin; j += 256) {
+    double acc = first_call ? 0.0 : aligned[(size_t)ch * nbin + j];
+    for (int s = 0; s < nsub; ++s) {
+      const double ws = w[(size_t)s * nchan + ch];
+      if (ws != 0.0 && fabs(ws) < 1e300) acc = fma(ws, (double)rot[((size_t)s * nchan + ch) * nbin + j], acc);
+    }
+    aligned[(size_t)ch * nbin + j] = acc;
+  }
+  if (threadIdx.x == 0) {
+    double t = first_call ? 0.0 : wsum[ch];
+    for (int s = 0; s < nsub; ++s) { const double ws = w[(size_t)s * nchan + ch]; if (ws != 0.0 && fabs(ws) < 1e300) t += ws; }
+    wsum[ch] = t;
+  }
+}
+
+// the slices of the fused ppalign sum (k_align_spec) added in a fixed order into spectrum rows + DC terms
+__global__ void __launch_bounds__(256) k_align_reduce_any(const double2* __restrict__ acc, const double* __restrict__ wparts,
+                                                           cx<double>* spec, double* dc, double* wsum, int nchan, int Npad, int nsplit) {
+  const int ch = blockIdx.x;
+  const size_t part = (size_t)nchan * Npad;
+  for (int k = threadIdx.x; k < Npad; k += 256) {
+    double2 v = make_double2(0.0, 0.0);
+    for (int q = 0; q < nsplit; ++q) { const double2 u = acc[q * part + (size_t)ch * Npad + k]; v.x += u.x; v.y += u.y; }
+    if (k == 0) { dc[ch] = v.y; v = make_double2(0.0, 0.0); }      // slot 0: y carries the DC sum
+    spec[(size_t)ch * Npad + k] = mk<double>(v.x, v.y);
+  }
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < nsplit; ++q) t += wparts[(size_t)q * nchan + ch];
+    wsum[ch] = t;
   }
 }
 

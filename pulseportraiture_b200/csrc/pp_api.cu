@@ -76,6 +76,11 @@ struct DBuf {
 
 struct pp_plan {
   int nchan = 0, nbin = 0, N = 0, device = 0;
+  // arbitrary (even, non power-of-two) nbin: rows are transformed by Bluestein kernels (bluestein.cuh) into an
+  // FP64 spectrum scratch of N = Npad slots per row; L = nbin/2 is the true number of harmonics, M the FFT length
+  bool anyn = false;
+  int L = 0, M = 0;
+  DBuf any_chirp, any_B, any_twM, any_tw2n, any_spec, any_dc, any_spec2, any_dc2;
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int chunk_req = 0;
@@ -252,6 +257,33 @@ static void launch_spectra16(bool i16, bool guess, bool keepd, dim3 grid, cudaSt
 #undef L16_
 }
 
+// ---- arbitrary nbin: Bluestein row transforms (bluestein.cuh) ----------------------------------------------
+#define DISPATCH_M(Mval, ...)                                   \
+  switch (Mval) {                                               \
+    case 64: { constexpr int MM = 64; __VA_ARGS__; } break;     \
+    case 128: { constexpr int MM = 128; __VA_ARGS__; } break;   \
+    case 256: { constexpr int MM = 256; __VA_ARGS__; } break;   \
+    case 512: { constexpr int MM = 512; __VA_ARGS__; } break;   \
+    case 1024: { constexpr int MM = 1024; __VA_ARGS__; } break; \
+    case 2048: { constexpr int MM = 2048; __VA_ARGS__; } break; \
+    case 4096: { constexpr int MM = 4096; __VA_ARGS__; } break; \
+    default: return fail(-1, "unsupported Bluestein length %d", (Mval)); \
+  }
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+template <int M> static cudaError_t any_attrs() {
+  const int bytes = 2 * M * (int)sizeof(cx<double>);
+  cudaError_t e;
+#define A_(fn) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); if (e != cudaSuccess) return e;
+  A_((k_fwd_any<M, false>)) A_((k_fwd_any<M, true>)) A_((k_inv_any<M, float>)) A_((k_inv_any<M, double>)) A_((k_cfft_row<M>))
+#undef A_
+  return cudaSuccess;
+}
+struct pp_plan;
+static AnyPlan any_dev(pp_plan* pl);
+static int launch_fwd_any(pp_plan* pl, const void* in, bool i16, const float* scl, const float* offs, long nrows,
+                          cx<double>* spec, double* dc);
+static int launch_inv_any(pp_plan* pl, const cx<double>* spec, const double* dc, void* out, long nrows, bool out_double);
+
 template <int N> static cudaError_t setup_attrs() {
   const int b32 = (int)fft_smem_bytes<N, float>(), b64 = (int)fft_smem_bytes<N, double>();
   cudaError_t e;
@@ -276,13 +308,20 @@ extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_pl
   if (!out) return fail(-1, "plan_out is NULL");
   *out = nullptr;
   if (nchan < 1) return fail(-1, "nchan must be >= 1 (got %d)", nchan);
-  if (nbin < 64 || nbin > 4096 || (nbin & (nbin - 1))) return fail(-1, "nbin must be a power of two in [64,4096] (got %d)", nbin);
+  if (nbin < 64 || nbin > 4096 || (nbin & 1)) return fail(-1, "nbin must be even and in [64,4096] (got %d)", nbin);
+  const bool pow2 = (nbin & (nbin - 1)) == 0;
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(-1, "device %d not available (%d devices)", device, ndev);
   CK(cudaSetDevice(device));
   pp_plan* pl = new pp_plan();
   pl->nchan = nchan; pl->nbin = nbin; pl->N = nbin / 2; pl->device = device;
+  if (!pow2) {   // any other even nbin: Npad slots per spectrum row, Bluestein transforms of length M (bluestein.cuh)
+    pl->anyn = true;
+    pl->L = nbin / 2;
+    pl->N = next_pow2(pl->L + 1);
+    pl->M = next_pow2(2 * pl->L - 1);
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   pl->l2_bytes = prop.l2CacheSize;
@@ -326,6 +365,34 @@ extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_pl
     DISPATCH_N(N, e = setup_attrs<NN>());
     CK(e);
     if (N == 1024) CK(spectra16_attrs());
+    if (pl->anyn) {
+      const int L = pl->L, M = pl->M;
+      DISPATCH_M(M, e = any_attrs<MM>());
+      CK(e);
+      std::vector<double2> chirp(L), b(M, make_double2(0.0, 0.0)), twM(M), tw2n(L / 2 + 1);
+      for (int j = 0; j < L; ++j) {                      // c_j = e^{-pi i j^2 / L}, the angle reduced in integers
+        const long r = ((long)j * j) % (2L * L);
+        const double ang = -M_PI * (double)r / (double)L;
+        chirp[j] = make_double2(cos(ang), sin(ang));
+      }
+      b[0] = make_double2(1.0, 0.0);
+      for (int m = 1; m < L; ++m) b[m] = b[M - m] = make_double2(chirp[m].x, -chirp[m].y);
+      for (int j = 0; j < M; ++j) twM[j] = unit_root(j, M);
+      for (int k = 0; k <= L / 2; ++k) tw2n[k] = unit_root(k, 2L * L);
+      CK(pl->any_chirp.need(sizeof(double2) * L));
+      CK(pl->any_B.need(sizeof(double2) * M));
+      CK(pl->any_twM.need(sizeof(double2) * M));
+      CK(pl->any_tw2n.need(sizeof(double2) * (L / 2 + 1)));
+      CK(cudaMemcpy(pl->any_chirp.p, chirp.data(), sizeof(double2) * L, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pl->any_B.p, b.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pl->any_twM.p, twM.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pl->any_tw2n.p, tw2n.data(), sizeof(double2) * (L / 2 + 1), cudaMemcpyHostToDevice));
+      // the chirp filter's transform, divided by M (the inverse transform of the convolution)
+      DISPATCH_M(M, (k_cfft_row<MM><<<1, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(
+                        pl->any_B.as<cx<double>>(), pl->any_twM.as<cx<double>>(), 1.0 / (double)MM)));
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(pl->stream));
+    }
     std::vector<double2> t8;
     DISPATCH_N(N, build_tw8<NN>(t8));
     CK(pl->tw8.need(t8.size() * sizeof(double2)));
@@ -339,7 +406,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -422,6 +489,61 @@ static int grid_table_general(pp_plan* pl, int Ns, double lo, double hi, const d
 // ----------------------------------------------------------------------------
 // model
 // ----------------------------------------------------------------------------
+static AnyPlan any_dev(pp_plan* pl) {
+  AnyPlan p;
+  p.chirp = pl->any_chirp.as<cx<double>>(); p.Bspec = pl->any_B.as<cx<double>>(); p.twM = pl->any_twM.as<cx<double>>();
+  p.tw2n = pl->any_tw2n.as<cx<double>>(); p.L = pl->L; p.Npad = pl->N;
+  return p;
+}
+static int launch_fwd_any(pp_plan* pl, const void* in, bool i16, const float* scl, const float* offs, long nrows,
+                          cx<double>* spec, double* dc) {
+  FwdAnyArgs a;
+  a.in = in; a.dat_scl = scl; a.dat_offs = offs; a.spec = spec; a.dc = dc; a.p = any_dev(pl); a.nrows = nrows;
+  const unsigned grid = (unsigned)std::min<long>(nrows, 148L * 64);
+  if (i16) { DISPATCH_M(pl->M, (k_fwd_any<MM, true><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  else { DISPATCH_M(pl->M, (k_fwd_any<MM, false><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  pl->stats.launches++;
+  return 0;
+}
+static int launch_inv_any(pp_plan* pl, const cx<double>* spec, const double* dc, void* out, long nrows, bool out_double) {
+  InvAnyArgs a;
+  a.spec = spec; a.dc = dc; a.out = out; a.p = any_dev(pl); a.nrows = nrows;
+  const unsigned grid = (unsigned)std::min<long>(nrows, 148L * 64);
+  if (out_double) { DISPATCH_M(pl->M, (k_inv_any<MM, double><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  else { DISPATCH_M(pl->M, (k_inv_any<MM, float><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  pl->stats.launches++;
+  return 0;
+}
+// rfft -> multiply (rotation / scattering kernel / response) -> irfft of nrows = a.nsub * a.nchan rows: one
+// fused kernel for nbin = 2^m, transform / multiply / transform through the spectrum scratch otherwise
+static int rotate_rows(pp_plan* pl, RotateArgs a, bool fp64) {
+  const int N = pl->N;
+  const long nrows = (long)a.nsub * a.nchan;
+  if (pl->anyn) {
+    CK(pl->any_spec2.need(sizeof(double2) * (size_t)nrows * N));
+    CK(pl->any_dc2.need(sizeof(double) * (size_t)nrows));
+    if (launch_fwd_any(pl, a.in, false, nullptr, nullptr, nrows, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>())) return -2;
+    k_rot_mul<<<(unsigned)nrows, 256, 0, pl->stream>>>(a, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>(), N, pl->L);
+    pl->stats.launches++;
+    return launch_inv_any(pl, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>(), a.out, nrows, false);
+  }
+  if (fp64) {
+    a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rotate<NN, double><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+    });
+  } else {
+    a.twN = pl->twN32.p; a.tw2N = pl->tw2N32.p;
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_rotate<NN, float><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a);
+    });
+  }
+  pl->stats.launches++;
+  return 0;
+}
+
 static int set_freqs_impl(pp_plan* pl, const double* freqs) {
   const int nchan = pl->nchan;
   std::vector<double> hf(nchan), hn2(nchan), hlg(nchan);
@@ -469,7 +591,7 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
   const float* dmodel = nullptr;
-  if (stage_in(pl, pl->model_stage, model, (size_t)nchan * 2 * N, &dmodel)) return -2;
+  if (stage_in(pl, pl->model_stage, model, (size_t)nchan * pl->nbin, &dmodel)) return -2;
   if (set_freqs_impl(pl, freqs)) return -2;
   CK(pl->mconj32.need(sizeof(float2) * (size_t)nchan * N));
   CK(pl->mconj64.need(sizeof(double2) * (size_t)nchan * N));
@@ -480,10 +602,16 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   a.model = dmodel; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
   a.mpow = pl->mpow.as<double>(); a.pn = pl->pn.as<double>();
   a.twN = pl->twN64.as<cx<double>>(); a.tw2N = pl->tw2N64.as<cx<double>>(); a.nchan = nchan;
-  DISPATCH_N(N, {
-    const int rows = RowGeom<NN>::kRows;
-    k_model<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
-  });
+  if (pl->anyn) {
+    CK(pl->any_spec2.need(sizeof(double2) * (size_t)nchan * N));
+    if (launch_fwd_any(pl, dmodel, false, nullptr, nullptr, nchan, pl->any_spec2.as<cx<double>>(), nullptr)) return -2;
+    k_model_from_spec<<<nchan, 256, 0, pl->stream>>>(pl->any_spec2.as<cx<double>>(), a.mconj32, a.mconj64, a.mpow, a.pn, N);
+  } else {
+    DISPATCH_N(N, {
+      const int rows = RowGeom<NN>::kRows;
+      k_model<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
+    });
+  }
   k_model_mean<<<(N + 127) / 128, 128, 0, pl->stream>>>(pl->mconj64.as<cx<double>>(), pl->mmean.as<float2>(), nchan, N);
   pl->stats.launches += 2;
   CK(cudaGetLastError());
@@ -657,24 +785,24 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     CK(pl->al_acc.need(sizeof(double2) * (size_t)align_nsplit * nchan * N));
     CK(pl->al_wparts.need(sizeof(double) * (size_t)align_nsplit * nchan));
     CK(pl->al_wsum.need(sizeof(double) * nchan));
-    CK(pl->al_out.need(sizeof(double) * (size_t)nchan * 2 * N));
+    CK(pl->al_out.need(sizeof(double) * (size_t)nchan * pl->nbin));
     CK(cudaMemsetAsync(pl->al_acc.p, 0, sizeof(double2) * (size_t)align_nsplit * nchan * N, pl->stream));
     CK(cudaMemsetAsync(pl->al_wparts.p, 0, sizeof(double) * (size_t)align_nsplit * nchan, pl->stream));
   }
   CK(pl->Xlo.need(sizeof(float2) * (size_t)chunk * nchan * std::min(N, 64)));
   if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
   const bool data_on_device = is_device_ptr(args->data);
-  if (data_on_device && (reinterpret_cast<uintptr_t>(args->data) & 15))
+  if (data_on_device && !pl->anyn && (reinterpret_cast<uintptr_t>(args->data) & 15))
     return fail(-1, "device data pointer must be 16-byte aligned");
-  const size_t sub_bytes = (size_t)nchan * 2 * N * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as the kernels read it
-  const size_t src_bytes = f64 ? (size_t)nchan * 2 * N * sizeof(double) : sub_bytes;           // ... and as the caller stores it
+  const size_t sub_bytes = (size_t)nchan * pl->nbin * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as the kernels read it
+  const size_t src_bytes = f64 ? (size_t)nchan * pl->nbin * sizeof(double) : sub_bytes;           // ... and as the caller stores it
   const char* data_bytes = reinterpret_cast<const char*>(args->data);
   if (!data_on_device || f64)
     for (int i = 0; i < 2; ++i) CK(pl->data_stage[i].need((size_t)chunk * sub_bytes));
   if (f64 && !data_on_device)
     for (int i = 0; i < 2; ++i) CK(pl->data_stage64[i].need((size_t)chunk * src_bytes));
   auto convert_f64 = [&](const void* src, void* dst, int ns, cudaStream_t st) {   // float64 rows -> float32 rows
-    const size_t n2 = (size_t)ns * nchan * N;
+    const size_t n2 = (size_t)ns * nchan * (pl->nbin / 2);
     k_cvt_f64_f32<<<(unsigned)std::min<size_t>((n2 + 255) / 256, 148 * 32), 256, 0, st>>>(
         static_cast<const double2*>(src), static_cast<float2*>(dst), n2);
     pl->stats.launches++;
@@ -795,7 +923,19 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      if (N == 1024 && G <= kSpec16MaxRows && std::is_same<SpecPlan<1024>, SpecPlan16>::value) {
+      a.dspec = nullptr; a.ddc = nullptr; a.nhalf = 0; a.kc_true = 0;
+      if (pl->anyn) {   // rows transformed by Bluestein into the spectrum scratch, then the same emit code
+        if (c == 0) {
+          CK(pl->any_spec.need(sizeof(double2) * (size_t)chunk * nchan * N));
+          CK(pl->any_dc.need(sizeof(double) * (size_t)chunk * nchan));
+        }
+        if (launch_fwd_any(pl, dchunk + (size_t)s0 * sub_bytes, i16, i16 ? dscl + (size_t)s0 * nchan : nullptr,
+                           i16 ? doffs + (size_t)s0 * nchan : nullptr, (long)ns * nchan, pl->any_spec.as<cx<double>>(),
+                           pl->any_dc.as<double>())) return -2;
+        a.dspec = pl->any_spec.as<cx<double>>(); a.ddc = pl->any_dc.as<double>();
+        a.nhalf = pl->L; a.kc_true = (3 * (pl->L + 1)) / 4;
+        DISPATCH_N(N, (k_spectra<NN, SpecPlan<NN>, false, true><<<dim3(gx, ns), SpecPlan<NN>::kThreads, 0, pl->stream>>>(a)));
+      } else if (N == 1024 && G <= kSpec16MaxRows && std::is_same<SpecPlan<1024>, SpecPlan16>::value) {
         launch_spectra16(i16, want_guess, want_align, dim3(gx, ns), pl->stream, a);
       } else if (i16) {
         DISPATCH_N(N, (k_spectra<NN, SpecPlan<NN>, true><<<dim3(gx, ns), SpecPlan<NN>::kThreads, spectra_smem_bytes<NN>(), pl->stream>>>(a)));
@@ -819,6 +959,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
         ga.nmodel = ns;  // one template per subint of the chunk
       }
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
+      ga.nhalf = pl->anyn ? pl->L : 0;
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
       ga.polish_tol = 1e-6;   // a start value (the last step is still applied): the Newton solver refines it
@@ -831,7 +972,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     PassArgs pa;
     pa.X = pl->X.as<float2>(); pa.Xlo = pl->Xlo.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
     pa.Ssn = pl->Ssn.as<double>(); pa.sigma = pl->sigma.as<double>(); pa.csum = pl->csum.as<double>(); pa.st = st;
-    pa.s0 = s0; pa.nchan = nchan; pa.N = N;
+    pa.s0 = s0; pa.nchan = nchan; pa.N = N; pa.nhalf = pl->anyn ? pl->L : 0;
     UpdateArgs ua;
     memset(&ua, 0, sizeof ua);
     ua.csum = pl->csum.as<double>(); ua.Ssn = pl->Ssn.as<double>(); ua.Sdn = pl->Sdn.as<double>(); ua.nu2 = pl->nu2.as<double>();
@@ -841,7 +982,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     ua.cov = pl->o_cov.as<double>(); ua.chi2 = pl->o_chi2.as<double>(); ua.red_chi2 = pl->o_rchi2.as<double>();
     ua.snr = pl->o_snr.as<double>(); ua.nfeval = pl->o_nfev.as<int>(); ua.rc = pl->o_rc.as<int>();
     ua.scales = pl->o_scales.as<double>(); ua.scale_errs = pl->o_serrs.as<double>(); ua.channel_snrs = pl->o_csnr.as<double>();
-    ua.s0 = s0; ua.nchan = nchan; ua.nbin = 2 * N; ua.max_iter = max_iter; ua.semantics = args->semantics;
+    ua.s0 = s0; ua.nchan = nchan; ua.nbin = pl->nbin; ua.max_iter = max_iter; ua.semantics = args->semantics;
     ua.fit_phi = ff[0] ? 1 : 0; ua.fit_dm = ff[1] ? 1 : 0; ua.is_toa = args->is_toa; ua.tol = tol; ua.box = box;
     ua.model_steps = pl->model_steps; ua.tol_model = (args->tol > 0 && args->tol < 1e-4) ? args->tol : 1e-4;
     Pass5Args p5;
@@ -850,7 +991,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>(); p5.lgf = pl->lgf.as<double>();
       p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
       p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
-      p5.log10_tau = args->log10_tau;
+      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0;
       memset(&u5, 0, sizeof u5);
       u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>();
       u5.freqs = pl->freqs.as<double>(); u5.P = dP; u5.nu_fit = pl->nu_fit.as<double>(); u5.nu_outs = dnuouts;
@@ -858,7 +999,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       u5.params = ua.params; u5.param_errs = ua.param_errs; u5.nu_out = ua.nu_out; u5.cov = ua.cov; u5.chi2 = ua.chi2;
       u5.red_chi2 = ua.red_chi2; u5.snr = ua.snr; u5.nfeval = ua.nfeval; u5.rc = ua.rc; u5.scales = ua.scales;
       u5.scale_errs = ua.scale_errs; u5.channel_snrs = ua.channel_snrs;
-      u5.s0 = s0; u5.nchan = nchan; u5.nbin = 2 * N; u5.max_iter = max_iter; u5.log10_tau = args->log10_tau;
+      u5.s0 = s0; u5.nchan = nchan; u5.nbin = pl->nbin; u5.max_iter = max_iter; u5.log10_tau = args->log10_tau;
       u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol; u5.box = box;
       u5.taylor_finish = pl->model_steps != 1;
       for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
@@ -938,12 +1079,20 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     fa.acc = pl->al_acc.as<double2>(); fa.wsum_parts = pl->al_wparts.as<double>(); fa.aligned = pl->al_out.as<double>();
     fa.wsum = pl->al_wsum.as<double>(); fa.twN = pl->twN64.p; fa.tw2N = pl->tw2N64.p;
     fa.nchan = nchan; fa.nsplit = align_nsplit;
-    DISPATCH_N(N, {
-      const int rows = RowGeom<NN>::kRows;
-      k_align_finish<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(fa);
-    });
+    if (pl->anyn) {
+      CK(pl->any_spec2.need(sizeof(double2) * (size_t)nchan * N));
+      CK(pl->any_dc2.need(sizeof(double) * (size_t)nchan));
+      k_align_reduce_any<<<nchan, 256, 0, pl->stream>>>(fa.acc, fa.wsum_parts, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>(),
+                                                        fa.wsum, nchan, N, align_nsplit);
+      if (launch_inv_any(pl, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>(), fa.aligned, nchan, true)) return -2;
+    } else {
+      DISPATCH_N(N, {
+        const int rows = RowGeom<NN>::kRows;
+        k_align_finish<NN><<<(nchan + rows - 1) / rows, 256, fft_smem_bytes<NN, double>(), pl->stream>>>(fa);
+      });
+    }
     pl->stats.launches++;
-    if (copy_out(pl, out->align_sum, pl->al_out.as<double>(), (size_t)nchan * 2 * N)) return -2;
+    if (copy_out(pl, out->align_sum, pl->al_out.as<double>(), (size_t)nchan * pl->nbin)) return -2;
     if (copy_out(pl, out->align_wsum, pl->al_wsum.as<double>(), (size_t)nchan)) return -2;
   }
   // ---- results (per-chunk copies were queued on the copy stream) -------------------------
@@ -970,6 +1119,16 @@ template <typename T> static const void* tw2(pp_plan* pl) { return sizeof(T) == 
 static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spec, int conj, double* noise, int bits,
                             int kc = -1) {
   const int N = pl->N;
+  if (pl->anyn) {   // Bluestein rows into the spectrum scratch, then float spectra / noise from it
+    const int L = pl->L;
+    CK(pl->any_spec2.need(sizeof(double2) * (size_t)nrows * N));
+    CK(pl->any_dc2.need(sizeof(double) * (size_t)nrows));
+    if (launch_fwd_any(pl, in, false, nullptr, nullptr, nrows, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>())) return -2;
+    k_rows_from_spec<<<nrows, 256, 0, pl->stream>>>(pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>(), spec, noise, N, L,
+                                                    kc >= 0 ? kc : (3 * (L + 1)) / 4, conj);
+    pl->stats.launches++;
+    return 0;
+  }
   RowsArgs a;
   a.in = in; a.spec = spec; a.noise = noise; a.nrows = nrows; a.conj = conj;
   a.kc = kc >= 0 ? kc : (3 * (N + 1)) / 4;
@@ -1020,8 +1179,8 @@ static int pshift_impl(pp_plan_t* pl, const float* profiles, int32_t n, const fl
   const int N = pl->N;
   const float *dprof, *dmod;
   const double* dnoise;
-  if (stage_in(pl, pl->rot_in, profiles, (size_t)n * 2 * N, &dprof)) return -2;
-  if (stage_in(pl, pl->model_stage, models, (size_t)nmodel * 2 * N, &dmod)) return -2;
+  if (stage_in(pl, pl->rot_in, profiles, (size_t)n * pl->nbin, &dprof)) return -2;
+  if (stage_in(pl, pl->model_stage, models, (size_t)nmodel * pl->nbin, &dmod)) return -2;
   if (stage_in(pl, pl->in_noise, noise, (size_t)n, &dnoise)) return -2;
   CK(pl->ps_spec.need(sizeof(float2) * (size_t)n * N));
   CK(pl->ps_mspec.need(sizeof(float2) * (size_t)nmodel * N));
@@ -1040,6 +1199,7 @@ static int pshift_impl(pp_plan_t* pl, const float* profiles, int32_t n, const fl
   ga.grid_general = general ? 1 : 0; ga.phi_lo = phi_lo; ga.phi_step = (phi_hi - phi_lo) / (double)(Ns - 1);
   ga.partial = pl->ps_spec.as<float2>(); ga.mconj = pl->ps_mspec.as<float2>(); ga.nparts = 1; ga.nmodel = nmodel;
   ga.N = N; ga.Ns = Ns; ga.wsum = nullptr; ga.noise = dnoise; ga.table = table; ga.s0 = 0; ga.polish_tol = 1e-14;
+  ga.nhalf = pl->anyn ? pl->L : 0;
   ga.phase = pl->ps_phase.as<double>(); ga.phase_err = pl->ps_perr.as<double>(); ga.scale = pl->ps_scale.as<double>();
   ga.scale_err = pl->ps_serr.as<double>(); ga.snr = pl->ps_snr.as<double>(); ga.red_chi2 = pl->ps_rchi2.as<double>();
   ga.lag = pl->ps_lag.as<int>();
@@ -1067,7 +1227,7 @@ extern "C" int pp_rotate_full_batch(pp_plan_t* pl, const float* in, float* outp,
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
-  const size_t tot = (size_t)nsub * nchan * 2 * N;
+  const size_t tot = (size_t)nsub * nchan * pl->nbin;
   const float* din;
   if (stage_in(pl, pl->rot_in, in, tot, &din)) return -2;
   float* dout = outp;
@@ -1083,21 +1243,8 @@ extern "C" int pp_rotate_full_batch(pp_plan_t* pl, const float* in, float* outp,
   RotateArgs a;
   a.in = din; a.out = dout; a.phase = dph; a.DM = ddm; a.P = dP; a.nu_ref = dnr; a.GM = dgm; a.nu_GM = dng;
   a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.resp = nullptr; a.nsub = nsub; a.nchan = nchan;
-  const long nrows = (long)nsub * nchan;
-  if (pl->fft_precision == 64) {
-    a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
-    DISPATCH_N(N, {
-      const int rows = RowGeom<NN>::kRows;
-      k_rotate<NN, double><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
-    });
-  } else {
-    a.twN = pl->twN32.p; a.tw2N = pl->tw2N32.p;
-    DISPATCH_N(N, {
-      const int rows = RowGeom<NN>::kRows;
-      k_rotate<NN, float><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, float>(), pl->stream>>>(a);
-    });
-  }
-  pl->stats.launches++;
+  (void)N;
+  if (rotate_rows(pl, a, pl->fft_precision == 64)) return -2;
   CK(cudaGetLastError());
   if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));
@@ -1115,14 +1262,14 @@ extern "C" int pp_apply_response_batch(pp_plan_t* pl, const float* in, float* ou
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
-  const size_t tot = (size_t)nsub * nchan * 2 * N;
+  const size_t tot = (size_t)nsub * nchan * pl->nbin;
   const float* din;
   if (stage_in(pl, pl->rot_in, in, tot, &din)) return -2;
   float* dout = outp;
   const bool out_dev = is_device_ptr(outp);
   if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
   const double* dresp;
-  if (stage_in(pl, pl->resp, resp, (size_t)nchan * (N + 1), &dresp)) return -2;
+  if (stage_in(pl, pl->resp, resp, (size_t)nchan * (pl->nbin / 2 + 1), &dresp)) return -2;
   if (!pl->gm_zero.p) {
     const double z = 0.0, o = 1.0;
     CK(pl->gm_zero.need(sizeof(double)));
@@ -1144,14 +1291,9 @@ extern "C" int pp_apply_response_batch(pp_plan_t* pl, const float* in, float* ou
   a.in = din; a.out = dout; a.phase = pl->rot_phase.as<double>(); a.DM = pl->rot_phase.as<double>();
   a.P = pl->rot_P.as<double>(); a.nu_ref = pl->rot_P.as<double>(); a.GM = nullptr; a.nu_GM = nullptr;
   a.nu2 = pl->nu2.as<double>(); a.taus = nullptr; a.resp = dresp; a.nsub = nsub; a.nchan = nchan;
-  a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
   if (!pl->nu2.p) { CK(pl->nu2.need(sizeof(double) * nchan)); CK(cudaMemsetAsync(pl->nu2.p, 0, sizeof(double) * nchan, pl->stream)); a.nu2 = pl->nu2.as<double>(); }
-  const long nrows = (long)nsub * nchan;
-  DISPATCH_N(N, {
-    const int rows = RowGeom<NN>::kRows;
-    k_rotate<NN, double><<<(unsigned)((nrows + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
-  });
-  pl->stats.launches++;
+  (void)N;
+  if (rotate_rows(pl, a, true)) return -2;
   CK(cudaGetLastError());
   if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));
@@ -1168,15 +1310,35 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
   const float* din;
-  if (stage_in(pl, pl->rot_in, data, (size_t)nsub * nchan * 2 * N, &din)) return -2;
+  if (stage_in(pl, pl->rot_in, data, (size_t)nsub * nchan * pl->nbin, &din)) return -2;
   const double *dph, *ddm, *dP, *dnr, *dw;
   if (stage_in(pl, pl->rot_phase, phase, (size_t)nsub, &dph)) return -2;
   if (stage_in(pl, pl->rot_dm, DM, (size_t)nsub, &ddm)) return -2;
   if (stage_in(pl, pl->rot_P, P, (size_t)nsub, &dP)) return -2;
   if (stage_in(pl, pl->rot_nuref, nu_ref, (size_t)nsub, &dnr)) return -2;
   if (stage_in(pl, pl->al_w, weights, (size_t)nsub * nchan, &dw)) return -2;
-  CK(pl->al_out.need(sizeof(double) * (size_t)nchan * 2 * N));
+  CK(pl->al_out.need(sizeof(double) * (size_t)nchan * pl->nbin));
   CK(pl->al_wsum.need(sizeof(double) * nchan));
+  if (pl->anyn) {   // rotate blocks of subints through the Bluestein transforms, add them up in double
+    const int blk = 64;
+    CK(pl->rot_out.need(sizeof(float) * (size_t)std::min(blk, nsub) * nchan * pl->nbin));
+    for (int s0 = 0; s0 < nsub; s0 += blk) {
+      const int ns = std::min(blk, nsub - s0);
+      RotateArgs r;
+      r.in = din + (size_t)s0 * nchan * pl->nbin; r.out = pl->rot_out.as<float>(); r.phase = dph + s0; r.DM = ddm + s0;
+      r.P = dP + s0; r.nu_ref = dnr + s0; r.GM = nullptr; r.nu_GM = nullptr; r.nu2 = pl->nu2.as<double>(); r.taus = nullptr;
+      r.resp = nullptr; r.nsub = ns; r.nchan = nchan;
+      if (rotate_rows(pl, r, true)) return -2;
+      k_wsum_rows<<<nchan, 256, 0, pl->stream>>>(pl->rot_out.as<float>(), dw + (size_t)s0 * nchan, pl->al_out.as<double>(),
+                                                 pl->al_wsum.as<double>(), ns, nchan, pl->nbin, s0 == 0);
+      pl->stats.launches++;
+    }
+    CK(cudaGetLastError());
+    if (copy_out(pl, aligned, pl->al_out.as<double>(), (size_t)nchan * pl->nbin)) return -2;
+    if (copy_out(pl, wsum, pl->al_wsum.as<double>(), (size_t)nchan)) return -2;
+    CK(cudaStreamSynchronize(pl->stream));
+    return 0;
+  }
   AlignArgs a;
   a.r.in = din; a.r.out = nullptr; a.r.phase = dph; a.r.DM = ddm; a.r.P = dP; a.r.nu_ref = dnr; a.r.GM = nullptr;
   a.r.nu_GM = nullptr; a.r.taus = nullptr; a.r.resp = nullptr; a.r.nu2 = pl->nu2.as<double>(); a.r.twN = pl->twN64.p; a.r.tw2N = pl->tw2N64.p;
@@ -1188,7 +1350,7 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   });
   pl->stats.launches++;
   CK(cudaGetLastError());
-  if (copy_out(pl, aligned, pl->al_out.as<double>(), (size_t)nchan * 2 * N)) return -2;
+  if (copy_out(pl, aligned, pl->al_out.as<double>(), (size_t)nchan * pl->nbin)) return -2;
   if (copy_out(pl, wsum, pl->al_wsum.as<double>(), (size_t)nchan)) return -2;
   CK(cudaStreamSynchronize(pl->stream));
   return 0;
@@ -1207,7 +1369,7 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
-  const size_t np = 2 + 6 * (size_t)ngauss, tot = (size_t)nchan * 2 * N;
+  const size_t np = 2 + 6 * (size_t)ngauss, tot = (size_t)nchan * pl->nbin;
   CK(pl->gm_params.need(sizeof(double) * np));
   CK(pl->gm_taus.need(sizeof(double) * nchan));
   CK(cudaMemcpyAsync(pl->gm_params.p, params, sizeof(double) * np, cudaMemcpyHostToDevice, pl->stream));
@@ -1216,7 +1378,7 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
   if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
   GaussModelArgs g;
   g.params = pl->gm_params.as<double>(); g.freqs = pl->freqs.as<double>(); g.out = dout; g.taus = pl->gm_taus.as<double>();
-  g.nu_ref = nu_ref; g.alpha = scattering_index; g.ngauss = ngauss; g.nchan = nchan; g.nbin = 2 * N;
+  g.nu_ref = nu_ref; g.alpha = scattering_index; g.ngauss = ngauss; g.nchan = nchan; g.nbin = pl->nbin;
   g.code_loc = model_code[0] - '0'; g.code_wid = model_code[1] - '0'; g.code_amp = model_code[2] - '0';
   k_gauss_model<<<nchan, 256, 0, pl->stream>>>(g);
   pl->stats.launches++;
@@ -1233,12 +1395,8 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
     a.in = dout; a.out = dout; a.phase = pl->gm_zero.as<double>(); a.DM = pl->gm_zero.as<double>();
     a.P = pl->gm_one.as<double>(); a.nu_ref = pl->gm_one.as<double>(); a.GM = nullptr; a.nu_GM = nullptr;
     a.nu2 = pl->nu2.as<double>(); a.taus = pl->gm_taus.as<double>(); a.resp = nullptr; a.nsub = 1; a.nchan = nchan;
-    a.twN = pl->twN64.p; a.tw2N = pl->tw2N64.p;
-    DISPATCH_N(N, {
-      const int rows = RowGeom<NN>::kRows;
-      k_rotate<NN, double><<<(unsigned)((nchan + rows - 1) / rows), 256, fft_smem_bytes<NN, double>(), pl->stream>>>(a);
-    });
-    pl->stats.launches++;
+    (void)N;
+    if (rotate_rows(pl, a, true)) return -2;
   }
   CK(cudaGetLastError());
   if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
@@ -1261,7 +1419,7 @@ extern "C" int pp_gen_spline_portrait(pp_plan_t* pl, const double* mean_prof, co
     return fail(-1, "the spline model arrays must be host arrays");
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
-  const int N = pl->N, nchan = pl->nchan, nbin = 2 * N;
+  const int nchan = pl->nchan, nbin = pl->nbin;
   const int ncoef = ncomp > 0 ? nknots - degree - 1 : 0;
   const size_t n_mean = nbin, n_eig = (size_t)nbin * ncomp, n_kn = ncomp > 0 ? nknots : 0, n_co = (size_t)ncomp * ncoef;
   const size_t total = n_mean + n_eig + n_kn + n_co;
@@ -1321,13 +1479,14 @@ extern "C" int pp_get_noise_batch(pp_plan_t* pl, const float* data, int32_t nsub
 extern "C" int pp_get_noise_cut_batch(pp_plan_t* pl, const float* data, int32_t nsub, int32_t kc, double* noise_out) {
   if (!pl || !data || !noise_out) return fail(-1, "NULL argument");
   if (nsub < 1) return fail(-1, "nsub must be >= 1");
-  if (kc > pl->N) return fail(-1, "kc must be <= nbin/2 (got %d)", kc);
+  if (kc > pl->nbin / 2) return fail(-1, "kc must be <= nbin/2 (got %d)", kc);
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
   const long nrows = (long)nsub * nchan;
   const float* din;
-  if (stage_in(pl, pl->rot_in, data, (size_t)nrows * 2 * N, &din)) return -2;
+  if (stage_in(pl, pl->rot_in, data, (size_t)nrows * pl->nbin, &din)) return -2;
+  (void)N;
   CK(pl->ps_noise.need(sizeof(double) * nrows));
   const int bits = pl->fft_precision ? pl->fft_precision : 64;
   if (launch_rfft_rows(pl, din, (int)nrows, nullptr, 0, pl->ps_noise.as<double>(), bits, kc)) return -2;

@@ -10,6 +10,7 @@ golden_v1.npz (make_golden.py) stays as it is.  New here:
             chi2 and snr^2 are of the same size (the strict 1e-8 chi2 bar)
   ir_*      instrumental_response_FT / _port_FT / gaussian_profile_FT values and a model with the response
   noise_*   get_noise_PS with frac != 4, get_noise_fit
+  nb_*      nbin that is not a power of two (1000, 1536, 100): phi+DM, five-parameter, FFTFIT grid, rotation
 Inputs are regenerated from the seeds by tests/synth.py; input checksums are stored.
 """
 from __future__ import annotations
@@ -154,6 +155,30 @@ put("noise", in_checksum=synth.checksum(data),
     ps_frac4=pl.get_noise_PS(data, frac=4, chans=True), ps_frac1=pl.get_noise_PS(data, frac=1, chans=True),
     ps_prof_frac8=pl.get_noise_PS(data[3], frac=8), fit_chans=pl.get_noise_fit(data, chans=True),
     fit_prof=pl.get_noise_fit(data[3]), fit_fact2=pl.get_noise_fit(data, fact=2.0, chans=True))
+
+# ---- nbin that is not a power of two (the reference takes any nbin: np.fft.rfft) ----------------------------
+for (nchan, nbin, seed) in [(64, 1000, 801), (32, 1536, 802), (16, 100, 803), (24, 3000, 804)]:
+    c = synth.make_case(nchan, nbin, 1500., 800., seed)
+    data, model, freqs, P = c["data"], c["model"], c["freqs"], c["P"]
+    case = "nb_%d" % seed
+    put(case, cfg=[nchan, nbin, 1500., 800., seed], in_checksum=synth.checksum(data), truth=[c["phi"], c["dDM"]])
+    errs = pl.get_noise(data, chans=True)
+    put(case, noise=errs, rot_row1=pl.rotate_data(data, 0.05, 1e-3, P, freqs, 1400.0)[1])
+    g = pl.fit_phase_shift(data.mean(0), model.mean(0), Ns=100)
+    bunch_fields(case, "ps", g, PS_FIELDS)
+    d1 = np.fft.rfft(data.mean(0)); d1[0] *= 0
+    m1 = np.fft.rfft(model.mean(0)); m1[0] *= 0
+    err = pl.get_noise(data.mean(0)) * np.sqrt(nbin / 2.0)
+    vals = np.array([pl.fit_phase_shift_function(x, m1, d1, err) for x in np.mgrid[-0.5:0.5:100j]])
+    put(case, grid_vals=vals, lag=int(np.argmin(vals)))
+    r = quiet_call(pl.fit_portrait, data, model, np.array([g.phase, 0.0]), P, freqs, errs=errs)
+    bunch_fields(case, "fp", r, FP_FIELDS)
+    r = quiet_call(ptl.fit_portrait_full, data, model, [g.phase, 0.0, 0.0, 0.0, 0.0], P, freqs, errs=errs,
+                   fit_flags=[1, 1, 0, 0, 0], log10_tau=False)
+    bunch_fields(case, "full", r, FULL_FIELDS)
+    print(case, "done", flush=True)
+full_case("nbfull_811", 32, 1000, 600., 400., 811, 50e-6, [1, 1, 0, 1, 1], True, 0, 1.5)
+full_case("nbfull_812", 32, 1536, 600., 400., 812, 50e-6, [1, 1, 1, 1, 1], True, 0, 1.5)
 
 out["meta/versions"] = np.array([np.__version__, scipy.__version__, sys.version.split()[0]])
 path = os.path.join(HERE, "golden_v2.npz")

@@ -65,8 +65,9 @@ def test_no_cpu_fallback(ffi):
         L.pp_plan_destroy(h)
     else:
         assert rc < 0 and len(L.pp_last_error()) > 0
-    assert L.pp_plan_create(8, 1000, 0, C.byref(h)) < 0        # not a power of two
-    assert b"power of two" in L.pp_last_error()
+    assert L.pp_plan_create(8, 1001, 0, C.byref(h)) < 0        # odd nbin: no real-FFT packing
+    assert b"even" in L.pp_last_error()
+    assert L.pp_plan_create(8, 8192, 0, C.byref(h)) < 0 and b"4096" in L.pp_last_error()
     assert L.pp_fit_batch(None, None, None) < 0
 
 

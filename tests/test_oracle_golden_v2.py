@@ -116,3 +116,28 @@ def test_noise_variants():
     assert rel(orc.get_noise_fit(data, chans=True), G2["noise/fit_chans"]) < 1e-12
     assert rel(orc.get_noise_fit(data[3]), G2["noise/fit_prof"]) < 1e-12
     assert rel(orc.get_noise_fit(data, fact=2.0, chans=True), G2["noise/fit_fact2"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", cases("nb_"))
+def test_non_power_of_two_nbin(case):
+    nchan, nbin, nu0, bw, seed = G2[case + "/cfg"]
+    nchan, nbin, seed = int(nchan), int(nbin), int(seed)
+    c = synth.make_case(nchan, nbin, nu0, bw, seed)
+    assert np.allclose(synth.checksum(c["data"]), G2[case + "/in_checksum"], rtol=1e-13)
+    data, model, freqs, P = c["data"], c["model"], c["freqs"], c["P"]
+    errs = orc.get_noise(data, chans=True)
+    assert rel(errs, G2[case + "/noise"]) < 1e-12
+    assert np.allclose(orc.rotate_data(data, 0.05, 1e-3, P, freqs, 1400.0)[1], G2[case + "/rot_row1"], atol=1e-10)
+    lag, grid, vals = orc.fit_phase_shift_grid(data.mean(0), model.mean(0), Ns=100)
+    assert lag == int(G2[case + "/lag"]) and rel(vals, G2[case + "/grid_vals"]) < 1e-9
+    g = orc.fit_phase_shift(data.mean(0), model.mean(0), Ns=100)
+    assert abs(g.phase - G2[case + "/ps.phase"]) < 1e-8
+    check_fp(case, "fp", orc.fit_portrait(data, model, np.array([g.phase, 0.0]), P, freqs, errs=errs))
+    r = orc.fit_portrait_full(data, model, [g.phase, 0.0, 0.0, 0.0, 0.0], P, freqs, errs=errs,
+                              fit_flags=[1, 1, 0, 0, 0], log10_tau=False)
+    check_full(case, "full", r, [1, 1, 0, 0, 0])
+
+
+@pytest.mark.parametrize("case", cases("nbfull_"))
+def test_non_power_of_two_nbin_five_parameters(case):
+    run_full_case(case)
