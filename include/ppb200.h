@@ -271,6 +271,12 @@ int pp_gen_spline_portrait(pp_plan_t* plan, const double* mean_prof,
                            const double* knots, int32_t nknots,
                            const double* coefs, int32_t degree, float* out);
 
+/* get_noise_fit(data, fact, chans=True) of pplib.py:2255-2284: the noise floor of each row's power
+ * spectrum starts at fact * find_kc(pows) (pplib.py:1465-1495, scipy.optimize.brute over a 20^3 grid of
+ * the b exp(-a k) + dc model of log10 pows, evaluated on the device). */
+int pp_get_noise_fit_batch(pp_plan_t* plan, const float* data, int32_t nsub, double fact,
+                           double* noise_out);
+
 /* Measured FP64 yardstick for the roofline record: DFMA thread-instructions per second of a kernel
  * of independent DFMA chains on the plan's device (no reference counterpart: measurement support). */
 int pp_measure_fp64(pp_plan_t* plan, double* dfma_per_second);

@@ -25,7 +25,7 @@ SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
            "pp_set_model", "pp_fit_batch",
            "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch", "pp_apply_response_batch",
            "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
-           "pp_get_noise_batch", "pp_get_noise_cut_batch", "pp_measure_fp64",
+           "pp_get_noise_batch", "pp_get_noise_cut_batch", "pp_get_noise_fit_batch", "pp_measure_fp64",
            "pp_plan_enable_timing", "pp_get_stats", "pp_host_alloc",
            "pp_host_free", "pp_last_error",
            "pp_abi_version"]
@@ -168,6 +168,8 @@ def lib():
     L.pp_get_noise_batch.restype = C.c_int
     L.pp_get_noise_cut_batch.argtypes = [vp, vp, i32, i32, vp]
     L.pp_get_noise_cut_batch.restype = C.c_int
+    L.pp_get_noise_fit_batch.argtypes = [vp, vp, i32, C.c_double, vp]
+    L.pp_get_noise_fit_batch.restype = C.c_int
     L.pp_measure_fp64.argtypes = [vp, C.POINTER(C.c_double)]
     L.pp_measure_fp64.restype = C.c_int
     L.pp_plan_enable_timing.argtypes = [vp, i32]

@@ -2174,6 +2174,8 @@ struct RowsArgs {
   const void* tw2N;
   int nrows, conj;
   int kc;               // first harmonic of the noise estimate (get_noise_PS: int((1 - 1/frac) nharm), pplib.py:2244)
+  double2* spec64;      // [nrows, N] FP64 spectra (slot layout) or null; dc64: [nrows] harmonic 0 (get_noise_fit)
+  double* dc64;
 };
 
 template <int N, typename T>
@@ -2210,9 +2212,11 @@ __global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
   double top = 0.0;
   float2* out = (a.spec && valid) ? a.spec + (size_t)row * N : nullptr;
   const float sgn = a.conj ? -1.f : 1.f;
+  double2* out64 = (a.spec64 && valid) ? a.spec64 + (size_t)row * N : nullptr;
   auto put = [&](int k, cx<T> d) {
     if (k >= kc) top += (double)(d.x * d.x + d.y * d.y);
     if (out) out[(k == N) ? 0 : k] = make_float2((float)d.x, sgn * (float)d.y);
+    if (out64) out64[(k == N) ? 0 : k] = make_double2((double)d.x, (double)d.y);
   };
 #pragma unroll
   for (int i = 0; i < G::kPairs; ++i) {
@@ -2227,6 +2231,7 @@ __global__ void __launch_bounds__(256) k_rfft_rows(RowsArgs a) {
   if (t_row == 0) {
     put(N, mk<T>(Z[0].x - Z[0].y, 0));
     if (kc == 0) { const double d0 = (double)(Z[0].x + Z[0].y); top += d0 * d0; }   // frac = 1: the DC term counts
+    if (a.dc64 && valid) a.dc64[row] = (double)(Z[0].x + Z[0].y);
   }
   if (a.noise) {
 #pragma unroll
@@ -2863,6 +2868,82 @@ __global__ void __launch_bounds__(256) k_align_reduce_any(const double2* __restr
     double t = 0.0;
     for (int q = 0; q < nsplit; ++q) t += wparts[(size_t)q * nchan + ch];
     wsum[ch] = t;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_noise_fit: get_noise_fit (pplib.py:2255-2284) -- the noise floor of a row's power spectrum starts
+// at fact * kc, kc from find_kc (pplib.py:1465-1495): scipy.optimize.brute (20 x 20 x 20 grid, no polish)
+// of chi2(a, b, dc) = sum_k (log10 pows_k - b e^{-a k} - dc)^2 over a in [1/nharm, 1], b in
+// [0, max - min], dc in [min, max] of log10 pows; the first k with e^{-a k} < 0.005.  One CTA per row:
+// the table e^{-a k} of one a at a time in shared memory, the 400 (b, dc) points of that slice spread over
+// the threads; flat argmin in scipy's C order (a slowest), lowest index on ties.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_noise_fit(const double2* __restrict__ spec, const double* __restrict__ dc, double* noise,
+                                                    int nslot, int L, int nyq_slot, double fact) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* y = reinterpret_cast<double*>(smem_raw);     // [L + 1] log10 pows
+  double* pw = y + (L + 1);                            // [L + 1] pows
+  double* ek = pw + (L + 1);                           // [L + 1] e^{-a k}
+  __shared__ double shv[8];
+  __shared__ int shi[8];
+  __shared__ double lim[2];
+  const long row = blockIdx.x;
+  const int tid = threadIdx.x, nh = L + 1;
+  const double inv_n = 1.0 / (double)(2 * L);
+  for (int k = tid; k < nh; k += 256) {
+    double p;
+    if (k == 0) p = dc[row] * dc[row];
+    else { const double2 d = spec[(size_t)row * nslot + (k == L ? nyq_slot : k)]; p = d.x * d.x + d.y * d.y; }
+    p *= inv_n;
+    pw[k] = p;
+    y[k] = log10(p);
+  }
+  __syncthreads();
+  if (tid < 32) {   // min / max of y
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (int k = tid; k < nh; k += 32) { lo = fmin(lo, y[k]); hi = fmax(hi, y[k]); }
+    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if (tid == 0) { lim[0] = lo; lim[1] = hi; }
+  }
+  __syncthreads();
+  const double ymin = lim[0], ymax = lim[1];
+  const double a_lo = 1.0 / (double)nh, a_st = (1.0 - a_lo) / 19.0, b_st = (ymax - ymin) / 19.0, d_st = (ymax - ymin) / 19.0;
+  double best = CUDART_INF;
+  int besti = 0x7fffffff;
+  for (int ia = 0; ia < 20; ++ia) {
+    const double av = (ia == 19) ? 1.0 : a_lo + ia * a_st;          // np.mgrid endpoints
+    __syncthreads();
+    for (int k = tid; k < nh; k += 256) ek[k] = exp(-av * (double)k);
+    __syncthreads();
+    for (int q = tid; q < 400; q += 256) {
+      const int ib = q / 20, id = q % 20;
+      const double bv = (ib == 19) ? (ymax - ymin) : ib * b_st, dv = (id == 19) ? ymax : ymin + id * d_st;
+      double c2 = 0.0;
+      for (int k = 0; k < nh; ++k) { const double r = y[k] - (bv * ek[k] + dv); c2 = fma(r, r, c2); }
+      const int flat = ia * 400 + q;
+      if (c2 < best || (c2 == best && flat < besti)) { best = c2; besti = flat; }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if ((tid & 31) == 0) { shv[tid >> 5] = best; shi[tid >> 5] = besti; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) if (shv[w] < best || (shv[w] == best && shi[w] < besti)) { best = shv[w]; besti = shi[w]; }
+    const int ia = besti / 400;
+    const double av = (ia == 19) ? 1.0 : a_lo + ia * a_st;
+    int kcrit = nh - 1;
+    for (int k = 0; k < nh; ++k) if (exp(-av * (double)k) < 0.005) { kcrit = k; break; }
+    double kf = fact * (double)kcrit;
+    if (kf >= (double)nh) kf = fmin((double)(int)(0.99 * nh), kf);
+    const int k0 = (int)kf;
+    double sum = 0.0;
+    for (int k = k0; k < nh; ++k) sum += pw[k];
+    noise[row] = sqrt(sum / (double)(nh - k0));
   }
 }
 

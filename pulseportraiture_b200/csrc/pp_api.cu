@@ -1117,7 +1117,7 @@ template <typename T> static const void* tw1(pp_plan* pl) { return sizeof(T) == 
 template <typename T> static const void* tw2(pp_plan* pl) { return sizeof(T) == 8 ? pl->tw2N64.p : pl->tw2N32.p; }
 
 static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spec, int conj, double* noise, int bits,
-                            int kc = -1) {
+                            int kc = -1, double2* spec64 = nullptr, double* dc64 = nullptr) {
   const int N = pl->N;
   if (pl->anyn) {   // Bluestein rows into the spectrum scratch, then float spectra / noise from it
     const int L = pl->L;
@@ -1132,6 +1132,7 @@ static int launch_rfft_rows(pp_plan* pl, const float* in, int nrows, float2* spe
   RowsArgs a;
   a.in = in; a.spec = spec; a.noise = noise; a.nrows = nrows; a.conj = conj;
   a.kc = kc >= 0 ? kc : (3 * (N + 1)) / 4;
+  a.spec64 = spec64; a.dc64 = dc64;
   if (bits == 64) {
     a.twN = tw1<double>(pl); a.tw2N = tw2<double>(pl);
     DISPATCH_N(N, {
@@ -1443,6 +1444,35 @@ extern "C" int pp_gen_spline_portrait(pp_plan_t* pl, const double* mean_prof, co
   pl->stats.launches++;
   CK(cudaGetLastError());
   if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+extern "C" int pp_get_noise_fit_batch(pp_plan_t* pl, const float* data, int32_t nsub, double fact, double* noise_out) {
+  if (!pl || !data || !noise_out) return fail(-1, "NULL argument");
+  if (nsub < 1) return fail(-1, "nsub must be >= 1");
+  if (!(fact > 0.0)) return fail(-1, "fact must be positive");
+  CK(cudaSetDevice(pl->device));
+  stats_begin(pl);
+  const int N = pl->N, nchan = pl->nchan, L = pl->nbin / 2;
+  const long nrows = (long)nsub * nchan;
+  const float* din;
+  if (stage_in(pl, pl->rot_in, data, (size_t)nrows * pl->nbin, &din)) return -2;
+  CK(pl->ps_noise.need(sizeof(double) * nrows));
+  CK(pl->any_spec2.need(sizeof(double2) * (size_t)nrows * N));
+  CK(pl->any_dc2.need(sizeof(double) * (size_t)nrows));
+  if (pl->anyn) {
+    if (launch_fwd_any(pl, din, false, nullptr, nullptr, nrows, pl->any_spec2.as<cx<double>>(), pl->any_dc2.as<double>())) return -2;
+  } else {
+    if (launch_rfft_rows(pl, din, (int)nrows, nullptr, 0, nullptr, 64, -1, pl->any_spec2.as<double2>(), pl->any_dc2.as<double>())) return -2;
+  }
+  const size_t smem = sizeof(double) * 3 * (size_t)(L + 1);
+  CK(cudaFuncSetAttribute(k_noise_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_noise_fit<<<(unsigned)nrows, 256, smem, pl->stream>>>(pl->any_spec2.as<double2>(), pl->any_dc2.as<double>(), pl->ps_noise.as<double>(),
+                                                          N, L, pl->anyn ? L : 0, fact);
+  pl->stats.launches++;
+  CK(cudaGetLastError());
+  if (copy_out(pl, noise_out, pl->ps_noise.as<double>(), (size_t)nrows)) return -2;
   CK(cudaStreamSynchronize(pl->stream));
   return 0;
 }

@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(64, PP_SPECTRA16_MINB) k_spectra16(SpectraArgs
         for (int r = 0; r < 16; ++r) Xrow[t + 64 * r] = make_float2(0.f, 0.f);
         a.Xlo[row * kLo + t] = make_float2(0.f, 0.f);
       }
+      if constexpr (KEEPD) {        // k_align_spec prefetches every row of the chunk: keep the skipped ones defined
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a.D[row * N + t + 64 * r] = make_float2(0.f, 0.f);
+        if (t == 0) a.Ddc[row] = 0.0;
+      }
       if (t < 2) rowsum[step][t] = make_double2(0.0, 0.0);
       fetch(step + 1);              // the staging buffer is free (nothing was copied for this row)
       continue;

@@ -304,6 +304,16 @@ class WidebandPlan(object):
             aligned.ctypes.data, wsum.ctypes.data), "pp_align_accumulate")
         return aligned, wsum
 
+    def get_noise_fit_batch(self, data, fact=1.1):
+        """get_noise_fit(chans=True) per row (pplib.py:2255-2284; the find_kc grid search runs on the device)."""
+        keep = []
+        nsub = int(data.shape[0])
+        ip = _ptr(data, np.float32, keep, "data", (nsub, self.nchan, self.nbin))
+        out = np.empty((nsub, self.nchan))
+        _ffi.check(self._lib.pp_get_noise_fit_batch(self._h, ip, nsub, float(fact), out.ctypes.data),
+                   "pp_get_noise_fit_batch")
+        return out
+
     def gen_gaussian_portrait(self, model_code, params, scattering_index, nu_ref, out=None, device_out=False):
         """Evolving-Gaussian model portrait on the device (pplib.py:853-930) for the plan's
         frequencies (set_freqs first).  ``params`` = [DC, tau_bin, (loc, m_loc, wid, m_wid, amp,

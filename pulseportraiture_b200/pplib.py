@@ -205,10 +205,25 @@ def get_scales(data, model, phase, DM, P, freqs, nu_ref=np.inf):
 
 # ---- A9: noise ------------------------------------------------------------------------
 def get_noise(data, method=default_noise_method, **kwargs):
-    """Off-pulse noise estimate (pplib.py:2206-2225); only method 'PS'."""
-    if method != "PS":
-        raise NotImplementedError("only the 'PS' noise method is on the hot path")
-    return get_noise_PS(data, **kwargs)
+    """Off-pulse noise estimate (pplib.py:2206-2225): "PS" or "fit"."""
+    if method == "PS":
+        return get_noise_PS(data, **kwargs)
+    if method == "fit":
+        return get_noise_fit(data, **kwargs)
+    print("Unknown get_noise method.")
+    return 0
+
+
+def get_noise_fit(data, fact=1.1, chans=False):
+    """Noise from the harmonics above fact * the cutoff a fit of b exp(-a k) + dc to the log power
+    spectrum finds (pplib.py:2255-2284, find_kc 1465-1495)."""
+    data = np.asarray(data)
+    if chans:
+        nchan, nbin = data.shape
+        return get_plan(nchan, nbin).get_noise_fit_batch(_f32(data)[None], fact)[0]
+    rav = data.ravel()
+    n = rav.size
+    return get_plan(1, n).get_noise_fit_batch(_f32(rav).reshape(1, 1, n), fact)[0, 0]
 
 
 def get_noise_PS(data, frac=4, chans=False):

@@ -168,3 +168,17 @@ def test_noise_frac_against_reference():
         assert rel(pplib.get_noise_PS(c["data"], frac=frac, chans=True), G2["noise/ps_frac%d" % frac]) < 1e-9
     assert rel(pplib.get_noise_PS(c["data"][3], frac=8), G2["noise/ps_prof_frac8"]) < 1e-9
     assert rel(pplib.get_noise(c["data"], method="PS", frac=8, chans=True), G2["noise/ps_frac8"]) < 1e-9
+
+
+def test_noise_fit_against_reference():
+    """get_noise(method='fit') (pplib.py:2255-2284): the find_kc grid search on the device."""
+    from pulseportraiture_b200 import pplib
+    c = synth.make_case(16, 512, 1500., 800., 701)
+    assert rel(pplib.get_noise_fit(c["data"], chans=True), G2["noise/fit_chans"]) < 1e-9
+    assert rel(pplib.get_noise(c["data"], method="fit", chans=True), G2["noise/fit_chans"]) < 1e-9
+    assert rel(pplib.get_noise_fit(c["data"][3]), G2["noise/fit_prof"]) < 1e-9
+    assert rel(pplib.get_noise_fit(c["data"], fact=2.0, chans=True), G2["noise/fit_fact2"]) < 1e-9
+    # any nbin
+    from oracle import pp_oracle as orc
+    c2 = synth.make_case(6, 1000, 1500., 800., 702)
+    assert rel(pplib.get_noise_fit(c2["data"], chans=True), orc.get_noise_fit(c2["data"], chans=True)) < 1e-9
