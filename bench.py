@@ -221,8 +221,8 @@ def run_reference(args):
 
 
 # FP64 thread-instructions the two main kernels execute (ncu source counters of the committed captures,
-# profiles/r02_k_spectra16.md and profiles/r01_k_pass2.md): per (row, thread) and per harmonic
-FP64_PER_THREAD_ROW_SPECTRA = 745.0
+# profiles/r02_k_spectra16.md, r02_k_pass2.md, traffic_r02.json): per (row, thread) and per harmonic
+FP64_PER_THREAD_ROW_SPECTRA = 712.3
 FP64_PER_HARMONIC_PASS2 = 17.56
 
 # per-subint scalars that travel in the host-side gather (TOA-level results; the per-channel arrays
