@@ -12,6 +12,7 @@
 #include <chrono>
 #include <type_traits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ppb200.h"
@@ -78,6 +79,13 @@ struct pp_plan {
   int nchan = 0, nbin = 0, N = 0, device = 0;
   // arbitrary (even, non power-of-two) nbin: rows are transformed by Bluestein kernels (bluestein.cuh) into an
   // FP64 spectrum scratch of N = Npad slots per row; L = nbin/2 is the true number of harmonics, M the FFT length
+  // pageable host input: pieces are copied into a ring of page-locked buffers by several host threads
+  // and sent from there (a plain cudaMemcpyAsync from pageable memory stages through one thread: ~10 GB/s)
+  static const int kPinSlots = 4;
+  static const size_t kPinPiece = 32u << 20;
+  void* pin_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pin_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long pin_count = 0;
   bool anyn = false;
   int L = 0, M = 0;
   DBuf any_chirp, any_B, any_twM, any_tw2n, any_spec, any_dc, any_spec2, any_dc2;
@@ -170,12 +178,16 @@ static bool is_device_ptr(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+static bool is_pinned_host_ptr(const void* p);
+static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st);
+
 template <typename T>
 static int stage_in(pp_plan* pl, DBuf& buf, const T* src, size_t n, const T** out) {
   if (!src) { *out = nullptr; return 0; }
   if (is_device_ptr(src)) { *out = src; return 0; }
   CK(buf.need(n * sizeof(T)));
-  CK(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, pl->stream));
+  const size_t bytes = n * sizeof(T);
+  CK(h2d_any(pl, buf.p, src, bytes, bytes < (8u << 20) || is_pinned_host_ptr(src), pl->stream));
   *out = buf.as<T>();
   return 0;
 }
@@ -421,6 +433,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   for (cudaEvent_t e : pl->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : pl->ev_chunk) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { cudaEventDestroy(pl->ev_copy[i]); cudaEventDestroy(pl->ev_free[i]); }
+  for (int i = 0; i < pp_plan::kPinSlots; ++i) { if (pl->pin_ring[i]) cudaFreeHost(pl->pin_ring[i]); if (pl->pin_ev[i]) cudaEventDestroy(pl->pin_ev[i]); }
   cudaStreamDestroy(pl->own_stream);
   cudaStreamDestroy(pl->copy_stream);
   delete pl;
@@ -623,6 +636,52 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
 // ----------------------------------------------------------------------------
 // fit
 // ----------------------------------------------------------------------------
+static bool is_pinned_host_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t n, int nthreads) {
+  if (nthreads <= 1 || n < (4u << 20)) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((n / nthreads) + 4095) & ~(size_t)4095;
+  for (int i = 1; i < nthreads; ++i) {
+    const size_t o = (size_t)i * per;
+    if (o >= n) break;
+    th.emplace_back([=]() { memcpy((char*)dst + o, (const char*)src + o, std::min(per, n - o)); });
+  }
+  memcpy(dst, src, std::min(per, n));
+  for (auto& t : th) t.join();
+}
+
+// host -> device on `st`: straight from page-locked memory, through the plan's page-locked ring otherwise
+static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st) {
+  if (src_pinned || bytes < (8u << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  static const int nthreads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  for (size_t off = 0; off < bytes; off += pp_plan::kPinPiece) {
+    const size_t len = std::min(pp_plan::kPinPiece, bytes - off);
+    const int slot = (int)(pl->pin_count++ % pp_plan::kPinSlots);
+    cudaError_t e;
+    if (!pl->pin_ring[slot]) {
+      e = cudaHostAlloc(&pl->pin_ring[slot], pp_plan::kPinPiece, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      e = cudaEventCreateWithFlags(&pl->pin_ev[slot], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    } else {
+      e = cudaEventSynchronize(pl->pin_ev[slot]);      // the copy that last used this slot has left it
+      if (e != cudaSuccess) return e;
+    }
+    parallel_memcpy(pl->pin_ring[slot], (const char*)src + off, len, nthreads);
+    e = cudaMemcpyAsync((char*)dst + off, pl->pin_ring[slot], len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(pl->pin_ev[slot], st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 static const int kMaxChunk = 32768;   // the chunk index is gridDim.y of the row kernels (<= 65535)
 static int pick_chunk(pp_plan* pl, int nsub, bool data_on_host, double bytes_per_sample = 4.0) {
   if (pl->chunk_req > 0) return std::min(std::min(pl->chunk_req, kMaxChunk), nsub);
@@ -792,6 +851,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->Xlo.need(sizeof(float2) * (size_t)chunk * nchan * std::min(N, 64)));
   if (want_guess) CK(pl->partial.need(sizeof(float2) * (size_t)chunk * nparts * N));
   const bool data_on_device = is_device_ptr(args->data);
+  const bool data_pinned = !data_on_device && is_pinned_host_ptr(args->data);
   if (data_on_device && !pl->anyn && (reinterpret_cast<uintptr_t>(args->data) & 15))
     return fail(-1, "device data pointer must be 16-byte aligned");
   const size_t sub_bytes = (size_t)nchan * pl->nbin * (i16 ? sizeof(int16_t) : sizeof(float));   // one subint as the kernels read it
@@ -856,8 +916,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
     if (e != cudaSuccess) return e;
     void* dst = f64 ? pl->data_stage64[b].p : pl->data_stage[b].p;
-    e = cudaMemcpyAsync(dst, data_bytes + (size_t)s0 * src_bytes, (size_t)ns * src_bytes,
-                        cudaMemcpyHostToDevice, pl->copy_stream);
+    e = h2d_any(pl, dst, data_bytes + (size_t)s0 * src_bytes, (size_t)ns * src_bytes, data_pinned, pl->copy_stream);
     if (e != cudaSuccess) return e;
     if (f64) convert_f64(dst, pl->data_stage[b].p, ns, pl->copy_stream);
     return cudaEventRecord(pl->ev_copy[b], pl->copy_stream);
