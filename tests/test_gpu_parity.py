@@ -644,7 +644,7 @@ def test_edge_cases(engine):
         with pytest.raises(PPError):
             pl.fit_batch(data[None], c["P"], fit_flags=(0, 0, 0, 0, 0))
     with pytest.raises(PPError):
-        engine.WidebandPlan(8, 1000)
+        engine.WidebandPlan(8, 1001)        # odd nbin (any even nbin <= 4096 is served: tests/test_gpu_anynbin.py)
     with pytest.raises(PPError):
         engine.WidebandPlan(8, 8192)
 
