@@ -107,6 +107,11 @@ class SharedGather(object):
         else:
             dist.barrier(group=group)
             self.shm = shared_memory.SharedMemory(name=name)
+            try:       # only the creating rank owns the segment: keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
         buf = np.ndarray((self.world, self.slot + 1), dtype=np.float64, buffer=self.shm.buf)
         self.buf = buf
 
