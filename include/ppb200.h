@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PPB200_ABI_VERSION 5
+#define PPB200_ABI_VERSION 6
 
 typedef struct pp_plan pp_plan_t;
 
@@ -68,6 +68,15 @@ int pp_plan_set_fft_precision(pp_plan_t* plan, int32_t bits);
  * evaluated on the data (more passes, same optimum; used by the tests to
  * check the model-based steps). */
 int pp_plan_set_model_steps(pp_plan_t* plan, int32_t steps);
+
+/* General (GM / tau / alpha) solver: its first Newton iterations run on the objective of the low harmonics
+ * only -- the leading groups of 16 harmonics that hold `frac` of the model's phase information
+ * sum_n sum_k k^2 |m_nk|^2 (default 0.99), a fraction of a pass over the cross-spectrum each -- and bring the
+ * start values to within a fraction of a sigma of the optimum; the full-resolution iterations that follow
+ * decide convergence exactly as without it (same optimum, fewer full passes).  frac = 0 disables the coarse
+ * stage, as do pp_plan_set_model_steps(plan, 1) and a model whose information is spread over more than half
+ * of the harmonics.  nfeval counts coarse and full evaluations alike. */
+int pp_plan_set_coarse(pp_plan_t* plan, double frac);
 
 /* Channel frequencies [nchan] MHz only (enough for pp_rotate_batch). */
 int pp_set_freqs(pp_plan_t* plan, const double* freqs);
@@ -303,6 +312,8 @@ typedef struct {
   double ms_total;         /* first launch -> last kernel of the call           */
   int32_t chunk;           /* subints per chunk used                            */
   int32_t timing_enabled;
+  int64_t coarse_launches; /* coarse (low-harmonic) iterations of the general solver, not in pass_launches */
+  double ms_coarse;        /* ... their pass + update kernels                   */
 } pp_stats_t;
 
 int pp_plan_enable_timing(pp_plan_t* plan, int32_t on);

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 
 # symbols declared in include/ppb200.h (checked by the CPU test-suite)
 SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
-           "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_set_freqs",
+           "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_plan_set_coarse", "pp_set_freqs",
            "pp_set_model", "pp_fit_batch",
            "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch", "pp_apply_response_batch",
            "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
@@ -110,7 +110,8 @@ class Stats(C.Structure):
                 ("pass_rows", C.c_int64), ("ms_spectra", C.c_double),
                 ("ms_guess", C.c_double), ("ms_pass", C.c_double),
                 ("ms_update", C.c_double), ("ms_total", C.c_double),
-                ("chunk", C.c_int32), ("timing_enabled", C.c_int32)]
+                ("chunk", C.c_int32), ("timing_enabled", C.c_int32),
+                ("coarse_launches", C.c_int64), ("ms_coarse", C.c_double)]
 
 
 _lib = None
@@ -140,6 +141,8 @@ def lib():
     L.pp_plan_set_fft_precision.restype = C.c_int
     L.pp_plan_set_model_steps.argtypes = [vp, i32]
     L.pp_plan_set_model_steps.restype = C.c_int
+    L.pp_plan_set_coarse.argtypes = [vp, C.c_double]
+    L.pp_plan_set_coarse.restype = C.c_int
     L.pp_set_freqs.argtypes = [vp, vp]
     L.pp_set_freqs.restype = C.c_int
     L.pp_set_model.argtypes = [vp, vp, vp]

@@ -1364,6 +1364,63 @@ __global__ void k_reset_state(SolverState st, int s0, int n) {
   st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
 }
 
+// end of the coarse stage of the general fit: every unfinished subint starts the full-resolution Newton
+// iterations from where the coarse ones left it (the objective changes: no comparison with the old value)
+__global__ void k_coarse_end(SolverState st, int s0, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = s0 + i;
+  if (st.done[s] == 1) return;
+  st.done[s] = 0;
+  st.fprev[s] = CUDART_INF;
+  st.lam[s] = 1.0;
+  for (int q = 0; q < 5; ++q) { st.xprev[(size_t)s * 5 + q] = st.x[(size_t)s * 5 + q]; st.step[(size_t)s * 5 + q] = 0.0; }
+}
+
+// number of subints of [s0, s0+n) still in the coarse stage
+__global__ void k_count_coarse(SolverState st, int s0, int n, int* out) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (st.done[s0 + i] == 0);
+  atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = cnt;
+}
+
+// Where the phase information of the (scattered) model sits, per group of 16 harmonics:
+//   info[j] = sum_n sum_{16 j <= k < 16 (j+1)} k^2 |m_nk|^2 |B_nk|^2,  |B_nk|^2 = 1 / (1 + (2 pi k tau_n)^2)
+// with tau_n from the start values of subint s (x = null: no scattering).  The host accumulates the groups and
+// takes the leading ones that hold coarse_frac of the total as the coarse objective of the general solver
+// (the Nyquist term is left out).
+__global__ void k_model_info(const double* mpow, const double* lgf, const double* x, const double* nu_fit, int log10_tau,
+                             double* info, int nchan, int N) {
+  const int j = blockIdx.x;
+  double tau = 0.0, alpha = 0.0, lg2nT = 0.0;
+  if (x) {
+    tau = log10_tau ? exp2(x[3] * 3.3219280948873623479) : x[3];
+    alpha = x[4];
+    lg2nT = log2(nu_fit[2]);
+  }
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nchan * 16; i += blockDim.x) {
+    const int n = i >> 4, k = j * 16 + (i & 15);
+    if (k == 0) continue;     // slot 0 holds the Nyquist harmonic
+    const double b = tau != 0.0 ? kTwoPi * (double)k * tau * exp2(alpha * (lgf[n] - lg2nT)) : 0.0;
+    v += (double)k * (double)k * mpow[(size_t)n * N + k] / fma(b, b, 1.0);
+  }
+  __shared__ double sh[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += sh[q];
+    info[j] = t;
+  }
+}
+
 // start values are moved into the box, as scipy's TNC does with x0
 __global__ void k_clamp_state(SolverState st, Box box, int s0, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1400,15 +1457,43 @@ struct Pass5Args {
   SolverState st;
   int s0, nchan, log10_tau;
   int nhalf;               // true nbin/2 (0: N)
+  int nj;                  // groups of 16 harmonics summed: N/16 = all of them; fewer = the coarse objective, which
+                           // also leaves the Nyquist term out and skips subints already coarse-converged (done == 3)
 };
 
 #ifndef PP_PASS5_MINB
 #define PP_PASS5_MINB 2
 #endif
+// 16-byte asynchronous copy global -> shared (L2 only), thread-private use: the issuing thread alone reads the
+// destination, after cp.async.wait_group
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory");
+}
+
+// k_pass5 keeps D iterations of loads (X row piece + |m|^2 piece, 16 bytes each per thread) in flight through a
+// thread-private ring in shared memory: the kernel is FP64-bound with 128 registers per thread and 16 warps per SM,
+// too few to cover the load latency from registers.
+template <int N> struct Pass5Ring {
+  static constexpr int NJ = N / 16;
+  static constexpr int D = NJ < 8 ? NJ : 8;
+  static constexpr int KJ = LoK<N>::value / 16;
+  static constexpr size_t kBytes = sizeof(float4) * 256 * (2 * D + KJ);
+};
+
 template <int N>
 __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int sl = blockIdx.y, s = a.s0 + sl;
-  if (a.st.done[s] == 1) return;
+  constexpr int NJ = N / 16;
+  const bool coarse = a.nj < NJ;
+  {
+    const int dn = a.st.done[s];
+    if (dn == 1 || (coarse && dn == 3)) return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int sub = lane >> 3, l8 = lane & 7;
   const int ch = blockIdx.x * 32 + w * 4 + sub;
@@ -1419,6 +1504,28 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double taun = 0.0;
   if (used) {
+    using R = Pass5Ring<N>;
+    constexpr int D = R::D, KJ = R::KJ;
+    float4* rv = reinterpret_cast<float4*>(smem_raw) + tid;   // [D][256] X pieces
+    float4* rm = rv + D * 256;                                 // [D][256] |m|^2 pieces (double2)
+    float4* rl = rm + D * 256;                                 // [KJ][256] float32 residuals of the low harmonics
+    const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N) + l8;
+    const float4* mrow = reinterpret_cast<const float4*>(a.mpow + (size_t)ch * N) + l8;
+    const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value) + l8;
+    const int nj = coarse ? a.nj : NJ;   // (the coarse objective has nj >= KJ)
+    auto issue = [&](int j) {            // one commit group per iteration, empty past the end
+      if (j < nj) {
+        cp_async16(rv + (j % D) * 256, row + j * 8);
+        cp_async16(rm + (j % D) * 256, mrow + j * 8);
+      }
+      cp_async_commit();
+    };
+    // the first loads go out before the phasor set-up
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) cp_async16(rl + j * 256, lorow + j * 8);
+#pragma unroll
+    for (int j = 0; j < D - 1; ++j) issue(j);
+
     const double* x = a.st.x + (size_t)s * 5;
     const double P = a.P[s];
     const double nD = a.nu_fit[(size_t)s * 3 + 0], nG = a.nu_fit[(size_t)s * 3 + 1], nT = a.nu_fit[(size_t)s * 3 + 2];
@@ -1432,8 +1539,6 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
       const double lr = x[4] * (a.lgf[ch] - log2(nT));
       taun = a.log10_tau ? exp2(fma(x[3], 3.3219280948873623479, lr)) : x[3] * exp2(lr);
     }
-    const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
-    const double2* mrow = reinterpret_cast<const double2*>(a.mpow + (size_t)ch * N);
     // phasors for k = 2 l8, 2 l8 + 1 and the step 16 from one sincospi by repeated squaring (as k_pass2)
     double c0, s0, c1, s1, cw, sw;
     cx<double> e1, e2, e4, e8, e16;
@@ -1454,7 +1559,7 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
     auto element = [&](double xr, double xi, double m, double c, double sn, double k) {
       const double zr = xr * c - xi * sn, zi = xr * sn + xi * c;      // X e^{i psi}
       const double b = k * wt;
-      const double b2 = b * b, den = b2 + 1.0;
+      const double den = fma(b, b, 1.0);
       double q;                                                       // |B|^2 = 1/(1 + b^2)
       asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));         // ~20 bits, then two Newton steps
       q = q * fma(-den, q, 2.0);
@@ -1474,36 +1579,41 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
       const double k2q2m = k2 * q * qm;
       acc[6] += qm;
       acc[7] += k2q2m;
-      acc[8] = fma(k2q2m, fma(4.0 * b2, q, -1.0), acc[8]);
+      acc[8] = fma(k2q2m, fma(-4.0, q, 3.0), acc[8]);                 // 4 b^2 q - 1 = 3 - 4 q
     };
-    constexpr int NJ = N / 16;
-    constexpr int KJ = LoK<N>::value / 16;
-    const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
     auto advance = [&]() {
       const double t0 = c0 * cw - s0 * sw; s0 = c0 * sw + s0 * cw; c0 = t0;
       const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
       k0 += 16.0; k1 += 16.0;
     };
+    // iteration j: wait for its group, read its slot, refill the slot read one iteration ago
+    auto fetch = [&](int j, float4& v, double2& mm) {
+      cp_async_wait<(D >= 2 ? D - 2 : 0)>();
+      v = rv[(j % D) * 256];
+      mm = *reinterpret_cast<const double2*>(rm + (j % D) * 256);
+      issue(j + D - 1);
+    };
     // the first KJ iterations carry the float32 residuals of the low harmonics
 #pragma unroll
     for (int j = 0; j < KJ; ++j) {
-      const float4 v = ld_stream(row + j * 8 + l8);
-      const float4 lo = ld_stream(lorow + j * 8 + l8);
-      const double2 mm = __ldg(mrow + j * 8 + l8);
+      float4 v; double2 mm;
+      fetch(j, v, mm);
+      const float4 lo = rl[j * 256];
       const bool z = (j == 0 && l8 == 0);
       element(z ? 0.0 : (double)v.x + (double)lo.x, z ? 0.0 : (double)v.y + (double)lo.y, z ? 0.0 : mm.x, c0, s0, k0);
       element((double)v.z + (double)lo.z, (double)v.w + (double)lo.w, mm.y, c1, s1, k1);
       advance();
     }
 #pragma unroll 2
-    for (int j = KJ; j < NJ; ++j) {
-      const float4 v = ld_stream(row + j * 8 + l8);
-      const double2 mm = __ldg(mrow + j * 8 + l8);
+    for (int j = KJ; j < nj; ++j) {
+      float4 v; double2 mm;
+      fetch(j, v, mm);
       element((double)v.x, (double)v.y, mm.x, c0, s0, k0);
       element((double)v.z, (double)v.w, mm.y, c1, s1, k1);
       advance();
     }
-    if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
+    row -= l8; lorow -= l8;
+    if (l8 == 0 && !coarse) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
       const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
       const double mn = __ldg(a.mpow + (size_t)ch * N);
@@ -1666,6 +1776,7 @@ __device__ inline int real_pos_roots(const double* c_in, int deg_in, double* out
 // ----------------------------------------------------------------------------
 struct Update5Args {
   const double* csum; const double* Sdn; const double* nu2; const double* freqs; const double* P;
+  const double* lgf;       // [nchan] log2(freqs)
   const double* nu_fit; const double* nu_outs; const int* nok;
   SolverState st;
   double* params; double* param_errs; double* nu_out; double* cov; double* chi2; double* red_chi2;
@@ -1673,7 +1784,10 @@ struct Update5Args {
   int s0, nchan, nbin, max_iter, log10_tau, option, is_toa;
   int flags[5];
   int taylor_finish;   // finish a converged fit from the sums at the last evaluated point (no final pass)
-  double tol;
+  int coarse;          // the sums are those of the low harmonics only (k_pass5 nj < N/16): Newton steps towards
+                       // the start point of the full-resolution iterations, no epilogue; a subint whose step is
+                       // <= ctol sigma waits in state done == 3
+  double tol, ctol;
   Box box;
 };
 
@@ -1692,14 +1806,15 @@ struct ChanJ {   // per-channel Jacobians of (theta_n, tau_n) w.r.t. the five pa
   double Jth[3], Jt[2], Ktt, Kta, Kaa, lnf, taun;
 };
 
-__device__ __forceinline__ ChanJ chan_jac(double nu, double n2, double P, double nD, double nG, double nT, double tau_lin,
+// lg2r = log2(nu_n / nu_tau) from the tabulated log2(nu_n): tau_n is one exp2, as in k_pass5
+__device__ __forceinline__ ChanJ chan_jac(double lg2r, double n2, double P, double nD, double nG, double tau_lin,
                                           double alpha, int log10_tau) {
   ChanJ j;
   j.Jth[0] = 1.0;
   j.Jth[1] = kDconst * (n2 - 1.0 / (nD * nD)) / P;                           // pptoaslib.py:222
   j.Jth[2] = kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P;  // :223
-  j.lnf = log(nu / nT);
-  j.taun = tau_lin * pow(nu / nT, alpha);
+  j.lnf = lg2r * 0.69314718055994530942;
+  j.taun = tau_lin * exp2(alpha * lg2r);
   const double ln10 = 2.302585092994045684;
   if (log10_tau) {                                                            // :246-274
     j.Jt[0] = ln10 * j.taun; j.Ktt = ln10 * j.Jt[0]; j.Kta = ln10 * j.lnf * j.taun;
@@ -1740,10 +1855,10 @@ __device__ __forceinline__ double chan_H(double C, double S, double d2C, double 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
+__global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
   const int s = a.s0 + blockIdx.x;
   const int state = a.st.done[s];
-  if (state == 1) return;
+  if (state == 1 || state == 3) return;
   __shared__ double sh[24 * (NT / 32)];
   __shared__ double bc[48];
   const int tid = threadIdx.x, nchan = a.nchan;
@@ -1755,6 +1870,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   double* stp = a.st.step + (size_t)s * 5;
   const double tau_lin = a.log10_tau ? pow(10.0, x[3]) : x[3];
   const double alpha = x[4];
+  const double lg2nT = log2(nT);
   // The epilogue reports the point x + dx: dx = 0 when the sums in csum were evaluated at the
   // reported point (final pass), or the last (converged, <= tol sigma) Newton step, in which case
   // the per-channel sums are carried there by their second-order Taylor series (chan_shift) and the
@@ -1780,7 +1896,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
       const double S = c[6];
       if (!(S > 0.0)) continue;
       if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_lin, alpha, a.log10_tau);
+      const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_lin, alpha, a.log10_tau);
       double dC[5], dS[5];
       chan_first(c, j, dC, dS);
       const double C = c[0];
@@ -1814,7 +1930,11 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
       else if (it > 1 && f > a.st.fprev[s] + 1e-12 * fabs(a.st.fprev[s])) {
         const double lam = a.st.lam[s] * 0.25;
         a.st.lam[s] = lam;
-        if (it >= a.max_iter || lam < 1e-6) { action = 3; rc = 1; }
+        if (a.coarse) {   // the coarse stage only prepares a start point: give up early, at the best point seen
+          if (lam < 1e-2) { for (int i = 0; i < 5; ++i) x[i] = xp[i]; a.st.done[s] = 3; }
+          else for (int i = 0; i < 5; ++i) x[i] = xp[i] + lam * stp[i];
+        }
+        else if (it >= a.max_iter || lam < 1e-6) { action = 3; rc = 1; }
         else for (int i = 0; i < 5; ++i) x[i] = xp[i] + lam * stp[i];
       } else {
         double H[25], g[5], L[25], d[5] = {0, 0, 0, 0, 0}, dr[5];
@@ -1875,10 +1995,12 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         if (clipped) for (int i = 0; i < 5; ++i) d[i] = xn[i] - x[i];
         bool conv = pd && sc == 1.0 && !clipped;
         bool tiny = conv;   // last step <= 0.1 tol sigma: the sums can be carried to the final point (chan_shift)
+        bool cconv = conv;  // coarse stage: last step <= ctol sigma
         if (conv) for (int i = 0; i < nfit; ++i) {
           const double sg = sqrt(2.0 * Inv[i * 5 + i]);     // 1-sigma from inv(H/2)
           if (!(fabs(dr[i]) <= a.tol * sg)) conv = false;
           if (!(fabs(dr[i]) <= 0.1 * a.tol * sg)) tiny = false;
+          if (!(fabs(dr[i]) <= a.ctol * sg)) cconv = false;
         }
         for (int i = 0; i < 5; ++i) { xp[i] = x[i]; stp[i] = d[i]; }
         a.st.fprev[s] = f;
@@ -1886,7 +2008,10 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
         for (int i = 0; i < 5; ++i) x[i] = xn[i];
         nfit = nfit_all;
         for (int i = 0; i < 5; ++i) idx[i] = idx_all[i];
-        if (conv && tiny && a.taylor_finish) {   // report x + d from the sums at x (no final pass)
+        if (a.coarse) {   // no epilogue from the coarse sums: wait (state 3) for the full-resolution iterations
+          if (cconv) a.st.done[s] = 3;
+        }
+        else if (conv && tiny && a.taylor_finish) {   // report x + d from the sums at x (no final pass)
           action = 4; rc = 0;
           for (int i = 0; i < 5; ++i) { bc[33 + i] = d[i]; bc[38 + i] = xn[i]; }
         }
@@ -1923,9 +2048,9 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
                          dx[2] * (kDconst * kDconst * (n2 * n2 - 1.0 / (nG * nG * nG * nG)) / P);
       double dta = 0.0;
       if (scat_on) {
-        const double lnf = log(a.freqs[n] / nT);
-        const double dl = (a.log10_tau ? 2.302585092994045684 * dx[3] : log1p(dx[3] / tau_lin)) + dx[4] * lnf;
-        dta = tau_lin * pow(a.freqs[n] / nT, alpha) * expm1(dl);
+        const double lg2r = a.lgf[n] - lg2nT;
+        const double dl = (a.log10_tau ? 2.302585092994045684 * dx[3] : log1p(dx[3] / tau_lin)) + dx[4] * lg2r * 0.69314718055994530942;
+        dta = tau_lin * exp2(alpha * lg2r) * expm1(dl);
       }
       chan_shift(c, dth, dta);
     }
@@ -1947,10 +2072,10 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_e, alpha_e, a.log10_tau);
+    const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_e, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
-    const double C = c[0], n2 = a.nu2[n], lnnu = log(a.freqs[n]);
+    const double C = c[0], n2 = a.nu2[n], lnnu = a.lgf[n] * 0.69314718055994530942;
     for (int p = 0; p < 5; ++p) {
       // Hessian row w.r.t. theta_n (= Hn[DM,p]/gDM_n etc.): d2C[theta,p], no S-dependence on theta
       const double d2 = (p < 3) ? c[2] * j.Jth[p] : c[5] * j.Jt[p - 3];
@@ -1986,7 +2111,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, nD, nG, nT, tau_e, alpha_e, a.log10_tau);
+    const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_e, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
     int q = 0;
@@ -2079,6 +2204,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
   const double noD = bc[2], noG = bc[3], noT = bc[4];
   // ---- re-reference phi and tau (pptoaslib.py:1052-1065) -----------------------------------
   const double tau_out_lin = tau_e * pow(noT / nT, alpha_e);
+  const double lg2noT = log2(noT);
   // ---- Hessian at the output frequencies, covariance incl. amplitudes (645-731) -------------
   double ho[15];
   for (int i = 0; i < 15; ++i) ho[i] = 0.0;
@@ -2088,7 +2214,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
     const double S = c[6];
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha_e, a.log10_tau);
+    const ChanJ j = chan_jac(a.lgf[n] - lg2noT, a.nu2[n], P, noD, noG, tau_out_lin, alpha_e, a.log10_tau);
     double dC[5], dS[5];
     chan_first(c, j, dC, dS);
     int q = 0;
@@ -2118,7 +2244,7 @@ __global__ void __launch_bounds__(NT) k_update5(Update5Args a) {
     double sc = 0.0, se = 0.0, csn = 0.0;
     if (S > 0.0) {
       if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-      const ChanJ j = chan_jac(a.freqs[n], a.nu2[n], P, noD, noG, noT, tau_out_lin, alpha_e, a.log10_tau);
+      const ChanJ j = chan_jac(a.lgf[n] - lg2noT, a.nu2[n], P, noD, noG, tau_out_lin, alpha_e, a.log10_tau);
       double dC[5], dS[5];
       chan_first(c, j, dC, dS);
       sc = c[0] / S;                                               // :688

@@ -98,12 +98,14 @@ struct pp_plan {
   DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, mmean_sub, model_stage;
   int fft_precision = 0;   // 0 auto, 32, 64
   int model_steps = 8;     // (phi, DM) solver: Newton steps on the local fourth-order model per pass
+  double coarse_frac = 0.99;   // general solver: share of the model's phase information the coarse objective keeps
+  std::vector<double> model_info;   // per group of 16 harmonics (scratch of the per-chunk choice)
   bool freqs_set = false;
   // FFTFIT grid tables keyed by Ns
   std::vector<std::pair<int, DBuf>> grid_tables;
   DBuf grid_general;   // table of the last grid with bounds other than [-0.5, 0.5]
   // per-batch staging of small inputs and per-subint / per-channel workspace
-  DBuf running, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
+  DBuf running, minfo, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
   DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
@@ -121,7 +123,7 @@ struct pp_plan {
   pp_stats_t stats;
 };
 
-enum { SP_SPECTRA = 0, SP_GUESS = 1, SP_PASS = 2, SP_UPDATE = 3, SP_TOTAL = 4 };
+enum { SP_SPECTRA = 0, SP_GUESS = 1, SP_PASS = 2, SP_UPDATE = 3, SP_TOTAL = 4, SP_COARSE = 5 };
 
 static cudaEvent_t get_event(pp_plan* pl) {
   if (pl->ev_used == pl->ev_pool.size()) {
@@ -163,6 +165,7 @@ static void stats_end(pp_plan* pl) {
       case SP_GUESS: pl->stats.ms_guess += ms; break;
       case SP_PASS: pl->stats.ms_pass += ms; break;
       case SP_UPDATE: pl->stats.ms_update += ms; break;
+      case SP_COARSE: pl->stats.ms_coarse += ms; break;
       case SP_TOTAL: pl->stats.ms_total += ms; break;
     }
   }
@@ -303,6 +306,7 @@ template <int N> static cudaError_t setup_attrs() {
   SET_((k_spectra<N>), (int)spectra_smem_bytes<N>())
   SET_((k_spectra<N, SpecPlan<N>, true>), (int)spectra_smem_bytes<N>())
   SET_((k_model<N>), b64)
+  SET_((k_pass5<N>), (int)Pass5Ring<N>::kBytes)
   SET_((k_rfft_rows<N, float>), b32)
   SET_((k_rfft_rows<N, double>), b64)
   SET_((k_align_accum<N>), b64)
@@ -418,7 +422,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->minfo, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -588,6 +592,28 @@ extern "C" int pp_plan_set_model_steps(pp_plan_t* pl, int32_t steps) {
   if (!pl) return fail(-1, "NULL plan");
   if (steps < 0 || steps > 64) return fail(-1, "model steps must be 0 (default) .. 64");
   pl->model_steps = steps == 0 ? 8 : steps;
+  return 0;
+}
+
+// The coarse objective of the general solver: the leading groups of 16 harmonics that hold `frac` of the
+// (scattered) model's phase information; 0 = no coarse stage (it would not be at most half of the harmonics).
+static int choose_coarse(const std::vector<double>& info, double frac, int N) {
+  const int NJ = N / 16;
+  if (!(frac > 0.0) || info.size() != (size_t)NJ || NJ < 8) return 0;
+  double tot = 0.0;
+  for (double v : info) tot += v;
+  if (!(tot > 0.0) || !(tot < INFINITY)) return 0;
+  double cum = 0.0;
+  int nj = NJ;
+  for (int j = 0; j < NJ; ++j) { cum += info[j]; if (cum >= frac * tot) { nj = j + 1; break; } }
+  nj = std::max(nj, 4);   // the groups that carry float32 residuals (LoK = 64 harmonics) are always summed
+  return 2 * nj <= NJ ? nj : 0;
+}
+
+extern "C" int pp_plan_set_coarse(pp_plan_t* pl, double frac) {
+  if (!pl) return fail(-1, "NULL plan");
+  if (!(frac >= 0.0 && frac < 1.0)) return fail(-1, "coarse fraction must be in [0, 1): 0 disables the coarse stage");
+  pl->coarse_frac = frac;
   return 0;
 }
 
@@ -1050,9 +1076,9 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>(); p5.lgf = pl->lgf.as<double>();
       p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
       p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
-      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0;
+      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0; p5.nj = N / 16;
       memset(&u5, 0, sizeof u5);
-      u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>();
+      u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>(); u5.lgf = pl->lgf.as<double>();
       u5.freqs = pl->freqs.as<double>(); u5.P = dP; u5.nu_fit = pl->nu_fit.as<double>(); u5.nu_outs = dnuouts;
       u5.nok = pl->nok.as<int>(); u5.st = st;
       u5.params = ua.params; u5.param_errs = ua.param_errs; u5.nu_out = ua.nu_out; u5.cov = ua.cov; u5.chi2 = ua.chi2;
@@ -1062,19 +1088,64 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol; u5.box = box;
       u5.taylor_finish = pl->model_steps != 1;
       for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
+      u5.coarse = 0; u5.ctol = 0.0;
+    }
+    auto launch_update5 = [&]() {   // many channels: more threads per subint for the per-channel chain rule
+      if (nchan >= 1024) k_update5<256><<<ns, 256, 0, pl->stream>>>(u5);
+      else k_update5<128><<<ns, 128, 0, pl->stream>>>(u5);
+    };
+    // Coarse stage of the general solver: Newton iterations on the objective of the low harmonics only (those
+    // that hold coarse_frac of the model's phase information: a fraction of a pass each) carry the start values
+    // to within a fraction of a sigma of the optimum; the full-resolution iterations below then need two passes.
+    int coarse_nj = 0;
+    if (general && max_iter > 0 && pl->coarse_frac > 0.0 && pl->model_steps != 1 && N >= 128) {
+      // where the information sits, with the scattering of the chunk's first subint at its start values
+      const bool scat = ff[3] || ff[4] || dscat || dinit;
+      CK(pl->minfo.need(sizeof(double) * (N / 16)));
+      pl->model_info.assign(N / 16, 0.0);
+      k_model_info<<<N / 16, 256, 0, pl->stream>>>(pl->mpow.as<double>(), pl->lgf.as<double>(), scat ? st.x + (size_t)s0 * 5 : nullptr,
+                                                   pl->nu_fit.as<double>() + (size_t)s0 * 3, args->log10_tau,
+                                                   pl->minfo.as<double>(), nchan, N);
+      pl->stats.launches++;
+      CK(cudaMemcpyAsync(pl->model_info.data(), pl->minfo.p, sizeof(double) * (N / 16), cudaMemcpyDeviceToHost, pl->stream));
+      CK(cudaStreamSynchronize(pl->stream));
+      coarse_nj = choose_coarse(pl->model_info, pl->coarse_frac, N);
+    }
+    if (coarse_nj > 0) {
+      const int max_coarse = std::min(max_iter, 12);
+      static const double ctol_env = getenv("PP_CTOL") ? atof(getenv("PP_CTOL")) : 0.0;   // (experiments)
+      p5.nj = coarse_nj; u5.coarse = 1; u5.ctol = ctol_env > 0 ? ctol_env : 0.05;
+      if (trace) { char b[64]; snprintf(b, sizeof b, "coarse stage: %d of %d harmonic groups", coarse_nj, N / 16); mark(b); }
+      for (int it = 0; it < max_coarse; ++it) {
+        {
+          SpanGuard g(pl, SP_COARSE);
+          DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5));
+          launch_update5();
+        }
+        pl->stats.launches += 2;
+        pl->stats.coarse_launches++;
+        if (it >= 2 && it + 1 < max_coarse) {
+          k_count_coarse<<<1, 256, 0, pl->stream>>>(st, s0, ns, pl->running.as<int>());
+          pl->stats.launches++;
+          int running = 0;
+          CK(cudaMemcpyAsync(&running, pl->running.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+          CK(cudaStreamSynchronize(pl->stream));
+          if (running == 0) break;
+        }
+      }
+      k_coarse_end<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
+      pl->stats.launches++;
+      p5.nj = N / 16; u5.coarse = 0;
     }
     for (int it = 0; it < n_launch_iter; ++it) {
       {
         SpanGuard g(pl, SP_PASS);
-        if (general) { DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(p5)); }
+        if (general) { DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5)); }
         else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(pa)); }
       }
       {
         SpanGuard g(pl, SP_UPDATE);
-        if (general) {   // many channels: more threads per subint for the per-channel chain rule
-          if (nchan >= 1024) k_update5<256><<<ns, 256, 0, pl->stream>>>(u5);
-          else k_update5<128><<<ns, 128, 0, pl->stream>>>(u5);
-        }
+        if (general) launch_update5();
         else k_update2<<<ns, 128, 0, pl->stream>>>(ua);
       }
       pl->stats.launches += 2;
@@ -1083,7 +1154,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       // launch of the full grid costs ~80 us, the poll ~20 us)
       // (when the previous chunk needed a third pass this one most likely does too: launch it
       // without asking first)
-      const bool poll = general ? (it >= 3) : (it >= 2 || (it == 1 && !expect_third));
+      const bool poll = general ? (it >= (coarse_nj > 0 ? 1 : 3)) : (it >= 2 || (it == 1 && !expect_third));
       if (it == 1 && pending_out >= 0) {   // this chunk's first passes are queued: now the old copies
         if (enqueue_results(pending_out)) return -2;
         pending_out = -1;

@@ -143,6 +143,11 @@ class WidebandPlan(object):
         1 = every step evaluated on the data)."""
         _ffi.check(self._lib.pp_plan_set_model_steps(self._h, int(steps)), "pp_plan_set_model_steps")
 
+    def set_coarse(self, frac):
+        """General solver: share of the model's phase information kept by the coarse (low-harmonic)
+        objective its first iterations run on (default 0.99; 0 = no coarse stage)."""
+        _ffi.check(self._lib.pp_plan_set_coarse(self._h, float(frac)), "pp_plan_set_coarse")
+
     def set_freqs(self, freqs):
         keep = []
         fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(ffi):
     for name in declared:
         assert hasattr(L, name), "missing symbol " + name
     assert sorted(ffi.SYMBOLS) == declared
-    assert L.pp_abi_version() == 5
+    assert L.pp_abi_version() == 6
 
 
 def test_struct_layouts_match_the_header(ffi, tmp_path):
