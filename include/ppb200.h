@@ -69,13 +69,15 @@ int pp_plan_set_fft_precision(pp_plan_t* plan, int32_t bits);
  * check the model-based steps). */
 int pp_plan_set_model_steps(pp_plan_t* plan, int32_t steps);
 
-/* General (GM / tau / alpha) solver: its first Newton iterations run on the objective of the low harmonics
- * only -- the leading groups of 16 harmonics that hold `frac` of the model's phase information
- * sum_n sum_k k^2 |m_nk|^2 (default 0.99), a fraction of a pass over the cross-spectrum each -- and bring the
- * start values to within a fraction of a sigma of the optimum; the full-resolution iterations that follow
- * decide convergence exactly as without it (same optimum, fewer full passes).  frac = 0 disables the coarse
- * stage, as do pp_plan_set_model_steps(plan, 1) and a model whose information is spread over more than half
- * of the harmonics.  nfeval counts coarse and full evaluations alike. */
+/* General (GM / tau / alpha) solver, coarse-to-fine start.  Its first Newton iterations run on cheaper objectives:
+ * the low harmonics only -- the leading groups of 16 harmonics that hold `frac` (default 0.99) of the phase
+ * information sum_n sum_k k^2 |m_nk|^2 |B_nk|^2 of the model scattered with the start values -- preceded, where
+ * that pays, by a level with fewer harmonics still (0.65 of the information) of every 2nd / 4th / 8th channel.
+ * Each costs a fraction of a pass over the cross-spectrum and brings the start values to within a fraction of a
+ * sigma of the optimum; the full-resolution iterations that follow decide convergence exactly as without it
+ * (same optimum and errors, two full passes instead of five to nine).  frac = 0 disables the coarse levels, as do
+ * pp_plan_set_model_steps(plan, 1) and a model whose information is spread over more than half of the harmonics.
+ * nfeval counts coarse and full evaluations alike; pp_stats_t tells them apart. */
 int pp_plan_set_coarse(pp_plan_t* plan, double frac);
 
 /* Channel frequencies [nchan] MHz only (enough for pp_rotate_batch). */

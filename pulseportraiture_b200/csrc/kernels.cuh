@@ -522,7 +522,6 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
       // the profile for the FFTFIT guess (its sigma comes out non-finite, so the fit skips it too)
       if (i == 0 && !(isfinite(d[0].x) && isfinite(d[0].y))) wrow = 0.f;
       float vx[NOUT], vy[NOUT];
-#pragma unroll
       double sa0 = 0.0, sa1 = 0.0;      // two chains: the power sum is latency, not throughput, bound
 #pragma unroll
       for (int q = 0; q < NOUT; ++q) {
@@ -882,8 +881,30 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return v;
 }
 
+// 16-byte asynchronous copy global -> shared (L2 only), thread-private use: the issuing thread alone reads the
+// destination, after cp.async.wait_group
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory");
+}
+
+// k_pass2 / k_pass5 can keep D iterations of loads (16 bytes per thread each) in flight through a thread-private ring
+// in shared memory instead of registers
+template <int N> struct Pass2Ring {
+  static constexpr int NJ = N / 16;
+  static constexpr int D = NJ < 8 ? NJ : 8;
+  static constexpr int KJ = LoK<N>::value / 16;
+  static constexpr size_t kBytes = sizeof(float4) * 256 * (D + KJ);
+};
+#ifndef PP_PASS2_RING
+#define PP_PASS2_RING 1
+#endif
+
 #ifndef PP_PASS2_MINB
-#define PP_PASS2_MINB 3
+#define PP_PASS2_MINB (PP_PASS2_RING ? 4 : 3)
 #endif
 template <int N>
 __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
@@ -916,8 +937,26 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
     // the first loads go out before the phasor set-up so that its latency is hidden
+#if PP_PASS2_RING
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* rv = reinterpret_cast<float4*>(smem_raw) + tid;   // [D][256] X pieces
+    float4* rl = rv + Pass2Ring<N>::D * 256;                  // [KJ][256] float32 residuals of the low harmonics
+    auto ring_issue = [&](int j) {                            // one commit group per iteration, empty past the end
+      if (j < NJ) cp_async16(rv + (j % Pass2Ring<N>::D) * 256, row + j * 8 + l8);
+      cp_async_commit();
+    };
+    if constexpr (KJ != NJ) {
+#pragma unroll
+      for (int j = 0; j < KJ; ++j) cp_async16(rl + j * 256, lorow + j * 8 + l8);
+#pragma unroll
+      for (int j = 0; j < Pass2Ring<N>::D - 1; ++j) ring_issue(j);
+    }
+    [[maybe_unused]] float4 qa[U], qb[U], ql[U];
+    if constexpr (false) {
+#else
     float4 qa[U], qb[U], ql[U];
     if constexpr (KJ != NJ) {
+#endif
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         qa[u] = ld_stream(row + u * 8 + l8);
@@ -965,6 +1004,26 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
       if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
       accum((double)v.x + (double)lo.x, (double)v.y + (double)lo.y, (double)v.z + (double)lo.z, (double)v.w + (double)lo.w);
     };
+#if PP_PASS2_RING
+    if constexpr (KJ != NJ) {
+      // iteration j: wait for its copy, read its slot, refill the slot read one iteration ago
+      constexpr int D = Pass2Ring<N>::D;
+#pragma unroll
+      for (int j = 0; j < KJ; ++j) {
+        cp_async_wait<D - 2>();
+        const float4 v = rv[(j % D) * 256], lo = rl[j * 256];
+        ring_issue(j + D - 1);
+        consume_lo(v, lo, j == 0);
+      }
+#pragma unroll 4
+      for (int j = KJ; j < NJ; ++j) {
+        cp_async_wait<D - 2>();
+        const float4 v = rv[(j % D) * 256];
+        ring_issue(j + D - 1);
+        consume(v);
+      }
+    } else
+#endif
     // software pipeline: the next group's loads are in flight while this one is consumed
     if constexpr (KJ == NJ) {     // N <= 64: every iteration has a lo part
 #pragma unroll
@@ -1459,21 +1518,12 @@ struct Pass5Args {
   int nhalf;               // true nbin/2 (0: N)
   int nj;                  // groups of 16 harmonics summed: N/16 = all of them; fewer = the coarse objective, which
                            // also leaves the Nyquist term out and skips subints already coarse-converged (done == 3)
+  int cstride;             // coarse objective: every cstride-th channel only (1: all)
 };
 
 #ifndef PP_PASS5_MINB
 #define PP_PASS5_MINB 2
 #endif
-// 16-byte asynchronous copy global -> shared (L2 only), thread-private use: the issuing thread alone reads the
-// destination, after cp.async.wait_group
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPEND> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory");
-}
-
 // k_pass5 keeps D iterations of loads (X row piece + |m|^2 piece, 16 bytes each per thread) in flight through a
 // thread-private ring in shared memory: the kernel is FP64-bound with 128 registers per thread and 16 warps per SM,
 // too few to cover the load latency from registers.
@@ -1496,7 +1546,7 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
   }
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int sub = lane >> 3, l8 = lane & 7;
-  const int ch = blockIdx.x * 32 + w * 4 + sub;
+  const int ch = (blockIdx.x * 32 + w * 4 + sub) * a.cstride;
   const bool inrange = ch < a.nchan;
   const int chc = inrange ? ch : a.nchan - 1;
   const bool used = inrange && a.Ssn[(size_t)s * a.nchan + chc] > 0.0;
@@ -1784,6 +1834,7 @@ struct Update5Args {
   int s0, nchan, nbin, max_iter, log10_tau, option, is_toa;
   int flags[5];
   int taylor_finish;   // finish a converged fit from the sums at the last evaluated point (no final pass)
+  int cstride;         // coarse: the sums exist for every cstride-th channel only (else 1)
   int coarse;          // the sums are those of the low harmonics only (k_pass5 nj < N/16): Newton steps towards
                        // the start point of the full-resolution iterations, no epilogue; a subint whose step is
                        // <= ctol sigma waits in state done == 3
@@ -1854,6 +1905,39 @@ __device__ __forceinline__ double chan_H(double C, double S, double d2C, double 
                  C * (dCa * dSb + dSa * dCb) * iS * iS);
 }
 
+// The same derivatives without the per-entry divisions: with r = C/S every gradient / Hessian entry of the
+// channel's -C^2/S is one of five scalars times products of the Jacobians,
+//   g_i = G1 Jth_i (i < 3), G2 Jt_i (i >= 3)
+//   H_ik = A Jth_i Jth_k (i, k < 3), M Jth_i Jt_k (i < 3 <= k), T1 Jt_i Jt_k + G2 K_ik (i, k >= 3)
+// (pptoaslib.py:572, 624-628 written out for dC_i = C_th Jth_i | C_t Jt_i, dS_i = 0 | S_t Jt_i).
+struct ChanK { double f, G1, G2, A, M, T1, r; };
+__device__ __forceinline__ ChanK chan_k(const double* c) {
+  const double iS = 1.0 / c[6];
+  const double r = c[0] * iS, r2 = r * r;
+  const double e = c[3] - r * c[7];
+  ChanK k;
+  k.r = r;
+  k.f = -c[0] * r;
+  k.G1 = -2.0 * r * c[1];
+  k.G2 = -2.0 * r * c[3] + r2 * c[7];
+  k.A = -2.0 * (r * c[2] + c[1] * c[1] * iS);
+  k.M = -2.0 * (r * c[5] + c[1] * iS * e);
+  k.T1 = -2.0 * (r * c[4] - 0.5 * r2 * c[8] + iS * e * e);
+  return k;
+}
+// adds the channel's Hessian (upper triangle, row-major: 00 01 02 03 04 11 12 13 14 22 23 24 33 34 44) to h
+__device__ __forceinline__ void chan_hess(const ChanK& k, const ChanJ& j, double* h) {
+  const double a1 = k.A * j.Jth[1], a2 = k.A * j.Jth[2];
+  const double m0 = k.M * j.Jt[0], m1 = k.M * j.Jt[1];
+  h[0] += k.A; h[1] += a1; h[2] += a2; h[3] += m0; h[4] += m1;
+  h[5] = fma(a1, j.Jth[1], h[5]); h[6] = fma(a1, j.Jth[2], h[6]); h[7] = fma(m0, j.Jth[1], h[7]); h[8] = fma(m1, j.Jth[1], h[8]);
+  h[9] = fma(a2, j.Jth[2], h[9]); h[10] = fma(m0, j.Jth[2], h[10]); h[11] = fma(m1, j.Jth[2], h[11]);
+  const double t0 = k.T1 * j.Jt[0], t1 = k.T1 * j.Jt[1];
+  h[12] += fma(t0, j.Jt[0], k.G2 * j.Ktt);
+  h[13] += fma(t0, j.Jt[1], k.G2 * j.Kta);
+  h[14] += fma(t1, j.Jt[1], k.G2 * j.Kaa);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
   const int s = a.s0 + blockIdx.x;
@@ -1889,26 +1973,28 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
     // ---- f, gradient, Hessian --------------------------------------------------------
     double v[23];
     for (int i = 0; i < 23; ++i) v[i] = 0.0;   // f, g[5], H upper [15], Sd, spare
-    double gmax1 = 0.0, gmax2 = 0.0;
-    for (int n = tid; n < nchan; n += NT) {
+    double gmax1 = -CUDART_INF, gmax2 = -CUDART_INF;   // max nu^-2, max -nu^-2
+    const int cst = a.coarse ? a.cstride : 1;
+    for (int n = tid * cst; n < nchan; n += NT * cst) {
       double c[9];
       for (int i = 0; i < 9; ++i) c[i] = cs[n * kNCsum + i];
       const double S = c[6];
       if (!(S > 0.0)) continue;
       if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
       const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_lin, alpha, a.log10_tau);
-      double dC[5], dS[5];
-      chan_first(c, j, dC, dS);
-      const double C = c[0];
-      v[0] -= C * C / S;
-      for (int i = 0; i < 5; ++i) v[1 + i] += (-2.0 * C * dC[i] / S + C * C * dS[i] / (S * S)) * fl[i];  // :572
-      int q = 6;
-      for (int i = 0; i < 5; ++i)
-        for (int k = i; k < 5; ++k, ++q)
-          v[q] += chan_H(C, S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * fl[i] * fl[k];
+      const ChanK k = chan_k(c);
+      v[0] += k.f;
+      v[1] += k.G1; v[2] = fma(k.G1, j.Jth[1], v[2]); v[3] = fma(k.G1, j.Jth[2], v[3]);   // :572
+      v[4] = fma(k.G2, j.Jt[0], v[4]); v[5] = fma(k.G2, j.Jt[1], v[5]);
+      chan_hess(k, j, v + 6);
       v[21] += a.Sdn[(size_t)s * nchan + n];
-      gmax1 = fmax(gmax1, fabs(j.Jth[1]));
-      gmax2 = fmax(gmax2, fabs(j.Jth[2]));
+      gmax1 = fmax(gmax1, a.nu2[n]);      // range of nu^-2 over the used channels (step limit below)
+      gmax2 = fmax(gmax2, -a.nu2[n]);
+    }
+    for (int i = 0; i < 5; ++i) v[1 + i] *= fl[i];
+    {
+      int q = 6;
+      for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) v[q] *= fl[i] * fl[k];
     }
     block_sum<23, NT>(v, sh);
     double gm[2] = {gmax1, gmax2};
@@ -1916,7 +2002,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
     __syncthreads();
     if ((tid & 31) == 0) { sh[tid >> 5] = gm[0]; sh[NT / 32 + (tid >> 5)] = gm[1]; }
     __syncthreads();
-    gmax1 = gmax2 = 0.0;
+    gmax1 = gmax2 = -CUDART_INF;
 #pragma unroll
     for (int q = 0; q < NT / 32; ++q) { gmax1 = fmax(gmax1, sh[q]); gmax2 = fmax(gmax2, sh[NT / 32 + q]); }
     if (tid == 0) {
@@ -1983,7 +2069,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
         // step limits: rotation of any channel <= 0.1 turn, log10(tau) <= 0.5, alpha <= 1,
         // linear tau: at most halve / grow by its own size
         double sc = 1.0;
-        const double rot = fabs(d[0]) + fabs(d[1]) * gmax1 + fabs(d[2]) * gmax2;
+        double rot;
+        {
+          // the rotation of channel n is the quadratic d0 + d1 K1 (nu_n^-2 - nu_D^-2) + d2 K2 (nu_n^-4 - nu_G^-4) in
+          // nu_n^-2: its largest modulus over the band (DM and GM steps along their common valley nearly cancel,
+          // the sum of the moduli would throttle them for many iterations)
+          const double K1 = kDconst / P, K2 = kDconst * kDconst / P;
+          const double q0 = d[0] - d[1] * K1 / (nD * nD) - d[2] * K2 / (nG * nG * nG * nG), q1 = d[1] * K1, q2 = d[2] * K2;
+          const double lo = -gmax2, hi = gmax1;
+          auto qv = [&](double t) { return fabs(fma(fma(q2, t, q1), t, q0)); };
+          rot = fmax(qv(lo), qv(hi));
+          if (q2 != 0.0) { const double tv = -0.5 * q1 / q2; if (tv > lo && tv < hi) rot = fmax(rot, qv(tv)); }
+          if (!(rot == rot)) rot = CUDART_INF;
+        }
         if (rot > 0.1) sc = fmin(sc, 0.1 / rot);
         if (a.log10_tau) { if (fabs(d[3]) > 0.5) sc = fmin(sc, 0.5 / fabs(d[3])); }
         else if (fl[3] && x[3] > 0.0 && fabs(d[3]) > 0.5 * x[3]) sc = fmin(sc, 0.5 * x[3] / fabs(d[3]));
@@ -2066,42 +2164,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
   for (int i = 0; i < 24; ++i) u[i] = 0.0;
   // u[0..14]: for j=0..4: sum h_th(j), sum nu^-2 h_th(j), sum nu^-4 h_th(j)
   // u[15..20]: for j in {0,1,3}: sum h_ln(j), sum ln(nu) h_ln(j) ; u[21]: f ; u[22]: Sd ; u[23]: snr^2
-  for (int n = tid; n < nchan; n += NT) {
-    double c[9];
-    load_c(n, c);
-    const double S = c[6];
-    if (!(S > 0.0)) continue;
-    if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
-    const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_e, alpha_e, a.log10_tau);
-    double dC[5], dS[5];
-    chan_first(c, j, dC, dS);
-    const double C = c[0], n2 = a.nu2[n], lnnu = a.lgf[n] * 0.69314718055994530942;
-    for (int p = 0; p < 5; ++p) {
-      // Hessian row w.r.t. theta_n (= Hn[DM,p]/gDM_n etc.): d2C[theta,p], no S-dependence on theta
-      const double d2 = (p < 3) ? c[2] * j.Jth[p] : c[5] * j.Jt[p - 3];
-      const double h = chan_H(C, S, d2, 0.0, c[1], dC[p], 0.0, dS[p]) * zfl[p];
-      u[3 * p] += h; u[3 * p + 1] += n2 * h; u[3 * p + 2] += n2 * n2 * h;
-    }
-    {
-      // Hessian row w.r.t. alpha divided by ln(nu_n/nu_tau): d/dalpha = lnf * tau_n d/dtau_n
-      const double Cta = c[3] * j.taun, Sta = c[7] * j.taun;
-      const double k10 = a.log10_tau ? 2.302585092994045684 * j.taun : (tau_e != 0.0 ? j.taun / tau_e : 0.0);
-      const int ps[3] = {0, 1, 3};
-      for (int q = 0; q < 3; ++q) {
-        const int p = ps[q];
-        double d2C, d2S;
-        if (p < 3) { d2C = c[5] * j.Jth[p] * j.taun; d2S = 0.0; }
-        else { d2C = c[4] * j.taun * j.Jt[0] + c[3] * k10; d2S = c[8] * j.taun * j.Jt[0] + c[7] * k10; }
-        const double h = chan_H(C, S, d2C, d2S, Cta, dC[p], Sta, dS[p]) * zfl[p];
-        u[15 + 2 * q] += h; u[16 + 2 * q] += lnnu * h;
-      }
-    }
-    u[21] -= C * C / S;
-    u[22] += a.Sdn[(size_t)s * nchan + n];
-    u[23] += C * C / S;
-  }
-  block_sum<24, NT>(u, sh);
-  // full Hessian at the fit frequencies (needed by some nu_zero formulas)
+  // (one loop: the theta_n- and alpha-rows for the nu_zero formulas and the full Hessian at the fit frequencies,
+  // which some of those formulas need as well)
   double hv[15];
   for (int i = 0; i < 15; ++i) hv[i] = 0.0;
   double fmean = 0.0;
@@ -2112,14 +2176,31 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
     const ChanJ j = chan_jac(a.lgf[n] - lg2nT, a.nu2[n], P, nD, nG, tau_e, alpha_e, a.log10_tau);
-    double dC[5], dS[5];
-    chan_first(c, j, dC, dS);
-    int q = 0;
-    for (int i = 0; i < 5; ++i)
-      for (int k = i; k < 5; ++k, ++q)
-        hv[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * zfl[i] * zfl[k];
+    const ChanK k = chan_k(c);
+    const double n2 = a.nu2[n], lnnu = a.lgf[n] * 0.69314718055994530942;
+    for (int p = 0; p < 5; ++p) {
+      // Hessian row w.r.t. theta_n (= Hn[DM,p]/gDM_n etc.): d2C[theta,p], no S-dependence on theta
+      const double h = (p < 3 ? k.A * j.Jth[p] : k.M * j.Jt[p - 3]) * zfl[p];
+      u[3 * p] += h; u[3 * p + 1] += n2 * h; u[3 * p + 2] += n2 * n2 * h;
+    }
+    {
+      // Hessian row w.r.t. alpha divided by ln(nu_n/nu_tau): d/dalpha = lnf * tau_n d/dtau_n
+      const double k10 = a.log10_tau ? 2.302585092994045684 * j.taun : (tau_e != 0.0 ? j.taun / tau_e : 0.0);
+      const double hs[3] = {k.M * j.taun * zfl[0], k.M * j.Jth[1] * j.taun * zfl[1],
+                            (k.T1 * j.taun * j.Jt[0] + k.G2 * k10) * zfl[3]};
+      for (int q = 0; q < 3; ++q) { u[15 + 2 * q] += hs[q]; u[16 + 2 * q] += lnnu * hs[q]; }
+    }
+    u[21] += k.f;
+    u[22] += a.Sdn[(size_t)s * nchan + n];
+    u[23] -= k.f;
+    chan_hess(k, j, hv);
     fmean += a.freqs[n];
   }
+  {
+    int q = 0;
+    for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) hv[q] *= zfl[i] * zfl[k];
+  }
+  block_sum<24, NT>(u, sh);
   block_sum<15, NT>(hv, sh);
   double fm[1] = {fmean};
   block_sum<1, NT>(fm, sh);
@@ -2215,12 +2296,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
     if (!(S > 0.0)) continue;
     if (!scat_on) { c[3] = c[4] = c[5] = c[7] = c[8] = 0.0; }
     const ChanJ j = chan_jac(a.lgf[n] - lg2noT, a.nu2[n], P, noD, noG, tau_out_lin, alpha_e, a.log10_tau);
-    double dC[5], dS[5];
-    chan_first(c, j, dC, dS);
+    chan_hess(chan_k(c), j, ho);
+  }
+  {
     int q = 0;
-    for (int i = 0; i < 5; ++i)
-      for (int k = i; k < 5; ++k, ++q)
-        ho[q] += chan_H(c[0], S, chan_d2C(c, j, i, k), chan_d2S(c, j, i, k), dC[i], dC[k], dS[i], dS[k]) * fl[i] * fl[k];
+    for (int i = 0; i < 5; ++i) for (int k = i; k < 5; ++k, ++q) ho[q] *= fl[i] * fl[k];
   }
   block_sum<15, NT>(ho, sh);
   if (tid == 0) {

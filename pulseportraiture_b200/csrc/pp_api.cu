@@ -307,6 +307,7 @@ template <int N> static cudaError_t setup_attrs() {
   SET_((k_spectra<N, SpecPlan<N>, true>), (int)spectra_smem_bytes<N>())
   SET_((k_model<N>), b64)
   SET_((k_pass5<N>), (int)Pass5Ring<N>::kBytes)
+  if (PP_PASS2_RING) { SET_((k_pass2<N>), (int)Pass2Ring<N>::kBytes) }
   SET_((k_rfft_rows<N, float>), b32)
   SET_((k_rfft_rows<N, double>), b64)
   SET_((k_align_accum<N>), b64)
@@ -1076,7 +1077,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>(); p5.lgf = pl->lgf.as<double>();
       p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
       p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
-      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0; p5.nj = N / 16;
+      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0; p5.nj = N / 16; p5.cstride = 1;
       memset(&u5, 0, sizeof u5);
       u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>(); u5.lgf = pl->lgf.as<double>();
       u5.freqs = pl->freqs.as<double>(); u5.P = dP; u5.nu_fit = pl->nu_fit.as<double>(); u5.nu_outs = dnuouts;
@@ -1088,7 +1089,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       u5.option = args->option; u5.is_toa = args->is_toa; u5.tol = tol; u5.box = box;
       u5.taylor_finish = pl->model_steps != 1;
       for (int i = 0; i < 5; ++i) u5.flags[i] = ff[i] ? 1 : 0;
-      u5.coarse = 0; u5.ctol = 0.0;
+      u5.coarse = 0; u5.ctol = 0.0; u5.cstride = 1;
     }
     auto launch_update5 = [&]() {   // many channels: more threads per subint for the per-channel chain rule
       if (nchan >= 1024) k_update5<256><<<ns, 256, 0, pl->stream>>>(u5);
@@ -1112,36 +1113,53 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       coarse_nj = choose_coarse(pl->model_info, pl->coarse_frac, N);
     }
     if (coarse_nj > 0) {
-      const int max_coarse = std::min(max_iter, 12);
-      static const double ctol_env = getenv("PP_CTOL") ? atof(getenv("PP_CTOL")) : 0.0;   // (experiments)
-      p5.nj = coarse_nj; u5.coarse = 1; u5.ctol = ctol_env > 0 ? ctol_env : 0.05;
-      if (trace) { char b[64]; snprintf(b, sizeof b, "coarse stage: %d of %d harmonic groups", coarse_nj, N / 16); mark(b); }
-      for (int it = 0; it < max_coarse; ++it) {
-        {
-          SpanGuard g(pl, SP_COARSE);
-          DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5));
-          launch_update5();
-        }
-        pl->stats.launches += 2;
-        pl->stats.coarse_launches++;
-        if (it >= 2 && it + 1 < max_coarse) {
-          k_count_coarse<<<1, 256, 0, pl->stream>>>(st, s0, ns, pl->running.as<int>());
-          pl->stats.launches++;
-          int running = 0;
-          CK(cudaMemcpyAsync(&running, pl->running.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
-          CK(cudaStreamSynchronize(pl->stream));
-          if (running == 0) break;
-        }
+      // Two levels: most of the iterations run on a cheaper objective still -- the harmonics that hold coarse_frac0
+      // of the information (when that is clearly fewer) of every cstride-th channel -- the second level then needs
+      // one or two.  A level is left once its Newton step is below ctol sigma (the step is still taken): the next
+      // level, or the full-resolution iterations, start next to that level's optimum either way.
+      struct { int nj, cstride; double ctol; } levels[2];
+      int nlev = 0;
+      {
+        int nj0 = choose_coarse(pl->model_info, std::min(0.65, pl->coarse_frac), N);
+        if (!(nj0 > 0 && 3 * nj0 <= 2 * coarse_nj)) nj0 = coarse_nj;
+        const int cst = nchan >= 2048 ? 8 : (nchan >= 512 ? 4 : (nchan >= 128 ? 2 : 1));
+        if (nj0 < coarse_nj || cst > 1) levels[nlev++] = {nj0, cst, 2.0};
+        levels[nlev++] = {coarse_nj, 1, 1.0};
       }
-      k_coarse_end<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
-      pl->stats.launches++;
-      p5.nj = N / 16; u5.coarse = 0;
+      u5.coarse = 1;
+      for (int lv = 0; lv < nlev; ++lv) {
+        const int max_coarse = std::min(max_iter, 12);
+        p5.nj = levels[lv].nj; p5.cstride = u5.cstride = levels[lv].cstride; u5.ctol = levels[lv].ctol;
+        const int gx5 = ((nchan + p5.cstride - 1) / p5.cstride + 31) / 32;
+        if (trace) { char b[96]; snprintf(b, sizeof b, "coarse level: %d of %d harmonic groups, every %d-th channel", p5.nj, N / 16, p5.cstride); mark(b); }
+        for (int it = 0; it < max_coarse; ++it) {
+          {
+            SpanGuard g(pl, SP_COARSE);
+            DISPATCH_N(N, k_pass5<NN><<<dim3(gx5, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5));
+            launch_update5();
+          }
+          pl->stats.launches += 2;
+          pl->stats.coarse_launches++;
+          // the first level starts far from its optimum (three iterations before asking), the second next to it
+          if (it >= (lv == 0 ? 2 : 0) && it + 1 < max_coarse) {
+            k_count_coarse<<<1, 256, 0, pl->stream>>>(st, s0, ns, pl->running.as<int>());
+            pl->stats.launches++;
+            int running = 0;
+            CK(cudaMemcpyAsync(&running, pl->running.p, sizeof(int), cudaMemcpyDeviceToHost, pl->stream));
+            CK(cudaStreamSynchronize(pl->stream));
+            if (running == 0) break;
+          }
+        }
+        k_coarse_end<<<(ns + 127) / 128, 128, 0, pl->stream>>>(st, s0, ns);
+        pl->stats.launches++;
+      }
+      p5.nj = N / 16; p5.cstride = u5.cstride = 1; u5.coarse = 0;
     }
     for (int it = 0; it < n_launch_iter; ++it) {
       {
         SpanGuard g(pl, SP_PASS);
         if (general) { DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5)); }
-        else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, 0, pl->stream>>>(pa)); }
+        else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, PP_PASS2_RING ? Pass2Ring<NN>::kBytes : 0, pl->stream>>>(pa)); }
       }
       {
         SpanGuard g(pl, SP_UPDATE);

@@ -235,3 +235,46 @@ def test_print_paz_cmds_mirrors_reference(tmp_path):
                                  outfile=str(tmp_path / "y.sh"))
     assert lines == ["paz -m -z 3 a.fits", "paz -m -z 4 a.fits"]
     assert ppzap.print_paz_cmds([], [], quiet=True) is None
+
+
+def test_general_solver_coarse_stage_same_optimum():
+    """The general solver's coarse-to-fine start (low harmonics of a channel subset first: ppb200.h
+    pp_plan_set_coarse) changes the path, not the answer: parameters within 1e-3 sigma and chi2 / errors to
+    rounding of the plain Newton iterations, with fewer full-resolution passes; masked channels included."""
+    from pulseportraiture_b200 import engine
+    nsub, nchan, nbin, nu0, bw, tau_s = 6, 256, 1024, 600., 400., 50e-6
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 9100 + s, tau_data_s=tau_s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    mask = np.ones((nsub, nchan), dtype=np.uint8)
+    mask[1, ::4] = 0            # the first level's channel subset (every 2nd channel here) loses half of its channels
+    mask[2, 10:90] = 0
+    scat = np.tile([0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0, -4.0], (nsub, 1))
+    for flags in ((1, 1, 0, 1, 1), (1, 1, 1, 1, 1), (1, 1, 0, 1, 0)):
+        out = {}
+        for frac in (0.0, 0.99):
+            with engine.WidebandPlan(nchan, nbin) as pl:
+                pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+                pl.set_coarse(frac)
+                pl.enable_timing(True)
+                r = pl.fit_batch(data, P, chan_mask=mask, fit_flags=flags, log10_tau=True, scat_guess=scat)
+                out[frac] = ({k: np.array(v) for k, v in r.items() if isinstance(v, np.ndarray)}, pl.stats())
+        (a, sa), (b, sb) = out[0.0], out[0.99]
+        assert sa["coarse_launches"] == 0 and sb["coarse_launches"] > 0
+        assert sb["pass_launches"] < sa["pass_launches"]
+        assert (a["return_code"] == 0).all() and (b["return_code"] == 0).all()
+        fit = np.array(flags, bool)
+        assert np.max(np.abs(a["params"] - b["params"])[:, fit] / a["param_errs"][:, fit]) < 1e-3
+        assert np.max(np.abs(b["param_errs"][:, fit] / a["param_errs"][:, fit] - 1)) < 1e-5
+        assert np.max(np.abs(b["chi2"] / a["chi2"] - 1)) < 1e-9
+        ok = mask.astype(bool)
+        assert np.max(np.abs(b["scales"][ok] / a["scales"][ok] - 1)) < 1e-4
+    # set_model_steps(1) (every step evaluated on the data) turns the coarse stage off as well
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+        pl.set_model_steps(1)
+        pl.fit_batch(data, P, fit_flags=(1, 1, 0, 1, 1), log10_tau=True, scat_guess=scat)
+        assert pl.stats()["coarse_launches"] == 0
+    with pytest.raises(Exception):
+        with engine.WidebandPlan(nchan, nbin) as pl:
+            pl.set_coarse(1.5)
