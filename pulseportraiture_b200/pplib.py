@@ -328,6 +328,19 @@ def guess_fit_freq(freqs, SNRs=None):
     return nu0 + diff
 
 
+def guess_fit_freq_batch(freqs, SNRs, mask):
+    """guess_fit_freq (pplib.py:2618-2632) of every row over its usable channels (mask != 0): [nsub, nchan] arrays
+    in, [nsub] out; rows without usable channels give 0."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    m = np.asarray(mask) != 0
+    w = np.where(m, np.asarray(SNRs, dtype=np.float64) * freqs ** -2, 0.0)
+    den = w.sum(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nu0 = 0.5 * (np.where(m, freqs, np.inf).min(axis=1) + np.where(m, freqs, -np.inf).max(axis=1))
+        out = nu0 + ((freqs - nu0[:, None]) * w).sum(axis=1) / den
+    return np.where(m.any(axis=1) & (den != 0), out, 0.0)
+
+
 def scattering_times(tau, alpha, freqs, nu_tau):
     """pplib.py:4049-4053."""
     return tau * (np.asarray(freqs, dtype=np.float64) / nu_tau) ** alpha

@@ -142,6 +142,8 @@ def load_data(filename, **kwargs):
 def _freq_tables(freqs):
     """Distinct rows of a [nsub, nchan] frequency array and the row each subint uses."""
     freqs = np.asarray(freqs, dtype=np.float64)
+    if freqs.ndim == 2 and len(freqs) and (freqs == freqs[0]).all():   # the usual archive: one table (no sort)
+        return freqs[:1].copy(), np.zeros(len(freqs), dtype=int)
     tables, table_of = np.unique(freqs, axis=0, return_inverse=True)
     return tables, np.asarray(table_of).reshape(-1)
 
@@ -373,9 +375,8 @@ class GetTOAs:
             if nu_fit_tuple is None and fit_scat:
                 # the scattering start value needs nu_fit_tau on the host (pptoas.py:402, 431-441)
                 nu_fits_in = np.zeros((nsub, 3))
-                for isub in ok_isubs:
-                    okc = np.asarray(d.ok_ichans[isub], dtype=int)
-                    nu_fits_in[isub, :] = pplib.guess_fit_freq(freqs[isub, okc], snrs[isub, okc])
+                nu_fits_in[ok_isubs, :] = pplib.guess_fit_freq_batch(freqs[ok_isubs], snrs[ok_isubs],
+                                                                    mask[ok_isubs])[:, None]
                 empty = nu_fits_in[:, 0] == 0
                 nu_fits_in[empty] = freqs[empty].mean(axis=1)[:, None]
                 mode = 0
@@ -435,7 +436,7 @@ class GetTOAs:
                 else:
                     flags = tuple(self.fit_flags)
                 groups.setdefault((int(table_of[isub]), flags), []).append(isub)
-            res = {}
+            res, flags_of = {}, {}
             fit_start = time.time()
             table_set = None
             for (t, flags), isubs in sorted(groups.items()):
@@ -461,8 +462,13 @@ class GetTOAs:
                     fit_flags=flags, log10_tau=self.log10_tau, option=0, is_toa=True,
                     Ns=100, semantics="full", bounds=fit_bounds,
                     scat_guess=None if scat_in is None else scat_in[idx])
-                for j, isub in enumerate(isubs):
-                    res[isub] = (flags, {k: v[j] for k, v in r.items()})
+                for k, v in r.items():                     # results of all groups, by subint
+                    if isinstance(v, np.ndarray) and len(v) == nidx:
+                        if k not in res:
+                            res[k] = np.zeros((nsub,) + v.shape[1:], dtype=v.dtype)
+                        res[k][idx] = v
+                for isub in isubs:
+                    flags_of[isub] = flags
             fit_duration = time.time() - fit_start
 
             phis = np.zeros(nsub); phi_errs = np.zeros(nsub)
@@ -479,20 +485,39 @@ class GetTOAs:
             covariances = np.zeros([nsub, self.nfit, self.nfit])
             nfevals = np.zeros(nsub, dtype="int"); rcs = np.zeros(nsub, dtype="int")
             nu_fits_arr = list(np.zeros([nsub, 3])); nu_refs_arr = list(np.zeros([nsub, 3]))
+            # everything that is the same arithmetic for every subint, for all of them at once
+            okm = mask.astype(bool)
+            okm[np.setdiff1d(np.arange(nsub), ok_isubs)] = False
+            if res:
+                scales[okm] = res["scales"][okm]
+                scale_errs[okm] = res["scale_errs"][okm]
+                channel_snrs[okm] = res["channel_snrs"][okm]
+            fmax = np.where(okm, freqs, -np.inf).max(axis=1)
+            fmin = np.where(okm, freqs, np.inf).min(axis=1)
+            if nu_fits_in is None:                          # pptoas.py:400-407
+                nu_fit_vals = np.zeros(nsub)
+                nu_fit_vals[ok_isubs] = pplib.guess_fit_freq_batch(freqs[ok_isubs], snrs[ok_isubs], mask[ok_isubs])
+            doppler = np.asarray(d.doppler_factors, dtype=np.float64)
+            subtimes = np.asarray(d.subtimes)
+            parangles = np.asarray(d.parallactic_angles) if print_parangle else None
+            tmplt = self.modelfile if isinstance(self.modelfile, str) else "array"
+            fe_be = d.frontend + "_" + d.backend
+            chbw = abs(d.bw) / nchan
+            ifit_of = {}
             for isub in ok_isubs:
-                flags, r = res[isub]
-                okc = np.asarray(d.ok_ichans[isub], dtype=int)
-                freqsx = freqs[isub, okc]
+                flags = flags_of[isub]
+                par, perr = res["params"][isub], res["param_errs"][isub]
+                nu_out = res["nu_out"][isub]
                 P = Ps[isub]
-                phi, phi_err = r["params"][0], r["param_errs"][0]
-                DM, DM_err = r["params"][1], r["param_errs"][1]
-                GM, GM_err = r["params"][2], r["param_errs"][2]
+                phi, phi_err = par[0], perr[0]
+                DM, DM_err = par[1], perr[1]
+                GM, GM_err = par[2], perr[2]
                 # TOA (pptoas.py:528-531)
                 TOA_mjd = d.epochs[isub] + MJD(0, ((phi * P) + d.backend_delay) / (3600 * 24.))
                 TOA_err = phi_err * P * 1e6
                 # Doppler correction (pptoas.py:539-549)
                 if self.bary:
-                    df = np.asarray(d.doppler_factors)[isub]
+                    df = doppler[isub]
                     if flags[1]:
                         DM *= df
                     if flags[2]:
@@ -500,31 +525,26 @@ class GetTOAs:
                 else:
                     df = 1.0
                 if print_flux:                              # pptoas.py:554-577
+                    okc = np.nonzero(okm[isub])[0]
                     means = np.asarray(models[table_of[isub]])[okc].mean(axis=1)
-                    profile_fluxes[isub, okc] = means * r["scales"][okc]
-                    profile_flux_errs[isub, okc] = abs(means) * r["scale_errs"][okc]
+                    profile_fluxes[isub, okc] = means * scales[isub, okc]
+                    profile_flux_errs[isub, okc] = abs(means) * scale_errs[isub, okc]
                     fluxes[isub], flux_errs[isub] = weighted_mean(profile_fluxes[isub, okc],
                                                                  profile_flux_errs[isub, okc])
-                    flux_freqs[isub], _ = weighted_mean(freqsx, profile_flux_errs[isub, okc])
-                nu_refs_arr[isub] = list(r["nu_out"])
+                    flux_freqs[isub], _ = weighted_mean(freqs[isub, okc], profile_flux_errs[isub, okc])
+                nu_refs_arr[isub] = list(nu_out)
                 if nu_fits_in is not None:                  # pptoas.py:400-407
                     nu_fits_arr[isub] = list(nu_fits_in[isub])
                 else:
-                    nu_fits_arr[isub] = [pplib.guess_fit_freq(freqsx, snrs[isub, okc])] * 3
+                    nu_fits_arr[isub] = [nu_fit_vals[isub]] * 3
                 phis[isub], phi_errs[isub] = phi, phi_err
                 TOAs[isub], TOA_errs[isub] = TOA_mjd, TOA_err
                 DMs[isub], DM_errs[isub] = DM, DM_err
                 GMs[isub], GM_errs[isub] = GM, GM_err
-                taus[isub], tau_errs[isub] = r["params"][3], r["param_errs"][3]
-                alphas[isub], alpha_errs[isub] = r["params"][4], r["param_errs"][4]
-                nfevals[isub] = r["nfeval"]
-                rcs[isub] = pplib.scipy_return_code(r["return_code"], method)   # pptoaslib.py:1017
-                scales[isub, okc] = r["scales"][okc]
-                scale_errs[isub, okc] = r["scale_errs"][okc]
-                snrs_out[isub] = r["snr"]
-                channel_snrs[isub, okc] = r["channel_snrs"][okc]
-                ifit = np.where(flags)[0]
-                cm = r["cov"][np.ix_(ifit, ifit)]
+                if flags not in ifit_of:
+                    ifit_of[flags] = np.where(flags)[0]
+                ifit = ifit_of[flags]
+                cm = res["cov"][isub][np.ix_(ifit, ifit)]
                 if cm.shape == covariances[isub].shape:
                     covariances[isub] = cm
                 else:                                       # pptoas.py:596-600
@@ -532,13 +552,13 @@ class GetTOAs:
                         for jj, b_ in enumerate(ifit):
                             if a_ < self.nfit and b_ < self.nfit:
                                 covariances[isub][a_, b_] = cm[ii, jj]
-                red_chi2s[isub] = r["red_chi2"]
+                snr, gof = res["snr"][isub], res["red_chi2"][isub]
                 toa_flags = {}                              # pptoas.py:604-651
                 DM_out, DM_err_out = (DM, DM_err) if flags[1] else (None, None)
                 if flags[2]:
                     toa_flags['gm'], toa_flags['gm_err'] = GM, GM_err
                 if flags[3]:                                # pptoas.py:611-624
-                    tau_r, tau_e = r["params"][3], r["param_errs"][3]
+                    tau_r, tau_e = par[3], perr[3]
                     if self.log10_tau:
                         toa_flags['scat_time'] = 10 ** tau_r * P / df * 1e6
                         toa_flags['log10_scat_time'] = tau_r + np.log10(P / df)
@@ -546,26 +566,26 @@ class GetTOAs:
                     else:
                         toa_flags['scat_time'] = tau_r * P / df * 1e6
                         toa_flags['scat_time_err'] = tau_e * P / df * 1e6
-                    toa_flags['scat_ref_freq'] = r["nu_out"][2] * df
-                    toa_flags['scat_ind'] = r["params"][4]
+                    toa_flags['scat_ref_freq'] = nu_out[2] * df
+                    toa_flags['scat_ind'] = par[4]
                 if flags[4]:
-                    toa_flags['scat_ind_err'] = r["param_errs"][4]
+                    toa_flags['scat_ind_err'] = perr[4]
                 toa_flags['be'] = d.backend
                 toa_flags['fe'] = d.frontend
-                toa_flags['f'] = d.frontend + "_" + d.backend
+                toa_flags['f'] = fe_be
                 toa_flags['nbin'] = nbin
                 toa_flags['nch'] = nchan
-                toa_flags['nchx'] = len(freqsx)
-                toa_flags['bw'] = freqsx.max() - freqsx.min()
-                toa_flags['chbw'] = abs(d.bw) / nchan
+                toa_flags['nchx'] = int(nok[isub])
+                toa_flags['bw'] = fmax[isub] - fmin[isub]
+                toa_flags['chbw'] = chbw
                 toa_flags['subint'] = int(isub)
-                toa_flags['tobs'] = np.asarray(d.subtimes)[isub]
-                toa_flags['fratio'] = freqsx.max() / freqsx.min()
-                toa_flags['tmplt'] = self.modelfile if isinstance(self.modelfile, str) else "array"
-                toa_flags['snr'] = r["snr"]
+                toa_flags['tobs'] = subtimes[isub]
+                toa_flags['fratio'] = fmax[isub] / fmin[isub]
+                toa_flags['tmplt'] = tmplt
+                toa_flags['snr'] = snr
                 if nu_ref_tuple is not None and nu_ref_tuple[0] is not None and np.all(flags[:2]):
                     toa_flags['phi_DM_cov'] = cm[0, 1]
-                toa_flags['gof'] = r["red_chi2"]
+                toa_flags['gof'] = gof
                 if print_phase:
                     toa_flags['phs'], toa_flags['phs_err'] = phi, phi_err
                 if print_flux:
@@ -573,12 +593,19 @@ class GetTOAs:
                     toa_flags['flux_err'] = flux_errs[isub]
                     toa_flags['flux_ref_freq'] = flux_freqs[isub]
                 if print_parangle:
-                    toa_flags['par_angle'] = np.asarray(d.parallactic_angles)[isub]
+                    toa_flags['par_angle'] = parangles[isub]
                 for k, v in addtnl_toa_flags.items():
                     toa_flags[k] = v
-                self.TOA_list.append(TOA(d.filename, r["nu_out"][0], TOA_mjd, TOA_err,
+                self.TOA_list.append(TOA(d.filename, nu_out[0], TOA_mjd, TOA_err,
                                          d.telescope, d.telescope_code, DM_out, DM_err_out,
                                          toa_flags))
+            oks = np.asarray(ok_isubs if res else [], dtype=int)
+            taus[oks], tau_errs[oks] = res["params"][oks, 3], res["param_errs"][oks, 3]
+            alphas[oks], alpha_errs[oks] = res["params"][oks, 4], res["param_errs"][oks, 4]
+            nfevals[oks] = res["nfeval"][oks]
+            rcs[oks] = [pplib.scipy_return_code(c, method) for c in res["return_code"][oks]]   # pptoaslib.py:1017
+            snrs_out[oks] = res["snr"][oks]
+            red_chi2s[oks] = res["red_chi2"][oks]
             # per-archive Delta-DM mean (pptoas.py:665-682)
             DeltaDMs = DMs - DM0_arch
             if np.all(DM_errs[ok_isubs]):
