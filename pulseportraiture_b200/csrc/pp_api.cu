@@ -182,7 +182,7 @@ static bool is_device_ptr(const void* p) {
 }
 
 static bool is_pinned_host_ptr(const void* p);
-static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st);
+static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st, bool narrow);
 
 template <typename T>
 static int stage_in(pp_plan* pl, DBuf& buf, const T* src, size_t n, const T** out) {
@@ -190,7 +190,7 @@ static int stage_in(pp_plan* pl, DBuf& buf, const T* src, size_t n, const T** ou
   if (is_device_ptr(src)) { *out = src; return 0; }
   CK(buf.need(n * sizeof(T)));
   const size_t bytes = n * sizeof(T);
-  CK(h2d_any(pl, buf.p, src, bytes, bytes < (8u << 20) || is_pinned_host_ptr(src), pl->stream));
+  CK(h2d_any(pl, buf.p, src, bytes, bytes < (8u << 20) || is_pinned_host_ptr(src), pl->stream, false));
   *out = buf.as<T>();
   return 0;
 }
@@ -683,10 +683,53 @@ static void parallel_memcpy(void* dst, const void* src, size_t n, int nthreads) 
   for (auto& t : th) t.join();
 }
 
-// host -> device on `st`: straight from page-locked memory, through the plan's page-locked ring otherwise
-static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st) {
-  if (src_pinned || bytes < (8u << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+// float64 -> float32 (round to nearest even, as the device's cvt.rn.f32.f64) while staging pageable rows
+static void parallel_narrow(float* dst, const double* src, size_t n, int nthreads) {
+  auto run = [](float* d, const double* s, size_t m) { for (size_t i = 0; i < m; ++i) d[i] = (float)s[i]; };
+  if (nthreads <= 1 || n < (1u << 20)) { run(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((n / nthreads) + 1023) & ~(size_t)1023;
+  for (int i = 1; i < nthreads; ++i) {
+    const size_t o = (size_t)i * per;
+    if (o >= n) break;
+    th.emplace_back([=]() { run(dst + o, src + o, std::min(per, n - o)); });
+  }
+  run(dst, src, std::min(per, n));
+  for (auto& t : th) t.join();
+}
+
+static bool h2d_stages(size_t bytes, bool src_pinned) { return !src_pinned && bytes >= (8u << 20); }
+
+// host -> device on `st`: straight from page-locked memory, through the plan's page-locked ring otherwise.
+// narrow: src holds float64 samples and dst receives them as float32 (only when the copy is staged: h2d_stages());
+// `bytes` counts source bytes.
+static cudaError_t h2d_any(pp_plan* pl, void* dst, const void* src, size_t bytes, bool src_pinned, cudaStream_t st,
+                           bool narrow) {
+  if (!h2d_stages(bytes, src_pinned)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
   static const int nthreads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  if (narrow) {
+    const size_t n = bytes / sizeof(double), per = pp_plan::kPinPiece / sizeof(float);
+    for (size_t off = 0; off < n; off += per) {
+      const size_t len = std::min(per, n - off);
+      const int slot = (int)(pl->pin_count++ % pp_plan::kPinSlots);
+      cudaError_t e;
+      if (!pl->pin_ring[slot]) {
+        e = cudaHostAlloc(&pl->pin_ring[slot], pp_plan::kPinPiece, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&pl->pin_ev[slot], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+      } else {
+        e = cudaEventSynchronize(pl->pin_ev[slot]);
+        if (e != cudaSuccess) return e;
+      }
+      parallel_narrow(static_cast<float*>(pl->pin_ring[slot]), static_cast<const double*>(src) + off, len, nthreads);
+      e = cudaMemcpyAsync(static_cast<float*>(dst) + off, pl->pin_ring[slot], len * sizeof(float), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      e = cudaEventRecord(pl->pin_ev[slot], st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   for (size_t off = 0; off < bytes; off += pp_plan::kPinPiece) {
     const size_t len = std::min(pp_plan::kPinPiece, bytes - off);
     const int slot = (int)(pl->pin_count++ % pp_plan::kPinSlots);
@@ -942,10 +985,13 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     const int s0 = cstart[c], ns = cstart[c + 1] - s0;
     cudaError_t e = cudaStreamWaitEvent(pl->copy_stream, pl->ev_free[b], 0);
     if (e != cudaSuccess) return e;
-    void* dst = f64 ? pl->data_stage64[b].p : pl->data_stage[b].p;
-    e = h2d_any(pl, dst, data_bytes + (size_t)s0 * src_bytes, (size_t)ns * src_bytes, data_pinned, pl->copy_stream);
+    // float64 rows from pageable memory are rounded to float32 by the host threads that stage them anyway (half
+    // the bytes over PCIe); from page-locked memory they cross as they are and a kernel on the copy stream rounds
+    const bool narrow = f64 && h2d_stages((size_t)ns * src_bytes, data_pinned);
+    void* dst = (f64 && !narrow) ? pl->data_stage64[b].p : pl->data_stage[b].p;
+    e = h2d_any(pl, dst, data_bytes + (size_t)s0 * src_bytes, (size_t)ns * src_bytes, data_pinned, pl->copy_stream, narrow);
     if (e != cudaSuccess) return e;
-    if (f64) convert_f64(dst, pl->data_stage[b].p, ns, pl->copy_stream);
+    if (f64 && !narrow) convert_f64(dst, pl->data_stage[b].p, ns, pl->copy_stream);
     return cudaEventRecord(pl->ev_copy[b], pl->copy_stream);
   };
   if (!data_on_device) {

@@ -29,6 +29,18 @@ def test_float64_input_needs_no_host_pass_and_is_bit_identical():
     for k in r32:
         assert np.array_equal(r32[k], r64[k], equal_nan=True), k
         assert np.array_equal(r32[k], r64d[k], equal_nan=True), k
+    # chunks of >= 8 MB from pageable memory: the host threads that stage them round to float32 on the way
+    c = synth.make_case(64, 2048, 1500., 800., 4500)
+    rng = np.random.RandomState(3)
+    d64 = c["data"][None] + rng.normal(0.0, 1.0, (40,) + c["data"].shape) + 1e-9
+    d32 = d64.astype(np.float32)
+    with WidebandPlan(64, 2048) as pl:
+        pl.set_model(c["model"].astype(np.float32), c["freqs"])
+        pl.set_chunk(16)
+        r32 = pl.fit_batch(d32, c["P"])
+        r64 = pl.fit_batch(d64, c["P"])
+    for k in r32:
+        assert np.array_equal(r32[k], r64[k], equal_nan=True), k
 
 
 def test_gettoas_dedispersed_archive_is_redispersed():
