@@ -1463,11 +1463,16 @@ __global__ void k_model_info(const double* mpow, const double* lgf, const double
     lg2nT = log2(nu_fit[2]);
   }
   double v = 0.0;
-  for (int i = threadIdx.x; i < nchan * 16; i += blockDim.x) {
-    const int n = i >> 4, k = j * 16 + (i & 15);
-    if (k == 0) continue;     // slot 0 holds the Nyquist harmonic
-    const double b = tau != 0.0 ? kTwoPi * (double)k * tau * exp2(alpha * (lgf[n] - lg2nT)) : 0.0;
-    v += (double)k * (double)k * mpow[(size_t)n * N + k] / fma(b, b, 1.0);
+  for (int n = threadIdx.x; n < nchan; n += blockDim.x) {
+    const double wt = tau != 0.0 ? kTwoPi * tau * exp2(alpha * (lgf[n] - lg2nT)) : 0.0;
+    const double* m = mpow + (size_t)n * N + j * 16;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int k = j * 16 + q;
+      if (k == 0) continue;     // slot 0 holds the Nyquist harmonic
+      const double b = (double)k * wt;
+      v += (double)k * (double)k * m[q] / fma(b, b, 1.0);
+    }
   }
   __shared__ double sh[32];
   v = warp_sum(v);

@@ -42,7 +42,7 @@ def launches(src, dst):
         a = agg.setdefault(key, [0, 0.0, r[ix["Grid Size"]], r[ix["Block Size"]]])
         a[0] += 1
         a[1] += val * unit[u]
-    ours = {k: v for k, v in agg.items() if k.startswith("ppb::")}
+    ours = {k: v for k, v in agg.items() if k.startswith("ppb::") or k.startswith("k_")}
     tot = sum(v[1] for v in ours.values())
     with open(dst, "w") as fh:
         fh.write("# ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n")
