@@ -831,6 +831,7 @@ struct SolverState {
   double* fprev;    // [nsub]
   double* lam;      // [nsub] backtracking factor
   int* iter;        // [nsub] passes done
+  int* iterc;       // [nsub] evaluations of the coarse objectives (general solver), not counted against max_iter
   int* done;        // [nsub] 0 running, 1 finished
 };
 
@@ -1400,7 +1401,7 @@ __global__ void k_init_state(SolverState st, const double* init, int s0, int n) 
     const double v = init ? init[(size_t)s * 5 + q] : 0.0;
     st.x[(size_t)s * 5 + q] = v; st.xprev[(size_t)s * 5 + q] = v; st.step[(size_t)s * 5 + q] = 0.0;
   }
-  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.iterc[s] = 0; st.done[s] = 0;
 }
 
 // number of subints of [s0, s0+n) that are not finished yet
@@ -1420,7 +1421,7 @@ __global__ void k_reset_state(SolverState st, int s0, int n) {
   if (i >= n) return;
   const int s = s0 + i;
   for (int q = 0; q < 5; ++q) { st.xprev[(size_t)s * 5 + q] = st.x[(size_t)s * 5 + q]; st.step[(size_t)s * 5 + q] = 0.0; }
-  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.done[s] = 0;
+  st.fprev[s] = 0.0; st.lam[s] = 1.0; st.iter[s] = 0; st.iterc[s] = 0; st.done[s] = 0;
 }
 
 // end of the coarse stage of the general fit: every unfinished subint starts the full-resolution Newton
@@ -2011,8 +2012,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
 #pragma unroll
     for (int q = 0; q < NT / 32; ++q) { gmax1 = fmax(gmax1, sh[q]); gmax2 = fmax(gmax2, sh[NT / 32 + q]); }
     if (tid == 0) {
-      const int it = a.st.iter[s] + 1;
-      a.st.iter[s] = it;
+      int it;
+      if (a.coarse) { it = a.st.iterc[s] + 1; a.st.iterc[s] = it; }   // (the levels' objectives differ: fprev is reset between them)
+      else { it = a.st.iter[s] + 1; a.st.iter[s] = it; }
       const double f = v[0];
       int action = 0;   // 0 continue, 1 go to final evaluation at x, 2 finish now (failure)
       int rc = 0;
@@ -2127,7 +2129,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
       if (action == 2) {                    // non-finite objective: report what we have
         double* po = a.params + (size_t)s * 5;
         for (int i = 0; i < 5; ++i) po[i] = x[i];
-        a.nfeval[s] = it; a.st.done[s] = 1;
+        a.nfeval[s] = a.st.iter[s] + a.st.iterc[s]; a.st.done[s] = 1;
       }
     }
     __syncthreads();
@@ -2367,7 +2369,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_update5(Update5Args a) {
     a.chi2[s] = chi2;
     a.red_chi2[s] = chi2 / ((double)nok * a.nbin - (double)(nfit + nok));
     a.snr[s] = sqrt(u[23]);
-    a.nfeval[s] = a.st.iter[s] + (state == 2 ? 1 : 0);
+    a.nfeval[s] = a.st.iter[s] + a.st.iterc[s] + (state == 2 ? 1 : 0);
     a.st.done[s] = 1;
   }
 }

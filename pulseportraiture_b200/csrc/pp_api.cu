@@ -107,7 +107,7 @@ struct pp_plan {
   // per-batch staging of small inputs and per-subint / per-channel workspace
   DBuf running, minfo, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
-  DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_done;
+  DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_iterc, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
   DBuf resp, rot_gm, rot_nugm, al_w, al_out, al_wsum, ps_phase, ps_perr, ps_scale, ps_serr, ps_snr, ps_rchi2, ps_lag, ps_spec, ps_mspec, ps_noise, rot_in, rot_out,
       rot_phase, rot_dm, rot_P, rot_nuref;
@@ -429,7 +429,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
                  &pl->in_nuouts, &pl->in_noise, &pl->in_models, &pl->nu_fit, &pl->nu_mean, &pl->wsum, &pl->nok, &pl->sigma,
                  &pl->Ssn, &pl->Sdn, &pl->csum, &pl->st_x, &pl->st_xprev, &pl->st_step, &pl->st_fprev, &pl->st_lam,
-                 &pl->st_iter, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
+                 &pl->st_iter, &pl->st_iterc, &pl->st_done, &pl->o_params, &pl->o_perrs, &pl->o_nuout, &pl->o_cov, &pl->o_chi2, &pl->o_rchi2,
                  &pl->o_snr, &pl->o_nfev, &pl->o_rc, &pl->o_scales, &pl->o_serrs, &pl->o_csnr, &pl->o_lag, &pl->o_phig,
                  &pl->ps_phase, &pl->ps_perr, &pl->ps_scale, &pl->ps_serr, &pl->ps_snr, &pl->ps_rchi2, &pl->ps_lag, &pl->Dspec, &pl->Ddc, &pl->al_acc, &pl->al_wparts, &pl->X, &pl->Xlo,
                  &pl->partial, &pl->data_stage[0], &pl->data_stage[1], &pl->data_stage64[0], &pl->data_stage64[1]};
@@ -876,6 +876,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
   CK(pl->st_fprev.need(sizeof(double) * nsub));
   CK(pl->st_lam.need(sizeof(double) * nsub));
   CK(pl->st_iter.need(sizeof(int) * nsub));
+  CK(pl->st_iterc.need(sizeof(int) * nsub));
   CK(pl->st_done.need(sizeof(int) * nsub));
   CK(pl->o_params.need(sizeof(double) * nsub * 5));
   CK(pl->o_perrs.need(sizeof(double) * nsub * 5));
@@ -945,7 +946,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
 
   SolverState st;
   st.x = pl->st_x.as<double>(); st.xprev = pl->st_xprev.as<double>(); st.step = pl->st_step.as<double>();
-  st.fprev = pl->st_fprev.as<double>(); st.lam = pl->st_lam.as<double>(); st.iter = pl->st_iter.as<int>();
+  st.fprev = pl->st_fprev.as<double>(); st.lam = pl->st_lam.as<double>(); st.iter = pl->st_iter.as<int>(); st.iterc = pl->st_iterc.as<int>();
   st.done = pl->st_done.as<int>();
 
   cudaEvent_t ev_t0 = nullptr;
