@@ -290,3 +290,33 @@ def test_general_solver_coarse_stage_same_optimum():
     with pytest.raises(Exception):
         with engine.WidebandPlan(nchan, nbin) as pl:
             pl.set_coarse(1.5)
+
+
+@pytest.mark.parametrize("nchan,nbin,log10_tau,tau_s", [(32, 256, True, 400e-6), (48, 512, False, 200e-6),
+                                                        (160, 2048, True, 100e-6), (64, 1024, False, 0.0)])
+def test_general_solver_coarse_stage_small_shapes(nchan, nbin, log10_tau, tau_s):
+    """The coarse levels at the corners of their rules: nbin = 256 (8 harmonic groups: at most 4 may be coarse),
+    fewer than 128 channels (no channel stride), linear tau, and a fit that starts at tau = 0 (scattering
+    derivatives off, pptoaslib.py:325-330): same optimum as the plain iterations in every case."""
+    from pulseportraiture_b200 import engine
+    nsub, nu0, bw = 4, 600., 200.
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 9300 + s, tau_data_s=tau_s, sigma=0.5) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    tau0 = 0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0
+    flags = (1, 1, 0, 1, 1) if tau_s else (1, 1, 1, 0, 0)
+    scat = np.tile([tau0, -4.0], (nsub, 1))
+    out = {}
+    for frac in (0.0, 0.99):
+        with engine.WidebandPlan(nchan, nbin) as pl:
+            pl.set_model(cases[0]["model"].astype(np.float32), freqs)
+            pl.set_coarse(frac)
+            r = pl.fit_batch(data, P, fit_flags=flags, log10_tau=log10_tau and tau_s > 0, scat_guess=scat)
+            out[frac] = ({k: np.array(v) for k, v in r.items() if isinstance(v, np.ndarray)}, pl.stats())
+    (a, sa), (b, sb) = out[0.0], out[0.99]
+    assert sa["coarse_launches"] == 0
+    assert (a["return_code"] == 0).all() and (b["return_code"] == 0).all()
+    fit = np.array(flags, bool)
+    assert np.max(np.abs(a["params"] - b["params"])[:, fit] / a["param_errs"][:, fit]) < 1e-3
+    assert np.max(np.abs(b["param_errs"][:, fit] / a["param_errs"][:, fit] - 1)) < 1e-5
+    assert np.max(np.abs(b["chi2"] / a["chi2"] - 1)) < 1e-9
