@@ -193,7 +193,8 @@ class WidebandPlan(object):
         log10_tau) and alpha as scipy's TNC takes them (None = unbounded).
 
         pinned_results=True returns views of plan-owned page-locked buffers
-        (full-speed D2H); they are overwritten by the next call on this plan."""
+        (full-speed D2H); they are overwritten by the next call on this plan and freed with it
+        (copy what must outlive the plan)."""
         keep = []
         if nsub is None:
             nsub = int(data.shape[0]) if hasattr(data, "shape") and len(data.shape) == 3 else 1
