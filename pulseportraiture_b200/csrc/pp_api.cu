@@ -88,7 +88,8 @@ struct pp_plan {
   unsigned long pin_count = 0;
   bool anyn = false;
   int L = 0, M = 0;
-  DBuf any_chirp, any_B, any_twM, any_tw2n, any_spec, any_dc, any_spec2, any_dc2;
+  DBuf any_chirp, any_B, any_twM, any_tw2n, any_twL, any_spec, any_dc, any_spec2, any_dc2;
+  std::vector<int> any_rad;   // radices of the direct transform of length L (empty: Bluestein)
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int chunk_req = 0;
@@ -400,6 +401,19 @@ extern "C" int pp_plan_create(int32_t nchan, int32_t nbin, int32_t device, pp_pl
       CK(pl->any_B.need(sizeof(double2) * M));
       CK(pl->any_twM.need(sizeof(double2) * M));
       CK(pl->any_tw2n.need(sizeof(double2) * (L / 2 + 1)));
+      {   // L = 2^a 3^b 5^c: radices of the direct transform (no radices: Bluestein)
+        int rest = L;
+        std::vector<int> rad;
+        while (rest % 5 == 0) { rad.push_back(5); rest /= 5; }
+        while (rest % 3 == 0) { rad.push_back(3); rest /= 3; }
+        while (rest % 4 == 0) { rad.push_back(4); rest /= 4; }
+        if (rest % 2 == 0) { rad.push_back(2); rest /= 2; }
+        if (rest == 1 && rad.size() <= 12 && !getenv("PP_FORCE_BLUESTEIN")) pl->any_rad = rad;
+        std::vector<double2> twL(L);
+        for (int j = 0; j < L; ++j) twL[j] = unit_root(j, L);
+        CK(pl->any_twL.need(sizeof(double2) * L));
+        CK(cudaMemcpy(pl->any_twL.p, twL.data(), sizeof(double2) * L, cudaMemcpyHostToDevice));
+      }
       CK(cudaMemcpy(pl->any_chirp.p, chirp.data(), sizeof(double2) * L, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(pl->any_B.p, b.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(pl->any_twM.p, twM.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
@@ -423,7 +437,7 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->minfo, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_twL, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->minfo, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
                  &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
@@ -511,6 +525,9 @@ static AnyPlan any_dev(pp_plan* pl) {
   AnyPlan p;
   p.chirp = pl->any_chirp.as<cx<double>>(); p.Bspec = pl->any_B.as<cx<double>>(); p.twM = pl->any_twM.as<cx<double>>();
   p.tw2n = pl->any_tw2n.as<cx<double>>(); p.L = pl->L; p.Npad = pl->N;
+  p.twL = pl->any_twL.as<cx<double>>();
+  p.nrad = (int)pl->any_rad.size();
+  for (int i = 0; i < 12; ++i) p.rad[i] = i < p.nrad ? pl->any_rad[i] : 1;
   return p;
 }
 static int launch_fwd_any(pp_plan* pl, const void* in, bool i16, const float* scl, const float* offs, long nrows,
@@ -518,8 +535,10 @@ static int launch_fwd_any(pp_plan* pl, const void* in, bool i16, const float* sc
   FwdAnyArgs a;
   a.in = in; a.dat_scl = scl; a.dat_offs = offs; a.spec = spec; a.dc = dc; a.p = any_dev(pl); a.nrows = nrows;
   const unsigned grid = (unsigned)std::min<long>(nrows, 148L * 64);
-  if (i16) { DISPATCH_M(pl->M, (k_fwd_any<MM, true><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
-  else { DISPATCH_M(pl->M, (k_fwd_any<MM, false><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  // (the direct mixed-radix transform works on 2 L points, the Bluestein convolution on 2 M)
+  const size_t sm = 2 * sizeof(cx<double>) * (pl->any_rad.empty() ? (size_t)pl->M : (size_t)pl->L);
+  if (i16) { DISPATCH_M(pl->M, (k_fwd_any<MM, true><<<grid, 256, sm, pl->stream>>>(a))); }
+  else { DISPATCH_M(pl->M, (k_fwd_any<MM, false><<<grid, 256, sm, pl->stream>>>(a))); }
   pl->stats.launches++;
   return 0;
 }
@@ -527,8 +546,9 @@ static int launch_inv_any(pp_plan* pl, const cx<double>* spec, const double* dc,
   InvAnyArgs a;
   a.spec = spec; a.dc = dc; a.out = out; a.p = any_dev(pl); a.nrows = nrows;
   const unsigned grid = (unsigned)std::min<long>(nrows, 148L * 64);
-  if (out_double) { DISPATCH_M(pl->M, (k_inv_any<MM, double><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
-  else { DISPATCH_M(pl->M, (k_inv_any<MM, float><<<grid, 256, 2 * MM * sizeof(cx<double>), pl->stream>>>(a))); }
+  const size_t sm = 2 * sizeof(cx<double>) * (pl->any_rad.empty() ? (size_t)pl->M : (size_t)pl->L);
+  if (out_double) { DISPATCH_M(pl->M, (k_inv_any<MM, double><<<grid, 256, sm, pl->stream>>>(a))); }
+  else { DISPATCH_M(pl->M, (k_inv_any<MM, float><<<grid, 256, sm, pl->stream>>>(a))); }
   pl->stats.launches++;
   return 0;
 }

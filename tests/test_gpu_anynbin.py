@@ -117,3 +117,36 @@ def test_any_nbin_model_generation_and_gettoas():
     params[1] = 30e-6 * 1000 / cs[0]["P"]
     m_dev2 = pplib.gen_gaussian_portrait_device(gm[1], params, gm[6], pplib.get_bin_centers(1000), freqs2, gm[2])
     assert np.abs(m_dev2 - m_sc).max() < 3e-6 * np.abs(m_sc).max()
+
+
+@pytest.mark.parametrize("nchan,nbin", [(16, 1000), (8, 1536), (6, 3000), (10, 120)])
+def test_mixed_radix_rows_match_bluestein_rows(nchan, nbin, monkeypatch):
+    """nbin/2 = 2^a 3^b 5^c takes the direct mixed-radix transform (bluestein.cuh fft_mixed); PP_FORCE_BLUESTEIN
+    keeps such a plan on the chirp-z path: both are the same DFT, so fits, noise and rotated rows agree to
+    rounding."""
+    from pulseportraiture_b200.engine import WidebandPlan
+    nsub = 5
+    cs = [synth.make_case(nchan, nbin, 1500., 800., 8800 + s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cs]).astype(np.float32)
+    P, freqs, model = cs[0]["P"], cs[0]["freqs"], cs[0]["model"].astype(np.float32)
+    out = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("PP_FORCE_BLUESTEIN", "1")
+        else:
+            monkeypatch.delenv("PP_FORCE_BLUESTEIN", raising=False)
+        with WidebandPlan(nchan, nbin) as pl:
+            pl.set_model(model, freqs)
+            r = pl.fit_batch(data, P)
+            rot = pl.rotate_batch(data, np.full(nsub, 0.123), np.full(nsub, 2e-3), P, 1400.0)
+            noise = pl.get_noise_batch(data)
+            out.append(({k: np.array(v) for k, v in r.items()}, np.array(rot), np.array(noise)))
+    (a, ra, na), (b, rb, nb_) = out
+    assert (a["return_code"] == 0).all() and (b["return_code"] == 0).all()
+    assert np.array_equal(a["lag_index"], b["lag_index"])
+    assert np.max(np.abs(a["params"][:, :2] - b["params"][:, :2]) / a["param_errs"][:, :2]) < 1e-6
+    assert np.max(np.abs(a["chi2"] / b["chi2"] - 1)) < 1e-11
+    assert np.max(np.abs(na / nb_ - 1)) < 1e-12
+    assert np.max(np.abs(ra - rb)) < 2e-6 * np.abs(data).max()
+    ref = orc.get_noise(cs[0]["data"], chans=True)
+    assert rel(na[0], ref) < 1e-9
