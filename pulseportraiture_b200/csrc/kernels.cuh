@@ -30,7 +30,7 @@ namespace ppb {
 constexpr double kDconst = 1.0 / 0.000241;  // pplib.py:48-51
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 #ifndef PP_SPECTRA_MINB
-#define PP_SPECTRA_MINB 5
+#define PP_SPECTRA_MINB 4
 #endif
 constexpr int kNCsum = 9;                   // per-channel sums kept per subint
 // The first kLoK slots of every X row also keep the float32 rounding residual

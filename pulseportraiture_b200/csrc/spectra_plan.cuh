@@ -14,7 +14,7 @@
 #include "fft16.cuh"
 
 #ifndef PP_SPECTRA_MINB
-#define PP_SPECTRA_MINB 5
+#define PP_SPECTRA_MINB 4
 #endif
 #ifndef PP_SPECTRA_R16
 #define PP_SPECTRA_R16 1

@@ -12,7 +12,8 @@ from pulseportraiture_b200.engine import WidebandPlan
 nsub = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 dev = torch.device("cuda", 0)
 out = []
-for nbin in (2048, 2000, 1024, 1000, 1536):
+NBINS = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [2048, 2000, 1024, 1000, 1536]
+for nbin in NBINS:
     freqs = np.linspace(bench.NU0 - bench.BW / 2 + bench.BW / 1024., bench.NU0 + bench.BW / 2 - bench.BW / 1024., 512)
     _, _, model = pplib.read_model(bench.GMODEL, pplib.get_bin_centers(nbin), freqs, bench.P_EXAMPLE, quiet=True)
     g = torch.Generator(device=dev); g.manual_seed(nbin)
