@@ -16,6 +16,9 @@
 #ifndef PP_SPECTRA_MINB
 #define PP_SPECTRA_MINB 4
 #endif
+#ifndef PP_SPECTRA_MINB_2048
+#define PP_SPECTRA_MINB_2048 2
+#endif
 #ifndef PP_SPECTRA_R16
 #define PP_SPECTRA_R16 1
 #endif
@@ -33,7 +36,7 @@ template <int N> struct SpecPlan8 {
   static constexpr int kT = S8::kT, kSlots = S8::kSlots, kThreads = S8::kThreads;
   static constexpr int kUnits = S8::kQuads, kOut = 4;
   static constexpr int kTwTotal = TwLayout<N>::kTotal;
-  static constexpr int kMinBlocks = (N >= 2048 ? 1 : PP_SPECTRA_MINB);
+  static constexpr int kMinBlocks = (N >= 2048 ? PP_SPECTRA_MINB_2048 : PP_SPECTRA_MINB);
   static constexpr int kStages = 2;
   static constexpr int kAcc = 0;
   static constexpr bool kMcLate = false;
