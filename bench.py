@@ -272,7 +272,7 @@ def run_ours(args):
     freqs, model = make_model()
     stream = torch.cuda.Stream(device=dev)
     plan = WidebandPlan(NCHAN, NBIN, device=local, stream=stream)
-    plan.set_model(model.astype(np.float32), freqs)
+    plan.set_model(np.ascontiguousarray(model, dtype=np.float64), freqs)   # float64, the reference's model type
     if args.chunk:
         plan.set_chunk(args.chunk)
     if args.fft:
@@ -406,13 +406,14 @@ def run_ours(args):
     st["pass_launches"] = int(round(st_sum["pass_launches"] / args.steps))
     B = 4.0 * NCHAN * NBIN                                               # bytes of one portrait
     npass = npass_sum / args.steps                                       # subint-passes over X per step
-    pass_bytes = npass * B                                               # X re-read per pass
-    spec_bytes = 2.0 * B * nsub                                          # read portrait + write X
+    keep = float(st.get("x_keep_frac", 1.0)) or 1.0                      # share of X the model's harmonic cut-off keeps
+    pass_bytes = npass * B * keep                                        # kept X re-read per pass
+    spec_bytes = (1.0 + keep) * B * nsub                                 # read portrait + write kept X
     hbm_peak, peak_src = peaks()
     fp64_peak = plan.measure_fp64()                                      # DFMA thread-instructions / s, measured here
     n_spec = -(-nsub // st["chunk"])
     fp64_spec = FP64_PER_THREAD_ROW_SPECTRA * 64.0 * NCHAN * nsub        # 64 threads per channel row
-    fp64_pass = FP64_PER_HARMONIC_PASS2 * (NBIN // 2) * NCHAN * npass
+    fp64_pass = FP64_PER_HARMONIC_PASS2 * (NBIN // 2) * keep * NCHAN * npass
     kern = {
         "k_spectra": {"algorithmic_bytes_per_launch": spec_bytes / n_spec, "launches": n_spec,
                       "ms": st["ms_spectra"],
@@ -439,8 +440,9 @@ def run_ours(args):
             "timing": "CUDA events around every launch of the timed steps, averaged per step",
             "chunk_subints": st["chunk"],
             # the whole step on the bytes it actually moves: portrait in, X out, X back in once per pass
-            "step_bytes_per_toa_actual": B * (2.0 + mp_t),
-            "step_frac_actual_bytes": nsub * B * (2.0 + mp_t) / (ms_step * 1e-3) / (hbm_peak * 1e9),
+            "x_keep_frac": keep,
+            "step_bytes_per_toa_actual": B * (1.0 + keep * (1.0 + mp_t)),
+            "step_frac_actual_bytes": nsub * B * (1.0 + keep * (1.0 + mp_t)) / (ms_step * 1e-3) / (hbm_peak * 1e9),
             # secondary bound: both main kernels are FP64 co-limited
             "fp64": {"peak_dfma_per_s": fp64_peak, "how": "pp_measure_fp64: independent DFMA chains, 4 CTAs x 256 threads per SM, "
                                                           "best of 3, measured in this run",
@@ -647,7 +649,7 @@ def config3_timing(dev, nsub):
                        "log10_tau, start tau = 0.8 x truth; evaluations = coarse (low harmonics of a channel "
                        "subset) + full passes, launches are per batch" % nsub, "unit": "TOAs/s"}
     with WidebandPlan(nchan, nbin, device=dev.index or 0) as pl:
-        pl.set_model(model.astype(np.float32), freqs)
+        pl.set_model(np.ascontiguousarray(model, dtype=np.float64), freqs)
         scat = np.tile([0.8 * (tau_s / P_EXAMPLE) * (freqs.mean() / nu0) ** alpha, alpha], (nsub, 1))
         for flags in ((1, 1, 0, 1, 1), (1, 1, 1, 1, 1)):
             kw = dict(fit_flags=flags, log10_tau=True, scat_guess=scat, pinned_results=True)

@@ -80,6 +80,15 @@ int pp_plan_set_model_steps(pp_plan_t* plan, int32_t steps);
  * nfeval counts coarse and full evaluations alike; pp_stats_t tells them apart. */
 int pp_plan_set_coarse(pp_plan_t* plan, double frac);
 
+/* Harmonic cut-off from the model.  The objective sees the data only through X_nk = d_nk conj(m_nk)
+ * (pplib.py:2136-2138, 1319-1322): where the model has no power the cross-spectrum carries nothing.  For every
+ * channel the kernels compute, store and stream only the leading groups of 16 harmonics outside which the model
+ * holds less than eps^2 of its k^2-weighted power sum_k k^2 |m_nk|^2 (default eps = 1e-10: chi^2 moves by < 2e-10
+ * relative, the parameters by ~1e-9 sigma; the noise level and Sd always use every harmonic of the data).  Smooth
+ * templates (Gaussian / spline models) keep a quarter of the harmonics or less; a template with a noise floor
+ * keeps them all.  eps = 0 keeps every harmonic of every channel.  pp_stats_t.x_keep_frac reports the kept share. */
+int pp_plan_set_model_cutoff(pp_plan_t* plan, double eps);
+
 /* Channel frequencies [nchan] MHz only (enough for pp_rotate_batch). */
 int pp_set_freqs(pp_plan_t* plan, const double* freqs);
 
@@ -87,6 +96,12 @@ int pp_set_freqs(pp_plan_t* plan, const double* freqs);
  * Computes conj(rfft(model)), |rfft(model)|^2 and p_n = sum_k |m_nk|^2 once
  * (pplib.py:2129-2130, 2138; pptoaslib.py:978-979). */
 int pp_set_model(pp_plan_t* plan, const float* model, const double* freqs);
+
+/* The same with the model portrait in float64, the reference's array type (pplib.py:2129): its spectrum then has
+ * no float32 rounding floor (~1e-15 of the peak power in every harmonic), which is what lets the harmonic cut-off
+ * above drop the harmonics an analytic template has no power in.  (Arbitrary nbin: rounded to float32 on the
+ * device, as pp_set_model.) */
+int pp_set_model_f64(pp_plan_t* plan, const double* model, const double* freqs);
 
 /* ---- batched wideband fit ------------------------------------------------
  * Replaces, per subint, the sequence of pptoas.GetTOAs.get_TOAs
@@ -316,6 +331,7 @@ typedef struct {
   int32_t timing_enabled;
   int64_t coarse_launches; /* coarse (low-harmonic) iterations of the general solver, not in pass_launches */
   double ms_coarse;        /* ... their pass + update kernels                   */
+  double x_keep_frac;      /* share of the cross-spectrum kept by the model's harmonic cut-off */
 } pp_stats_t;
 
 int pp_plan_enable_timing(pp_plan_t* plan, int32_t on);

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 
 # symbols declared in include/ppb200.h (checked by the CPU test-suite)
 SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
-           "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_plan_set_coarse", "pp_set_freqs",
+           "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_plan_set_coarse", "pp_plan_set_model_cutoff", "pp_set_freqs", "pp_set_model_f64",
            "pp_set_model", "pp_fit_batch",
            "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch", "pp_apply_response_batch",
            "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
@@ -111,7 +111,8 @@ class Stats(C.Structure):
                 ("ms_guess", C.c_double), ("ms_pass", C.c_double),
                 ("ms_update", C.c_double), ("ms_total", C.c_double),
                 ("chunk", C.c_int32), ("timing_enabled", C.c_int32),
-                ("coarse_launches", C.c_int64), ("ms_coarse", C.c_double)]
+                ("coarse_launches", C.c_int64), ("ms_coarse", C.c_double),
+                ("x_keep_frac", C.c_double)]
 
 
 _lib = None
@@ -143,10 +144,14 @@ def lib():
     L.pp_plan_set_model_steps.restype = C.c_int
     L.pp_plan_set_coarse.argtypes = [vp, C.c_double]
     L.pp_plan_set_coarse.restype = C.c_int
+    L.pp_plan_set_model_cutoff.argtypes = [vp, C.c_double]
+    L.pp_plan_set_model_cutoff.restype = C.c_int
     L.pp_set_freqs.argtypes = [vp, vp]
     L.pp_set_freqs.restype = C.c_int
     L.pp_set_model.argtypes = [vp, vp, vp]
     L.pp_set_model.restype = C.c_int
+    L.pp_set_model_f64.argtypes = [vp, vp, vp]
+    L.pp_set_model_f64.restype = C.c_int
     L.pp_fit_batch.argtypes = [vp, C.POINTER(FitArgs), C.POINTER(FitOut)]
     L.pp_fit_batch.restype = C.c_int
     L.pp_fit_phase_shift_batch.argtypes = [vp, vp, i32, vp, i32, vp, i32,

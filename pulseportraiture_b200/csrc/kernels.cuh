@@ -104,6 +104,7 @@ __device__ __forceinline__ double wrap_phase(double phi) {
 // ----------------------------------------------------------------------------
 struct ModelArgs {
   const float* model;   // [nchan, 2N]
+  const double* model64;  // the same rows in double (then `model` is unused): no float32 rounding floor in the spectrum
   cx<float>* mconj32;   // [nchan, N] conj(m), slot layout
   cx<double>* mconj64;  // [nchan, N]
   double* mpow;         // [nchan, N] |m|^2, slot layout
@@ -129,13 +130,21 @@ __global__ void __launch_bounds__(256) k_model(ModelArgs a) {
   cx<T>* bufB = bufA + N;
   const int ch = blockIdx.x * G::kRows + r;
   const bool valid = ch < a.nchan;
-  const float4* src = reinterpret_cast<const float4*>(a.model + (size_t)(valid ? ch : 0) * 2 * N);
+  if (a.model64) {
+    const double2* src = reinterpret_cast<const double2*>(a.model64 + (size_t)(valid ? ch : 0) * 2 * N);
+    for (int j = t_row; j < N; j += G::kTRow) {
+      const double2 v = valid ? src[j] : make_double2(0.0, 0.0);
+      bufA[j] = mk<T>(v.x, v.y);
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(a.model + (size_t)(valid ? ch : 0) * 2 * N);
 #pragma unroll
-  for (int m = 0; m < G::kLoads; ++m) {
-    const int i4 = t_row + m * G::kTRow;
-    const float4 v = valid ? src[i4] : make_float4(0, 0, 0, 0);
-    bufA[2 * i4] = mk<T>(v.x, v.y);
-    bufA[2 * i4 + 1] = mk<T>(v.z, v.w);
+    for (int m = 0; m < G::kLoads; ++m) {
+      const int i4 = t_row + m * G::kTRow;
+      const float4 v = valid ? src[i4] : make_float4(0, 0, 0, 0);
+      bufA[2 * i4] = mk<T>(v.x, v.y);
+      bufA[2 * i4 + 1] = mk<T>(v.z, v.w);
+    }
   }
   __syncthreads();
   cx<T>* Z = fft_forward<N, G::kTRow, T>(bufA, bufB, twN, t_row);
@@ -332,6 +341,8 @@ struct SpectraArgs {
   const cx<double>* dspec;   // [chunk,nchan,N] or null
   const double* ddc;         // [chunk,nchan] harmonic 0 of those rows
   int nhalf, kc_true;        // true nbin/2; first harmonic of the noise estimate, int(0.75 (nhalf + 1))
+  const int* njn;            // [nchan] groups of 16 harmonics where the model has power (k_model_cutoff): X is stored
+                             // for those only, the pass kernels read no others (null: all)
 };
 
 template <int N, class PL = SpecPlan<N>, bool I16 = false, bool FROMSPEC = false>
@@ -449,6 +460,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
     const bool first = (t == 0);
     auto slot_of = [&](int i, int q) -> int { return PL::slot_of(t, i, q, first); };
     const bool doX = a.X != nullptr && inrange;
+    const int kcut = (a.njn && inrange) ? 16 * a.njn[ch] : N;
     const cx<F>* mc = a.mconj64 + (size_t)(inrange ? ch : 0) * N;
     const cx<float>* mcf = a.mconj32 + (size_t)(inrange ? ch : 0) * N;
     static_assert(!kMcLate || kMix, "late conj(model) loads: mixed-precision plans only");
@@ -547,6 +559,7 @@ __global__ void __launch_bounds__(PL::kThreads, PL::kMinBlocks) k_spectra(Spectr
         for (int q = 0; q < NOUT; ++q) {
           const int idx = NOUT * i + q;
           const int sk = slot_of(i, q);
+          if (sk >= kcut) continue;      // the model has no power there: never read
           bool lo;
           if constexpr (kMix) lo = (i == 0 && q == 0) && (t < kLo);
           else lo = true;
@@ -869,6 +882,7 @@ struct PassArgs {
   SolverState st;
   int s0, nchan, N;
   int nhalf;               // true nbin/2 of the noise normalisation (0: N; arbitrary nbin runs on N = Npad slots)
+  const int* njn;          // [nchan] groups of 16 harmonics where the model has power (k_model_cutoff); N/16 = all
 };
 
 // streaming 16-byte load: read-only path, do not keep in L1
@@ -900,12 +914,8 @@ template <int N> struct Pass2Ring {
   static constexpr int KJ = LoK<N>::value / 16;
   static constexpr size_t kBytes = sizeof(float4) * 256 * (D + KJ);
 };
-#ifndef PP_PASS2_RING
-#define PP_PASS2_RING 1
-#endif
-
 #ifndef PP_PASS2_MINB
-#define PP_PASS2_MINB (PP_PASS2_RING ? 4 : 3)
+#define PP_PASS2_MINB 4
 #endif
 template <int N>
 __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
@@ -930,40 +940,23 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
     theta -= rint(theta);
     const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N);
     constexpr int NJ = N / 16;
-#ifndef PP_PASS2_U
-#define PP_PASS2_U 4
-#endif
-    constexpr int U = NJ >= 2 * PP_PASS2_U ? PP_PASS2_U : (NJ >= 8 ? 4 : (NJ >= 2 ? NJ / 2 : 1));   // loads kept in flight per buffer
-    constexpr int NG = NJ / U;                                 // groups (even)
     constexpr int KJ = LoK<N>::value / 16;                     // iterations that carry lo parts
+    constexpr int D = Pass2Ring<N>::D;
+    const int nj = a.njn[ch];                                  // groups of 16 harmonics the model has power in (>= KJ)
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value);
-    // the first loads go out before the phasor set-up so that its latency is hidden
-#if PP_PASS2_RING
+    // the X row pieces arrive through a thread-private ring in shared memory (cp.async, D iterations in flight);
+    // the first copies go out before the phasor set-up so that its latency is hidden
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* rv = reinterpret_cast<float4*>(smem_raw) + tid;   // [D][256] X pieces
-    float4* rl = rv + Pass2Ring<N>::D * 256;                  // [KJ][256] float32 residuals of the low harmonics
+    float4* rl = rv + D * 256;                                // [KJ][256] float32 residuals of the low harmonics
     auto ring_issue = [&](int j) {                            // one commit group per iteration, empty past the end
-      if (j < NJ) cp_async16(rv + (j % Pass2Ring<N>::D) * 256, row + j * 8 + l8);
+      if (j < nj) cp_async16(rv + (j % D) * 256, row + j * 8 + l8);
       cp_async_commit();
     };
-    if constexpr (KJ != NJ) {
 #pragma unroll
-      for (int j = 0; j < KJ; ++j) cp_async16(rl + j * 256, lorow + j * 8 + l8);
+    for (int j = 0; j < KJ; ++j) cp_async16(rl + j * 256, lorow + j * 8 + l8);
 #pragma unroll
-      for (int j = 0; j < Pass2Ring<N>::D - 1; ++j) ring_issue(j);
-    }
-    [[maybe_unused]] float4 qa[U], qb[U], ql[U];
-    if constexpr (false) {
-#else
-    float4 qa[U], qb[U], ql[U];
-    if constexpr (KJ != NJ) {
-#endif
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        qa[u] = ld_stream(row + u * 8 + l8);
-        ql[u] = u < KJ ? ld_stream(lorow + u * 8 + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    for (int j = 0; j < D - 1; ++j) ring_issue(j);
     // element (j, e): complex index 16 j + 2 l8 + e, harmonic k = index (slot 0 = Nyquist).
     // Phasors e^{2 pi i k theta} for k = 2 l8, 2 l8 + 1 and the step 16 from one sincospi and
     // repeated squaring (phase error ~1e-15 rad, far inside the chi^2 tolerance).
@@ -982,7 +975,6 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
       cw = e16.x; sw = e16.y;
     }
     double k0 = (double)(2 * l8), k1 = (double)(2 * l8 + 1);
-    static_assert(KJ <= U || KJ == NJ, "lo parts sit in the first group, or everywhere (N <= 64)");
     auto accum = [&](double xr0, double xi0, double xr1, double xi1) {
       const double re0 = xr0 * c0 - xi0 * s0, im0 = xr0 * s0 + xi0 * c0;
       const double re1 = xr1 * c1 - xi1 * s1, im1 = xr1 * s1 + xi1 * c1;
@@ -999,71 +991,24 @@ __global__ void __launch_bounds__(256, PP_PASS2_MINB) k_pass2(PassArgs a) {
       const double t1 = c1 * cw - s1 * sw; s1 = c1 * sw + s1 * cw; c1 = t1;
       k0 += 16.0; k1 += 16.0;
     };
-    auto consume = [&](float4 v) { accum((double)v.x, (double)v.y, (double)v.z, (double)v.w); };
-    // the first KJ iterations carry the float32 residuals of the low harmonics
-    auto consume_lo = [&](float4 v, float4 lo, bool first) {
-      if (first && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
+    // iteration j: wait for its copy, read its slot, refill the slot read one iteration ago.
+    // The first KJ iterations carry the float32 residuals of the low harmonics.
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      cp_async_wait<(D >= 2 ? D - 2 : 0)>();
+      float4 v = rv[(j % D) * 256], lo = rl[j * 256];
+      ring_issue(j + D - 1);
+      if (j == 0 && l8 == 0) { v.x = 0.f; v.y = 0.f; lo.x = 0.f; lo.y = 0.f; }   // slot 0 is handled below
       accum((double)v.x + (double)lo.x, (double)v.y + (double)lo.y, (double)v.z + (double)lo.z, (double)v.w + (double)lo.w);
-    };
-#if PP_PASS2_RING
-    if constexpr (KJ != NJ) {
-      // iteration j: wait for its copy, read its slot, refill the slot read one iteration ago
-      constexpr int D = Pass2Ring<N>::D;
-#pragma unroll
-      for (int j = 0; j < KJ; ++j) {
-        cp_async_wait<D - 2>();
-        const float4 v = rv[(j % D) * 256], lo = rl[j * 256];
-        ring_issue(j + D - 1);
-        consume_lo(v, lo, j == 0);
-      }
-#pragma unroll 4
-      for (int j = KJ; j < NJ; ++j) {
-        cp_async_wait<D - 2>();
-        const float4 v = rv[(j % D) * 256];
-        ring_issue(j + D - 1);
-        consume(v);
-      }
-    } else
-#endif
-    // software pipeline: the next group's loads are in flight while this one is consumed
-    if constexpr (KJ == NJ) {     // N <= 64: every iteration has a lo part
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        consume_lo(ld_stream(row + j * 8 + l8), ld_stream(lorow + j * 8 + l8), j == 0);
-    } else if constexpr (NG == 1) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) consume_lo(qa[u], ql[u], u == 0);
-    } else {
-      // first pair of groups, peeled: only group 0 has lo parts
-#pragma unroll
-      for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + (U + u) * 8 + l8);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u < KJ) consume_lo(qa[u], ql[u], u == 0);
-        else if (u == 0) consume_lo(qa[u], make_float4(0.f, 0.f, 0.f, 0.f), true);
-        else consume(qa[u]);
-      }
-      if (2 < NG) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + (2 * U + u) * 8 + l8);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) consume(qb[u]);
-#pragma unroll 1
-      for (int gI = 2; gI < NG; gI += 2) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) qb[u] = ld_stream(row + ((gI + 1) * U + u) * 8 + l8);
-#pragma unroll
-        for (int u = 0; u < U; ++u) consume(qa[u]);
-        if (gI + 2 < NG) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) qa[u] = ld_stream(row + ((gI + 2) * U + u) * 8 + l8);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) consume(qb[u]);
-      }
     }
-    if (l8 == 0) {  // Nyquist harmonic k = N stored in slot 0
+#pragma unroll 4
+    for (int j = KJ; j < nj; ++j) {
+      cp_async_wait<(D >= 2 ? D - 2 : 0)>();
+      const float4 v = rv[(j % D) * 256];
+      ring_issue(j + D - 1);
+      accum((double)v.x, (double)v.y, (double)v.z, (double)v.w);
+    }
+    if (l8 == 0 && nj == NJ) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
       const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
       const double xnx = (double)xh.x + (double)xl.x, xny = (double)xh.y + (double)xl.y;
@@ -1449,6 +1394,37 @@ __global__ void k_count_coarse(SolverState st, int s0, int n, int* out) {
   if (threadIdx.x == 0) *out = cnt;
 }
 
+// Harmonic cut-off of a model channel: the objective sees the data only through X_nk = d_nk conj(m_nk), so the
+// harmonics where the model has no power carry nothing.  njn[n] = the leading groups of 16 harmonics outside which
+// the information-weighted model power, sum k^2 |m_nk|^2, is below eps2 (1e-20) of its total: by Cauchy-Schwarz the
+// neglected part of C_n is below 1e-10 ||d_n|| ||m_n||, i.e. chi^2 moves by < 2e-10 relative and the parameters by
+// ~1e-9 sigma.  Smooth templates (Gaussian / spline models) keep a fraction of the harmonics; a template
+// with a noise floor keeps them all (njn = N/16, which also keeps the Nyquist term).  One CTA per channel.
+__global__ void __launch_bounds__(256) k_model_cutoff(const double* mpow, int* njn, int N, int kj_min, double eps2) {
+  __shared__ double grp[129];   // per group of 16 harmonics; [NJ] = the Nyquist term
+  const int n = blockIdx.x, NJ = N / 16;
+  const double* m = mpow + (size_t)n * N;
+  for (int j = threadIdx.x; j <= NJ; j += blockDim.x) {
+    double v = 0.0;
+    if (j < NJ) {
+      for (int q = 0; q < 16; ++q) { const int k = 16 * j + q; if (k > 0) v += (double)k * (double)k * m[k]; }
+    } else v = (double)N * (double)N * m[0];
+    grp[j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int j = 0; j <= NJ; ++j) tot += grp[j];
+    int keep = NJ;
+    if (tot > 0.0 && tot < CUDART_INF) {
+      double tail = grp[NJ];                       // dropping any group drops the Nyquist term as well
+      while (keep > kj_min && tail + grp[keep - 1] <= eps2 * tot) { tail += grp[keep - 1]; --keep; }
+      if (!(tail <= eps2 * tot)) keep = NJ;        // the Nyquist term alone is too much: keep everything
+    }
+    njn[n] = keep;
+  }
+}
+
 // Where the phase information of the (scattered) model sits, per group of 16 harmonics:
 //   info[j] = sum_n sum_{16 j <= k < 16 (j+1)} k^2 |m_nk|^2 |B_nk|^2,  |B_nk|^2 = 1 / (1 + (2 pi k tau_n)^2)
 // with tau_n from the start values of subint s (x = null: no scattering).  The host accumulates the groups and
@@ -1525,6 +1501,7 @@ struct Pass5Args {
   int nj;                  // groups of 16 harmonics summed: N/16 = all of them; fewer = the coarse objective, which
                            // also leaves the Nyquist term out and skips subints already coarse-converged (done == 3)
   int cstride;             // coarse objective: every cstride-th channel only (1: all)
+  const int* njn;          // [nchan] groups of 16 harmonics where the model has power (k_model_cutoff)
 };
 
 #ifndef PP_PASS5_MINB
@@ -1568,7 +1545,7 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
     const float4* row = reinterpret_cast<const float4*>(a.X + ((size_t)sl * a.nchan + ch) * N) + l8;
     const float4* mrow = reinterpret_cast<const float4*>(a.mpow + (size_t)ch * N) + l8;
     const float4* lorow = reinterpret_cast<const float4*>(a.Xlo + ((size_t)sl * a.nchan + ch) * LoK<N>::value) + l8;
-    const int nj = coarse ? a.nj : NJ;   // (the coarse objective has nj >= KJ)
+    const int nj = min(a.nj, a.njn[ch]);   // harmonics the model has power in (>= KJ groups), fewer on a coarse level
     auto issue = [&](int j) {            // one commit group per iteration, empty past the end
       if (j < nj) {
         cp_async16(rv + (j % D) * 256, row + j * 8);
@@ -1669,7 +1646,7 @@ __global__ void __launch_bounds__(256, PP_PASS5_MINB) k_pass5(Pass5Args a) {
       advance();
     }
     row -= l8; lorow -= l8;
-    if (l8 == 0 && !coarse) {  // Nyquist harmonic k = N stored in slot 0
+    if (l8 == 0 && nj == NJ) {  // Nyquist harmonic k = N stored in slot 0
       const float2 xh = __ldg(reinterpret_cast<const float2*>(row));
       const float2 xl = __ldg(reinterpret_cast<const float2*>(lorow));
       const double mn = __ldg(a.mpow + (size_t)ch * N);

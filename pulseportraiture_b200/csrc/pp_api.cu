@@ -96,9 +96,11 @@ struct pp_plan {
   int l2_bytes = 0, sm_count = 0;
   bool model_set = false;
   // tables + model
-  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, mmean_sub, model_stage;
+  DBuf tw8, twN32, tw2N32, twN64, tw2N64, freqs, nu2, lgf, gm_params, gm_taus, gm_zero, gm_one, mconj32, mconj64, mpow, pn, mmean, mmean_sub, model_stage, model_stage64;
   int fft_precision = 0;   // 0 auto, 32, 64
   int model_steps = 8;     // (phi, DM) solver: Newton steps on the local fourth-order model per pass
+  double cutoff_eps2 = 1e-20;  // harmonics outside which the model holds less than this share of its k^2-weighted power are skipped
+  double x_keep = 1.0;         // ... which leaves this share of the cross-spectrum to compute, store and stream
   double coarse_frac = 0.99;   // general solver: share of the model's phase information the coarse objective keeps
   std::vector<double> model_info;   // per group of 16 harmonics (scratch of the per-chunk choice)
   bool freqs_set = false;
@@ -106,7 +108,7 @@ struct pp_plan {
   std::vector<std::pair<int, DBuf>> grid_tables;
   DBuf grid_general;   // table of the last grid with bounds other than [-0.5, 0.5]
   // per-batch staging of small inputs and per-subint / per-channel workspace
-  DBuf running, minfo, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
+  DBuf running, minfo, njn, in_scat, in_scl, in_offs, in_P, in_errs, in_mask, in_w, in_init, in_dmg, in_snrs, in_nufits, in_nuouts, in_noise, in_models;
   DBuf nu_fit, nu_mean, wsum, nok, sigma, Ssn, Sdn, csum;
   DBuf st_x, st_xprev, st_step, st_fprev, st_lam, st_iter, st_iterc, st_done;
   DBuf o_params, o_perrs, o_nuout, o_cov, o_chi2, o_rchi2, o_snr, o_nfev, o_rc, o_scales, o_serrs, o_csnr, o_lag, o_phig;
@@ -308,7 +310,7 @@ template <int N> static cudaError_t setup_attrs() {
   SET_((k_spectra<N, SpecPlan<N>, true>), (int)spectra_smem_bytes<N>())
   SET_((k_model<N>), b64)
   SET_((k_pass5<N>), (int)Pass5Ring<N>::kBytes)
-  if (PP_PASS2_RING) { SET_((k_pass2<N>), (int)Pass2Ring<N>::kBytes) }
+  SET_((k_pass2<N>), (int)Pass2Ring<N>::kBytes)
   SET_((k_rfft_rows<N, float>), b32)
   SET_((k_rfft_rows<N, double>), b64)
   SET_((k_align_accum<N>), b64)
@@ -437,8 +439,8 @@ extern "C" void pp_plan_destroy(pp_plan_t* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   cudaStreamSynchronize(pl->stream);
-  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_twL, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->minfo, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
-                 &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
+  DBuf* all[] = {&pl->any_chirp, &pl->any_B, &pl->any_twM, &pl->any_tw2n, &pl->any_twL, &pl->any_spec, &pl->any_dc, &pl->any_spec2, &pl->any_dc2, &pl->resp, &pl->rot_gm, &pl->rot_nugm, &pl->al_w, &pl->al_out, &pl->al_wsum, &pl->running, &pl->minfo, &pl->njn, &pl->in_scat, &pl->in_scl, &pl->in_offs, &pl->tw8, &pl->twN32, &pl->tw2N32, &pl->twN64, &pl->tw2N64, &pl->freqs, &pl->nu2, &pl->lgf, &pl->gm_params, &pl->gm_taus, &pl->gm_zero, &pl->gm_one, &pl->mconj32, &pl->mconj64, &pl->mpow,
+                 &pl->pn, &pl->mmean, &pl->mmean_sub, &pl->model_stage, &pl->model_stage64, &pl->ps_spec, &pl->ps_mspec, &pl->ps_noise, &pl->rot_in, &pl->rot_out,
                  &pl->rot_phase, &pl->rot_dm, &pl->rot_P, &pl->rot_nuref,
                  &pl->in_P, &pl->in_errs, &pl->in_mask, &pl->in_w, &pl->in_init, &pl->in_dmg, &pl->in_snrs, &pl->in_nufits,
                  &pl->in_nuouts, &pl->in_noise, &pl->in_models, &pl->nu_fit, &pl->nu_mean, &pl->wsum, &pl->nok, &pl->sigma,
@@ -480,6 +482,7 @@ extern "C" int pp_plan_enable_timing(pp_plan_t* pl, int32_t on) {
 extern "C" int pp_get_stats(pp_plan_t* pl, pp_stats_t* st) {
   if (!pl || !st) return fail(-1, "NULL argument");
   *st = pl->stats;
+  st->x_keep_frac = pl->x_keep;
   return 0;
 }
 
@@ -631,6 +634,29 @@ static int choose_coarse(const std::vector<double>& info, double frac, int N) {
   return 2 * nj <= NJ ? nj : 0;
 }
 
+static int model_cutoffs(pp_plan* pl) {
+  const int N = pl->N, nchan = pl->nchan, NJ = N / 16, KJ = (N < 64 ? N : 64) / 16;
+  CK(pl->njn.need(sizeof(int) * nchan));
+  k_model_cutoff<<<nchan, 256, 0, pl->stream>>>(pl->mpow.as<double>(), pl->njn.as<int>(), N, KJ, pl->cutoff_eps2);
+  pl->stats.launches++;
+  std::vector<int> h(nchan);
+  CK(cudaMemcpyAsync(h.data(), pl->njn.p, sizeof(int) * nchan, cudaMemcpyDeviceToHost, pl->stream));
+  CK(cudaStreamSynchronize(pl->stream));
+  double keep = 0.0;
+  for (int v : h) keep += v;
+  pl->x_keep = keep / ((double)nchan * NJ);
+  return 0;
+}
+
+extern "C" int pp_plan_set_model_cutoff(pp_plan_t* pl, double eps) {
+  if (!pl) return fail(-1, "NULL plan");
+  if (!(eps >= 0.0 && eps < 1e-3)) return fail(-1, "model cut-off must be in [0, 1e-3): 0 keeps every harmonic");
+  CK(cudaSetDevice(pl->device));
+  pl->cutoff_eps2 = eps * eps;
+  if (pl->model_set && model_cutoffs(pl)) return -2;
+  return 0;
+}
+
 extern "C" int pp_plan_set_coarse(pp_plan_t* pl, double frac) {
   if (!pl) return fail(-1, "NULL plan");
   if (!(frac >= 0.0 && frac < 1.0)) return fail(-1, "coarse fraction must be in [0, 1): 0 disables the coarse stage");
@@ -645,13 +671,24 @@ extern "C" int pp_plan_set_fft_precision(pp_plan_t* pl, int32_t bits) {
   return 0;
 }
 
-extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* freqs) {
-  if (!pl || !model || !freqs) return fail(-1, "NULL argument");
+static int set_model_impl(pp_plan* pl, const float* model, const double* model64, const double* freqs) {
   CK(cudaSetDevice(pl->device));
   stats_begin(pl);
   const int N = pl->N, nchan = pl->nchan;
   const float* dmodel = nullptr;
-  if (stage_in(pl, pl->model_stage, model, (size_t)nchan * pl->nbin, &dmodel)) return -2;
+  const double* dmodel64 = nullptr;
+  const size_t nsamp = (size_t)nchan * pl->nbin;
+  if (model64) {
+    if (stage_in(pl, pl->model_stage64, model64, nsamp, &dmodel64)) return -2;
+    if (pl->anyn) {   // the arbitrary-nbin rows take float32 input: round on the device
+      CK(pl->model_stage.need(sizeof(float) * nsamp));
+      const size_t n2 = nsamp / 2;
+      k_cvt_f64_f32<<<(unsigned)std::min<size_t>((n2 + 255) / 256, 148 * 32), 256, 0, pl->stream>>>(
+          reinterpret_cast<const double2*>(dmodel64), pl->model_stage.as<float2>(), n2);
+      dmodel = pl->model_stage.as<float>();
+      dmodel64 = nullptr;
+    }
+  } else if (stage_in(pl, pl->model_stage, model, nsamp, &dmodel)) return -2;
   if (set_freqs_impl(pl, freqs)) return -2;
   CK(pl->mconj32.need(sizeof(float2) * (size_t)nchan * N));
   CK(pl->mconj64.need(sizeof(double2) * (size_t)nchan * N));
@@ -659,7 +696,7 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   CK(pl->pn.need(sizeof(double) * nchan));
   CK(pl->mmean.need(sizeof(float2) * N));
   ModelArgs a;
-  a.model = dmodel; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
+  a.model = dmodel; a.model64 = dmodel64; a.mconj32 = pl->mconj32.as<cx<float>>(); a.mconj64 = pl->mconj64.as<cx<double>>();
   a.mpow = pl->mpow.as<double>(); a.pn = pl->pn.as<double>();
   a.twN = pl->twN64.as<cx<double>>(); a.tw2N = pl->tw2N64.as<cx<double>>(); a.nchan = nchan;
   if (pl->anyn) {
@@ -675,9 +712,19 @@ extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* fre
   k_model_mean<<<(N + 127) / 128, 128, 0, pl->stream>>>(pl->mconj64.as<cx<double>>(), pl->mmean.as<float2>(), nchan, N);
   pl->stats.launches += 2;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(pl->stream));
+  if (model_cutoffs(pl)) return -2;
   pl->model_set = true;
   return 0;
+}
+
+extern "C" int pp_set_model(pp_plan_t* pl, const float* model, const double* freqs) {
+  if (!pl || !model || !freqs) return fail(-1, "NULL argument");
+  return set_model_impl(pl, model, nullptr, freqs);
+}
+
+extern "C" int pp_set_model_f64(pp_plan_t* pl, const double* model, const double* freqs) {
+  if (!pl || !model || !freqs) return fail(-1, "NULL argument");
+  return set_model_impl(pl, nullptr, model, freqs);
 }
 
 // ----------------------------------------------------------------------------
@@ -1076,7 +1123,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       a.sigma = pl->sigma.as<double>(); a.Ssn = pl->Ssn.as<double>(); a.Sdn = pl->Sdn.as<double>();
       a.tw8 = pl->tw8.as<cx<double>>();
       a.s0 = s0; a.nchan = nchan; a.G = G; a.nparts = nparts;
-      a.dspec = nullptr; a.ddc = nullptr; a.nhalf = 0; a.kc_true = 0;
+      a.dspec = nullptr; a.ddc = nullptr; a.nhalf = 0; a.kc_true = 0; a.njn = pl->njn.as<int>();
       if (pl->anyn) {   // rows transformed by Bluestein into the spectrum scratch, then the same emit code
         if (c == 0) {
           CK(pl->any_spec.need(sizeof(double2) * (size_t)chunk * nchan * N));
@@ -1125,7 +1172,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
     PassArgs pa;
     pa.X = pl->X.as<float2>(); pa.Xlo = pl->Xlo.as<float2>(); pa.nu2 = pl->nu2.as<double>(); pa.P = dP; pa.nu_fit = pl->nu_fit.as<double>();
     pa.Ssn = pl->Ssn.as<double>(); pa.sigma = pl->sigma.as<double>(); pa.csum = pl->csum.as<double>(); pa.st = st;
-    pa.s0 = s0; pa.nchan = nchan; pa.N = N; pa.nhalf = pl->anyn ? pl->L : 0;
+    pa.s0 = s0; pa.nchan = nchan; pa.N = N; pa.nhalf = pl->anyn ? pl->L : 0; pa.njn = pl->njn.as<int>();
     UpdateArgs ua;
     memset(&ua, 0, sizeof ua);
     ua.csum = pl->csum.as<double>(); ua.Ssn = pl->Ssn.as<double>(); ua.Sdn = pl->Sdn.as<double>(); ua.nu2 = pl->nu2.as<double>();
@@ -1144,7 +1191,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       p5.X = pl->X.as<float2>(); p5.Xlo = pl->Xlo.as<float2>(); p5.mpow = pl->mpow.as<double>(); p5.nu2 = pl->nu2.as<double>(); p5.lgf = pl->lgf.as<double>();
       p5.freqs = pl->freqs.as<double>(); p5.P = dP; p5.nu_fit = pl->nu_fit.as<double>(); p5.Ssn = pl->Ssn.as<double>();
       p5.sigma = pl->sigma.as<double>(); p5.csum = pl->csum.as<double>(); p5.st = st; p5.s0 = s0; p5.nchan = nchan;
-      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0; p5.nj = N / 16; p5.cstride = 1;
+      p5.log10_tau = args->log10_tau; p5.nhalf = pl->anyn ? pl->L : 0; p5.nj = N / 16; p5.cstride = 1; p5.njn = pl->njn.as<int>();
       memset(&u5, 0, sizeof u5);
       u5.csum = pl->csum.as<double>(); u5.Sdn = pl->Sdn.as<double>(); u5.nu2 = pl->nu2.as<double>(); u5.lgf = pl->lgf.as<double>();
       u5.freqs = pl->freqs.as<double>(); u5.P = dP; u5.nu_fit = pl->nu_fit.as<double>(); u5.nu_outs = dnuouts;
@@ -1226,7 +1273,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       {
         SpanGuard g(pl, SP_PASS);
         if (general) { DISPATCH_N(N, k_pass5<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass5Ring<NN>::kBytes, pl->stream>>>(p5)); }
-        else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, PP_PASS2_RING ? Pass2Ring<NN>::kBytes : 0, pl->stream>>>(pa)); }
+        else { DISPATCH_N(N, k_pass2<NN><<<dim3((nchan + 31) / 32, ns), 256, Pass2Ring<NN>::kBytes, pl->stream>>>(pa)); }
       }
       {
         SpanGuard g(pl, SP_UPDATE);

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(64, PP_SPECTRA16_MINB) k_spectra16(SpectraArgs
     __syncthreads();   // staged row consumed; the previous row's split reads of buf and of the model row are done
     fetch(step + 1);
     const bool doX = a.X != nullptr;
+    const int kcut = a.njn ? 16 * a.njn[ch] : N;
     if (doX && !(EXP & 1)) fetch_model(ch);
     dft16(v);
     {
@@ -243,6 +244,9 @@ __global__ void __launch_bounds__(64, PP_SPECTRA16_MINB) k_spectra16(SpectraArgs
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float2* const dst = (q & 1) ? Xo - 256 * (q >> 1) : Xe + 256 * (q >> 1);
+          // slots at and above the model's harmonic cut-off are never read (slot 0 of the special unit is the
+          // Nyquist term: read only when nothing is cut)
+          if (((q & 1) ? N - po - 256 * (q >> 1) : p + 256 * (q >> 1)) >= kcut) continue;
           if (i == 0 && q == 0) {                   // slot t < 64: double product, float value + float residual
             const cx<F> pr = cmul(d[0], mc64);
             const float2 xv = make_float2((float)pr.x, (float)pr.y);

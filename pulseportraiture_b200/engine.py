@@ -148,6 +148,11 @@ class WidebandPlan(object):
         objective its first iterations run on (default 0.99; 0 = no coarse stage)."""
         _ffi.check(self._lib.pp_plan_set_coarse(self._h, float(frac)), "pp_plan_set_coarse")
 
+    def set_model_cutoff(self, eps):
+        """Harmonics outside which a model channel holds less than eps^2 of its k^2-weighted power are
+        neither computed, stored nor streamed (default 1e-10; 0 = keep every harmonic)."""
+        _ffi.check(self._lib.pp_plan_set_model_cutoff(self._h, float(eps)), "pp_plan_set_model_cutoff")
+
     def set_freqs(self, freqs):
         keep = []
         fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",
@@ -171,11 +176,19 @@ class WidebandPlan(object):
         return {n: getattr(st, n) for n, _ in st._fields_}
 
     def set_model(self, model, freqs):
+        """Model portrait [nchan, nbin] (numpy array or torch tensor, host or CUDA).  float64 models go to the
+        device as they are (pp_set_model_f64: no float32 rounding floor in the model spectrum, which the
+        harmonic cut-off needs to be effective); anything else is taken as float32."""
         keep = []
-        mp = _ptr(model, np.float32, keep, "model", (self.nchan, self.nbin))
         fp = _ptr(np.asarray(freqs, dtype=np.float64), np.float64, keep, "freqs",
                   (self.nchan,))
-        _ffi.check(self._lib.pp_set_model(self._h, mp, fp), "pp_set_model")
+        is64 = (str(model.dtype).endswith("float64")) if hasattr(model, "dtype") else False
+        if is64:
+            mp = _ptr(model, np.float64, keep, "model", (self.nchan, self.nbin))
+            _ffi.check(self._lib.pp_set_model_f64(self._h, mp, fp), "pp_set_model_f64")
+        else:
+            mp = _ptr(model, np.float32, keep, "model", (self.nchan, self.nbin))
+            _ffi.check(self._lib.pp_set_model(self._h, mp, fp), "pp_set_model")
         self.freqs = np.array(freqs, dtype=np.float64)
 
     # ---- batched wideband fit ---------------------------------------------------

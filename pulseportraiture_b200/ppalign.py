@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import pplib
-from .pplib import get_plan, _f32, fit_phase_shift, rotate_data, DataBunch  # noqa: F401
+from .pplib import get_plan, _f32, _mdl, fit_phase_shift, rotate_data, DataBunch  # noqa: F401
 from .pptoas import load_data
 
 
@@ -130,7 +130,7 @@ def align_archives(metafile, initial_guess, fit_dm=True, tscrunch=False, pscrunc
                 model_ichans = np.array([np.argmin(abs(model_freqs - f)) for f in freqs])
             dup = model_ichans is not None and len(np.unique(model_ichans)) != len(model_ichans)
             pl = get_plan(nchan_d, nbin)
-            pl.set_model(_f32(model_port if model_ichans is None else model_port[model_ichans]), freqs)
+            pl.set_model(_mdl(model_port if model_ichans is None else model_port[model_ichans]), freqs)
             ok_isubs = np.asarray(d.ok_isubs, dtype=int)
             nsub = len(ok_isubs)
             mask = np.zeros((nsub, nchan_d), dtype=np.uint8)

@@ -97,6 +97,13 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _mdl(a):
+    """A model portrait as set_model takes it: float32 arrays as they are, everything else as float64 (the
+    reference's array type; no float32 rounding floor in the model spectrum)."""
+    a = np.asarray(a)
+    return np.ascontiguousarray(a, dtype=np.float32 if a.dtype == np.float32 else np.float64)
+
+
 def _dev(a):
     """Portrait data as the device takes them without a host pass: float32 and float64 arrays go as
     they are (float64 is rounded to float32 on the device, PP_DATA_F64), anything else via float64."""
@@ -158,7 +165,7 @@ def fit_portrait(data, model, init_params, P, freqs, nu_fit=None, nu_out=None,
     nchan, nbin = data.shape
     freqs = np.asarray(freqs, dtype=np.float64)
     pl = get_plan(nchan, nbin)
-    pl.set_model(_f32(model), freqs)
+    pl.set_model(_mdl(model), freqs)
     init = np.zeros((1, 5))
     init[0, 0], init[0, 1] = init_params[0], init_params[1]
     nu_fits = None if nu_fit is None else np.full((1, 3), float(nu_fit))
@@ -193,7 +200,7 @@ def get_scales(data, model, phase, DM, P, freqs, nu_ref=np.inf):
     data = np.asarray(data)
     nchan, nbin = data.shape
     pl = get_plan(nchan, nbin)
-    pl.set_model(_f32(model), np.asarray(freqs, dtype=np.float64))
+    pl.set_model(_mdl(model), np.asarray(freqs, dtype=np.float64))
     init = np.zeros((1, 5))
     init[0, 0], init[0, 1] = phase, DM
     nu = 1e300 if np.isinf(nu_ref) else float(nu_ref)

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import pplib
 from .pplib import DataBunch, read_model, gen_gaussian_portrait, scattering_alpha  # noqa: F401
-from .pplib import get_plan, _f32, _dev
+from .pplib import get_plan, _f32, _dev, _mdl
 
 max_nfile = 999                                  # pptoas.py:18-23
 rm_baseline = bool(pplib.F0_fact)                # pptoas.py:25-29
@@ -441,7 +441,7 @@ class GetTOAs:
             table_set = None
             for (t, flags), isubs in sorted(groups.items()):
                 if t != table_set:
-                    pl.set_model(_f32(models[t]), tables[t])
+                    pl.set_model(_mdl(models[t]), tables[t])
                     table_set = t
                 idx = np.asarray(isubs, dtype=int)
                 if len(idx) > 1 and np.all(np.diff(idx) == 1):

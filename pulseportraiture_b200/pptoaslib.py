@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32, _dev,  # noqa: F401
+from .pplib import (DataBunch, RCSTRINGS, Dconst, _check_bounds, _f32, _dev, _mdl,  # noqa: F401
                     get_plan, scattering_times, scattering_portrait_FT, scipy_return_code, _RC_BENIGN)
 
 
@@ -114,7 +114,7 @@ def fit_portrait_full(data_port, model_port, init_params, P, freqs,
     nchan, nbin = data_port.shape
     freqs = np.asarray(freqs, dtype=np.float64)
     pl = get_plan(nchan, nbin)
-    pl.set_model(_f32(model_port), freqs)
+    pl.set_model(_mdl(model_port), freqs)
     init = np.array(init_params, dtype=np.float64).reshape(1, 5)
 
     def three(vals):
@@ -179,7 +179,7 @@ def get_scales_full(params, data_port, model_port, P, freqs, nu_DM, nu_GM, nu_ta
     data_port = np.asarray(data_port)
     nchan, nbin = data_port.shape
     pl = get_plan(nchan, nbin)
-    pl.set_model(_f32(model_port), np.asarray(freqs, dtype=np.float64))
+    pl.set_model(_mdl(model_port), np.asarray(freqs, dtype=np.float64))
     nus = np.array([[nu_DM, nu_GM, nu_tau]], dtype=np.float64)
     r = pl.fit_batch(_f32(data_port)[None], P,
                      errs=None if errs is None else np.asarray(errs, dtype=np.float64)[None],

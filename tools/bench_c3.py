@@ -34,7 +34,7 @@ for a in range(0, nsub, 16):
     data[a:b] = clean.to(torch.float32) + 1.5 * torch.randn(clean.shape, generator=g, device=dev, dtype=torch.float32)
 torch.cuda.synchronize()
 pl = WidebandPlan(NCHAN, NBIN)
-pl.set_model(model.astype(np.float32), freqs)
+pl.set_model(np.ascontiguousarray(model, dtype=np.float64), freqs)
 nu_fit = freqs.mean()
 scat = np.tile([0.8 * (tau_s / P) * (nu_fit / NU0) ** alpha, alpha], (nsub, 1))
 kw = dict(fit_flags=flags, log10_tau=True, scat_guess=scat, pinned_results=True)

@@ -41,7 +41,7 @@ k = torch.arange(mFT.shape[-1], device=dev, dtype=torch.float64)
 nu2 = torch.from_numpy(freqs ** -2.0 - NU0 ** -2.0).to(dev)
 data = torch.empty((batch, NCHAN, NBIN), dtype=torch.float32, device=dev)
 pl = WidebandPlan(NCHAN, NBIN, device=local)
-pl.set_model(model.astype(np.float32), freqs)
+pl.set_model(np.ascontiguousarray(model, dtype=np.float64), freqs)
 a0, b0 = shard_range(total, rank, world)                       # this rank's part of the campaign
 shg = SharedGather(batch, 6, group=gloo, tag="c4") if world > 1 else None
 # untimed warm-up (buffer allocation, first launches) on a noise-only batch of the campaign's shape
