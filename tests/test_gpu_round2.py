@@ -320,3 +320,51 @@ def test_general_solver_coarse_stage_small_shapes(nchan, nbin, log10_tau, tau_s)
     assert np.max(np.abs(a["params"] - b["params"])[:, fit] / a["param_errs"][:, fit]) < 1e-3
     assert np.max(np.abs(b["param_errs"][:, fit] / a["param_errs"][:, fit] - 1)) < 1e-5
     assert np.max(np.abs(b["chi2"] / a["chi2"] - 1)) < 1e-9
+
+
+def test_model_harmonic_cutoff_changes_nothing_measurable():
+    """The harmonic cut-off (ppb200.h pp_plan_set_model_cutoff): harmonics where a float64 analytic model has no
+    power are neither stored nor streamed.  Against the same plan with the cut-off off: chi2 within 1e-9, parameters
+    within 1e-6 sigma, errors / scales to rounding, for the (phi, DM) and the general solver; a template with a
+    noise floor keeps every harmonic; a float32 copy of the model (rounding floor) keeps far more than the
+    float64 one."""
+    from pulseportraiture_b200 import engine
+    nsub, nchan, nbin, nu0, bw, tau_s = 6, 64, 2048, 1500., 800., 20e-6
+    cases = [synth.make_case(nchan, nbin, nu0, bw, 9500 + s, tau_data_s=tau_s) for s in range(nsub)]
+    data = np.stack([c["data"] for c in cases]).astype(np.float32)
+    P, freqs = cases[0]["P"], cases[0]["freqs"]
+    _, model = synth.example_model(nchan, nbin, nu0, bw)        # float64 as generated (make_case rounds its copy)
+    scat = np.tile([0.8 * tau_s / P * (freqs.mean() / nu0) ** -4.0, -4.0], (nsub, 1))
+    mask = np.ones((nsub, nchan), dtype=np.uint8)
+    mask[1, 5:20] = 0
+    for kw in (dict(), dict(fit_flags=(1, 1, 0, 1, 1), log10_tau=True, scat_guess=scat)):
+        out = {}
+        for eps in (0.0, 1e-10):
+            with engine.WidebandPlan(nchan, nbin) as pl:
+                pl.set_model_cutoff(eps)
+                pl.set_model(model, freqs)                      # float64
+                r = pl.fit_batch(data, P, chan_mask=mask, **kw)
+                out[eps] = ({k: np.array(v) for k, v in r.items()}, pl.stats()["x_keep_frac"])
+        (a, ka), (b, kb) = out[0.0], out[1e-10]
+        assert ka == 1.0 and 0.05 < kb < 0.6
+        assert (a["return_code"] == 0).all() and (b["return_code"] == 0).all()
+        fit = a["param_errs"][0] > 0
+        assert np.max(np.abs(a["params"] - b["params"])[:, fit] / a["param_errs"][:, fit]) < 1e-6
+        assert np.max(np.abs(b["chi2"] / a["chi2"] - 1)) < 1e-9
+        assert np.max(np.abs(b["param_errs"][:, fit] / a["param_errs"][:, fit] - 1)) < 1e-8
+        ok = mask.astype(bool)
+        assert np.max(np.abs(b["scales"][ok] / a["scales"][ok] - 1)) < 1e-7
+        assert np.array_equal(a["lag_index"], b["lag_index"])
+    with engine.WidebandPlan(nchan, nbin) as pl:
+        pl.set_model(model.astype(np.float32), freqs)           # float32: rounding floor in every harmonic
+        k32 = pl.stats()["x_keep_frac"]
+        pl.set_model(model + np.random.RandomState(1).normal(0.0, 1e-3, model.shape), freqs)   # a noisy template
+        knoisy = pl.stats()["x_keep_frac"]
+        pl.set_model(model, freqs)
+        k64 = pl.stats()["x_keep_frac"]
+        pl.set_model_cutoff(0.0)                                # re-evaluated for the model already set
+        assert pl.stats()["x_keep_frac"] == 1.0
+    assert knoisy == 1.0 and k64 < 0.6 and k32 > k64
+    with pytest.raises(Exception):
+        with engine.WidebandPlan(nchan, nbin) as pl:
+            pl.set_model_cutoff(0.5)
