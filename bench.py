@@ -441,6 +441,11 @@ def run_ours(args):
             "chunk_subints": st["chunk"],
             # the whole step on the bytes it actually moves: portrait in, X out, X back in once per pass
             "x_keep_frac": keep,
+            # the same kernel time against the bytes it moved before the harmonic cut-off (read portrait + write ALL of
+            # X): comparable with the round-1 figure; the kernel is FP64-bound, its time does not depend on the stores
+            "frac_on_full_x_bytes": 2.0 * B * nsub / (kern["k_spectra"]["ms"] * 1e-3) / (hbm_peak * 1e9),
+            "note": "dominant kernel k_spectra16 is FP64-pipe bound (roofline.fp64); frac counts the algorithmic bytes "
+                    "it moves now (portrait in + kept x_keep_frac of X out)",
             "step_bytes_per_toa_actual": B * (1.0 + keep * (1.0 + mp_t)),
             "step_frac_actual_bytes": nsub * B * (1.0 + keep * (1.0 + mp_t)) / (ms_step * 1e-3) / (hbm_peak * 1e9),
             # secondary bound: both main kernels are FP64 co-limited
