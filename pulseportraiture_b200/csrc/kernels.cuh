@@ -663,6 +663,8 @@ struct GuessArgs {
   const float2* mconj;     // [nmodel, N] conj(model spectrum)
   int nparts, nmodel, N, Ns;
   int nhalf;               // true nbin/2 when the spectra sit in N = Npad > nbin/2 slots (arbitrary nbin), else 0
+  int nused;               // the grid and the polish sum over slots 1..nused only (the model's harmonic cut-off: the
+                           // products d_k conj(m_k) beyond it are nothing); 0 or N: all of them, Nyquist included
   double polish_tol;       // stop the exact polish when |dx| < polish_tol [rot]
   const double* wsum;      // [n] divisor of the partial sum, or null (=1)
   const double* noise;     // [n] time-domain sigma or null (measure from spectrum)
@@ -731,6 +733,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   // (two independent FP64 recurrences, no table look-up or index arithmetic in the loop); Y_k is a
   // shared-memory broadcast.  Harmonic N sits in slot 0.
   const int M = a.Ns - 1;
+  const int NU = (a.nused > 0 && a.nused < N) ? (a.nused & ~1) : N;   // even
   double bv = CUDART_INF;
   int bi = 0x7fffffff;
   for (int j0 = w * 32; j0 < a.Ns; j0 += 256) {
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
       cx<double> po = rho, pe = rho2;                 // harmonics 1 and 2
       double acc_o = 0.0, acc_e = 0.0;
 #pragma unroll 4
-      for (int m = 0; m < N / 2; ++m) {
+      for (int m = 0; m < NU / 2; ++m) {
         const double2 yo = Y[2 * m + 1];
         const double2 ye = Y[(2 * m + 2 == N) ? 0 : 2 * m + 2];
         acc_o = fma(yo.x, po.x, fma(-yo.y, po.y, acc_o));
@@ -777,7 +780,8 @@ __global__ void __launch_bounds__(256) k_guess(GuessArgs a) {
   // ---- exact polish: safeguarded Newton on C'(phi) = 0 inside the bracket ------
   for (int it = 0; it < 60; ++it) {
     double u[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < N; i += 256) {
+    for (int i = tid; i < (NU < N ? NU + 1 : N); i += 256) {
+      if (i == 0 && NU < N) continue;          // slot 0 is the Nyquist harmonic
       const int k = (i == 0) ? N : i;
       double c, sn;
       cis2pi((double)k * x, c, sn);

@@ -100,6 +100,7 @@ struct pp_plan {
   int fft_precision = 0;   // 0 auto, 32, 64
   int model_steps = 8;     // (phi, DM) solver: Newton steps on the local fourth-order model per pass
   double cutoff_eps2 = 1e-20;  // harmonics outside which the model holds less than this share of its k^2-weighted power are skipped
+  int kmax_used = 0;           // 16 x the largest per-channel cut-off (0: not set)
   double x_keep = 1.0;         // ... which leaves this share of the cross-spectrum to compute, store and stream
   double coarse_frac = 0.99;   // general solver: share of the model's phase information the coarse objective keeps
   std::vector<double> model_info;   // per group of 16 harmonics (scratch of the per-chunk choice)
@@ -643,8 +644,10 @@ static int model_cutoffs(pp_plan* pl) {
   CK(cudaMemcpyAsync(h.data(), pl->njn.p, sizeof(int) * nchan, cudaMemcpyDeviceToHost, pl->stream));
   CK(cudaStreamSynchronize(pl->stream));
   double keep = 0.0;
-  for (int v : h) keep += v;
+  int vmax = 0;
+  for (int v : h) { keep += v; vmax = std::max(vmax, v); }
   pl->x_keep = keep / ((double)nchan * NJ);
+  pl->kmax_used = 16 * vmax;
   return 0;
 }
 
@@ -1160,6 +1163,7 @@ extern "C" int pp_fit_batch(pp_plan_t* pl, const pp_fit_args_t* args, const pp_f
       }
       ga.N = N; ga.Ns = Ns; ga.wsum = pl->wsum.as<double>(); ga.noise = nullptr; ga.table = table; ga.s0 = s0;
       ga.nhalf = pl->anyn ? pl->L : 0;
+      ga.nused = pl->kmax_used;   // the mean model has no power beyond the largest channel cut-off
       ga.phase = pl->o_phig.as<double>(); ga.lag = pl->o_lag.as<int>();
       ga.x = st.x; ga.DMg = ddmg; ga.P = dP; ga.nu_mean = pl->nu_mean.as<double>(); ga.nu_fit = pl->nu_fit.as<double>();
       ga.polish_tol = 1e-6;   // a start value (the last step is still applied): the Newton solver refines it
