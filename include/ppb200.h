@@ -284,6 +284,12 @@ int pp_gen_gaussian_portrait(pp_plan_t* plan, const char* model_code,
                              const double* params, int32_t ngauss,
                              double scattering_index, double nu_ref, float* out);
 
+/* The same portrait in float64 (an unscattered model is evaluated and stored in double: what pp_set_model_f64
+ * and the harmonic cut-off want; a scattered one, tau != 0, passes through float32 rows). */
+int pp_gen_gaussian_portrait_f64(pp_plan_t* plan, const char* model_code,
+                             const double* params, int32_t ngauss,
+                             double scattering_index, double nu_ref, double* out);
+
 /* B-spline (PCA) model portrait on the device: replaces pplib.gen_spline_portrait
  * (pplib.py:932-956) as called by read_spline_model (pplib.py:2955-2987;
  * pptoas.py:376-379):  out[n,:] = mean_prof + sum_c s_c(freqs[n]) * eigvec[:,c]

@@ -24,7 +24,7 @@ SYMBOLS = ["pp_plan_create", "pp_plan_destroy", "pp_plan_set_stream",
            "pp_plan_set_chunk", "pp_plan_set_fft_precision", "pp_plan_set_model_steps", "pp_plan_set_coarse", "pp_plan_set_model_cutoff", "pp_set_freqs", "pp_set_model_f64",
            "pp_set_model", "pp_fit_batch",
            "pp_fit_phase_shift_batch", "pp_fit_phase_shift_batch_bounds", "pp_rotate_batch", "pp_rotate_full_batch", "pp_apply_response_batch",
-           "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_spline_portrait",
+           "pp_align_accumulate", "pp_gen_gaussian_portrait", "pp_gen_gaussian_portrait_f64", "pp_gen_spline_portrait",
            "pp_get_noise_batch", "pp_get_noise_cut_batch", "pp_get_noise_fit_batch", "pp_measure_fp64",
            "pp_plan_enable_timing", "pp_get_stats", "pp_host_alloc",
            "pp_host_free", "pp_last_error",
@@ -170,6 +170,8 @@ def lib():
     L.pp_align_accumulate.restype = C.c_int
     L.pp_gen_gaussian_portrait.argtypes = [vp, C.c_char_p, vp, i32, C.c_double, C.c_double, vp]
     L.pp_gen_gaussian_portrait.restype = C.c_int
+    L.pp_gen_gaussian_portrait_f64.argtypes = [vp, C.c_char_p, vp, i32, C.c_double, C.c_double, vp]
+    L.pp_gen_gaussian_portrait_f64.restype = C.c_int
     L.pp_gen_spline_portrait.argtypes = [vp, vp, vp, i32, vp, i32, vp, i32, vp]
     L.pp_gen_spline_portrait.restype = C.c_int
     L.pp_get_noise_batch.argtypes = [vp, vp, i32, vp]

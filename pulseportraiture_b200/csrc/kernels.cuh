@@ -2452,6 +2452,7 @@ struct GaussModelArgs {
   const double* params;   // [2 + 6 ngauss]: DC, tau [bin], (loc, m_loc, wid, m_wid, amp, m_amp) per component
   const double* freqs;    // [nchan]
   float* out;             // [nchan, nbin]
+  double* out64;          // the same in double when non-null (then `out` is unused)
   double* taus;           // [nchan] out: (tau/nbin) (nu/nu_ref)^alpha [rot]
   double nu_ref, alpha;
   int ngauss, nchan, nbin;
@@ -2515,8 +2516,14 @@ __global__ void __launch_bounds__(256) k_gauss_model(GaussModelArgs a) {
       const double z = (wrapx(x, g_mean[g]) - g_mean[g]) * g_isig[g];
       if (fabs(z) < 20.0) v += g_amp[g] * exp(-0.5 * z * z);
     }
-    a.out[(size_t)ch * nbin + i] = (float)v;
+    if (a.out64) a.out64[(size_t)ch * nbin + i] = v;
+    else a.out[(size_t)ch * nbin + i] = (float)v;
   }
+}
+
+// float32 -> float64 (a scattered model is formed in float32 rows by k_rotate)
+__global__ void __launch_bounds__(256) k_cvt_f32_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (double)in[i];
 }
 
 // ----------------------------------------------------------------------------

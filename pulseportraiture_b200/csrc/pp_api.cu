@@ -1623,9 +1623,9 @@ extern "C" int pp_align_accumulate(pp_plan_t* pl, const float* data, int32_t nsu
   return 0;
 }
 
-extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, const double* params, int32_t ngauss,
-                                        double scattering_index, double nu_ref, float* outp) {
-  if (!pl || !model_code || !params || !outp) return fail(-1, "NULL argument");
+static int gen_gaussian_impl(pp_plan* pl, const char* model_code, const double* params, int32_t ngauss,
+                             double scattering_index, double nu_ref, float* outp, double* outp64) {
+  if (!pl || !model_code || !params || !(outp || outp64)) return fail(-1, "NULL argument");
   if (ngauss < 0 || ngauss > kMaxGauss) return fail(-1, "ngauss must be in [0, %d]", kMaxGauss);
   if (strlen(model_code) < 3) return fail(-1, "model_code needs three characters (loc, wid, amp)");
   for (int i = 0; i < 3; ++i)
@@ -1640,16 +1640,27 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
   CK(pl->gm_params.need(sizeof(double) * np));
   CK(pl->gm_taus.need(sizeof(double) * nchan));
   CK(cudaMemcpyAsync(pl->gm_params.p, params, sizeof(double) * np, cudaMemcpyHostToDevice, pl->stream));
-  float* dout = outp;
-  const bool out_dev = is_device_ptr(outp);
-  if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  const bool scat = params[1] != 0.0;          // the scattering multiply works on float32 rows
+  const bool want64 = outp64 != nullptr;
+  const bool out_dev = is_device_ptr(want64 ? (const void*)outp64 : (const void*)outp);
+  float* dout = nullptr;
+  double* dout64 = nullptr;
+  if (want64) {
+    dout64 = outp64;
+    if (!out_dev) { CK(pl->model_stage64.need(sizeof(double) * tot)); dout64 = pl->model_stage64.as<double>(); }
+    if (scat) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  } else {
+    dout = outp;
+    if (!out_dev) { CK(pl->rot_out.need(sizeof(float) * tot)); dout = pl->rot_out.as<float>(); }
+  }
   GaussModelArgs g;
-  g.params = pl->gm_params.as<double>(); g.freqs = pl->freqs.as<double>(); g.out = dout; g.taus = pl->gm_taus.as<double>();
+  g.params = pl->gm_params.as<double>(); g.freqs = pl->freqs.as<double>(); g.taus = pl->gm_taus.as<double>();
+  g.out = dout; g.out64 = (want64 && !scat) ? dout64 : nullptr;
   g.nu_ref = nu_ref; g.alpha = scattering_index; g.ngauss = ngauss; g.nchan = nchan; g.nbin = pl->nbin;
   g.code_loc = model_code[0] - '0'; g.code_wid = model_code[1] - '0'; g.code_amp = model_code[2] - '0';
   k_gauss_model<<<nchan, 256, 0, pl->stream>>>(g);
   pl->stats.launches++;
-  if (params[1] != 0.0) {   // scattering: rfft, times 1/(1 + 2 pi i k tau_n), irfft (pplib.py:921-927), in place
+  if (scat) {   // scattering: rfft, times 1/(1 + 2 pi i k tau_n), irfft (pplib.py:921-927), in place
     if (!pl->gm_zero.p) {
       const double z = 0.0, o = 1.0;
       CK(pl->gm_zero.need(sizeof(double)));
@@ -1664,11 +1675,28 @@ extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, c
     a.nu2 = pl->nu2.as<double>(); a.taus = pl->gm_taus.as<double>(); a.resp = nullptr; a.nsub = 1; a.nchan = nchan;
     (void)N;
     if (rotate_rows(pl, a, true)) return -2;
+    if (want64) {
+      k_cvt_f32_f64<<<(unsigned)std::min<size_t>((tot + 255) / 256, 148 * 32), 256, 0, pl->stream>>>(dout, dout64, tot);
+      pl->stats.launches++;
+    }
   }
   CK(cudaGetLastError());
-  if (!out_dev) CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  if (!out_dev) {
+    if (want64) CK(cudaMemcpyAsync(outp64, dout64, sizeof(double) * tot, cudaMemcpyDeviceToHost, pl->stream));
+    else CK(cudaMemcpyAsync(outp, dout, sizeof(float) * tot, cudaMemcpyDeviceToHost, pl->stream));
+  }
   CK(cudaStreamSynchronize(pl->stream));
   return 0;
+}
+
+extern "C" int pp_gen_gaussian_portrait(pp_plan_t* pl, const char* model_code, const double* params, int32_t ngauss,
+                                        double scattering_index, double nu_ref, float* outp) {
+  return gen_gaussian_impl(pl, model_code, params, ngauss, scattering_index, nu_ref, outp, nullptr);
+}
+
+extern "C" int pp_gen_gaussian_portrait_f64(pp_plan_t* pl, const char* model_code, const double* params, int32_t ngauss,
+                                            double scattering_index, double nu_ref, double* outp) {
+  return gen_gaussian_impl(pl, model_code, params, ngauss, scattering_index, nu_ref, nullptr, outp);
 }
 
 extern "C" int pp_gen_spline_portrait(pp_plan_t* pl, const double* mean_prof, const double* eigvec, int32_t ncomp,

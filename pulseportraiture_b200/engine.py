@@ -333,26 +333,31 @@ class WidebandPlan(object):
                    "pp_get_noise_fit_batch")
         return out
 
-    def gen_gaussian_portrait(self, model_code, params, scattering_index, nu_ref, out=None, device_out=False):
+    def gen_gaussian_portrait(self, model_code, params, scattering_index, nu_ref, out=None, device_out=False,
+                              dtype=np.float32):
         """Evolving-Gaussian model portrait on the device (pplib.py:853-930) for the plan's
         frequencies (set_freqs first).  ``params`` = [DC, tau_bin, (loc, m_loc, wid, m_wid, amp,
-        m_amp) * ngauss].  Returns float32 [nchan, nbin]: a numpy array, or a torch CUDA
-        tensor with ``device_out=True`` (ready for set_model without a host round trip)."""
+        m_amp) * ngauss].  Returns [nchan, nbin] of ``dtype`` (float32, or float64: evaluated and stored in
+        double): a numpy array, or a torch CUDA tensor with ``device_out=True`` (ready for set_model without a
+        host round trip)."""
         params = np.ascontiguousarray(params, dtype=np.float64)
         if params.ndim != 1 or (params.size - 2) % 6:
             raise ValueError("params must have 2 + 6*ngauss entries")
         ngauss = (params.size - 2) // 6
+        f64 = np.dtype(dtype) == np.float64
         if out is None:
             if device_out:
                 import torch
-                out = torch.empty((self.nchan, self.nbin), dtype=torch.float32,
+                out = torch.empty((self.nchan, self.nbin), dtype=torch.float64 if f64 else torch.float32,
                                   device=torch.device("cuda", self.device))
             else:
-                out = np.empty((self.nchan, self.nbin), dtype=np.float32)
+                out = np.empty((self.nchan, self.nbin), dtype=np.float64 if f64 else np.float32)
+        else:
+            f64 = str(out.dtype).endswith("float64")
         op = out.data_ptr() if _is_torch(out) else out.ctypes.data
-        _ffi.check(self._lib.pp_gen_gaussian_portrait(
-            self._h, str(model_code).encode("ascii"), params.ctypes.data, int(ngauss),
-            float(scattering_index), float(nu_ref), op), "pp_gen_gaussian_portrait")
+        fn = self._lib.pp_gen_gaussian_portrait_f64 if f64 else self._lib.pp_gen_gaussian_portrait
+        _ffi.check(fn(self._h, str(model_code).encode("ascii"), params.ctypes.data, int(ngauss),
+                      float(scattering_index), float(nu_ref), op), "pp_gen_gaussian_portrait")
         return out
 
     def gen_spline_portrait(self, mean_prof, eigvec, tck, out=None, device_out=False):

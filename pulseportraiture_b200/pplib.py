@@ -433,7 +433,8 @@ def gen_gaussian_portrait_device(model_code, params, scattering_index, phases, f
     """gen_gaussian_portrait (pplib.py:853-930) evaluated by the CUDA kernel
     ``k_gauss_model`` (+ the scattering multiply of ``k_rotate``): the per-archive /
     per-subint model build of pptoas.py:356-379.  ``phases`` must be the bin centres
-    of get_bin_centers(nbin).  Returns float64 [nchan, nbin] (float32 precision)."""
+    of get_bin_centers(nbin).  Returns float64 [nchan, nbin], evaluated in double (a scattered model,
+    tau != 0, passes through float32 rows)."""
     if len(join_ichans):
         raise NotImplementedError("join parameters are a ppgauss feature")
     nbin, nchan = len(phases), len(freqs)
@@ -441,7 +442,7 @@ def gen_gaussian_portrait_device(model_code, params, scattering_index, phases, f
         raise ValueError("the device generator works on get_bin_centers(nbin)")
     pl = get_plan(nchan, nbin)
     pl.set_freqs(np.asarray(freqs, dtype=np.float64))
-    return pl.gen_gaussian_portrait(model_code, params, scattering_index, nu_ref).astype(np.float64)
+    return pl.gen_gaussian_portrait(model_code, params, scattering_index, nu_ref, dtype=np.float64)
 
 
 def gen_spline_portrait(mean_prof, freqs, eigvec, tck, nbin=None, device=False):

@@ -69,6 +69,12 @@ def test_device_model_vs_oracle(code, tau_s, nchan, nbin, nu0, bw):
         out = pl.gen_gaussian_portrait(code, _params(gm, tau_s * nbin / P), gm["alpha"], gm["nu_ref"])
         assert out.dtype == np.float32
         assert np.max(np.abs(out - ref)) <= 2 * F32 * np.max(np.abs(ref))
+        # the float64 generator (pp_gen_gaussian_portrait_f64): double evaluation when there is no scattering
+        out64 = pl.gen_gaussian_portrait(code, _params(gm, tau_s * nbin / P), gm["alpha"], gm["nu_ref"], dtype=np.float64)
+        assert out64.dtype == np.float64
+        assert np.max(np.abs(out64 - ref)) <= (1e-13 if tau_s == 0 else 2 * F32) * np.max(np.abs(ref))
+        pl.set_model(out64, freqs)                        # (float64 models go through pp_set_model_f64)
+        assert 0.0 < pl.stats()["x_keep_frac"] <= 1.0
         # device-resident output feeds set_model directly: same fit as with the host model
         import torch
         dev = pl.gen_gaussian_portrait(code, _params(gm, tau_s * nbin / P), gm["alpha"], gm["nu_ref"], device_out=True)
