@@ -170,3 +170,30 @@ def test_bounds_and_frequency_table_helpers():
     assert np.array_equal(tables[0], fA) and np.array_equal(tables[1], fB)
     tables, table_of = pptoas._freq_tables(np.tile(fA, (4, 1)))
     assert tables.shape == (1, 8) and list(table_of) == [0, 0, 0, 0]
+
+
+def test_round2_host_helpers():
+    """Host-side helpers added in round 2 (no GPU): the batched guess_fit_freq, the model-array policy of the
+    facade, the scipy return-code mapping."""
+    from pulseportraiture_b200 import pplib
+    from oracle import pp_oracle as orc
+    rng = np.random.RandomState(11)
+    f = np.sort(rng.uniform(400.0, 800.0, (6, 40)), axis=1)
+    snr = rng.uniform(0.0, 5.0, (6, 40))
+    m = rng.rand(6, 40) > 0.3
+    m[4] = False                                             # a subint without usable channels
+    got = pplib.guess_fit_freq_batch(f, snr, m)
+    for i in range(6):
+        if m[i].any():
+            assert abs(got[i] - pplib.guess_fit_freq(f[i, m[i]], snr[i, m[i]])) < 1e-10
+            assert abs(got[i] - orc.guess_fit_freq(f[i, m[i]], snr[i, m[i]])) < 1e-10
+        else:
+            assert got[i] == 0.0
+    # models: float32 arrays stay float32, everything else reaches the device as float64 (pp_set_model_f64)
+    a64 = np.arange(12.0).reshape(3, 4)
+    assert pplib._mdl(a64).dtype == np.float64 and pplib._mdl(a64.astype(np.float32)).dtype == np.float32
+    assert pplib._mdl(a64.astype(np.int32)).dtype == np.float64 and pplib._mdl(a64[:, ::2]).flags.c_contiguous
+    # device solver codes -> the codes the reference's scipy method would report for the same outcome
+    assert [pplib.scipy_return_code(c, "TNC") for c in (0, 1, 3)] == [1, 3, 6]
+    assert [pplib.scipy_return_code(c, "trust-ncg") for c in (0, 1, 3)] == [2, 1, 3]
+    assert pplib.scipy_return_code(0, "Newton-CG") == 0
